@@ -1,0 +1,243 @@
+/*
+ * librvae_b200 - C ABI of the B200-native hot path for the rawaudiovae frame-level VAE.
+ *
+ * The reference (kelseyicotton/rawaudiovae_kelsey) is pure Python/PyTorch and has no FFI of its own; each entry
+ * point below names the reference call site (file:line under the reference repo) whose work it replaces. The
+ * binding a maintainer of the reference would add is a ctypes stub - see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller (PyTorch) owns every buffer,
+ *     the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and CUDA-graph capturable;
+ *   - return value 0 = ok; non-zero = error code (1 invalid argument, 2 unsupported shape, 3 driver, 4 state,
+ *     1000 + cudaError_t); rvae_last_error() returns a thread-local description;
+ *   - activations are row-major [frames, features]; weights are row-major [out_features, in_features] exactly
+ *     as torch.nn.Linear stores them (rawvae/model.py:13-17);
+ *   - bf16 planes: a tensor `t` is carried as t_hi = bf16(t) and, in fp32-emulation mode, t_lo = bf16(t - t_hi).
+ *     Passing NULL for every *_lo pointer selects bf16 mode;
+ *   - shape constraints of the sm_100a kernels: segment_length, n_units, latent_dim multiples of 64.
+ */
+#ifndef RVAE_B200_H
+#define RVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVAE_ABI_VERSION 1
+
+typedef struct rvae_ctx rvae_ctx;   /* per-device context (SM count, launch counter) */
+typedef struct rvae_plan rvae_plan; /* a bound training / inference step for fixed shapes and buffers */
+
+/* activation codes for rvae_linear_act_fwd */
+#define RVAE_ACT_NONE 0
+#define RVAE_ACT_RELU 1
+#define RVAE_ACT_TANH 2        /* accurate tanhf */
+#define RVAE_ACT_TANH_APPROX 3 /* tanh.approx.f32 (bf16 mode) */
+
+/* precision modes of a plan */
+#define RVAE_PRECISION_BF16 0 /* bf16 operands, fp32 accumulate */
+#define RVAE_PRECISION_FP32 1 /* split-bf16 (hi+lo) operands, 3 tensor-core passes, ~2^-16 relative */
+
+int rvae_abi_version(void);
+const char* rvae_last_error(void);
+
+int rvae_ctx_create(int device, rvae_ctx** out);
+void rvae_ctx_destroy(rvae_ctx* ctx);
+int rvae_ctx_num_sms(const rvae_ctx* ctx);
+/* number of kernels launched through this context so far (bench.py "gpu_launches") */
+uint64_t rvae_ctx_launch_count(const rvae_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Framing and resynthesis (rawvae/dataset.py)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Frame f of the batch = audio_pad[idx*hop : idx*hop + S] with idx = frame_idx[f] (if non-NULL) else
+ * first_frame + f; samples at or beyond n_samples read as 0 (the reference zero-pads: dataset.py:102-104,
+ * 141-143, 61-63). Replaces AudioDataset.__getitem__ (dataset.py:108-118), TestDataset.__getitem__ (:147-157),
+ * IterableAudioDataset.process_data's slicing loop (:68-75) and default_collate's stack.
+ * audio is float32 (audio_is_i16 = 0) or int16 PCM scaled by 1/32768 (audio_is_i16 = 1). Any of the three
+ * outputs may be NULL (at least one of out_hi / out_f32 required). Outputs are [n_frames, S]. */
+int rvae_frame_gather(rvae_ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples,
+                      const int64_t* frame_idx, int64_t first_frame, int64_t n_frames, int hop, int S,
+                      void* out_hi, void* out_lo, float* out_f32, void* stream);
+
+/* Overlap-add resynthesis: out[t] = mean over the frames covering t of frames[i, t - i*hop], t in [0, n_out).
+ * With hop == S this is frames.view(-1) (train_iterable.py:246, tutorial.ipynb:543). frames is fp32 [n_frames, S]. */
+int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out,
+                     int64_t n_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Elementwise pieces of the model / loss / optimizer
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* eps ~ N(0,1), Philox4x32-10 + Box-Muller keyed by (seed, offset). Replaces torch.randn_like (model.py:25). */
+int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* fp32 -> bf16 planes (hi, optional lo). Used for weight shadows and fp32 inputs. */
+int rvae_split_bf16(rvae_ctx* ctx, const float* src, int64_t n, void* hi, void* lo, void* stream);
+
+/* z = mu + eps * exp(0.5 * logvar) (model.py:23-26), fp32. */
+int rvae_reparameterize(rvae_ctx* ctx, const float* mu, const float* logvar, const float* eps, int64_t n, float* z,
+                        void* stream);
+
+/* loss = mean((xhat-x)^2) + beta * (-0.5) * mean(1 + logvar - mu^2 - exp(logvar)) (model.py:38-46).
+ * acc is a 2-double scratch accumulator; loss_out a device float. */
+int rvae_loss_fwd(rvae_ctx* ctx, const float* xhat, const float* x, const float* mu, const float* logvar,
+                  int64_t B, int S, int L, float beta, double* acc, float* loss_out, void* stream);
+
+/* Gradients of that loss w.r.t. xhat, mu, logvar, times the upstream scalar *grad_out (NULL = 1). */
+int rvae_loss_bwd(rvae_ctx* ctx, const float* xhat, const float* x, const float* mu, const float* logvar,
+                  int64_t B, int S, int L, float beta, const float* grad_out, float* g_xhat, float* g_mu,
+                  float* g_logvar, void* stream);
+
+/* da4 = g_xhat * (1 - xhat^2) as bf16 planes (tanh backward, autograd's TanhBackward for model.py:30). */
+int rvae_tanh_bwd(rvae_ctx* ctx, const float* g_xhat, const float* xhat, int64_t n, void* da_hi, void* da_lo,
+                  void* stream);
+
+/* out[n] (+)= sum over rows of a bf16 [M, N] matrix (hi + optional lo): bias gradients (AddmmBackward's sum). */
+int rvae_colsum(rvae_ctx* ctx, const void* hi, const void* lo, int64_t M, int N, int ld, float* out, int accumulate,
+                void* stream);
+
+/* *step += 1 (device scalar), then rvae_adam_step reads it. */
+int rvae_step_inc(rvae_ctx* ctx, float* step, void* stream);
+
+/* Fused Adam over a flat fp32 buffer (torch.optim.Adam semantics; train.py:163,193; train_iterable.py:180,210):
+ *   g' = g*grad_scale (+ weight_decay*p); m += (1-b1)(g'-m); v = b2 v + (1-b2) g'^2;
+ *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps),  t = *step.
+ * Optionally re-emits the bf16 shadow planes of p (what the GEMMs read). */
+int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, const float* step, void* shadow_hi,
+                   void* shadow_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * tcgen05 GEMMs with fused epilogues (rawvae/model.py:19-35 forward; autograd backward of the same)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* y = act(x W^T + b): x [M,K], W [N,K], b [N] (NULL = none). Outputs: y_hi/y_lo bf16 planes and/or y_f32,
+ * all [M,N]. Replaces F.relu(self.fc1(x)) (model.py:20), F.relu(self.fc3(z)) (:29), F.tanh(self.fc4(h3)) (:30). */
+int rvae_linear_act_fwd(rvae_ctx* ctx, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                        const float* bias, int M, int N, int K, int act, void* y_hi, void* y_lo, float* y_f32,
+                        void* stream);
+
+/* Encoder head + reparameterisation + KL (model.py:21,23-26,45): W2 = [fc21.weight; fc22.weight] stacked [2L,K],
+ * b2 = [fc21.bias; fc22.bias] [2L]; mu, logvar fp32 [M,L]; z = mu + eps*exp(logvar/2) as bf16 planes.
+ * Optional extras for the backward pass: esh = eps*sigma/2, g_mu = kl_grad_scale*mu,
+ * g_logvar = kl_grad_scale*(exp(logvar)-1)/2 (all fp32 [M,L]); kl_acc[0] += sum(1+logvar-mu^2-exp(logvar)). */
+int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w2_hi, const void* w2_lo,
+                         const float* b2, int M, int L, int K, const float* eps, float* mu, float* logvar,
+                         void* z_hi, void* z_lo, float* esh, float* g_mu, float* g_logvar, float kl_grad_scale,
+                         double* kl_acc, void* stream);
+
+/* Decoder output + reconstruction loss + its gradient (model.py:30,39): xhat = tanh(h3 W4^T + b4) [M,S] (fp32,
+ * optional); mse_acc[0] += sum((xhat-x)^2); da4 = grad_scale*(xhat-x)*(1-xhat^2) as bf16 planes (optional),
+ * grad_scale = 2/(B*S). x is given as bf16 planes. */
+int rvae_out_tanh_mse_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w4_hi, const void* w4_lo,
+                          const float* b4, int M, int S, int K, const void* x_hi, const void* x_lo, int tanh_approx,
+                          float* xhat, void* da_hi, void* da_lo, float grad_scale, double* mse_acc, void* stream);
+
+/* dX = (dY W) * [mask > 0]: dY [M,Kd], W [Kd,N] row-major (the Linear weight [out=Kd, in=N]), mask bf16 [M,N]
+ * (NULL = no mask). AddmmBackward dgrad + ReluBackward (threshold_backward) for fc4->h3 and fc21/fc22->h1. */
+int rvae_dgrad_relu(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, int M,
+                    int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, void* stream);
+
+/* Latent backward: dz = da3 W3 (W3 [H,L]); d_ml[:, :L] = dz + g_mu; d_ml[:, L:] = dz*esh + g_logvar; d_ml is bf16
+ * planes [M, 2L]. Backward of reparameterize (model.py:24-26) merged with the KL gradient. */
+int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, const void* w3_hi, const void* w3_lo,
+                      int M, int L, int H, const float* esh, const float* g_mu, const float* g_logvar, void* dml_hi,
+                      void* dml_lo, void* stream);
+
+/* dW (+)= dY^T X: dY [B,M], X [B,N], dW fp32 [M,N]. accumulate = 0 overwrites (single split), 1 adds (red.add;
+ * dW must hold the running sum, e.g. zeros). k_splits = 0 lets the library choose. AddmmBackward wgrad. */
+int rvae_wgrad(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, int B, int M,
+               int N, float* dW, int accumulate, int k_splits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Plan: the whole step (forward + loss + backward + Adam) for fixed shapes and bound buffers, issued from C so
+ * one call enqueues every kernel (train.py:184-193, train_iterable.py:200-210).
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Flat parameter layout (fp32 elements), used for params / grads / exp_avg / exp_avg_sq / bf16 shadows:
+ *   W1 [H,S] | W2 = [fc21.weight; fc22.weight] [2L,H] | W3 [H,L] | W4 [S,H] | b1 [H] | b2 [2L] | b3 [H] | b4 [S] */
+typedef struct rvae_layout {
+  int64_t w1, w2, w3, w4, b1, b2, b3, b4; /* element offsets */
+  int64_t total;                          /* total elements (5 772 800 for default.ini) */
+} rvae_layout;
+
+int rvae_param_layout(int S, int H, int L, rvae_layout* out);
+
+typedef struct rvae_plan_buffers {
+  float* params;    /* [total] fp32 master weights */
+  float* grads;     /* [total] fp32 gradients (written every step) */
+  float* exp_avg;   /* [total] */
+  float* exp_avg_sq;/* [total] */
+  float* step;      /* device scalar, Adam step count t as fp32 (torch state format) */
+  void* shadow_hi;  /* [total] bf16 */
+  void* shadow_lo;  /* [total] bf16, fp32 mode only (else NULL) */
+  void* workspace;  /* rvae_plan_workspace_bytes() bytes, 256-byte aligned */
+} rvae_plan_buffers;
+
+int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int precision, rvae_plan** out);
+void rvae_plan_destroy(rvae_plan* plan);
+size_t rvae_plan_workspace_bytes(const rvae_plan* plan);
+int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* bufs);
+
+/* Refresh the bf16 shadow planes from the fp32 master weights (after load_state_dict / manual edits). */
+int rvae_plan_sync_shadow(rvae_plan* plan, void* stream);
+
+/* Load a batch into the plan's input buffer: frames gathered from a wav buffer (see rvae_frame_gather) ... */
+int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                          const int64_t* frame_idx, int64_t first_frame, int batch, int hop, void* stream);
+/* ... or an fp32 [batch, S] matrix already on the device. */
+int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* stream);
+
+/* eps for the loaded batch: copy from a caller tensor (parity runs) or generate with Philox (seed, offset). */
+int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream);
+int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, void* stream);
+
+/* Redirect the fp32 results of the next forward calls into caller tensors ([batch,L], [batch,L], [batch,S]);
+ * NULL = keep them in the workspace. Used by the autograd wrapper so returned tensors outlive the step. */
+int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat);
+
+/* Forward. fused_loss = 1: the epilogues also accumulate the MSE / KL sums and emit the loss gradients
+ * (da4, g_mu, g_logvar) so that rvae_plan_backward can run without a separate loss kernel
+ * (model.py:32-35 + :38-46 + the head of loss.backward()). fused_loss = 0: plain model(x) - xhat, mu, logvar
+ * (+ what an external backward needs). want_xhat: materialise xhat fp32 (always done when fused_loss = 0). */
+int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_xhat, void* stream);
+/* Backward from external upstream gradients (autograd path): g_xhat [batch,S], g_mu, g_logvar [batch,L] fp32,
+ * xhat = the forward's output. Runs tanh backward then all four stages. */
+int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const float* xhat, const float* g_mu,
+                                const float* g_logvar, void* stream);
+/* Backward stage s = 0..3 (fc4 | fc3 | fc21+fc22 | fc1 gradients complete after stage s - the allreduce buckets,
+ * in backward-completion order); stage -1 runs all four. Gradients land in bufs.grads. */
+int rvae_plan_backward(rvae_plan* plan, int stage, void* stream);
+/* loss -> *loss_out (device float, may be NULL), clears the loss sums, *step += 1. */
+int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream);
+/* Adam over the flat buffers (+ shadow refresh). grad_scale = 1/world_size under data parallelism. */
+int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, void* stream);
+/* forward + finish_loss + backward(-1) + adam in one call (single-GPU training step). */
+int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, float* loss_out, void* stream);
+
+/* Device pointers into the workspace for the current batch (valid after forward): fp32 [batch, ...]. */
+const float* rvae_plan_mu(const rvae_plan* plan);
+const float* rvae_plan_logvar(const rvae_plan* plan);
+const float* rvae_plan_xhat(const rvae_plan* plan);
+const float* rvae_plan_eps(const rvae_plan* plan);
+/* gradient bucket s (see rvae_plan_backward): pointer into bufs.grads and element count. Buckets 0..3 are the
+ * four weight matrices in backward-completion order; bucket 4 is the bias block. */
+int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count);
+
+/* Inference: decode latents z (fp32 [batch, L]) -> xhat fp32 [batch, S] (model.py:28-30). */
+int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out, void* stream);
+/* Inference: encode the loaded batch -> mu, logvar (model.py:19-21); results via rvae_plan_mu/logvar. */
+int rvae_plan_encode(rvae_plan* plan, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVAE_B200_H */

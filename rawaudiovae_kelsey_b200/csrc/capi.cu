@@ -1,0 +1,712 @@
+// C ABI (include/rvae_b200.h): context, op-level entry points and the plan that issues a whole training or
+// inference step from C. No torch types cross this boundary.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "../../include/rvae_b200.h"
+#include "common.h"
+
+namespace rvae {
+const char* last_error();
+}
+
+using namespace rvae;
+
+struct rvae_ctx {
+  Ctx c;
+};
+
+static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline const __nv_bfloat16* BF(const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+static inline __nv_bfloat16* BF(void* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+
+extern "C" {
+
+int rvae_abi_version(void) { return RVAE_ABI_VERSION; }
+const char* rvae_last_error(void) { return rvae::last_error(); }
+
+int rvae_ctx_create(int device, rvae_ctx** out) {
+  RVAE_REQUIRE(out != nullptr, RVAE_ERR_INVALID, "ctx_create: null out");
+  int count = 0;
+  RVAE_CUDA(cudaGetDeviceCount(&count));
+  RVAE_REQUIRE(device >= 0 && device < count, RVAE_ERR_INVALID, "ctx_create: device %d of %d", device, count);
+  cudaDeviceProp prop;
+  RVAE_CUDA(cudaGetDeviceProperties(&prop, device));
+  RVAE_REQUIRE(prop.major == 10, RVAE_ERR_UNSUPPORTED,
+               "device %d is sm_%d%d; librvae_b200 contains sm_100a code only (no fallback path)", device, prop.major,
+               prop.minor);
+  rvae_ctx* ctx = new (std::nothrow) rvae_ctx();
+  RVAE_REQUIRE(ctx != nullptr, RVAE_ERR_INVALID, "ctx_create: out of host memory");
+  ctx->c.device = device;
+  ctx->c.num_sms = prop.multiProcessorCount;
+  ctx->c.launches = 0;
+  ctx->c.force_block_n = 0;
+  if (const char* e = getenv("RVAE_BLOCK_N")) ctx->c.force_block_n = atoi(e);
+  *out = ctx;
+  return RVAE_OK;
+}
+void rvae_ctx_destroy(rvae_ctx* ctx) { delete ctx; }
+int rvae_ctx_num_sms(const rvae_ctx* ctx) { return ctx ? ctx->c.num_sms : 0; }
+uint64_t rvae_ctx_launch_count(const rvae_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+#define CTX_OR_FAIL(ctx) RVAE_REQUIRE((ctx) != nullptr, RVAE_ERR_INVALID, "null rvae_ctx")
+
+int rvae_frame_gather(rvae_ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples,
+                      const int64_t* frame_idx, int64_t first_frame, int64_t n_frames, int hop, int S, void* out_hi,
+                      void* out_lo, float* out_f32, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_frame_gather(&ctx->c, audio, audio_is_i16, n_samples, frame_idx, first_frame, n_frames, hop, S,
+                             BF(out_hi), BF(out_lo), out_f32, S_(stream));
+}
+int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
+                     void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_overlap_add(&ctx->c, frames, n_frames, S, hop, out, n_out, S_(stream));
+}
+int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_randn(&ctx->c, out, n, seed, offset, S_(stream));
+}
+int rvae_split_bf16(rvae_ctx* ctx, const float* src, int64_t n, void* hi, void* lo, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_split_bf16(&ctx->c, src, n, BF(hi), BF(lo), S_(stream));
+}
+int rvae_reparameterize(rvae_ctx* ctx, const float* mu, const float* logvar, const float* eps, int64_t n, float* z,
+                        void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_reparam(&ctx->c, mu, logvar, eps, n, z, S_(stream));
+}
+int rvae_loss_fwd(rvae_ctx* ctx, const float* xhat, const float* x, const float* mu, const float* logvar, int64_t B,
+                  int S, int L, float beta, double* acc, float* loss_out, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_loss_fwd(&ctx->c, xhat, x, mu, logvar, B, S, L, beta, acc, loss_out, S_(stream));
+}
+int rvae_loss_bwd(rvae_ctx* ctx, const float* xhat, const float* x, const float* mu, const float* logvar, int64_t B,
+                  int S, int L, float beta, const float* grad_out, float* g_xhat, float* g_mu, float* g_logvar,
+                  void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_loss_bwd(&ctx->c, xhat, x, mu, logvar, B, S, L, beta, grad_out, g_xhat, g_mu, g_logvar, S_(stream));
+}
+int rvae_tanh_bwd(rvae_ctx* ctx, const float* g_xhat, const float* xhat, int64_t n, void* da_hi, void* da_lo,
+                  void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_tanh_bwd(&ctx->c, g_xhat, xhat, n, BF(da_hi), BF(da_lo), S_(stream));
+}
+int rvae_colsum(rvae_ctx* ctx, const void* hi, const void* lo, int64_t M, int N, int ld, float* out, int accumulate,
+                void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_colsum(&ctx->c, BF(hi), BF(lo), M, N, ld, out, accumulate, S_(stream));
+}
+int rvae_step_inc(rvae_ctx* ctx, float* step, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_step_inc(&ctx->c, step, S_(stream));
+}
+int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, const float* step, void* shadow_hi,
+                   void* shadow_lo, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_adam(&ctx->c, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step, BF(shadow_hi),
+                     BF(shadow_lo), S_(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GEMM-level ops
+// ---------------------------------------------------------------------------------------------------------
+static GemmDesc desc_base(int epi, int M, int N, int K) {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.epi = epi; d.M = M; d.N = N; d.K = K;
+  return d;
+}
+static Operand op(const void* hi, const void* lo, int major, int ld) {
+  Operand o;
+  o.hi = BF(hi); o.lo = BF(lo); o.major = major; o.ld = ld;
+  return o;
+}
+
+int rvae_linear_act_fwd(rvae_ctx* ctx, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                        const float* bias, int M, int N, int K, int act, void* y_hi, void* y_lo, float* y_f32,
+                        void* stream) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(y_hi || y_f32, RVAE_ERR_INVALID, "linear_act_fwd: no output buffer");
+  GemmDesc d = desc_base(EPI_LINEAR, M, N, K);
+  d.A = op(x_hi, x_lo, MAJOR_K, K);
+  d.B = op(w_hi, w_lo, MAJOR_K, K);
+  d.args.bias = bias; d.args.act = act; d.args.ldo = N;
+  d.args.out_hi = BF(y_hi); d.args.out_lo = BF(y_lo); d.args.out_f32 = y_f32;
+  return gemm_launch(&ctx->c, d, S_(stream));
+}
+
+int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w2_hi, const void* w2_lo,
+                         const float* b2, int M, int L, int K, const float* eps, float* mu, float* logvar, void* z_hi,
+                         void* z_lo, float* esh, float* g_mu, float* g_logvar, float kl_grad_scale, double* kl_acc,
+                         void* stream) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(b2 && mu && logvar, RVAE_ERR_INVALID, "encode_head_fwd: null buffer");
+  GemmDesc d = desc_base(EPI_HEAD, M, 2 * L, K);
+  d.head_L = L;
+  d.A = op(h_hi, h_lo, MAJOR_K, K);
+  d.B = op(w2_hi, w2_lo, MAJOR_K, K);
+  d.args.bias = b2; d.args.in0 = eps; d.args.out_f32 = mu; d.args.out_f32_b = logvar;
+  d.args.out_hi = BF(z_hi); d.args.out_lo = BF(z_lo);
+  d.args.aux0 = esh; d.args.aux1 = g_mu; d.args.aux2 = g_logvar;
+  d.args.c0 = kl_grad_scale; d.args.loss_acc = kl_acc; d.args.L = L; d.args.ldo = L;
+  return gemm_launch(&ctx->c, d, S_(stream));
+}
+
+int rvae_out_tanh_mse_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w4_hi, const void* w4_lo,
+                          const float* b4, int M, int S, int K, const void* x_hi, const void* x_lo, int tanh_approx,
+                          float* xhat, void* da_hi, void* da_lo, float grad_scale, double* mse_acc, void* stream) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(b4 && x_hi, RVAE_ERR_INVALID, "out_tanh_mse_fwd: null buffer");
+  GemmDesc d = desc_base(EPI_OUT, M, S, K);
+  d.A = op(h_hi, h_lo, MAJOR_K, K);
+  d.B = op(w4_hi, w4_lo, MAJOR_K, K);
+  d.args.bias = b4; d.args.in0 = x_hi; d.args.in1 = x_lo; d.args.out_f32 = xhat;
+  d.args.out_hi = BF(da_hi); d.args.out_lo = BF(da_lo);
+  d.args.act = tanh_approx ? ACT_TANH_APPROX : ACT_TANH;
+  d.args.c0 = grad_scale; d.args.loss_acc = mse_acc; d.args.ldo = S;
+  return gemm_launch(&ctx->c, d, S_(stream));
+}
+
+int rvae_dgrad_relu(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, int M,
+                    int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, void* stream) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(dx_hi, RVAE_ERR_INVALID, "dgrad_relu: null output");
+  GemmDesc d = desc_base(EPI_DRELU, M, N, Kd);
+  d.A = op(dy_hi, dy_lo, MAJOR_K, Kd);
+  d.B = op(w_hi, w_lo, MAJOR_MN, N);
+  d.args.in0 = mask; d.args.out_hi = BF(dx_hi); d.args.out_lo = BF(dx_lo); d.args.ldo = N;
+  return gemm_launch(&ctx->c, d, S_(stream));
+}
+
+int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, const void* w3_hi, const void* w3_lo,
+                      int M, int L, int H, const float* esh, const float* g_mu, const float* g_logvar, void* dml_hi,
+                      void* dml_lo, void* stream) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(esh && g_mu && g_logvar && dml_hi, RVAE_ERR_INVALID, "dgrad_latent: null buffer");
+  GemmDesc d = desc_base(EPI_DZ, M, L, H);
+  d.A = op(da3_hi, da3_lo, MAJOR_K, H);
+  d.B = op(w3_hi, w3_lo, MAJOR_MN, L);
+  d.args.in0 = esh; d.args.in1 = g_mu; d.args.in2 = g_logvar;
+  d.args.out_hi = BF(dml_hi); d.args.out_lo = BF(dml_lo); d.args.ldo = 2 * L; d.args.L = L;
+  return gemm_launch(&ctx->c, d, S_(stream));
+}
+
+int rvae_wgrad(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, int B, int M,
+               int N, float* dW, int accumulate, int k_splits, void* stream) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(dW, RVAE_ERR_INVALID, "wgrad: null output");
+  RVAE_REQUIRE(M % 64 == 0, RVAE_ERR_UNSUPPORTED, "wgrad: M=%d must be a multiple of 64", M);
+  GemmDesc d = desc_base(EPI_WGRAD, M, N, B);
+  d.A = op(dy_hi, dy_lo, MAJOR_MN, M);
+  d.B = op(x_hi, x_lo, MAJOR_MN, N);
+  d.args.out_f32 = dW; d.args.ldo = N; d.args.accumulate = accumulate;
+  d.k_splits = accumulate ? k_splits : 1;
+  return gemm_launch(&ctx->c, d, S_(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// parameter layout
+// ---------------------------------------------------------------------------------------------------------
+int rvae_param_layout(int S, int H, int L, rvae_layout* out) {
+  RVAE_REQUIRE(out, RVAE_ERR_INVALID, "param_layout: null out");
+  RVAE_REQUIRE(S > 0 && H > 0 && L > 0 && S % 64 == 0 && H % 64 == 0 && L % 64 == 0, RVAE_ERR_UNSUPPORTED,
+               "segment_length=%d, n_units=%d, latent_dim=%d must be positive multiples of 64", S, H, L);
+  int64_t o = 0;
+  out->w1 = o; o += (int64_t)H * S;
+  out->w2 = o; o += (int64_t)2 * L * H;
+  out->w3 = o; o += (int64_t)H * L;
+  out->w4 = o; o += (int64_t)S * H;
+  out->b1 = o; o += H;
+  out->b2 = o; o += 2 * L;
+  out->b3 = o; o += H;
+  out->b4 = o; o += S;
+  out->total = o;
+  return RVAE_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Planes {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+};
+
+enum GemmId { G_F1, G_F2, G_F3, G_F4_OUT, G_F4_LIN, G_B4W, G_B4D, G_B3W, G_B3D, G_B2W, G_B2D, G_B1W, G_COUNT };
+
+struct GemmSet {
+  PreparedGemm g[G_COUNT];
+  bool ready[G_COUNT];
+};
+
+}  // namespace
+
+struct rvae_plan {
+  rvae_ctx* ctx;
+  int S, H, L, max_batch, precision;
+  rvae_layout lay;
+  rvae_plan_buffers bufs;
+  bool bound;
+  size_t ws_bytes;
+  // workspace sections
+  Planes x, h1, z, h3, da4, da3, dml, da1;
+  float *mu, *lv, *eps, *esh, *gmu, *glv, *xhat;
+  double* loss_acc;
+  // redirected outputs
+  float *out_mu, *out_lv, *out_xhat;
+  int batch;        // current batch
+  bool have_eps;
+  std::map<int, GemmSet> sets;  // prepared GEMMs per batch size
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Walks the workspace layout; with base == nullptr only sizes are computed.
+size_t carve(rvae_plan* p, uint8_t* base) {
+  const size_t B = p->max_batch, S = p->S, H = p->H, L = p->L;
+  const bool lo = p->precision == RVAE_PRECISION_FP32;
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* r = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return r;
+  };
+  auto planes = [&](Planes& pl, size_t elems) {
+    pl.hi = reinterpret_cast<__nv_bfloat16*>(take(elems * 2));
+    pl.lo = lo ? reinterpret_cast<__nv_bfloat16*>(take(elems * 2)) : nullptr;
+  };
+  planes(p->x, B * S);
+  planes(p->h1, B * H);
+  planes(p->z, B * L);
+  planes(p->h3, B * H);
+  planes(p->da4, B * S);
+  planes(p->da3, B * H);
+  planes(p->dml, B * 2 * L);
+  planes(p->da1, B * H);
+  p->mu = reinterpret_cast<float*>(take(B * L * 4));
+  p->lv = reinterpret_cast<float*>(take(B * L * 4));
+  p->eps = reinterpret_cast<float*>(take(B * L * 4));
+  p->esh = reinterpret_cast<float*>(take(B * L * 4));
+  p->gmu = reinterpret_cast<float*>(take(B * L * 4));
+  p->glv = reinterpret_cast<float*>(take(B * L * 4));
+  p->xhat = reinterpret_cast<float*>(take(B * S * 4));
+  p->loss_acc = reinterpret_cast<double*>(take(2 * sizeof(double)));
+  return off;
+}
+
+Operand opnd(const Planes& pl, int major, int ld) {
+  Operand o;
+  o.hi = pl.hi; o.lo = pl.lo; o.major = major; o.ld = ld;
+  return o;
+}
+Operand wopnd(const rvae_plan* p, int64_t off, int major, int ld) {
+  Operand o;
+  o.hi = BF(p->bufs.shadow_hi) + off;
+  o.lo = p->bufs.shadow_lo ? BF(p->bufs.shadow_lo) + off : nullptr;
+  o.major = major; o.ld = ld;
+  return o;
+}
+
+int prepare(rvae_plan* p, GemmSet& gs, int id) {
+  if (gs.ready[id]) return RVAE_OK;
+  const int B = p->batch, S = p->S, H = p->H, L = p->L;
+  const rvae_layout& ly = p->lay;
+  float* params = p->bufs.params;
+  float* grads = p->bufs.grads;
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  const bool bf16_mode = p->precision == RVAE_PRECISION_BF16;
+  switch (id) {
+    case G_F1:
+      d.epi = EPI_LINEAR; d.M = B; d.N = H; d.K = S;
+      d.A = opnd(p->x, MAJOR_K, S); d.B = wopnd(p, ly.w1, MAJOR_K, S);
+      d.args.bias = params + ly.b1; d.args.act = ACT_RELU; d.args.ldo = H;
+      d.args.out_hi = p->h1.hi; d.args.out_lo = p->h1.lo;
+      break;
+    case G_F2:
+      d.epi = EPI_HEAD; d.M = B; d.N = 2 * L; d.K = H; d.head_L = L;
+      d.A = opnd(p->h1, MAJOR_K, H); d.B = wopnd(p, ly.w2, MAJOR_K, H);
+      d.args.bias = params + ly.b2; d.args.in0 = p->eps; d.args.out_f32 = p->mu; d.args.out_f32_b = p->lv;
+      d.args.out_hi = p->z.hi; d.args.out_lo = p->z.lo; d.args.aux0 = p->esh; d.args.aux1 = p->gmu;
+      d.args.aux2 = p->glv; d.args.loss_acc = p->loss_acc + 1; d.args.L = L; d.args.ldo = L;
+      break;
+    case G_F3:
+      d.epi = EPI_LINEAR; d.M = B; d.N = H; d.K = L;
+      d.A = opnd(p->z, MAJOR_K, L); d.B = wopnd(p, ly.w3, MAJOR_K, L);
+      d.args.bias = params + ly.b3; d.args.act = ACT_RELU; d.args.ldo = H;
+      d.args.out_hi = p->h3.hi; d.args.out_lo = p->h3.lo;
+      break;
+    case G_F4_OUT:
+      d.epi = EPI_OUT; d.M = B; d.N = S; d.K = H;
+      d.A = opnd(p->h3, MAJOR_K, H); d.B = wopnd(p, ly.w4, MAJOR_K, H);
+      d.args.bias = params + ly.b4; d.args.in0 = p->x.hi; d.args.in1 = p->x.lo; d.args.out_f32 = p->xhat;
+      d.args.out_hi = p->da4.hi; d.args.out_lo = p->da4.lo;
+      d.args.act = bf16_mode ? ACT_TANH_APPROX : ACT_TANH;
+      d.args.loss_acc = p->loss_acc; d.args.ldo = S;
+      break;
+    case G_F4_LIN:
+      d.epi = EPI_LINEAR; d.M = B; d.N = S; d.K = H;
+      d.A = opnd(p->h3, MAJOR_K, H); d.B = wopnd(p, ly.w4, MAJOR_K, H);
+      d.args.bias = params + ly.b4; d.args.act = bf16_mode ? ACT_TANH_APPROX : ACT_TANH; d.args.ldo = S;
+      d.args.out_f32 = p->xhat;
+      break;
+    case G_B4W:
+      d.epi = EPI_WGRAD; d.M = S; d.N = H; d.K = B;
+      d.A = opnd(p->da4, MAJOR_MN, S); d.B = opnd(p->h3, MAJOR_MN, H);
+      d.args.out_f32 = grads + ly.w4; d.args.ldo = H; d.args.accumulate = 1;
+      break;
+    case G_B4D:
+      d.epi = EPI_DRELU; d.M = B; d.N = H; d.K = S;
+      d.A = opnd(p->da4, MAJOR_K, S); d.B = wopnd(p, ly.w4, MAJOR_MN, H);
+      d.args.in0 = p->h3.hi; d.args.out_hi = p->da3.hi; d.args.out_lo = p->da3.lo; d.args.ldo = H;
+      break;
+    case G_B3W:
+      d.epi = EPI_WGRAD; d.M = H; d.N = L; d.K = B;
+      d.A = opnd(p->da3, MAJOR_MN, H); d.B = opnd(p->z, MAJOR_MN, L);
+      d.args.out_f32 = grads + ly.w3; d.args.ldo = L; d.args.accumulate = 1;
+      break;
+    case G_B3D:
+      d.epi = EPI_DZ; d.M = B; d.N = L; d.K = H;
+      d.A = opnd(p->da3, MAJOR_K, H); d.B = wopnd(p, ly.w3, MAJOR_MN, L);
+      d.args.in0 = p->esh; d.args.in1 = p->gmu; d.args.in2 = p->glv;
+      d.args.out_hi = p->dml.hi; d.args.out_lo = p->dml.lo; d.args.ldo = 2 * L; d.args.L = L;
+      break;
+    case G_B2W:
+      d.epi = EPI_WGRAD; d.M = 2 * L; d.N = H; d.K = B;
+      d.A = opnd(p->dml, MAJOR_MN, 2 * L); d.B = opnd(p->h1, MAJOR_MN, H);
+      d.args.out_f32 = grads + ly.w2; d.args.ldo = H; d.args.accumulate = 1;
+      break;
+    case G_B2D:
+      d.epi = EPI_DRELU; d.M = B; d.N = H; d.K = 2 * L;
+      d.A = opnd(p->dml, MAJOR_K, 2 * L); d.B = wopnd(p, ly.w2, MAJOR_MN, H);
+      d.args.in0 = p->h1.hi; d.args.out_hi = p->da1.hi; d.args.out_lo = p->da1.lo; d.args.ldo = H;
+      break;
+    case G_B1W:
+      d.epi = EPI_WGRAD; d.M = H; d.N = S; d.K = B;
+      d.A = opnd(p->da1, MAJOR_MN, H); d.B = opnd(p->x, MAJOR_MN, S);
+      d.args.out_f32 = grads + ly.w1; d.args.ldo = S; d.args.accumulate = 1;
+      break;
+    default:
+      return set_error(RVAE_ERR_INVALID, "plan: bad gemm id %d", id);
+  }
+  RVAE_CHECK(gemm_prepare(&p->ctx->c, d, &gs.g[id]));
+  gs.ready[id] = true;
+  return RVAE_OK;
+}
+
+int get_set(rvae_plan* p, GemmSet** out) {
+  auto it = p->sets.find(p->batch);
+  if (it == p->sets.end()) {
+    GemmSet gs;
+    memset(&gs, 0, sizeof(gs));
+    it = p->sets.emplace(p->batch, gs).first;
+  }
+  *out = &it->second;
+  return RVAE_OK;
+}
+
+int run(rvae_plan* p, int id, cudaStream_t st, const EpiArgs* override_args = nullptr) {
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  RVAE_CHECK(prepare(p, *gs, id));
+  if (override_args) {
+    PreparedGemm g = gs->g[id];
+    const int L = g.params.epi.L;
+    g.params.epi = *override_args;
+    if (g.params.epi.L == 0) g.params.epi.L = L;
+    return gemm_run(&p->ctx->c, g, st);
+  }
+  return gemm_run(&p->ctx->c, gs->g[id], st);
+}
+
+int check_ready(const rvae_plan* p, bool need_batch) {
+  RVAE_REQUIRE(p != nullptr, RVAE_ERR_INVALID, "null rvae_plan");
+  RVAE_REQUIRE(p->bound, RVAE_ERR_STATE, "plan: rvae_plan_bind has not been called");
+  if (need_batch) RVAE_REQUIRE(p->batch > 0, RVAE_ERR_STATE, "plan: no batch loaded");
+  return RVAE_OK;
+}
+
+int backward_stage(rvae_plan* p, int stage, const EpiArgs* dz_override, cudaStream_t st) {
+  Ctx* c = &p->ctx->c;
+  const int B = p->batch, S = p->S, H = p->H, L = p->L;
+  const rvae_layout& ly = p->lay;
+  float* grads = p->bufs.grads;
+  switch (stage) {
+    case 0:
+      RVAE_CUDA(cudaMemsetAsync(grads + ly.w4, 0, sizeof(float) * (size_t)S * H, st));
+      RVAE_CHECK(run(p, G_B4W, st));
+      RVAE_CHECK(launch_colsum(c, p->da4.hi, p->da4.lo, B, S, S, grads + ly.b4, 0, st));
+      return RVAE_OK;
+    case 1:
+      RVAE_CHECK(run(p, G_B4D, st));
+      RVAE_CUDA(cudaMemsetAsync(grads + ly.w3, 0, sizeof(float) * (size_t)H * L, st));
+      RVAE_CHECK(run(p, G_B3W, st));
+      RVAE_CHECK(launch_colsum(c, p->da3.hi, p->da3.lo, B, H, H, grads + ly.b3, 0, st));
+      return RVAE_OK;
+    case 2:
+      RVAE_CHECK(run(p, G_B3D, st, dz_override));
+      RVAE_CUDA(cudaMemsetAsync(grads + ly.w2, 0, sizeof(float) * (size_t)2 * L * H, st));
+      RVAE_CHECK(run(p, G_B2W, st));
+      RVAE_CHECK(launch_colsum(c, p->dml.hi, p->dml.lo, B, 2 * L, 2 * L, grads + ly.b2, 0, st));
+      return RVAE_OK;
+    case 3:
+      RVAE_CHECK(run(p, G_B2D, st));
+      RVAE_CUDA(cudaMemsetAsync(grads + ly.w1, 0, sizeof(float) * (size_t)H * S, st));
+      RVAE_CHECK(run(p, G_B1W, st));
+      RVAE_CHECK(launch_colsum(c, p->da1.hi, p->da1.lo, B, H, H, grads + ly.b1, 0, st));
+      return RVAE_OK;
+    default:
+      return set_error(RVAE_ERR_INVALID, "plan_backward: stage %d not in -1..3", stage);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int precision, rvae_plan** out) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(out, RVAE_ERR_INVALID, "plan_create: null out");
+  RVAE_REQUIRE(max_batch > 0, RVAE_ERR_INVALID, "plan_create: max_batch=%d", max_batch);
+  RVAE_REQUIRE(precision == RVAE_PRECISION_BF16 || precision == RVAE_PRECISION_FP32, RVAE_ERR_INVALID,
+               "plan_create: precision %d", precision);
+  rvae_layout lay;
+  RVAE_CHECK(rvae_param_layout(S, H, L, &lay));
+  rvae_plan* p = new (std::nothrow) rvae_plan();
+  RVAE_REQUIRE(p, RVAE_ERR_INVALID, "plan_create: out of host memory");
+  p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
+  p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false;
+  p->out_mu = p->out_lv = p->out_xhat = nullptr;
+  memset(&p->bufs, 0, sizeof(p->bufs));
+  p->ws_bytes = carve(p, nullptr);
+  *out = p;
+  return RVAE_OK;
+}
+
+void rvae_plan_destroy(rvae_plan* plan) { delete plan; }
+
+size_t rvae_plan_workspace_bytes(const rvae_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
+  RVAE_REQUIRE(plan && b, RVAE_ERR_INVALID, "plan_bind: null argument");
+  RVAE_REQUIRE(b->params && b->shadow_hi && b->workspace, RVAE_ERR_INVALID,
+               "plan_bind: params, shadow_hi and workspace are required");
+  RVAE_REQUIRE(plan->precision == RVAE_PRECISION_BF16 || b->shadow_lo, RVAE_ERR_INVALID,
+               "plan_bind: fp32 mode needs shadow_lo");
+  RVAE_REQUIRE((reinterpret_cast<uintptr_t>(b->workspace) & 255) == 0, RVAE_ERR_INVALID,
+               "plan_bind: workspace must be 256-byte aligned");
+  plan->bufs = *b;
+  if (plan->precision == RVAE_PRECISION_BF16) plan->bufs.shadow_lo = nullptr;
+  carve(plan, reinterpret_cast<uint8_t*>(b->workspace));
+  plan->sets.clear();
+  plan->bound = true;
+  plan->batch = 0;
+  return RVAE_OK;
+}
+
+int rvae_plan_sync_shadow(rvae_plan* plan, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  return launch_split_bf16(&plan->ctx->c, plan->bufs.params, plan->lay.total, BF(plan->bufs.shadow_hi),
+                           BF(plan->bufs.shadow_lo), S_(stream));
+}
+
+int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                          const int64_t* frame_idx, int64_t first_frame, int batch, int hop, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(batch > 0 && batch <= plan->max_batch, RVAE_ERR_INVALID, "plan_load_frames: batch %d not in 1..%d",
+               batch, plan->max_batch);
+  plan->batch = batch;
+  plan->have_eps = false;
+  return launch_frame_gather(&plan->ctx->c, audio, audio_is_i16, n_samples, frame_idx, first_frame, batch, hop,
+                             plan->S, plan->x.hi, plan->x.lo, nullptr, S_(stream));
+}
+
+int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(x, RVAE_ERR_INVALID, "plan_load_batch: null x");
+  RVAE_REQUIRE(batch > 0 && batch <= plan->max_batch, RVAE_ERR_INVALID, "plan_load_batch: batch %d not in 1..%d",
+               batch, plan->max_batch);
+  plan->batch = batch;
+  plan->have_eps = false;
+  return launch_split_bf16(&plan->ctx->c, x, (int64_t)batch * plan->S, plan->x.hi, plan->x.lo, S_(stream));
+}
+
+int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  RVAE_REQUIRE(eps, RVAE_ERR_INVALID, "plan_set_eps: null eps");
+  RVAE_CUDA(cudaMemcpyAsync(plan->eps, eps, sizeof(float) * (size_t)plan->batch * plan->L, cudaMemcpyDeviceToDevice,
+                            S_(stream)));
+  plan->have_eps = true;
+  return RVAE_OK;
+}
+
+int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  plan->have_eps = true;
+  return launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset, S_(stream));
+}
+
+int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat) {
+  RVAE_REQUIRE(plan, RVAE_ERR_INVALID, "null rvae_plan");
+  plan->out_mu = mu; plan->out_lv = logvar; plan->out_xhat = xhat;
+  return RVAE_OK;
+}
+
+int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_xhat, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  RVAE_REQUIRE(plan->have_eps, RVAE_ERR_STATE, "plan_forward: call rvae_plan_set_eps / rvae_plan_gen_eps first");
+  cudaStream_t st = S_(stream);
+  rvae_plan* p = plan;
+  const double BL = (double)p->batch * p->L, BS = (double)p->batch * p->S;
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+
+  RVAE_CHECK(run(p, G_F1, st));
+  {
+    RVAE_CHECK(prepare(p, *gs, G_F2));
+    EpiArgs a = gs->g[G_F2].params.epi;
+    if (p->out_mu) a.out_f32 = p->out_mu;
+    if (p->out_lv) a.out_f32_b = p->out_lv;
+    if (fused_loss) {
+      a.c0 = (float)((double)kl_beta / BL);
+    } else {
+      a.aux1 = nullptr; a.aux2 = nullptr; a.loss_acc = nullptr; a.c0 = 0.f;
+    }
+    RVAE_CHECK(run(p, G_F2, st, &a));
+  }
+  RVAE_CHECK(run(p, G_F3, st));
+  if (fused_loss) {
+    RVAE_CHECK(prepare(p, *gs, G_F4_OUT));
+    EpiArgs a = gs->g[G_F4_OUT].params.epi;
+    a.c0 = (float)(2.0 / BS);
+    a.out_f32 = want_xhat ? (p->out_xhat ? p->out_xhat : p->xhat) : nullptr;
+    RVAE_CHECK(run(p, G_F4_OUT, st, &a));
+  } else {
+    RVAE_CHECK(prepare(p, *gs, G_F4_LIN));
+    EpiArgs a = gs->g[G_F4_LIN].params.epi;
+    a.out_f32 = p->out_xhat ? p->out_xhat : p->xhat;
+    RVAE_CHECK(run(p, G_F4_LIN, st, &a));
+  }
+  return RVAE_OK;
+}
+
+int rvae_plan_backward(rvae_plan* plan, int stage, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  RVAE_REQUIRE(plan->bufs.grads, RVAE_ERR_STATE, "plan_backward: no grads buffer bound");
+  if (stage == -1) {
+    for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(plan, s, nullptr, S_(stream)));
+    return RVAE_OK;
+  }
+  return backward_stage(plan, stage, nullptr, S_(stream));
+}
+
+int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const float* xhat, const float* g_mu,
+                                const float* g_logvar, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  RVAE_REQUIRE(plan->bufs.grads, RVAE_ERR_STATE, "plan_backward_external: no grads buffer bound");
+  RVAE_REQUIRE(g_xhat && xhat && g_mu && g_logvar, RVAE_ERR_INVALID, "plan_backward_external: null gradient");
+  rvae_plan* p = plan;
+  cudaStream_t st = S_(stream);
+  RVAE_CHECK(launch_tanh_bwd(&p->ctx->c, g_xhat, xhat, (int64_t)p->batch * p->S, p->da4.hi, p->da4.lo, st));
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  RVAE_CHECK(prepare(p, *gs, G_B3D));
+  EpiArgs a = gs->g[G_B3D].params.epi;
+  a.in1 = g_mu;
+  a.in2 = g_logvar;
+  for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(p, s, s == 2 ? &a : nullptr, st));
+  return RVAE_OK;
+}
+
+int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  return launch_loss_finalize(&plan->ctx->c, plan->loss_acc, plan->batch, plan->S, plan->L, kl_beta, loss_out,
+                              plan->bufs.step, S_(stream));
+}
+
+int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  const rvae_plan_buffers& b = plan->bufs;
+  RVAE_REQUIRE(b.grads && b.exp_avg && b.exp_avg_sq && b.step, RVAE_ERR_STATE,
+               "plan_adam: grads / exp_avg / exp_avg_sq / step not bound");
+  return launch_adam(&plan->ctx->c, b.params, b.grads, b.exp_avg, b.exp_avg_sq, plan->lay.total, lr, beta1, beta2, eps,
+                     weight_decay, grad_scale, b.step, BF(b.shadow_hi), BF(b.shadow_lo), S_(stream));
+}
+
+int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, float* loss_out, void* stream) {
+  RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, stream));
+  RVAE_CHECK(rvae_plan_finish_loss(plan, kl_beta, loss_out, stream));
+  RVAE_CHECK(rvae_plan_backward(plan, -1, stream));
+  return rvae_plan_adam(plan, lr, beta1, beta2, eps, weight_decay, 1.0f, stream);
+}
+
+const float* rvae_plan_mu(const rvae_plan* plan) { return plan ? plan->mu : nullptr; }
+const float* rvae_plan_logvar(const rvae_plan* plan) { return plan ? plan->lv : nullptr; }
+const float* rvae_plan_xhat(const rvae_plan* plan) { return plan ? plan->xhat : nullptr; }
+const float* rvae_plan_eps(const rvae_plan* plan) { return plan ? plan->eps : nullptr; }
+
+int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count) {
+  RVAE_REQUIRE(plan && ptr && count, RVAE_ERR_INVALID, "plan_bucket: null argument");
+  RVAE_REQUIRE(plan->bound && plan->bufs.grads, RVAE_ERR_STATE, "plan_bucket: grads not bound");
+  const rvae_layout& ly = plan->lay;
+  float* g = plan->bufs.grads;
+  const int64_t S = plan->S, H = plan->H, L = plan->L;
+  switch (s) {
+    case 0: *ptr = g + ly.w4; *count = S * H; break;
+    case 1: *ptr = g + ly.w3; *count = H * L; break;
+    case 2: *ptr = g + ly.w2; *count = 2 * L * H; break;
+    case 3: *ptr = g + ly.w1; *count = H * S; break;
+    case 4: *ptr = g + ly.b1; *count = ly.total - ly.b1; break;
+    default: return set_error(RVAE_ERR_INVALID, "plan_bucket: bucket %d not in 0..4", s);
+  }
+  return RVAE_OK;
+}
+
+int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(z && xhat_out, RVAE_ERR_INVALID, "plan_decode: null buffer");
+  RVAE_REQUIRE(batch > 0 && batch <= plan->max_batch, RVAE_ERR_INVALID, "plan_decode: batch %d not in 1..%d", batch,
+               plan->max_batch);
+  rvae_plan* p = plan;
+  cudaStream_t st = S_(stream);
+  p->batch = batch;
+  p->have_eps = false;
+  RVAE_CHECK(launch_split_bf16(&p->ctx->c, z, (int64_t)batch * p->L, p->z.hi, p->z.lo, st));
+  RVAE_CHECK(run(p, G_F3, st));
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  RVAE_CHECK(prepare(p, *gs, G_F4_LIN));
+  EpiArgs a = gs->g[G_F4_LIN].params.epi;
+  a.out_f32 = xhat_out;
+  return run(p, G_F4_LIN, st, &a);
+}
+
+int rvae_plan_encode(rvae_plan* plan, void* stream) {
+  RVAE_CHECK(check_ready(plan, true));
+  rvae_plan* p = plan;
+  cudaStream_t st = S_(stream);
+  RVAE_CHECK(run(p, G_F1, st));
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  RVAE_CHECK(prepare(p, *gs, G_F2));
+  EpiArgs a = gs->g[G_F2].params.epi;
+  if (p->out_mu) a.out_f32 = p->out_mu;
+  if (p->out_lv) a.out_f32_b = p->out_lv;
+  a.in0 = nullptr; a.out_hi = nullptr; a.out_lo = nullptr;
+  a.aux0 = nullptr; a.aux1 = nullptr; a.aux2 = nullptr; a.loss_acc = nullptr;
+  return run(p, G_F2, st, &a);
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Internal (non-ABI) declarations shared by the translation units of librvae_b200.so.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "gemm.cuh"
+
+namespace rvae {
+
+// Error codes returned across the C ABI (0 = ok). CUDA runtime errors are returned as 1000 + cudaError_t.
+enum : int {
+  RVAE_OK = 0,
+  RVAE_ERR_INVALID = 1,      // bad argument (null pointer, misaligned buffer, negative size)
+  RVAE_ERR_UNSUPPORTED = 2,  // shape not supported by the sm_100a kernels (see DESIGN.md constraints)
+  RVAE_ERR_DRIVER = 3,       // cuTensorMapEncodeTiled or driver entry point failure
+  RVAE_ERR_STATE = 4,        // plan not bound / wrong call order
+  RVAE_ERR_CUDA_BASE = 1000,
+};
+
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t err, const char* what);
+
+#define RVAE_CUDA(expr)                                       \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::rvae::cuda_error(_e, #expr); \
+  } while (0)
+
+#define RVAE_CHECK(expr)           \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != RVAE_OK) return _rc; \
+  } while (0)
+
+#define RVAE_REQUIRE(cond, code, ...)                        \
+  do {                                                       \
+    if (!(cond)) return ::rvae::set_error(code, __VA_ARGS__); \
+  } while (0)
+
+struct Ctx {
+  int device;
+  int num_sms;
+  int force_block_n;  // 0 = heuristic, 128 / 256 = forced (env RVAE_BLOCK_N, for experiments)
+  uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
+};
+
+// A bf16 GEMM operand. K-major: storage [mn][k] (k contiguous, row pitch ld). MN-major: storage [k][mn].
+struct Operand {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;  // optional residual plane (fp32 emulation)
+  int major;
+  int ld;  // elements
+};
+
+struct GemmDesc {
+  int epi;
+  int M, N, K;
+  Operand A, B;
+  EpiArgs args;
+  int head_L;    // EPI_HEAD: latent width L (B holds 2L stacked rows, N must equal 2L)
+  int k_splits;  // EPI_WGRAD: requested split-K (0 = choose)
+};
+
+struct PreparedGemm {
+  GemmParams params;
+  int block_n;
+  int variant;  // index into the kernel table
+  int grid;
+  int smem_bytes;
+};
+
+int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out);
+int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream);
+int gemm_launch(Ctx* ctx, const GemmDesc& d, cudaStream_t stream);  // prepare + run
+
+// Elementwise launchers (elementwise.cu)
+int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples, const int64_t* frame_idx,
+                        int64_t first_frame, int64_t n_frames, int hop, int S, __nv_bfloat16* out_hi,
+                        __nv_bfloat16* out_lo, float* out_f32, cudaStream_t stream);
+int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
+                       cudaStream_t stream);
+int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t stream);
+int launch_split_bf16(Ctx* ctx, const float* src, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                      cudaStream_t stream);
+int launch_colsum(Ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t M, int N, int ld, float* out,
+                  int accumulate, cudaStream_t stream);
+int launch_loss_fwd(Ctx* ctx, const float* xhat, const float* x, const float* mu, const float* lv, int64_t B, int S,
+                    int L, float beta, double* acc, float* loss_out, cudaStream_t stream);
+int launch_loss_bwd(Ctx* ctx, const float* xhat, const float* x, const float* mu, const float* lv, int64_t B, int S,
+                    int L, float beta, const float* grad_out, float* g_xhat, float* g_mu, float* g_lv,
+                    cudaStream_t stream);
+int launch_tanh_bwd(Ctx* ctx, const float* g_xhat, const float* xhat, int64_t n, __nv_bfloat16* da_hi,
+                    __nv_bfloat16* da_lo, cudaStream_t stream);
+int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps, int64_t n, float* z,
+                   cudaStream_t stream);
+int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, float* step,
+                         cudaStream_t stream);
+int launch_adam(Ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
+                __nv_bfloat16* shadow_lo, cudaStream_t stream);
+int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream);
+
+}  // namespace rvae

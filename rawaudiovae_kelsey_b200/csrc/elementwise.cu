@@ -1,0 +1,572 @@
+// HBM-bound kernels of the hot path: framing / overlap-add, Philox normal noise, bf16 plane splitting,
+// bias-gradient column sums, the fused reparameterisation + reconstruction/KL loss kernels, and fused Adam.
+// All are coalesced, 128-bit vectorised, grid-strided with grids sized in multiples of the SM count.
+#include "common.h"
+
+namespace rvae {
+
+static inline int grid_for(const Ctx* ctx, int64_t work_items, int threads, int max_waves = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(ctx->num_sms) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+#define RVAE_LAUNCH_CHECK(ctx)           \
+  do {                                   \
+    RVAE_CUDA(cudaGetLastError());       \
+    (ctx)->launches++;                   \
+  } while (0)
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return ptx::pack_bf16x2(a, b); }
+
+__device__ __forceinline__ float block_sum_to_warp0(float v, float* smem) {
+  // returns the block total in every thread of warp 0
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    t = (lane < nw) ? smem[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-D1 framing: frame f = audio_pad[idx*hop : idx*hop + S], zero beyond n_samples (the reference zero-pads the
+// tail, rawvae/dataset.py:102-104,141-143). idx = frame_idx[f] (shuffled map-style batches) or first_frame + f
+// (streaming / sequential). One thread converts 8 consecutive samples.
+// ------------------------------------------------------------------------------------------------
+template <bool I16>
+__global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_samples,
+                                    const int64_t* __restrict__ frame_idx, int64_t first_frame, int64_t n_frames,
+                                    int hop, int S, __nv_bfloat16* __restrict__ out_hi,
+                                    __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32) {
+  const int vec_per_frame = S >> 3;
+  const int64_t total = n_frames * vec_per_frame;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / vec_per_frame;
+    const int c = static_cast<int>(i - f * vec_per_frame) << 3;
+    const int64_t fi = frame_idx ? frame_idx[f] : first_frame + f;
+    const int64_t s0 = fi * hop + c;
+    float v[8];
+    if (s0 + 8 <= n_samples && s0 >= 0) {
+      if constexpr (I16) {
+        const int16_t* a = reinterpret_cast<const int16_t*>(audio) + s0;
+        if ((s0 & 7) == 0) {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(a));
+          const int16_t* h = reinterpret_cast<const int16_t*>(&t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = h[j] * (1.0f / 32768.0f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldg(a + j) * (1.0f / 32768.0f);
+        }
+      } else {
+        const float* a = reinterpret_cast<const float*>(audio) + s0;
+        if ((s0 & 3) == 0) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(a));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(a) + 1);
+          v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
+          v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldg(a + j);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t s = s0 + j;
+        float x = 0.f;
+        if (s >= 0 && s < n_samples) {
+          if constexpr (I16) x = reinterpret_cast<const int16_t*>(audio)[s] * (1.0f / 32768.0f);
+          else x = reinterpret_cast<const float*>(audio)[s];
+        }
+        v[j] = x;
+      }
+    }
+    const int64_t o = f * S + c;
+    if (out_hi) {
+      *reinterpret_cast<uint4*>(out_hi + o) =
+          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    }
+    if (out_lo) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+      *reinterpret_cast<uint4*>(out_lo + o) =
+          make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+    }
+    if (out_f32) {
+      float4* d = reinterpret_cast<float4*>(out_f32 + o);
+      d[0] = make_float4(v[0], v[1], v[2], v[3]);
+      d[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples, const int64_t* frame_idx,
+                        int64_t first_frame, int64_t n_frames, int hop, int S, __nv_bfloat16* out_hi,
+                        __nv_bfloat16* out_lo, float* out_f32, cudaStream_t stream) {
+  RVAE_REQUIRE(audio && (out_hi || out_f32), RVAE_ERR_INVALID, "frame_gather: null buffer");
+  RVAE_REQUIRE(S > 0 && S % 8 == 0 && hop > 0, RVAE_ERR_UNSUPPORTED, "frame_gather: S=%d must be a multiple of 8", S);
+  if (n_frames <= 0) return RVAE_OK;
+  const int threads = 256;
+  const int grid = grid_for(ctx, n_frames * (S / 8), threads, 16);
+  if (audio_is_i16)
+    frame_gather_kernel<true><<<grid, threads, 0, stream>>>(audio, n_samples, frame_idx, first_frame, n_frames, hop, S,
+                                                            out_hi, out_lo, out_f32);
+  else
+    frame_gather_kernel<false><<<grid, threads, 0, stream>>>(audio, n_samples, frame_idx, first_frame, n_frames, hop,
+                                                             S, out_hi, out_lo, out_f32);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-D2 overlap-add resynthesis (gather form, no atomics): out[t] = sum_i frames[i, t - i*hop] / count(t)
+// over the frames i that cover sample t. With hop == S this is the reference's frames.view(-1).
+// ------------------------------------------------------------------------------------------------
+__global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_frames, int S, int hop,
+                                   float* __restrict__ out, int64_t n_out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_out; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i_hi = t / hop;
+    if (i_hi > n_frames - 1) i_hi = n_frames - 1;
+    int64_t i_lo = (t - S + hop) / hop;  // ceil((t - S + 1) / hop) for t - S + 1 > 0
+    if (t - S + 1 <= 0) i_lo = 0;
+    float acc = 0.f;
+    int cnt = 0;
+    for (int64_t i = i_lo; i <= i_hi; ++i) {
+      const int64_t off = t - i * hop;
+      if (off >= 0 && off < S) {
+        acc += __ldg(frames + i * S + off);
+        ++cnt;
+      }
+    }
+    out[t] = cnt > 0 ? acc / static_cast<float>(cnt) : 0.f;
+  }
+}
+
+int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
+                       cudaStream_t stream) {
+  RVAE_REQUIRE(frames && out, RVAE_ERR_INVALID, "overlap_add: null buffer");
+  RVAE_REQUIRE(S > 0 && hop > 0 && hop <= S, RVAE_ERR_UNSUPPORTED, "overlap_add: need 0 < hop <= S");
+  if (n_out <= 0) return RVAE_OK;
+  const int threads = 256;
+  overlap_add_kernel<<<grid_for(ctx, n_out, threads, 16), threads, 0, stream>>>(frames, n_frames, S, hop, out, n_out);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller: eps ~ N(0,1) for the reparameterisation (rawvae/model.py:25, torch.randn_like).
+// Counter = (element index / 4, offset); key = seed. Statistically equivalent to, not bit-identical with, torch's
+// generator - parity runs inject eps explicitly.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+  const int64_t nvec = (n + 3) >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(offset),
+                     static_cast<uint32_t>(offset >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = (static_cast<float>(c[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+      const float u2 = (static_cast<float>(c[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float r = sqrtf(-2.0f * logf(u1));
+      float s, co;
+      sincospif(2.0f * u2, &s, &co);
+      z[2 * h] = r * co;
+      z[2 * h + 1] = r * s;
+    }
+    const int64_t o = i << 2;
+    if (o + 4 <= n) {
+      *reinterpret_cast<float4*>(out + o) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+      for (int j = 0; j < 4 && o + j < n; ++j) out[o + j] = z[j];
+    }
+  }
+}
+
+int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t stream) {
+  RVAE_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, RVAE_ERR_INVALID, "randn: bad output buffer");
+  if (n <= 0) return RVAE_OK;
+  const int threads = 256;
+  randn_kernel<<<grid_for(ctx, (n + 3) / 4, threads, 8), threads, 0, stream>>>(out, n, seed, offset);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 hi (+ residual lo) planes
+// ------------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo) {
+  const int64_t nvec = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<uint4*>(hi)[i] =
+        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    if (lo) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+      reinterpret_cast<uint4*>(lo)[i] =
+          make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+    }
+  }
+  // tail (n % 8)
+  if (blockIdx.x == 0) {
+    for (int64_t j = (nvec << 3) + threadIdx.x; j < n; j += blockDim.x) {
+      const float v = src[j];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[j] = h;
+      if (lo) lo[j] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+int launch_split_bf16(Ctx* ctx, const float* src, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                      cudaStream_t stream) {
+  RVAE_REQUIRE(src && hi, RVAE_ERR_INVALID, "split_bf16: null buffer");
+  RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(hi) |
+                 reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+               RVAE_ERR_INVALID, "split_bf16: buffers must be 16-byte aligned");
+  if (n <= 0) return RVAE_OK;
+  const int threads = 256;
+  split_bf16_kernel<<<grid_for(ctx, (n + 7) / 8, threads, 8), threads, 0, stream>>>(src, n, hi, lo);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bias gradients: out[n] (+)= sum_m (hi[m,n] + lo[m,n]). Each block owns a 64-column strip and a slab of rows;
+// a thread accumulates 2 adjacent columns (one bf16x2 load) down the slab, warps combine through smem, one
+// atomicAdd per column per block.
+// ------------------------------------------------------------------------------------------------
+constexpr int kColsumRowsPerBlock = 256;
+
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t M,
+                              int N, int ld, float* __restrict__ out) {
+  __shared__ float part[8][64];
+  const int strip = blockIdx.x;           // 64 columns
+  const int lane = threadIdx.x & 31;      // 2 columns each
+  const int warp = threadIdx.x >> 5;      // 8 warps interleave rows
+  const int col = strip * 64 + lane * 2;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kColsumRowsPerBlock;
+  int64_t r1 = r0 + kColsumRowsPerBlock;
+  if (r1 > M) r1 = M;
+  float s0 = 0.f, s1 = 0.f;
+  if (col < N) {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(hi + r * ld + col);
+      float2 f = __bfloat1622float2(h);
+      if (lo) {
+        const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(lo + r * ld + col));
+        f.x += g.x; f.y += g.y;
+      }
+      s0 += f.x; s1 += f.y;
+    }
+  }
+  part[warp][lane * 2] = s0;
+  part[warp][lane * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+    const int c = strip * 64 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, t);
+  }
+}
+
+int launch_colsum(Ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t M, int N, int ld, float* out,
+                  int accumulate, cudaStream_t stream) {
+  RVAE_REQUIRE(hi && out, RVAE_ERR_INVALID, "colsum: null buffer");
+  RVAE_REQUIRE(N % 2 == 0 && ld % 2 == 0, RVAE_ERR_UNSUPPORTED, "colsum: N and ld must be even");
+  if (!accumulate) RVAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
+  if (M <= 0) return RVAE_OK;
+  dim3 grid((N + 63) / 64, static_cast<unsigned>((M + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock));
+  colsum_kernel<<<grid, 256, 0, stream>>>(hi, lo, M, N, ld, out);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-L1/K-L2 fused loss (rawvae/model.py:38-46): acc[0] += sum (xhat-x)^2, acc[1] += sum (1+lv-mu^2-e^lv),
+// warp-shuffle + block reduction, one double atomic per block. loss_finalize turns the sums into
+//   mse/(B*S) + beta * (-0.5) * kl/(B*L)   and clears the accumulators for the next step.
+// ------------------------------------------------------------------------------------------------
+__global__ void loss_fwd_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
+                                const float* __restrict__ mu, const float* __restrict__ lv, int64_t n_rec,
+                                int64_t n_lat, double* __restrict__ acc) {
+  __shared__ float red[32];
+  float mse = 0.f, kl = 0.f;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nv = n_rec >> 2;
+  for (int64_t i = tid; i < nv; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xhat) + i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+    mse += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (int64_t i = (nv << 2) + tid; i < n_rec; i += stride) {
+    const float d = xhat[i] - x[i];
+    mse += d * d;
+  }
+  const int64_t lvn = n_lat >> 2;
+  for (int64_t i = tid; i < lvn; i += stride) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + i);
+    const float4 l = __ldg(reinterpret_cast<const float4*>(lv) + i);
+    kl += (1.f + l.x - m.x * m.x - expf(l.x)) + (1.f + l.y - m.y * m.y - expf(l.y)) +
+          (1.f + l.z - m.z * m.z - expf(l.z)) + (1.f + l.w - m.w * m.w - expf(l.w));
+  }
+  for (int64_t i = (lvn << 2) + tid; i < n_lat; i += stride) kl += 1.f + lv[i] - mu[i] * mu[i] - expf(lv[i]);
+  const float tm = block_sum_to_warp0(mse, red);
+  const float tk = block_sum_to_warp0(kl, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc, static_cast<double>(tm));
+    atomicAdd(acc + 1, static_cast<double>(tk));
+  }
+}
+
+__global__ void loss_finalize_kernel(double* __restrict__ acc, double inv_rec, double kl_scale,
+                                     float* __restrict__ loss_out, float* __restrict__ step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double loss = acc[0] * inv_rec + kl_scale * acc[1];
+    if (loss_out) *loss_out = static_cast<float>(loss);
+    acc[0] = 0.0;
+    acc[1] = 0.0;
+    if (step) *step += 1.0f;
+  }
+}
+
+int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, float* step,
+                         cudaStream_t stream) {
+  RVAE_REQUIRE(acc, RVAE_ERR_INVALID, "loss_finalize: null accumulator");
+  const double inv_rec = 1.0 / (static_cast<double>(B) * S);
+  const double kl_scale = -0.5 * static_cast<double>(beta) / (static_cast<double>(B) * L);
+  loss_finalize_kernel<<<1, 32, 0, stream>>>(acc, inv_rec, kl_scale, loss_out, step);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+int launch_loss_fwd(Ctx* ctx, const float* xhat, const float* x, const float* mu, const float* lv, int64_t B, int S,
+                    int L, float beta, double* acc, float* loss_out, cudaStream_t stream) {
+  RVAE_REQUIRE(xhat && x && mu && lv && acc && loss_out, RVAE_ERR_INVALID, "loss_fwd: null buffer");
+  RVAE_REQUIRE(B > 0, RVAE_ERR_INVALID, "loss_fwd: empty batch");
+  RVAE_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), stream));
+  const int threads = 256;
+  const int grid = grid_for(ctx, B * S / 4, threads, 4);
+  loss_fwd_kernel<<<grid, threads, 0, stream>>>(xhat, x, mu, lv, B * S, B * L, acc);
+  RVAE_LAUNCH_CHECK(ctx);
+  return launch_loss_finalize(ctx, acc, B, S, L, beta, loss_out, nullptr, stream);
+}
+
+// d loss / d xhat, mu, logvar scaled by the upstream gradient (a device scalar; nullptr = 1).
+__global__ void loss_bwd_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
+                                const float* __restrict__ mu, const float* __restrict__ lv, int64_t n_rec,
+                                int64_t n_lat, float c_rec, float c_kl, const float* __restrict__ grad_out,
+                                float* __restrict__ g_xhat, float* __restrict__ g_mu, float* __restrict__ g_lv) {
+  const float g = grad_out ? __ldg(grad_out) : 1.f;
+  const float cr = c_rec * g, ck = c_kl * g;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nv = n_rec >> 2;
+  for (int64_t i = tid; i < nv; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xhat) + i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+    reinterpret_cast<float4*>(g_xhat)[i] =
+        make_float4(cr * (a.x - b.x), cr * (a.y - b.y), cr * (a.z - b.z), cr * (a.w - b.w));
+  }
+  for (int64_t i = (nv << 2) + tid; i < n_rec; i += stride) g_xhat[i] = cr * (xhat[i] - x[i]);
+  for (int64_t i = tid; i < n_lat; i += stride) {
+    g_mu[i] = ck * mu[i];
+    g_lv[i] = 0.5f * ck * (expf(lv[i]) - 1.f);
+  }
+}
+
+int launch_loss_bwd(Ctx* ctx, const float* xhat, const float* x, const float* mu, const float* lv, int64_t B, int S,
+                    int L, float beta, const float* grad_out, float* g_xhat, float* g_mu, float* g_lv,
+                    cudaStream_t stream) {
+  RVAE_REQUIRE(xhat && x && mu && lv && g_xhat && g_mu && g_lv, RVAE_ERR_INVALID, "loss_bwd: null buffer");
+  RVAE_REQUIRE(B > 0, RVAE_ERR_INVALID, "loss_bwd: empty batch");
+  const float c_rec = static_cast<float>(2.0 / (static_cast<double>(B) * S));
+  const float c_kl = static_cast<float>(static_cast<double>(beta) / (static_cast<double>(B) * L));
+  const int threads = 256;
+  loss_bwd_kernel<<<grid_for(ctx, B * S / 4, threads, 8), threads, 0, stream>>>(xhat, x, mu, lv, B * S, B * L, c_rec,
+                                                                              c_kl, grad_out, g_xhat, g_mu, g_lv);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// da4 = g_xhat * (1 - xhat^2) as bf16 planes (operand of the fc4 dgrad / wgrad GEMMs).
+__global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat, int64_t n,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t nvec = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * i);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * i + 1);
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(xhat) + 2 * i);
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(xhat) + 2 * i + 1);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gv[j] * (1.f - xv[j] * xv[j]);
+    reinterpret_cast<uint4*>(hi)[i] =
+        make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    if (lo) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+      reinterpret_cast<uint4*>(lo)[i] =
+          make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+    }
+  }
+}
+
+int launch_tanh_bwd(Ctx* ctx, const float* g_xhat, const float* xhat, int64_t n, __nv_bfloat16* da_hi,
+                    __nv_bfloat16* da_lo, cudaStream_t stream) {
+  RVAE_REQUIRE(g_xhat && xhat && da_hi, RVAE_ERR_INVALID, "tanh_bwd: null buffer");
+  RVAE_REQUIRE(n % 8 == 0, RVAE_ERR_UNSUPPORTED, "tanh_bwd: element count must be a multiple of 8");
+  if (n <= 0) return RVAE_OK;
+  const int threads = 256;
+  tanh_bwd_kernel<<<grid_for(ctx, n / 8, threads, 8), threads, 0, stream>>>(g_xhat, xhat, n, da_hi, da_lo);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// Standalone reparameterisation z = mu + eps * exp(logvar / 2) (rawvae/model.py:23-26) for the inference API.
+__global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                               const float* __restrict__ eps, int64_t n, float* __restrict__ z) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
+}
+
+int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps, int64_t n, float* z,
+                   cudaStream_t stream) {
+  RVAE_REQUIRE(mu && lv && eps && z, RVAE_ERR_INVALID, "reparam: null buffer");
+  if (n <= 0) return RVAE_OK;
+  const int threads = 256;
+  reparam_kernel<<<grid_for(ctx, n, threads, 8), threads, 0, stream>>>(mu, lv, eps, n, z);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-A1 fused Adam (torch.optim.Adam defaults semantics, train.py:163,193): one pass over the flat parameter
+// buffer, float4 loads/stores (28 B/param), optionally re-emitting the bf16 shadow planes the GEMMs read.
+//   t = *step (already incremented); m = m + (1-b1)(g-m); v = b2 v + (1-b2) g^2;
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, float grad_scale, const float* __restrict__ step,
+                            __nv_bfloat16* __restrict__ sh_hi, __nv_bfloat16* __restrict__ sh_lo) {
+  // bias corrections in double, as torch computes them on the host (python floats)
+  const double t = static_cast<double>(__ldg(step));
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const float sqrt_bc2 = static_cast<float>(sqrt(bc2));
+  const int64_t nvec = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = ga[j] * grad_scale;
+      if (weight_decay != 0.f) gr = fmaf(weight_decay, pa[j], gr);
+      ma[j] = ma[j] + (1.f - beta1) * (gr - ma[j]);
+      va[j] = beta2 * va[j] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(va[j]) / sqrt_bc2 + eps;
+      pa[j] = pa[j] - step_size * (ma[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (sh_hi) {
+      reinterpret_cast<uint2*>(sh_hi)[i] = make_uint2(pack2(pa[0], pa[1]), pack2(pa[2], pa[3]));
+      if (sh_lo) {
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = pa[j] - __bfloat162float(__float2bfloat16_rn(pa[j]));
+        reinterpret_cast<uint2*>(sh_lo)[i] = make_uint2(pack2(r[0], r[1]), pack2(r[2], r[3]));
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t j = (nvec << 2) + threadIdx.x; j < n; j += blockDim.x) {
+      float gr = g[j] * grad_scale;
+      if (weight_decay != 0.f) gr = fmaf(weight_decay, p[j], gr);
+      const float mj = m[j] + (1.f - beta1) * (gr - m[j]);
+      const float vj = beta2 * v[j] + (1.f - beta2) * gr * gr;
+      const float pj = p[j] - step_size * (mj / (sqrtf(vj) / sqrt_bc2 + eps));
+      m[j] = mj; v[j] = vj; p[j] = pj;
+      if (sh_hi) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(pj);
+        sh_hi[j] = h;
+        if (sh_lo) sh_lo[j] = __float2bfloat16_rn(pj - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+int launch_adam(Ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
+                __nv_bfloat16* shadow_lo, cudaStream_t stream) {
+  RVAE_REQUIRE(p && g && m && v && step, RVAE_ERR_INVALID, "adam: null buffer");
+  RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+               RVAE_ERR_INVALID, "adam: p/g/m/v must be 16-byte aligned");
+  RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(shadow_hi) | reinterpret_cast<uintptr_t>(shadow_lo)) & 7) == 0,
+               RVAE_ERR_INVALID, "adam: shadow planes must be 8-byte aligned");
+  if (n <= 0) return RVAE_OK;
+  const int threads = 256;
+  adam_kernel<<<grid_for(ctx, (n + 3) / 4, threads, 8), threads, 0, stream>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step, shadow_hi, shadow_lo);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+__global__ void step_inc_kernel(float* step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1.0f;
+}
+
+int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream) {
+  RVAE_REQUIRE(step, RVAE_ERR_INVALID, "step_inc: null step");
+  step_inc_kernel<<<1, 32, 0, stream>>>(step);
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+}  // namespace rvae

@@ -1,0 +1,444 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]        (bf16 operands, fp32 accumulation in TMEM)
+//
+// One CTA per SM loops over 128 x BLOCK_N output tiles (x split-K slices for the weight-gradient GEMMs):
+//   warp 0 (one lane)  : TMA producer   - fills a STAGES-deep ring of {A tile, B tile} in 128B-swizzled smem
+//   warp 1 (one lane)  : UMMA issuer    - tcgen05.mma 128 x BLOCK_N x 16 into one of two TMEM accumulators
+//   warps 2..5         : epilogue       - tcgen05.ld the finished accumulator, apply the fused epilogue
+//                                         (bias/ReLU/tanh, reparameterisation+KL, tanh+MSE+dL/da, ReLU mask, ...)
+// so the epilogue of tile i overlaps the MMAs of tile i+1 (double-buffered TMEM, 2 x BLOCK_N columns).
+//
+// Operands may be K-major (row = m or n, K contiguous: activations / weights in the forward pass) or
+// MN-major (row = k, M or N contiguous: weights in dgrad, activations in wgrad) - no transposed copies are
+// ever materialised; only the TMA box and the UMMA descriptor change.
+//
+// "fp32 mode" runs the same kernel with num_passes = 3 over split operands (x = hi + lo, both bf16):
+// hi*hi + hi*lo + lo*hi accumulated in the same fp32 TMEM accumulator (error ~2^-16 relative).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace rvae {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxPasses = 3;
+
+enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
+enum : int { EPI_LINEAR = 0, EPI_HEAD = 1, EPI_OUT = 2, EPI_DRELU = 3, EPI_DZ = 4, EPI_WGRAD = 5 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_TANH_APPROX = 3 };
+
+// Epilogue arguments. Slot meaning per epilogue kind:
+//   LINEAR : v = acc + bias[n]; act(v) -> out_hi (bf16) [, out_lo (bf16 residual)] [, out_f32]
+//   HEAD   : tile columns [0,half) are mu, [half,BLOCK_N) are logvar of the same latent columns.
+//            mu -> out_f32, logvar -> out_f32_b, eps <- in0 (f32, NULL = 0), z = mu + eps*exp(lv/2) -> out_hi/out_lo,
+//            aux0 <- eps*sigma/2 (f32, for backward), aux1 <- c0*mu, aux2 <- c0*(e^lv-1)/2 (KL gradients),
+//            loss_acc[0] += sum(1 + lv - mu^2 - e^lv)
+//   OUT    : xh = tanh(acc + bias[n]) -> out_f32 (optional); x <- in0 (bf16 hi) [+ in1 (bf16 lo)];
+//            loss_acc[0] += sum((xh-x)^2); da = c0*(xh-x)*(1-xh^2) -> out_hi/out_lo
+//   DRELU  : v = acc * [in0[m,n] > 0] (in0 bf16, optional) -> out_hi/out_lo
+//   DZ     : dz = acc; dmu = dz + in1[m,n]; dlv = dz*in0[m,n] + in2[m,n] (all f32 [M, L]);
+//            dmu -> out_hi[m, n], dlv -> out_hi[m, L + n] (ldo = 2L) [, out_lo likewise]
+//   WGRAD  : out_f32[m, n] (+)= acc   (red.add when accumulate != 0, plain store otherwise)
+struct EpiArgs {
+  const float* bias;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;
+  float* out_f32_b;
+  const void* in0;
+  const void* in1;
+  const void* in2;
+  float* aux0;
+  float* aux1;
+  float* aux2;
+  double* loss_acc;
+  int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and of bf16 inputs in0/in1
+  int act;   // LINEAR / OUT activation
+  int L;     // HEAD / DZ latent width
+  int accumulate;
+  float c0;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmA[kMaxPasses];
+  CUtensorMap tmB[kMaxPasses];
+  int M, N, K;
+  int num_passes;
+  int m_blocks, n_blocks;
+  int k_splits, kb_per_split, kb_total;
+  int b_tile_stride;  // K-major B: row advance per n-block
+  int b_half_stride;  // K-major B: row offset of the second half-tile load
+  EpiArgs epi;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = (kAccStages * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes;
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Store COUNT consecutive fp32 values of one output row as bf16 (hi plane and optional residual plane).
+template <int COUNT>
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* hi_row, __nv_bfloat16* lo_row, const float (&v)[COUNT]) {
+  uint4* dh = reinterpret_cast<uint4*>(hi_row);
+#pragma unroll
+  for (int i = 0; i < COUNT / 8; ++i) {
+    dh[i] = make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                       ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  }
+  if (lo_row != nullptr) {
+    uint4* dl = reinterpret_cast<uint4*>(lo_row);
+#pragma unroll
+    for (int i = 0; i < COUNT / 8; ++i) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = v[8 * i + j] - __bfloat162float(__float2bfloat16_rn(v[8 * i + j]));
+      dl[i] = make_uint4(ptx::pack_bf16x2(r[0], r[1]), ptx::pack_bf16x2(r[2], r[3]), ptx::pack_bf16x2(r[4], r[5]),
+                         ptx::pack_bf16x2(r[6], r[7]));
+    }
+  }
+}
+
+template <int COUNT>
+__device__ __forceinline__ void store_row_f32(float* row, const float (&v)[COUNT]) {
+  float4* d = reinterpret_cast<float4*>(row);
+#pragma unroll
+  for (int i = 0; i < COUNT / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+template <int COUNT>
+__device__ __forceinline__ void load_row_f32(const float* row, float (&v)[COUNT]) {
+  const float4* s = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < COUNT / 4; ++i) {
+    float4 t = __ldg(s + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+
+template <int COUNT>
+__device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* row, float (&v)[COUNT]) {
+  const uint4* s = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+  for (int i = 0; i < COUNT / 8; ++i) {
+    uint4 t = __ldg(s + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(h[j]);
+      v[8 * i + 2 * j] = f.x;
+      v[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.num_passes; ++i) {
+      ptx::prefetch_tensormap(&p.tmA[i]);
+      ptx::prefetch_tensormap(&p.tmB[i]);
+    }
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < Cfg::kAccStages; ++i) {
+      ptx::mbar_init(&tmem_full_bar[i], 1);
+      ptx::mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int total_units = tiles * p.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int ks = u / tiles;
+        const int tile = u - ks * tiles;
+        const int n_blk = tile / p.m_blocks;
+        const int m_blk = tile - n_blk * p.m_blocks;
+        const int m0 = m_blk * kBlockM;
+        const int kb_begin = ks * p.kb_per_split;
+        const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
+        for (int pass = 0; pass < p.num_passes; ++pass) {
+          const CUtensorMap* tmA = &p.tmA[pass];
+          const CUtensorMap* tmB = &p.tmB[pass];
+          for (int kb = kb_begin; kb < kb_begin + kb_count; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint8_t* sA = smem + stage * Cfg::kStageBytes;
+            uint8_t* sB = sA + Cfg::kABytes;
+            const int k0 = kb * kBlockK;
+            if constexpr (A_MAJOR == MAJOR_K) {
+              ptx::tma_load_2d(sA, tmA, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < kBlockM / 64; ++i)
+                ptx::tma_load_2d(sA + i * (kBlockK * 128), tmA, &full_bar[stage], m0 + i * 64, k0);
+            }
+            if constexpr (B_MAJOR == MAJOR_K) {
+              const int r0 = n_blk * p.b_tile_stride;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                ptx::tma_load_2d(sB + h * (Cfg::kBBytes / 2), tmB, &full_bar[stage], k0, r0 + h * p.b_half_stride);
+            } else {
+              const int n0 = n_blk * BLOCK_N;
+#pragma unroll
+              for (int i = 0; i < BLOCK_N / 64; ++i)
+                ptx::tma_load_2d(sB + i * (kBlockK * 128), tmB, &full_bar[stage], n0 + i * 64, k0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int ks = u / tiles;
+        const int kb_begin = ks * p.kb_per_split;
+        const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
+        const int iters = kb_count * p.num_passes;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int it = 0; it < iters; ++it) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = (A_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 2), 0, 1024)
+                                                        : ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
+            const uint64_t bdesc = (B_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 2), 0, 1024)
+                                                        : ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
+            ptx::umma_bf16<1>(d_tmem, adesc, bdesc, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit<1>(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit<1>(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+        if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // tcgen05.ld: a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const EpiArgs& e = p.epi;
+    float loss_local = 0.f;
+    uint32_t as = 0, aphase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int ks = u / tiles;
+      const int tile = u - ks * tiles;
+      const int n_blk = tile / p.m_blocks;
+      const int m_blk = tile - n_blk * p.m_blocks;
+      const int m = m_blk * kBlockM + row_in_tile;
+      const bool row_ok = m < p.M;
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_base + as * BLOCK_N;
+
+      if constexpr (EPI == EPI_HEAD) {
+        constexpr int kHalf = BLOCK_N / 2;
+        const int L = e.L;
+        for (int c = 0; c < kHalf; c += 16) {
+          __syncwarp();
+          uint32_t rm[16], rl[16];
+          ptx::tmem_ld_32x16(t_acc + c, rm);
+          ptx::tmem_ld_32x16(t_acc + kHalf + c, rl);
+          ptx::tmem_ld_wait();
+          const int col = n_blk * kHalf + c;
+          if (row_ok && col < L) {
+            const size_t off = static_cast<size_t>(m) * L + col;
+            float eps[16], mu[16], lv[16], z[16], esh[16], gmu[16], glv[16];
+            if (e.in0) {
+              load_row_f32<16>(reinterpret_cast<const float*>(e.in0) + off, eps);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) eps[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              mu[j] = __uint_as_float(rm[j]) + __ldg(e.bias + col + j);
+              lv[j] = __uint_as_float(rl[j]) + __ldg(e.bias + L + col + j);
+              const float sig = expf(0.5f * lv[j]);
+              const float var = sig * sig;
+              z[j] = fmaf(eps[j], sig, mu[j]);
+              esh[j] = 0.5f * eps[j] * sig;
+              gmu[j] = e.c0 * mu[j];
+              glv[j] = 0.5f * e.c0 * (var - 1.f);
+              loss_local += (1.f + lv[j]) - fmaf(mu[j], mu[j], var);
+            }
+            store_row_f32<16>(e.out_f32 + off, mu);
+            store_row_f32<16>(e.out_f32_b + off, lv);
+            if (e.out_hi) store_row_bf16<16>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, z);
+            if (e.aux0) store_row_f32<16>(e.aux0 + off, esh);
+            if (e.aux1) store_row_f32<16>(e.aux1 + off, gmu);
+            if (e.aux2) store_row_f32<16>(e.aux2 + off, glv);
+          }
+        }
+      } else {
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          __syncwarp();
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_acc + c, r);
+          ptx::tmem_ld_wait();
+          const int n = n_blk * BLOCK_N + c;
+          if (row_ok && n < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const size_t off = static_cast<size_t>(m) * e.ldo + n;
+
+          if constexpr (EPI == EPI_LINEAR) {
+            if (e.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
+            }
+            if (e.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (e.act == ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            } else if (e.act == ACT_TANH_APPROX) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = ptx::tanh_approx(v[j]);
+            }
+            if (e.out_hi) store_row_bf16<32>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, v);
+            if (e.out_f32) store_row_f32<32>(e.out_f32 + off, v);
+          } else if constexpr (EPI == EPI_OUT) {
+            float x[32];
+            load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, x);
+            if (e.in1) {
+              float xl[32];
+              load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] += xl[j];
+            }
+            float da[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = v[j] + __ldg(e.bias + n + j);
+              const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
+              const float d = xh - x[j];
+              loss_local = fmaf(d, d, loss_local);
+              da[j] = e.c0 * d * (1.f - xh * xh);
+              v[j] = xh;
+            }
+            if (e.out_f32) store_row_f32<32>(e.out_f32 + off, v);
+            if (e.out_hi) store_row_bf16<32>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, da);
+          } else if constexpr (EPI == EPI_DRELU) {
+            if (e.in0) {
+              float h[32];
+              load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, h);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (h[j] > 0.f) ? v[j] : 0.f;
+            }
+            store_row_bf16<32>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, v);
+          } else if constexpr (EPI == EPI_DZ) {
+            const int L = e.L;
+            const size_t loff = static_cast<size_t>(m) * L + n;
+            float esh[32], g[32], dl[32];
+            load_row_f32<32>(reinterpret_cast<const float*>(e.in0) + loff, esh);
+            load_row_f32<32>(reinterpret_cast<const float*>(e.in2) + loff, g);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dl[j] = fmaf(v[j], esh[j], g[j]);
+            load_row_f32<32>(reinterpret_cast<const float*>(e.in1) + loff, g);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += g[j];
+            const size_t ooff = static_cast<size_t>(m) * e.ldo + n;
+            store_row_bf16<32>(e.out_hi + ooff, e.out_lo ? e.out_lo + ooff : nullptr, v);
+            store_row_bf16<32>(e.out_hi + ooff + L, e.out_lo ? e.out_lo + ooff + L : nullptr, dl);
+          } else if constexpr (EPI == EPI_WGRAD) {
+            float* dst = e.out_f32 + off;
+            if (e.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) ptx::red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              store_row_f32<32>(dst, v);
+            }
+          }
+          }  // row_ok && n < N
+        }
+      }
+      // release the accumulator back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
+    }
+    if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
+      const float s = warp_sum(loss_local);
+      if (lane == 0 && e.loss_acc) atomicAdd(e.loss_acc, static_cast<double>(s));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace rvae

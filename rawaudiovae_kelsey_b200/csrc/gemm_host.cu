@@ -1,0 +1,238 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding, tile/split-K selection, kernel table and launch.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+
+namespace rvae {
+
+// ------------------------------------------------------------------------------------------------
+// error state (thread local; read through rvae_last_error())
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_error(cudaError_t err, const char* what) {
+  snprintf(g_last_error, sizeof(g_last_error), "CUDA error %d (%s) in %s", (int)err, cudaGetErrorString(err), what);
+  return RVAE_ERR_CUDA_BASE + (int)err;
+}
+const char* last_error() { return g_last_error; }
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows with pitch `ld` elements; 128-byte swizzle; OOB reads zero.
+static int encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld,
+                          uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  RVAE_REQUIRE(fn != nullptr, RVAE_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  RVAE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, RVAE_ERR_INVALID, "operand base %p not 16-byte aligned",
+               base);
+  RVAE_REQUIRE((ld * 2) % 16 == 0, RVAE_ERR_UNSUPPORTED, "operand row pitch %llu elements not a multiple of 8",
+               (unsigned long long)ld);
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVAE_REQUIRE(r == CUDA_SUCCESS, RVAE_ERR_DRIVER,
+               "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu box %u x %u", (int)r,
+               (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)ld, box0, box1);
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel table
+// ------------------------------------------------------------------------------------------------
+typedef void (*GemmKernel)(const GemmParams);
+
+struct Variant {
+  int block_n, a_major, b_major, epi;
+  GemmKernel fn;
+  int smem;
+};
+
+#define RVAE_VARIANT(BN, AM, BM, EP) \
+  { BN, AM, BM, EP, gemm_kernel<BN, AM, BM, EP>, GemmCfg<BN>::kSmemBytes }
+
+static const Variant kVariants[] = {
+    RVAE_VARIANT(256, MAJOR_K, MAJOR_K, EPI_LINEAR),  RVAE_VARIANT(128, MAJOR_K, MAJOR_K, EPI_LINEAR),
+    RVAE_VARIANT(256, MAJOR_K, MAJOR_K, EPI_HEAD),    RVAE_VARIANT(128, MAJOR_K, MAJOR_K, EPI_HEAD),
+    RVAE_VARIANT(256, MAJOR_K, MAJOR_K, EPI_OUT),     RVAE_VARIANT(128, MAJOR_K, MAJOR_K, EPI_OUT),
+    RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_DRELU),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_DRELU),
+    RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_DZ),     RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_DZ),
+    RVAE_VARIANT(256, MAJOR_MN, MAJOR_MN, EPI_WGRAD), RVAE_VARIANT(128, MAJOR_MN, MAJOR_MN, EPI_WGRAD),
+};
+static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+static int find_variant(int block_n, int a_major, int b_major, int epi) {
+  for (int i = 0; i < kNumVariants; ++i)
+    if (kVariants[i].block_n == block_n && kVariants[i].a_major == a_major && kVariants[i].b_major == b_major &&
+        kVariants[i].epi == epi)
+      return i;
+  return -1;
+}
+
+static int configure_variants() {
+  static int rc = -1;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    rc = RVAE_OK;
+    for (int i = 0; i < kNumVariants; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kVariants[i].fn),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kVariants[i].smem);
+      if (e != cudaSuccess) {
+        rc = cuda_error(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        break;
+      }
+    }
+  });
+  return rc;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Pick the N tile: fewer, fatter tiles are more efficient per FLOP, but whole waves over the SMs matter more.
+static int choose_block_n(const Ctx* ctx, int M, int N, bool allow128, bool allow256) {
+  if (ctx->force_block_n == 128 && allow128) return 128;
+  if (ctx->force_block_n == 256 && allow256) return 256;
+  if (!allow256) return 128;
+  if (!allow128) return 256;
+  const int mb = ceil_div(M, kBlockM);
+  const double c256 = 1.0 * ceil_div(mb * ceil_div(N, 256), ctx->num_sms);
+  const double c128 = 0.6 * ceil_div(mb * ceil_div(N, 128), ctx->num_sms);
+  return (c128 < c256) ? 128 : 256;
+}
+
+int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
+  RVAE_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, RVAE_ERR_INVALID, "gemm: empty problem %d x %d x %d", d.M, d.N, d.K);
+  RVAE_REQUIRE(d.A.hi && d.B.hi, RVAE_ERR_INVALID, "gemm: null operand");
+  RVAE_REQUIRE(d.N % 64 == 0, RVAE_ERR_UNSUPPORTED, "gemm: N=%d must be a multiple of 64", d.N);
+  RVAE_CHECK(configure_variants());
+
+  PreparedGemm& g = *out;
+  memset(&g, 0, sizeof(g));
+  GemmParams& p = g.params;
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.epi = d.args;
+
+  int block_n;
+  if (d.epi == EPI_HEAD) {
+    const int L = d.head_L;
+    RVAE_REQUIRE(d.N == 2 * L && L % 64 == 0, RVAE_ERR_UNSUPPORTED, "head gemm: N=%d must be 2*L, L=%d %% 64 == 0",
+                 d.N, L);
+    block_n = (L % 128 == 0) ? choose_block_n(ctx, d.M, d.N, true, true) : 128;
+    p.n_blocks = L / (block_n / 2);
+    p.b_tile_stride = block_n / 2;
+    p.b_half_stride = L;
+    p.epi.L = L;
+  } else {
+    block_n = choose_block_n(ctx, d.M, d.N, true, true);
+    p.n_blocks = ceil_div(d.N, block_n);
+    p.b_tile_stride = block_n;
+    p.b_half_stride = block_n / 2;
+  }
+  p.m_blocks = ceil_div(d.M, kBlockM);
+  p.kb_total = ceil_div(d.K, kBlockK);
+
+  // split-K only where the epilogue is a linear accumulation (weight gradients)
+  int splits = 1;
+  if (d.epi == EPI_WGRAD) {
+    const int tiles = p.m_blocks * p.n_blocks;
+    if (d.k_splits > 0) {
+      splits = d.k_splits;
+    } else {
+      // smallest split (<= 8, >= 8 k-blocks each) whose last wave is >= 90% full; else the best seen
+      double best = 0.0;
+      for (int s = 1; s <= 8 && p.kb_total / s >= 8; ++s) {
+        const int units = tiles * s;
+        const double eff = (double)units / (ceil_div(units, ctx->num_sms) * (double)ctx->num_sms);
+        if (eff > best + 1e-9) { best = eff; splits = s; }
+        if (eff >= 0.90) break;
+      }
+    }
+    if (splits > p.kb_total) splits = p.kb_total;
+    RVAE_REQUIRE(splits == 1 || d.args.accumulate, RVAE_ERR_INVALID, "wgrad: split-K needs accumulate=1");
+  }
+  p.kb_per_split = ceil_div(p.kb_total, splits);
+  p.k_splits = ceil_div(p.kb_total, p.kb_per_split);  // every split owns >= 1 k-block
+
+  // passes: hi*hi (+ hi*lo + lo*hi when both operands carry a residual plane)
+  const Operand* pa[kMaxPasses];
+  const void* a_ptr[kMaxPasses];
+  const void* b_ptr[kMaxPasses];
+  (void)pa;
+  int np = 0;
+  if (d.A.lo && d.B.lo) {
+    a_ptr[np] = d.A.lo; b_ptr[np] = d.B.hi; ++np;
+    a_ptr[np] = d.A.hi; b_ptr[np] = d.B.lo; ++np;
+  } else if (d.A.lo) {
+    a_ptr[np] = d.A.lo; b_ptr[np] = d.B.hi; ++np;
+  } else if (d.B.lo) {
+    a_ptr[np] = d.A.hi; b_ptr[np] = d.B.lo; ++np;
+  }
+  a_ptr[np] = d.A.hi; b_ptr[np] = d.B.hi; ++np;
+  p.num_passes = np;
+
+  const int b_rows = (d.epi == EPI_HEAD) ? d.N : d.N;
+  for (int i = 0; i < np; ++i) {
+    if (d.A.major == MAJOR_K)
+      RVAE_CHECK(encode_bf16_2d(&p.tmA[i], a_ptr[i], d.K, d.M, d.A.ld, kBlockK, kBlockM));
+    else
+      RVAE_CHECK(encode_bf16_2d(&p.tmA[i], a_ptr[i], d.M, d.K, d.A.ld, 64, kBlockK));
+    if (d.B.major == MAJOR_K)
+      RVAE_CHECK(encode_bf16_2d(&p.tmB[i], b_ptr[i], d.K, b_rows, d.B.ld, kBlockK, block_n / 2));
+    else
+      RVAE_CHECK(encode_bf16_2d(&p.tmB[i], b_ptr[i], d.N, d.K, d.B.ld, 64, kBlockK));
+  }
+
+  g.block_n = block_n;
+  g.variant = find_variant(block_n, d.A.major, d.B.major, d.epi);
+  RVAE_REQUIRE(g.variant >= 0, RVAE_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d majors (%d,%d) epilogue %d",
+               block_n, d.A.major, d.B.major, d.epi);
+  const int units = p.m_blocks * p.n_blocks * p.k_splits;
+  g.grid = units < ctx->num_sms ? units : ctx->num_sms;
+  g.smem_bytes = kVariants[g.variant].smem;
+  return RVAE_OK;
+}
+
+int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream) {
+  kVariants[g.variant].fn<<<g.grid, kGemmThreads, g.smem_bytes, stream>>>(g.params);
+  RVAE_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return RVAE_OK;
+}
+
+int gemm_launch(Ctx* ctx, const GemmDesc& d, cudaStream_t stream) {
+  PreparedGemm g;
+  RVAE_CHECK(gemm_prepare(ctx, d, &g));
+  return gemm_run(ctx, g, stream);
+}
+
+}  // namespace rvae
