@@ -112,8 +112,8 @@ def main(case):
         f32, hi, lo = ops.frame_gather(audio, N, hop, S, out_bf16=True, out_lo=True)
         print("frames exact", bool((f32 == ref).all()), "hi exact", bool((hi == ref.to(torch.bfloat16)).all()),
               "hi+lo", rel(hi.float() + lo.float(), ref))
-        idx = torch.randperm(N, device=dev)[:777]
-        f32, _, _ = ops.frame_gather(audio, 777, hop, S, frame_idx=idx)
+        idx = torch.randperm(N, device=dev)[:700].contiguous()
+        f32, _, _ = ops.frame_gather(audio, 700, hop, S, frame_idx=idx)
         print("gather exact", bool((f32 == ref[idx]).all()))
         a16 = (audio * 32767).to(torch.int16)
         f32, _, _ = ops.frame_gather(a16, N, hop, S)
