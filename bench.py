@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: training frames/sec (forward + loss + backward + Adam) of the default.ini VAE
+(S=1024, H=2048, L=256) on synthetic 44.1 kHz sine+noise audio, 8192 frames per GPU per step (BASELINE.json
+configs[1]; weak scaling for N > 1).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+
+Prints ONE JSON line on rank 0. See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+S, H, L = 1024, 2048, 256            # default.ini:5,18-19
+HOP = 128                            # default.ini:4
+KL_BETA, LR = 1e-4, 1e-4             # default.ini:20,26
+BATCH = 8192                         # BASELINE.json configs[1]
+SR = 44100
+FLOP_PER_FRAME = 30408704            # fwd + bwd GEMMs only (no fc1 dgrad)
+WORKLOAD = "default.ini VAE (S=1024,H=2048,L=256) bf16 training, batch 8192 frames/GPU, synthetic 44.1 kHz sine+noise audio"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def synth_corpus(n_files: int, seconds: float, seed: int = 1234) -> np.ndarray:
+    """SURVEY.md 8(d) synthetic wav folder, concatenated as train.py:118-126 does: float32 = int16 PCM / 32768."""
+    from oracle.rawvae_oracle import synth_wav  # data generator only (shared with the tests); not a compute path
+    rng = np.random.default_rng(seed)
+    return np.concatenate([synth_wav(rng, int(seconds * SR), SR) for _ in range(n_files)])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_steps(n_steps: int, warmup: int, threads: int, frames: int = BATCH):
+    """The reference's training-loop body (train_iterable.py:200-210) restated by the oracle port, fp32, torch CPU
+    with all host threads - i.e. the same ATen kernels the reference's own CPU path runs. Returns per-step seconds."""
+    from oracle import rawvae_oracle as O
+    torch.set_num_threads(threads)
+    p = O.init_params(S, H, L, seed=0)
+    st = O.adam_init(p)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand(frames, S, generator=gen) * 2 - 1
+    times = []
+    for i in range(warmup + n_steps):
+        eps = torch.randn(frames, L, generator=gen)
+        t0 = time.perf_counter()
+        O.train_step(p, st, x, eps, KL_BETA, LR)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    # bounded sample: a step is a full 8192-frame batch when the whole run fits ~150 s, else a smaller batch
+    probe = cpu_train_steps(1, 1, threads)[0]
+    frames = BATCH
+    budget = 150.0
+    while frames > 512 and probe * (frames / BATCH) * (args.steps + args.warmup) > budget:
+        frames //= 2
+    times = cpu_train_steps(args.steps, args.warmup, threads, frames)
+    total = sum(times)
+    fps = frames * len(times) / total
+    out = {
+        "impl": "reference", "metric": "train frames/sec (fwd+bwd+Adam)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": frames, "device": "host CPU"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} training steps of {frames} frames each, oracle port (torch CPU fp32, "
+                                   f"{threads} threads, {total:.1f} s)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    from rawaudiovae_kelsey_b200 import dist as rdist
+    from rawaudiovae_kelsey_b200 import ops
+    from rawaudiovae_kelsey_b200.model import FrameBatch, FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    from rawvae.model import VAE
+    import torch.distributed as dist
+
+    rank, world, local_rank = rdist.init_from_env("nccl")
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # model + optimizer (random init of the default.ini architecture)
+    torch.manual_seed(0)
+    model = VAE(S, H, L, precision=args.precision).to(dev)
+    model.eps_seed = 1 + rank
+    opt = Adam(model.parameters(), lr=LR)
+    if world > 1:
+        step_fn = rdist.DataParallelTrainStep(model, opt, KL_BETA, global_batch=BATCH * world)
+    else:
+        step_fn = FusedTrainStep(model, opt, KL_BETA)
+
+    # synthetic corpus resident in HBM (every rank holds it; rank r draws its own frame indices)
+    corpus = synth_corpus(args.files, args.seconds)
+    audio = torch.from_numpy(corpus).to(dev)
+    n_frames = (len(corpus) + HOP - 1) // HOP - S // HOP + 1
+    total_steps = args.warmup + args.steps
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    frame_idx = torch.randint(0, n_frames, (total_steps, BATCH), generator=g, device=dev, dtype=torch.int64)
+
+    def device_step(i):
+        return step_fn(FrameBatch(audio, BATCH, HOP, S, frame_idx=frame_idx[i]))
+
+    # ---- value: inputs resident in HBM, whole step = framing + fwd + loss + bwd (+ allreduce) + Adam
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.launch_count(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.warmup, total_steps):
+        loss = device_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count(dev) - l0
+    clk = clocks.stop() if rank == 0 else None
+    last_loss = float(loss)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = BATCH * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: HOST buffers. Every step the host supplies the next chunk of the wav stream from pinned memory
+    # (train_iterable.py's streaming pattern: 8192 consecutive frames at hop 128 = 1 049 472 samples), the GPU
+    # frames it, trains on it, and the step's loss is read back to pinned host memory.
+    chunk = (BATCH - 1) * HOP + S
+    n_chunks = max(1, (len(corpus) - chunk) // (BATCH * HOP))
+    host_audio = torch.from_numpy(corpus).pin_memory()
+    host_loss = torch.zeros(total_steps, dtype=torch.float32).pin_memory()
+    dbuf = [torch.empty(chunk, dtype=torch.float32, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+
+    def e2e_step(i):
+        b = i % 2
+        off = ((i * world + rank) % n_chunks) * BATCH * HOP
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            dbuf[b].copy_(host_audio[off:off + chunk], non_blocking=True)       # H2D from pinned memory
+            ready[b].record(copy_stream)
+        main.wait_event(ready[b])
+        loss = step_fn(FrameBatch(dbuf[b], BATCH, HOP, S, first_frame=0))
+        freed[b].record(main)
+        host_loss[i].copy_(loss, non_blocking=True)                             # D2H read of the step's result
+        return loss
+
+    for b in range(2):
+        freed[b].record(main)
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.warmup, total_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t)
+    e2e_value = BATCH * world * args.steps / (e2e_ms * 1e-3)
+    assert np.isfinite(host_loss.numpy()).all()
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMMs), timed live with CUDA events on the launch stream
+    roofline, breakdown = None, None
+    if rank == 0:
+        plan = model._plan_for(BATCH)
+        plan.enable_timing(True)
+        nroof = min(args.steps, 20)
+        for i in range(nroof):
+            device_step(args.warmup + i)
+        torch.cuda.synchronize()
+        tm = plan.read_timing()
+        plan.enable_timing(False)
+        gemm_ms = sum(v[0] for v in tm.values()) / nroof
+        flops = sum(v[1] * v[2] for v in tm.values()) / nroof
+        passes = 3 if args.precision == "fp32" else 1
+        achieved = flops / (gemm_ms * 1e-3) / 1e12
+        peak = peaks["bf16_sustained"]
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "rvae::gemm_kernel<*> (11 launches/step)",
+                    "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
+                    "algorithmic_flops_per_step": flops, "gemm_ms_per_step": gemm_ms,
+                    "tensor_passes": passes}
+        breakdown = {k: {"us": 1e3 * v[0] / max(v[1], 1), "tflops": (v[2] / (v[0] / max(v[1], 1) * 1e-3) / 1e12)
+                         if v[0] > 0 else None} for k, v in tm.items() if v[1] > 0}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t1 = cpu_train_steps(1, 1, threads)[0]
+        n = int(min(30, max(3, round(15.0 / max(t1, 1e-3)))))
+        times = cpu_train_steps(n, 0, threads)
+        cpu_baseline = {"value": BATCH * len(times) / sum(times), "unit": "frames/s", "cores": threads, "kind": "port",
+                        "sample": f"{len(times)} full {BATCH}-frame training steps of the oracle port "
+                                  f"(torch CPU fp32, {threads} threads, {sum(times):.1f} s)"}
+
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        frac_of_peak = value * FLOP_PER_FRAME / world / 1e12 / peaks["bf16_sustained"]
+        out = {
+            "metric": "train frames/sec (fwd+bwd+Adam)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "hop": HOP,
+                       "precision": args.precision, "parallelism": f"dp{world}",
+                       "l2": "per-step working set ~330 MB (activations + weights + moments) exceeds the 126 MB L2; "
+                             "a different random 8192-frame gather from a %.0f MB corpus every step" % (corpus.nbytes / 1e6),
+                       "corpus": f"{args.files} files x {args.seconds:.0f} s, 0.5*sin+0.05*noise, rng 1234"},
+            "frac_of_bf16_peak_whole_step": frac_of_peak,
+            "final_loss": last_loss,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": chunk * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "path": "pinned host wav-stream chunk -> H2D -> FusedTrainStep(FrameBatch) -> loss D2H"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roofline,
+            "gemm_breakdown": breakdown,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--files", type=int, default=32)
+    ap.add_argument("--seconds", type=float, default=30.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        return 1
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

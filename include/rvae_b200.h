@@ -188,9 +188,12 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* bufs);
 /* Refresh the bf16 shadow planes from the fp32 master weights (after load_state_dict / manual edits). */
 int rvae_plan_sync_shadow(rvae_plan* plan, void* stream);
 
-/* Load a batch into the plan's input buffer: frames gathered from a wav buffer (see rvae_frame_gather) ... */
+/* Load a batch into the plan's input buffer: `count` frames gathered from a wav buffer (see rvae_frame_gather)
+ * into rows [row_offset, row_offset + count). row_offset = 0 starts a new batch; a batch that straddles several
+ * files (train_iterable.py's stream) is appended run by run; the batch size becomes row_offset + count ... */
 int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
-                          const int64_t* frame_idx, int64_t first_frame, int batch, int hop, void* stream);
+                          const int64_t* frame_idx, int64_t first_frame, int count, int hop, int row_offset,
+                          void* stream);
 /* ... or an fp32 [batch, S] matrix already on the device. */
 int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* stream);
 
@@ -201,6 +204,11 @@ int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, void* str
 /* Redirect the fp32 results of the next forward calls into caller tensors ([batch,L], [batch,L], [batch,S]);
  * NULL = keep them in the workspace. Used by the autograd wrapper so returned tensors outlive the step. */
 int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat);
+
+/* Data parallelism: normalise the loss (and therefore its gradients) by the GLOBAL batch size instead of the
+ * local one, so that a plain SUM all-reduce over ranks yields exactly the single-process gradient of the
+ * concatenated batch, also when shards are unequal. 0 (default) = use the local batch size. */
+int rvae_plan_set_global_batch(rvae_plan* plan, int64_t global_batch);
 
 /* Forward. fused_loss = 1: the epilogues also accumulate the MSE / KL sums and emit the loss gradients
  * (da4, g_mu, g_logvar) so that rvae_plan_backward can run without a separate loss kernel
@@ -231,6 +239,14 @@ const float* rvae_plan_eps(const rvae_plan* plan);
 /* gradient bucket s (see rvae_plan_backward): pointer into bufs.grads and element count. Buckets 0..3 are the
  * four weight matrices in backward-completion order; bucket 4 is the bias block. */
 int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count);
+
+/* Per-kernel device timing (bench.py roofline): when enabled, every tcgen05 GEMM launch of the plan is bracketed
+ * by CUDA events on the launch stream. rvae_plan_read_timing synchronises those events and returns, per GEMM slot
+ * g in [0, 12), the accumulated milliseconds, launch count and algorithmic FLOPs per launch (2*M*N*K); it then
+ * clears the accumulators. Slot order: F1, F2, F3, F4(out), F4(linear), B4w, B4d, B3w, B3d, B2w, B2d, B1w. */
+#define RVAE_NUM_GEMM_SLOTS 12
+int rvae_plan_enable_timing(rvae_plan* plan, int enable);
+int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double* flops_per_launch);
 
 /* Inference: decode latents z (fp32 [batch, L]) -> xhat fp32 [batch, S] (model.py:28-30). */
 int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out, void* stream);

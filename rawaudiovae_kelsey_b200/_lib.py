@@ -63,11 +63,12 @@ SIGNATURES = {
     "rvae_plan_workspace_bytes": (c_size_t, [P]),
     "rvae_plan_bind": (c_int, [P, C.POINTER(PlanBuffers)]),
     "rvae_plan_sync_shadow": (c_int, [P, P]),
-    "rvae_plan_load_frames": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, P]),
+    "rvae_plan_load_frames": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, c_int, P]),
     "rvae_plan_load_batch": (c_int, [P, P, c_int, P]),
     "rvae_plan_set_eps": (c_int, [P, P, P]),
     "rvae_plan_gen_eps": (c_int, [P, c_uint64, c_uint64, P]),
     "rvae_plan_set_outputs": (c_int, [P, P, P, P]),
+    "rvae_plan_set_global_batch": (c_int, [P, c_int64]),
     "rvae_plan_forward": (c_int, [P, c_float, c_int, c_int, P]),
     "rvae_plan_backward": (c_int, [P, c_int, P]),
     "rvae_plan_backward_external": (c_int, [P, P, P, P, P, P]),
@@ -79,6 +80,8 @@ SIGNATURES = {
     "rvae_plan_xhat": (P, [P]),
     "rvae_plan_eps": (P, [P]),
     "rvae_plan_bucket": (c_int, [P, c_int, C.POINTER(P), C.POINTER(c_int64)]),
+    "rvae_plan_enable_timing": (c_int, [P, c_int]),
+    "rvae_plan_read_timing": (c_int, [P, P, P, P]),
     "rvae_plan_decode": (c_int, [P, P, c_int, P, P]),
     "rvae_plan_encode": (c_int, [P, P]),
 }

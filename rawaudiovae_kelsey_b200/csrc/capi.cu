@@ -4,6 +4,8 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "../../include/rvae_b200.h"
 #include "common.h"
@@ -263,8 +265,16 @@ struct rvae_plan {
   // redirected outputs
   float *out_mu, *out_lv, *out_xhat;
   int batch;        // current batch
+  int64_t global_batch;  // loss normalisation under data parallelism (0 = local batch)
   bool have_eps;
   std::map<int, GemmSet> sets;  // prepared GEMMs per batch size
+  // optional per-GEMM timing
+  bool timing;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<std::pair<int, int>> ev_used;  // (gemm id, pool index)
+  double t_ms[G_COUNT];
+  int64_t t_n[G_COUNT];
+  double t_flops[G_COUNT];
 };
 
 namespace {
@@ -415,10 +425,7 @@ int get_set(rvae_plan* p, GemmSet** out) {
   return RVAE_OK;
 }
 
-int run(rvae_plan* p, int id, cudaStream_t st, const EpiArgs* override_args = nullptr) {
-  GemmSet* gs;
-  RVAE_CHECK(get_set(p, &gs));
-  RVAE_CHECK(prepare(p, *gs, id));
+int run_untimed(rvae_plan* p, GemmSet* gs, int id, cudaStream_t st, const EpiArgs* override_args) {
   if (override_args) {
     PreparedGemm g = gs->g[id];
     const int L = g.params.epi.L;
@@ -427,6 +434,27 @@ int run(rvae_plan* p, int id, cudaStream_t st, const EpiArgs* override_args = nu
     return gemm_run(&p->ctx->c, g, st);
   }
   return gemm_run(&p->ctx->c, gs->g[id], st);
+}
+
+int run(rvae_plan* p, int id, cudaStream_t st, const EpiArgs* override_args = nullptr) {
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  RVAE_CHECK(prepare(p, *gs, id));
+  if (!p->timing) return run_untimed(p, gs, id, st, override_args);
+  const size_t slot = p->ev_used.size();
+  if (slot >= p->ev_pool.size()) {
+    cudaEvent_t a, b;
+    RVAE_CUDA(cudaEventCreate(&a));
+    RVAE_CUDA(cudaEventCreate(&b));
+    p->ev_pool.emplace_back(a, b);
+  }
+  RVAE_CUDA(cudaEventRecord(p->ev_pool[slot].first, st));
+  RVAE_CHECK(run_untimed(p, gs, id, st, override_args));
+  RVAE_CUDA(cudaEventRecord(p->ev_pool[slot].second, st));
+  p->ev_used.emplace_back(id, (int)slot);
+  const GemmParams& gp = gs->g[id].params;
+  p->t_flops[id] = 2.0 * gp.M * gp.N * gp.K;
+  return RVAE_OK;
 }
 
 int check_ready(const rvae_plan* p, bool need_batch) {
@@ -485,7 +513,9 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   rvae_plan* p = new (std::nothrow) rvae_plan();
   RVAE_REQUIRE(p, RVAE_ERR_INVALID, "plan_create: out of host memory");
   p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
-  p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false;
+  p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
+  p->timing = false;
+  for (int i = 0; i < G_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
   p->out_mu = p->out_lv = p->out_xhat = nullptr;
   memset(&p->bufs, 0, sizeof(p->bufs));
   p->ws_bytes = carve(p, nullptr);
@@ -493,7 +523,41 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   return RVAE_OK;
 }
 
-void rvae_plan_destroy(rvae_plan* plan) { delete plan; }
+void rvae_plan_destroy(rvae_plan* plan) {
+  if (!plan) return;
+  for (auto& e : plan->ev_pool) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  delete plan;
+}
+
+int rvae_plan_enable_timing(rvae_plan* plan, int enable) {
+  RVAE_REQUIRE(plan, RVAE_ERR_INVALID, "null rvae_plan");
+  plan->timing = enable != 0;
+  return RVAE_OK;
+}
+
+int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double* flops_per_launch) {
+  RVAE_REQUIRE(plan && ms && launches && flops_per_launch, RVAE_ERR_INVALID, "plan_read_timing: null argument");
+  static_assert(G_COUNT == RVAE_NUM_GEMM_SLOTS, "slot count");
+  for (auto& u : plan->ev_used) {
+    auto& e = plan->ev_pool[u.second];
+    RVAE_CUDA(cudaEventSynchronize(e.second));
+    float t = 0.f;
+    RVAE_CUDA(cudaEventElapsedTime(&t, e.first, e.second));
+    plan->t_ms[u.first] += t;
+    plan->t_n[u.first] += 1;
+  }
+  plan->ev_used.clear();
+  for (int i = 0; i < G_COUNT; ++i) {
+    ms[i] = (float)plan->t_ms[i];
+    launches[i] = plan->t_n[i];
+    flops_per_launch[i] = plan->t_flops[i];
+    plan->t_ms[i] = 0; plan->t_n[i] = 0;
+  }
+  return RVAE_OK;
+}
 
 size_t rvae_plan_workspace_bytes(const rvae_plan* plan) { return plan ? plan->ws_bytes : 0; }
 
@@ -521,14 +585,19 @@ int rvae_plan_sync_shadow(rvae_plan* plan, void* stream) {
 }
 
 int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
-                          const int64_t* frame_idx, int64_t first_frame, int batch, int hop, void* stream) {
+                          const int64_t* frame_idx, int64_t first_frame, int count, int hop, int row_offset,
+                          void* stream) {
   RVAE_CHECK(check_ready(plan, false));
-  RVAE_REQUIRE(batch > 0 && batch <= plan->max_batch, RVAE_ERR_INVALID, "plan_load_frames: batch %d not in 1..%d",
-               batch, plan->max_batch);
-  plan->batch = batch;
+  RVAE_REQUIRE(count > 0 && row_offset >= 0 && row_offset + count <= plan->max_batch, RVAE_ERR_INVALID,
+               "plan_load_frames: rows %d..%d outside 0..%d", row_offset, row_offset + count, plan->max_batch);
+  RVAE_REQUIRE(row_offset == 0 || row_offset == plan->batch, RVAE_ERR_STATE,
+               "plan_load_frames: row_offset %d does not continue the loaded batch (%d rows)", row_offset,
+               plan->batch);
+  plan->batch = row_offset + count;
   plan->have_eps = false;
-  return launch_frame_gather(&plan->ctx->c, audio, audio_is_i16, n_samples, frame_idx, first_frame, batch, hop,
-                             plan->S, plan->x.hi, plan->x.lo, nullptr, S_(stream));
+  const size_t off = (size_t)row_offset * plan->S;
+  return launch_frame_gather(&plan->ctx->c, audio, audio_is_i16, n_samples, frame_idx, first_frame, count, hop,
+                             plan->S, plan->x.hi + off, plan->x.lo ? plan->x.lo + off : nullptr, nullptr, S_(stream));
 }
 
 int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* stream) {
@@ -562,12 +631,19 @@ int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat
   return RVAE_OK;
 }
 
+int rvae_plan_set_global_batch(rvae_plan* plan, int64_t global_batch) {
+  RVAE_REQUIRE(plan && global_batch >= 0, RVAE_ERR_INVALID, "plan_set_global_batch: bad argument");
+  plan->global_batch = global_batch;
+  return RVAE_OK;
+}
+
 int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_xhat, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
   RVAE_REQUIRE(plan->have_eps, RVAE_ERR_STATE, "plan_forward: call rvae_plan_set_eps / rvae_plan_gen_eps first");
   cudaStream_t st = S_(stream);
   rvae_plan* p = plan;
-  const double BL = (double)p->batch * p->L, BS = (double)p->batch * p->S;
+  const double nb = p->global_batch > 0 ? (double)p->global_batch : (double)p->batch;
+  const double BL = nb * p->L, BS = nb * p->S;
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));
 
@@ -630,7 +706,8 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
 
 int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
-  return launch_loss_finalize(&plan->ctx->c, plan->loss_acc, plan->batch, plan->S, plan->L, kl_beta, loss_out,
+  const int64_t nb = plan->global_batch > 0 ? plan->global_batch : plan->batch;
+  return launch_loss_finalize(&plan->ctx->c, plan->loss_acc, nb, plan->S, plan->L, kl_beta, loss_out,
                               plan->bufs.step, S_(stream));
 }
 

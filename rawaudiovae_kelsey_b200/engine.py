@@ -1,0 +1,202 @@
+"""Host-side engine: flat parameter storage + the rvae_plan (C ABI) that runs whole steps.
+
+`FlatState` owns the fp32 master weights, gradients, Adam moments, the device step counter and the bf16 shadow
+planes in the layout of `rvae_param_layout` (W1 | W2=[fc21;fc22] | W3 | W4 | b1 | b2 | b3 | b4). The nn.Module
+parameters are views into it, so `state_dict()` stays reference-compatible while one kernel can update everything.
+`Plan` binds those buffers plus a workspace to an rvae_plan for a maximum batch size.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+PRECISIONS = {"bf16": ops.PRECISION_BF16, "fp32": ops.PRECISION_FP32}
+
+# parameter name -> (layout field, row offset factor) ; fc21/fc22 share the stacked W2 / b2 blocks
+PARAM_SLOTS = ("fc1.weight", "fc1.bias", "fc21.weight", "fc21.bias", "fc22.weight", "fc22.bias",
+               "fc3.weight", "fc3.bias", "fc4.weight", "fc4.bias")
+
+
+def param_layout(S: int, H: int, L: int) -> _lib.Layout:
+    lay = _lib.Layout()
+    check(_lib.load().rvae_param_layout(S, H, L, C.byref(lay)))
+    return lay
+
+
+def param_offsets(S: int, H: int, L: int) -> Dict[str, Tuple[int, Tuple[int, ...]]]:
+    """name -> (element offset in the flat buffer, shape)."""
+    lay = param_layout(S, H, L)
+    return {
+        "fc1.weight": (lay.w1, (H, S)), "fc1.bias": (lay.b1, (H,)),
+        "fc21.weight": (lay.w2, (L, H)), "fc21.bias": (lay.b2, (L,)),
+        "fc22.weight": (lay.w2 + L * H, (L, H)), "fc22.bias": (lay.b2 + L, (L,)),
+        "fc3.weight": (lay.w3, (H, L)), "fc3.bias": (lay.b3, (H,)),
+        "fc4.weight": (lay.w4, (S, H)), "fc4.bias": (lay.b4, (S,)),
+    }
+
+
+class FlatState:
+    def __init__(self, S: int, H: int, L: int, device: torch.device, precision: str = "bf16"):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.S, self.H, self.L = S, H, L
+        self.device = device
+        self.precision = precision
+        self.offsets = param_offsets(S, H, L)
+        self.total = int(param_layout(S, H, L).total)
+        z = lambda dt: torch.zeros(self.total, dtype=dt, device=device)
+        self.params = z(torch.float32)
+        self.grads = z(torch.float32)
+        self.exp_avg = z(torch.float32)
+        self.exp_avg_sq = z(torch.float32)
+        self.step = torch.zeros((), dtype=torch.float32, device=device)
+        self.shadow_hi = z(torch.bfloat16)
+        self.shadow_lo = z(torch.bfloat16) if precision == "fp32" else None
+        self.shadow_version = -1  # sum of parameter version counters at the last shadow refresh
+
+    def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[off:off + n].view(shape)
+
+    def sync_shadow(self) -> None:
+        lib = _lib.load()
+        check(lib.rvae_split_bf16(ops.ctx(self.device), self.params.data_ptr(), self.total,
+                                  self.shadow_hi.data_ptr(),
+                                  self.shadow_lo.data_ptr() if self.shadow_lo is not None else None,
+                                  torch.cuda.current_stream().cuda_stream))
+
+
+class Plan:
+    """rvae_plan bound to a FlatState and a zero-initialised workspace for batches up to `max_batch` frames."""
+
+    def __init__(self, flat: FlatState, max_batch: int):
+        lib = _lib.load()
+        self.flat = flat
+        self.max_batch = int(max_batch)
+        self.lib = lib
+        self.handle = C.c_void_p()
+        with torch.cuda.device(flat.device):
+            check(lib.rvae_plan_create(ops.ctx(flat.device), flat.S, flat.H, flat.L, self.max_batch,
+                                       PRECISIONS[flat.precision], C.byref(self.handle)))
+            nbytes = int(lib.rvae_plan_workspace_bytes(self.handle))
+            self.workspace = torch.zeros(nbytes + 256, dtype=torch.uint8, device=flat.device)
+            base = self.workspace.data_ptr()
+            aligned = (base + 255) // 256 * 256
+            bufs = _lib.PlanBuffers(flat.params.data_ptr(), flat.grads.data_ptr(), flat.exp_avg.data_ptr(),
+                                    flat.exp_avg_sq.data_ptr(), flat.step.data_ptr(), flat.shadow_hi.data_ptr(),
+                                    flat.shadow_lo.data_ptr() if flat.shadow_lo is not None else None, aligned)
+            check(lib.rvae_plan_bind(self.handle, C.byref(bufs)))
+        self.batch = 0
+        self.token = 0  # bumped whenever a new batch is loaded (activations of older forwards are gone)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.rvae_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    # ---- inputs
+    def load_batch(self, x: torch.Tensor) -> None:
+        if not x.is_cuda:
+            raise _lib.RvaeError("input batch must be a CUDA tensor; there is no CPU fallback")
+        x = x.reshape(-1, self.flat.S)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        check(self.lib.rvae_plan_load_batch(self.handle, x.data_ptr(), x.shape[0], self._stream()))
+        self.batch = x.shape[0]
+        self.token += 1
+
+    def load_frames(self, audio: torch.Tensor, count: int, hop: int, *, frame_idx: Optional[torch.Tensor] = None,
+                    first_frame: int = 0, row_offset: int = 0) -> None:
+        if audio.dtype not in (torch.float32, torch.int16) or not audio.is_cuda or not audio.is_contiguous():
+            raise _lib.RvaeError("audio must be a contiguous CUDA float32 / int16 tensor")
+        if frame_idx is not None and (frame_idx.dtype != torch.int64 or not frame_idx.is_cuda
+                                      or frame_idx.numel() != count or not frame_idx.is_contiguous()):
+            raise _lib.RvaeError("frame_idx must be a contiguous CUDA int64 tensor with `count` entries")
+        check(self.lib.rvae_plan_load_frames(self.handle, audio.data_ptr(), int(audio.dtype == torch.int16),
+                                             audio.numel(), frame_idx.data_ptr() if frame_idx is not None else None,
+                                             first_frame, count, hop, row_offset, self._stream()))
+        self.batch = row_offset + count
+        if row_offset == 0:
+            self.token += 1
+
+    def set_eps(self, eps: torch.Tensor) -> None:
+        if eps.dtype != torch.float32 or not eps.is_cuda or not eps.is_contiguous():
+            eps = eps.to(device=self.flat.device, dtype=torch.float32).contiguous()
+        if eps.numel() != self.batch * self.flat.L:
+            raise _lib.RvaeError(f"eps has {eps.numel()} elements, expected {self.batch}x{self.flat.L}")
+        check(self.lib.rvae_plan_set_eps(self.handle, eps.data_ptr(), self._stream()))
+
+    def gen_eps(self, seed: int, offset: int) -> None:
+        check(self.lib.rvae_plan_gen_eps(self.handle, seed, offset, self._stream()))
+
+    def set_outputs(self, mu=None, logvar=None, xhat=None) -> None:
+        p = lambda t: t.data_ptr() if t is not None else None
+        check(self.lib.rvae_plan_set_outputs(self.handle, p(mu), p(logvar), p(xhat)))
+
+    def set_global_batch(self, global_batch: int) -> None:
+        check(self.lib.rvae_plan_set_global_batch(self.handle, int(global_batch)))
+
+    # ---- steps
+    def forward(self, kl_beta: float, fused_loss: bool, want_xhat: bool) -> None:
+        check(self.lib.rvae_plan_forward(self.handle, kl_beta, int(fused_loss), int(want_xhat), self._stream()))
+
+    def backward(self, stage: int = -1) -> None:
+        check(self.lib.rvae_plan_backward(self.handle, stage, self._stream()))
+
+    def backward_external(self, g_xhat, xhat, g_mu, g_logvar) -> None:
+        check(self.lib.rvae_plan_backward_external(self.handle, g_xhat.data_ptr(), xhat.data_ptr(), g_mu.data_ptr(),
+                                                   g_logvar.data_ptr(), self._stream()))
+
+    def finish_loss(self, kl_beta: float, loss_out: Optional[torch.Tensor]) -> None:
+        check(self.lib.rvae_plan_finish_loss(self.handle, kl_beta,
+                                             loss_out.data_ptr() if loss_out is not None else None, self._stream()))
+
+    def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0) -> None:
+        check(self.lib.rvae_plan_adam(self.handle, lr, beta1, beta2, eps, weight_decay, grad_scale, self._stream()))
+
+    def train_step(self, kl_beta, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                   loss_out: Optional[torch.Tensor] = None) -> None:
+        check(self.lib.rvae_plan_train_step(self.handle, kl_beta, lr, beta1, beta2, eps, weight_decay,
+                                            loss_out.data_ptr() if loss_out is not None else None, self._stream()))
+
+    def encode(self) -> None:
+        check(self.lib.rvae_plan_encode(self.handle, self._stream()))
+
+    def decode(self, z: torch.Tensor, xhat_out: torch.Tensor) -> None:
+        check(self.lib.rvae_plan_decode(self.handle, z.data_ptr(), z.shape[0], xhat_out.data_ptr(), self._stream()))
+        self.batch = z.shape[0]
+        self.token += 1
+
+    GEMM_SLOTS = ("F1", "F2", "F3", "F4_out", "F4_lin", "B4w", "B4d", "B3w", "B3d", "B2w", "B2d", "B1w")
+
+    def enable_timing(self, on: bool) -> None:
+        check(self.lib.rvae_plan_enable_timing(self.handle, int(on)))
+
+    def read_timing(self):
+        """{slot: (total_ms, launches, flops_per_launch)} since the last read (synchronises the timing events)."""
+        n = len(self.GEMM_SLOTS)
+        ms, cnt, fl = (C.c_float * n)(), (C.c_int64 * n)(), (C.c_double * n)()
+        check(self.lib.rvae_plan_read_timing(self.handle, ms, cnt, fl))
+        return {k: (float(ms[i]), int(cnt[i]), float(fl[i])) for i, k in enumerate(self.GEMM_SLOTS)}
+
+    def bucket(self, s: int) -> torch.Tensor:
+        """Gradient bucket s as a view of flat.grads (0..3 = W4, W3, W2, W1 in backward order; 4 = biases)."""
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        check(self.lib.rvae_plan_bucket(self.handle, s, C.byref(ptr), C.byref(cnt)))
+        off = (ptr.value - self.flat.grads.data_ptr()) // 4
+        return self.flat.grads[off:off + cnt.value]

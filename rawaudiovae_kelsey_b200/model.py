@@ -1,0 +1,342 @@
+"""Drop-in for the reference's rawvae/model.py: `VAE` and `loss_function` with the same names, signatures and
+tensor semantics, computed by the sm_100a kernels behind include/rvae_b200.h.
+
+Reference contract mirrored here (file:line in kelseyicotton/rawaudiovae_kelsey):
+  VAE.__init__(segment_length, n_units, latent_dim)        rawvae/model.py:6-17   (same submodule names / init order)
+  VAE.encode(x) -> (mu, logvar)                            rawvae/model.py:19-21
+  VAE.reparameterize(mu, logvar) -> z                      rawvae/model.py:23-26
+  VAE.decode(z) -> x_hat                                   rawvae/model.py:28-30
+  VAE.forward(x) -> (x_hat, mu, logvar), x.view(-1, S)     rawvae/model.py:32-35
+  loss_function(recon_x, x, mu, logvar, kl_beta, S)        rawvae/model.py:38-46
+
+CUDA tensors only: CPU inputs raise (the north star forbids a CPU fallback). Parameters stay fp32 nn.Parameters
+named fc1/fc21/fc22/fc3/fc4 so checkpoints load both ways; they are views into one flat buffer (engine.FlatState)
+so the fused Adam kernel and the gradient all-reduce see contiguous memory.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, engine, ops
+
+_PRIVATE = ("_flat", "_plans", "_eps_counter")
+
+
+class FrameBatch:
+    """A batch described by frame indices into a device-resident wav buffer (produced by dataset.GpuFrameLoader).
+    Passing it to VAE.forward / FusedTrainStep fuses framing into the batch load: frames are gathered straight into
+    the bf16 operand buffer of fc1 and never materialised as an fp32 [B, S] tensor."""
+
+    def __init__(self, audio: torch.Tensor, n_frames: int, hop: int, segment_length: int,
+                 frame_idx: Optional[torch.Tensor] = None, first_frame: int = 0):
+        self.audio, self.n_frames, self.hop, self.segment_length = audio, int(n_frames), int(hop), int(segment_length)
+        self.frame_idx, self.first_frame = frame_idx, int(first_frame)
+
+    @property
+    def shape(self):
+        return (self.n_frames, self.segment_length)
+
+    def __len__(self):
+        return self.n_frames
+
+    def to(self, *args, **kwargs):  # `data.to(device)` in the training loops is a no-op for a device batch
+        return self
+
+    def materialize(self) -> torch.Tensor:
+        """fp32 [B, S] frames (what the reference's DataLoader would have produced)."""
+        f32, _, _ = ops.frame_gather(self.audio, self.n_frames, self.hop, self.segment_length,
+                                     frame_idx=self.frame_idx, first_frame=self.first_frame)
+        return f32
+
+    def view(self, *shape):
+        return self.materialize().view(*shape)
+
+
+class VAE(nn.Module):
+    __module__ = "rawvae.model"  # whole-module pickles (best_model.pt / last_model.pt) resolve like the reference's
+
+    def __init__(self, segment_length, n_units, latent_dim, precision: str = "bf16"):
+        super(VAE, self).__init__()
+        self.segment_length = segment_length
+        self.n_units = n_units
+        self.latent_dim = latent_dim
+        # same creation order as the reference => identical default init for a given torch.manual_seed
+        self.fc1 = nn.Linear(segment_length, n_units)
+        self.fc21 = nn.Linear(n_units, latent_dim)
+        self.fc22 = nn.Linear(n_units, latent_dim)
+        self.fc3 = nn.Linear(latent_dim, n_units)
+        self.fc4 = nn.Linear(n_units, segment_length)
+        self.precision = precision      # "bf16" (bf16 operands, fp32 accumulate) or "fp32" (split-bf16, 3 passes)
+        self.eps_source = "philox"      # "philox": in-library Philox noise; "torch": torch.randn on the CUDA generator
+        self.eps_seed = None            # philox seed (default: torch.initial_seed())
+        self._flat: Optional[engine.FlatState] = None
+        self._plans: Dict[int, engine.Plan] = {}
+        self._eps_counter = 0
+
+    # ------------------------------------------------------------------ pickling / device moves
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in _PRIVATE:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__.setdefault("precision", "bf16")
+        self.__dict__.setdefault("eps_source", "philox")
+        self.__dict__.setdefault("eps_seed", None)
+        self._flat, self._plans, self._eps_counter = None, {}, 0
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._flat, self._plans = None, {}
+        p = self.fc1.weight
+        if p.is_cuda:
+            self._ensure_flat()
+        return out
+
+    def set_precision(self, precision: str) -> "VAE":
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(engine.PRECISIONS)}")
+        if precision != self.precision:
+            self.precision = precision
+            self._flat, self._plans = None, {}
+        return self
+
+    # ------------------------------------------------------------------ flat storage
+    def _named(self) -> List:
+        return [(n, p) for n, p in self.named_parameters()]
+
+    def _ensure_flat(self) -> engine.FlatState:
+        """Make every parameter a view of one flat fp32 buffer (idempotent) and keep the bf16 shadows fresh."""
+        p0 = self.fc1.weight
+        if not p0.is_cuda:
+            raise _lib.RvaeError("VAE parameters are on the CPU: call model.to('cuda') - there is no CPU fallback")
+        flat = getattr(self, "_flat", None)
+        named = self._named()
+        ok = flat is not None and flat.device == p0.device and flat.precision == self.precision
+        if ok:
+            base = flat.params.data_ptr()
+            for n, p in named:
+                off, shape = flat.offsets[n]
+                if p.data_ptr() != base + 4 * off or tuple(p.shape) != shape or p.dtype != torch.float32:
+                    ok = False
+                    break
+        if not ok:
+            S, H, L = self.segment_length, self.n_units, self.latent_dim
+            for n, p in named:
+                if p.dtype != torch.float32:
+                    raise _lib.RvaeError(f"parameter {n} is {p.dtype}; master weights must stay float32")
+            flat = engine.FlatState(S, H, L, p0.device, self.precision)
+            with torch.no_grad():
+                for n, p in named:
+                    v = flat.view(flat.params, n)
+                    v.copy_(p.data)
+                    p.data = v
+                    p.grad = None
+                    p._rvae_flat = (flat, n)
+            self._flat, self._plans = flat, {}
+            flat.shadow_version = -1
+        version = sum(p._version for _, p in named)
+        if version != flat.shadow_version:
+            flat.sync_shadow()
+            flat.shadow_version = version
+        return flat
+
+    def _plan_for(self, batch: int) -> engine.Plan:
+        flat = self._ensure_flat()
+        best = None
+        for mb, pl in self._plans.items():
+            if mb >= batch and (best is None or mb < best.max_batch):
+                best = pl
+        if best is None:
+            self._plans = {}  # drop smaller workspaces
+            best = engine.Plan(flat, batch)
+            self._plans[batch] = best
+        return best
+
+    # ------------------------------------------------------------------ noise
+    def _eps_args(self):
+        seed = self.eps_seed if self.eps_seed is not None else torch.initial_seed()
+        off = self._eps_counter
+        self._eps_counter += 1
+        return int(seed) & 0xFFFFFFFFFFFFFFFF, off
+
+    def _set_eps(self, plan: engine.Plan, eps: Optional[torch.Tensor]) -> None:
+        if eps is not None:
+            plan.set_eps(eps)
+        elif self.eps_source == "torch":
+            plan.set_eps(torch.randn((plan.batch, self.latent_dim), device=self._flat.device))
+        else:
+            plan.gen_eps(*self._eps_args())
+
+    # ------------------------------------------------------------------ reference API
+    def _load(self, src):
+        """Load a batch into a plan: a CUDA tensor (any shape with numel % S == 0), a FrameBatch, or a list of
+        FrameBatch runs (a streaming batch that straddles files)."""
+        if isinstance(src, FrameBatch):
+            src = [src]
+        if isinstance(src, (list, tuple)) and src and all(isinstance(r, FrameBatch) for r in src):
+            total = sum(r.n_frames for r in src)
+            plan = self._plan_for(total)
+            row = 0
+            for r in src:
+                if r.segment_length != self.segment_length:
+                    raise _lib.RvaeError("FrameBatch segment_length does not match the model")
+                plan.load_frames(r.audio, r.n_frames, r.hop, frame_idx=r.frame_idx, first_frame=r.first_frame,
+                                 row_offset=row)
+                row += r.n_frames
+            return plan
+        x = src
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a torch.Tensor, a FrameBatch or a list of FrameBatch")
+        if not x.is_cuda:
+            raise _lib.RvaeError("input is a CPU tensor: move it to the GPU - there is no CPU fallback")
+        x = x.view(-1, self.segment_length)
+        plan = self._plan_for(x.shape[0])
+        plan.load_batch(x)
+        return plan
+
+    def encode(self, x):
+        """(mu, logvar) = (fc21(relu(fc1 x)), fc22(relu(fc1 x))) - inference path, returns detached tensors."""
+        plan = self._load(x)
+        dev = self._flat.device
+        mu = torch.empty((plan.batch, self.latent_dim), dtype=torch.float32, device=dev)
+        lv = torch.empty_like(mu)
+        plan.set_outputs(mu, lv, None)
+        plan.encode()
+        plan.set_outputs(None, None, None)
+        return mu, lv
+
+    def reparameterize(self, mu, logvar, eps: Optional[torch.Tensor] = None):
+        """z = mu + eps * exp(0.5 * logvar). Accepts float64 inputs (tutorial.ipynb:922) - computed in fp32."""
+        if not mu.is_cuda:
+            raise _lib.RvaeError("reparameterize: CPU tensors are not supported (no CPU fallback)")
+        dt = mu.dtype
+        m32, l32 = mu.float().contiguous(), logvar.float().contiguous()
+        if eps is None:
+            if self.eps_source == "torch":
+                eps = torch.randn_like(m32)
+            else:
+                seed, off = self._eps_args()
+                eps = ops.randn(m32.shape, seed, off, device=m32.device)
+        z = ops.reparameterize(m32, l32, eps.float().contiguous())
+        return z.to(dt)
+
+    def decode(self, z):
+        """x_hat = tanh(fc4(relu(fc3 z))) - inference path, returns a detached tensor."""
+        if not z.is_cuda:
+            raise _lib.RvaeError("decode: CPU tensors are not supported (no CPU fallback)")
+        z = z.reshape(-1, self.latent_dim).float().contiguous()
+        plan = self._plan_for(z.shape[0])
+        out = torch.empty((z.shape[0], self.segment_length), dtype=torch.float32, device=z.device)
+        plan.decode(z, out)
+        return out
+
+    def forward(self, x, eps: Optional[torch.Tensor] = None):
+        """(x_hat, mu, logvar); differentiable w.r.t. the parameters (loss.backward() works as in the reference).
+        `eps` optionally injects the reparameterisation noise (parity tests); the reference draws it internally."""
+        self._ensure_flat()
+        params = [p for _, p in self._named()]
+        return _VAEForward.apply(self, x, eps, *params)
+
+
+class _VAEForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: VAE, x, eps, *params):
+        plan = model._load(x)
+        model._set_eps(plan, eps)
+        dev = model._flat.device
+        B, S, L = plan.batch, model.segment_length, model.latent_dim
+        xhat = torch.empty((B, S), dtype=torch.float32, device=dev)
+        mu = torch.empty((B, L), dtype=torch.float32, device=dev)
+        lv = torch.empty((B, L), dtype=torch.float32, device=dev)
+        plan.set_outputs(mu, lv, xhat)
+        plan.forward(0.0, fused_loss=False, want_xhat=True)
+        plan.set_outputs(None, None, None)
+        ctx.model, ctx.plan, ctx.token = model, plan, plan.token
+        ctx.save_for_backward(xhat)
+        return xhat, mu, lv
+
+    @staticmethod
+    def backward(ctx, g_xhat, g_mu, g_lv):
+        model, plan = ctx.model, ctx.plan
+        (xhat,) = ctx.saved_tensors
+        if plan.token != ctx.token:
+            raise RuntimeError("the activations of this forward pass were overwritten by a later forward on the "
+                               "same model; call backward() before running the model again")
+        flat = model._flat
+        B, L = xhat.shape[0], model.latent_dim
+        z = lambda ref, shape: torch.zeros(shape, dtype=torch.float32, device=xhat.device) if ref is None \
+            else ref.float().contiguous()
+        g_xhat, g_mu, g_lv = z(g_xhat, xhat.shape), z(g_mu, (B, L)), z(g_lv, (B, L))
+        named = model._named()
+        # un-alias gradients that already live in the flat buffer (gradient accumulation / set_to_none=False)
+        g0 = flat.grads.data_ptr()
+        g1 = g0 + 4 * flat.total
+        for _, p in named:
+            if p.grad is not None and g0 <= p.grad.data_ptr() < g1:
+                p.grad = p.grad.clone()
+        plan.backward_external(g_xhat, xhat, g_mu, g_lv)
+        grads = tuple(flat.view(flat.grads, n) for n, _ in named)
+        return (None, None, None) + grads
+
+
+class _LossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, recon_x, x, mu, logvar, kl_beta):
+        ctx.save_for_backward(recon_x, x, mu, logvar)
+        ctx.kl_beta = kl_beta
+        return ops.loss_fwd(recon_x, x, mu, logvar, kl_beta)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        recon_x, x, mu, logvar = ctx.saved_tensors
+        g = grad_out.float().contiguous() if grad_out is not None else None
+        g_x, g_mu, g_lv = ops.loss_bwd(recon_x, x, mu, logvar, ctx.kl_beta, g)
+        return g_x, None, g_mu, g_lv, None
+
+
+# Reconstruction + KL divergence losses (mean over all elements, as the reference's mse_loss default / torch.mean)
+def loss_function(recon_x, x, mu, logvar, kl_beta, segment_length):
+    if isinstance(x, FrameBatch):
+        x = x.materialize()
+    if not recon_x.is_cuda:
+        raise _lib.RvaeError("loss_function: CPU tensors are not supported (no CPU fallback)")
+    x = x.view(-1, segment_length)
+    c = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+    return _LossFunction.apply(c(recon_x), c(x), c(mu), c(logvar), float(kl_beta))
+
+
+class FusedTrainStep:
+    """zero_grad + forward + loss + backward + Adam (train_iterable.py:200-210) as ONE C call: every kernel of the
+    step is enqueued by rvae_plan_train_step, the loss gradients are produced by the forward epilogues, and the
+    loss lands in a device-side ring so the host never has to synchronise per step.
+
+        step = FusedTrainStep(model, optimizer, kl_beta)
+        loss = step(data)            # 0-dim CUDA tensor (a slot of the ring); .item() only when you log
+    """
+
+    def __init__(self, model: VAE, optimizer, kl_beta: float, ring: int = 64):
+        self.model, self.optimizer, self.kl_beta = model, optimizer, float(kl_beta)
+        self.ring = None
+        self.ring_size = ring
+        self.i = 0
+
+    def __call__(self, data, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        model = self.model
+        plan = model._load(data)
+        model._set_eps(plan, eps)
+        if self.ring is None:
+            self.ring = torch.zeros(self.ring_size, dtype=torch.float32, device=model._flat.device)
+        slot = self.ring[self.i % self.ring_size]
+        self.i += 1
+        g = self.optimizer.param_groups[0]
+        if hasattr(self.optimizer, "bind_flat"):
+            self.optimizer.bind_flat(model._flat)
+        b1, b2 = g["betas"]
+        plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=slot)
+        return slot

@@ -1,0 +1,395 @@
+"""GPU parity tests (-m gpu): the sm_100a path, called through the C ABI, against the CPU oracle and the committed
+golden vectors of the reference. Tolerances are BASELINE.json's: frame indices bit-exact; fp32 mode <= 1e-4
+relative; bf16 mode <= 2e-2 relative; loss curves within 1 % over 1k steps."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+FP32_TOL = 1e-4
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().flatten()
+    b = torch.as_tensor(b).detach().double().cpu().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from rawaudiovae_kelsey_b200 import _lib
+    assert _lib.library_path().exists(), "librvae_b200.so missing - the CUDA extension must be built in-tree"
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def small(golden_dir):
+    return np.load(golden_dir / "model_small.npz")
+
+
+def make_model(small, prefix, dev, precision):
+    from rawvae.model import VAE
+    from oracle.rawvae_oracle import PARAM_NAMES
+    S, H, L, B, steps = (int(v) for v in small["meta"])
+    m = VAE(S, H, L, precision=precision)
+    m.load_state_dict({k: torch.from_numpy(small[f"{prefix}/{k}"]) for k in PARAM_NAMES})
+    return m.to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ golden, small dims
+@pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", FP32_TOL)])
+def test_forward_backward_vs_reference_golden(dev, small, precision, tol):
+    from rawvae.model import loss_function
+    from oracle.rawvae_oracle import PARAM_NAMES
+    S, H, L, B, steps = (int(v) for v in small["meta"])
+    kl_beta, lr = (float(v) for v in small["hyper"])
+    model = make_model(small, "init", dev, precision)
+    x = torch.from_numpy(small["x"]).to(dev)
+    eps = torch.from_numpy(small["eps"][0]).to(dev)
+    xh, mu, lv = model(x, eps=eps)
+    assert xh.shape == (B, S) and mu.shape == (B, L) and lv.shape == (B, L)
+    assert rel(xh, small["x_hat"]) < tol
+    assert rel(mu, small["mu"]) < tol
+    assert rel(lv, small["logvar"]) < tol
+    loss = loss_function(xh, x, mu, lv, kl_beta, S)
+    assert loss.dim() == 0
+    assert abs(loss.item() - float(small["losses"][0])) < tol * abs(float(small["losses"][0]))
+    loss.backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert rel(p.grad, small["grad/" + k]) < tol, k
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", FP32_TOL)])
+def test_three_adam_steps_vs_reference_golden(dev, small, precision, tol):
+    """The reference loop body (train_iterable.py:200-210) through the drop-in API, 3 steps."""
+    from rawvae.model import loss_function
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L, B, steps = (int(v) for v in small["meta"])
+    kl_beta, lr = (float(v) for v in small["hyper"])
+    model = make_model(small, "init", dev, precision)
+    opt = Adam(model.parameters(), lr=lr)
+    x = torch.from_numpy(small["x"]).to(dev)
+    for s in range(steps):
+        opt.zero_grad()
+        xh, mu, lv = model(x, eps=torch.from_numpy(small["eps"][s]).to(dev))
+        loss = loss_function(xh, x, mu, lv, kl_beta, S)
+        loss.backward()
+        opt.step()
+        assert abs(loss.item() - float(small["losses"][s])) < tol * abs(float(small["losses"][s]))
+    sd = model.state_dict()
+    for k in sd:
+        # parameters move by ~lr per step: compare the UPDATE, not the weights, so the tolerance means something
+        upd = sd[k].cpu().double() - torch.from_numpy(small["init/" + k]).double()
+        ref = torch.from_numpy(small["final/" + k]).double() - torch.from_numpy(small["init/" + k]).double()
+        assert rel(upd, ref) < (0.1 if precision == "bf16" else 2e-3), k   # Adam's sign-like update amplifies noise
+    ost = opt.state_dict()
+    assert sorted(ost["state"][0].keys()) == ["exp_avg", "exp_avg_sq", "step"]
+    assert float(ost["state"][0]["step"]) == steps
+    names = [k for k, _ in model.named_parameters()]
+    for i, k in enumerate(names):
+        assert rel(ost["state"][i]["exp_avg"], small["exp_avg/" + k]) < tol * 2, k
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", FP32_TOL)])
+def test_fused_train_step_matches_oracle(dev, small, precision, tol):
+    """rvae_plan_train_step (one C call per step) against the oracle's explicit forward/backward/Adam."""
+    from rawvae.model import FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    from oracle import rawvae_oracle as O
+    S, H, L, B, steps = (int(v) for v in small["meta"])
+    kl_beta, lr = (float(v) for v in small["hyper"])
+    model = make_model(small, "init", dev, precision)
+    opt = Adam(model.parameters(), lr=lr)
+    step = FusedTrainStep(model, opt, kl_beta)
+    p = {k: torch.from_numpy(small["init/" + k]).double() for k in O.PARAM_NAMES}
+    st = O.adam_init(p)
+    x = torch.from_numpy(small["x"])
+    for s in range(steps):
+        eps = torch.from_numpy(small["eps"][s])
+        loss = step(x.to(dev), eps=eps.to(dev))
+        ref = O.train_step(p, st, x.double(), eps.double(), kl_beta, lr)
+        assert abs(loss.item() - ref) < tol * abs(ref)
+        assert abs(ref - float(small["losses"][s])) < 1e-5 * abs(ref)
+    flat = model._flat
+    for k in O.PARAM_NAMES:
+        assert rel(flat.view(flat.exp_avg, k), st[k]["exp_avg"]) < tol * 2, k
+    assert float(flat.step) == steps
+    # bf16 shadow planes follow the fp32 master weights
+    assert rel(flat.shadow_hi.float(), flat.params) < 4e-3
+
+
+def test_default_ini_dims_fused_step(dev, golden_dir):
+    """default.ini dimensions (S=1024, H=2048, L=256), B=256: loss and gradient norms against the reference's
+    summary; weights regenerated from the seed exactly as the reference does (torch.manual_seed(0); VAE(...))."""
+    from rawvae.model import VAE, loss_function
+    g = json.loads((golden_dir / "model_default_summary.json").read_text())
+    S, H, L, B = g["S"], g["H"], g["L"], g["B"]
+    torch.manual_seed(0)
+    model = VAE(S, H, L).to(dev)
+    assert sum(p.numel() for p in model.parameters()) == g["n_params"]
+    assert list(model.state_dict().keys()) == g["state_dict_keys"]
+    gen = torch.Generator().manual_seed(1)
+    x = (torch.rand(B, S, generator=gen) * 2 - 1).to(dev)
+    eps = torch.randn(B, L, generator=gen).to(dev)
+    for precision, tol in (("bf16", BF16_TOL), ("fp32", FP32_TOL)):
+        model.set_precision(precision)
+        model.zero_grad()
+        xh, mu, lv = model(x, eps=eps)
+        loss = loss_function(xh, x, mu, lv, g["kl_beta"], S)
+        loss.backward()
+        assert abs(loss.item() - g["losses"][0]) < tol * g["losses"][0]
+        for name, t in (("x_hat", xh), ("mu", mu), ("logvar", lv)):
+            assert abs(float(t.double().norm()) - g[name]["norm"]) < tol * g[name]["norm"], name
+        for k, p in model.named_parameters():
+            assert abs(float(p.grad.double().norm()) - g["grads"][k]["norm"]) < tol * g["grads"][k]["norm"], k
+
+
+# ------------------------------------------------------------------------------------------------ larger, oracle on the fly
+@pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", FP32_TOL)])
+def test_activations_and_gradients_vs_oracle_ragged_batch(dev, precision, tol):
+    """A ragged batch (B=300, not a multiple of the 128-row tile) at S=256, H=320, L=64: every activation and
+    gradient tensor against the fp64 oracle."""
+    from rawvae.model import VAE, loss_function
+    from oracle import rawvae_oracle as O
+    S, H, L, B, beta = 256, 320, 64, 300, 1e-2
+    torch.manual_seed(3)
+    model = VAE(S, H, L, precision=precision).to(dev)
+    p64 = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(B, S, generator=gen) * 2 - 1
+    eps = torch.randn(B, L, generator=gen)
+    xh, mu, lv = model(x.to(dev), eps=eps.to(dev))
+    loss = loss_function(xh, x.to(dev), mu, lv, beta, S)
+    loss.backward()
+    act = O.forward(p64, x.double(), eps.double())
+    ref_loss = O.loss_function(act["x_hat"], act["x"], act["mu"], act["logvar"], beta, S)
+    gr = O.backward(p64, act, beta)
+    assert rel(xh, act["x_hat"]) < tol and rel(mu, act["mu"]) < tol and rel(lv, act["logvar"]) < tol
+    assert abs(loss.item() - float(ref_loss)) < tol * float(ref_loss)
+    for k, prm in model.named_parameters():
+        assert rel(prm.grad, gr[k]) < tol, k
+
+
+def test_loss_curve_1k_steps_within_one_percent(dev, small):
+    """1000 optimizer steps on a fixed batch with a fresh eps every step: the bf16 fused path's loss curve stays
+    within 1 % of the fp64 oracle's, step by step (BASELINE.json north_star)."""
+    from rawvae.model import FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    from oracle import rawvae_oracle as O
+    S, H, L, B, _ = (int(v) for v in small["meta"])
+    kl_beta, lr, n = 1e-4, 1e-3, 1000
+    model = make_model(small, "init", dev, "bf16")
+    opt = Adam(model.parameters(), lr=lr)
+    step = FusedTrainStep(model, opt, kl_beta, ring=n)
+    p = {k: torch.from_numpy(small["init/" + k]).double() for k in O.PARAM_NAMES}
+    st = O.adam_init(p)
+    x = torch.from_numpy(small["x"])
+    gen = torch.Generator().manual_seed(11)
+    eps_all = torch.randn(n, B, L, generator=gen)
+    eps_dev = eps_all.to(dev)
+    xd = x.to(dev)
+    ref = []
+    for s in range(n):
+        step(xd, eps=eps_dev[s])
+        ref.append(O.train_step(p, st, x.double(), eps_all[s].double(), kl_beta, lr))
+    got = step.ring.cpu().double().numpy()
+    ref = np.array(ref)
+    err = np.abs(got - ref) / ref
+    assert ref[-1] < 0.5 * ref[0], "the oracle should be learning"
+    assert err.max() < 0.01, f"max loss-curve deviation {err.max():.4f}"
+
+
+# ------------------------------------------------------------------------------------------------ framing / resynthesis
+def test_framing_bit_exact_vs_reference_golden(dev, golden_dir):
+    from rawaudiovae_kelsey_b200 import ops
+    from rawvae.dataset import AudioDataset, TestDataset
+    ds = np.load(golden_dir / "dataset.npz")
+    for n in (22087, 1024, 1025, 2048, 1151, 1152):
+        audio = ds[f"audio_{n}"]
+        a = AudioDataset(audio, 1024, 44100, 128)
+        t = TestDataset(audio, 1024, 44100)
+        assert [len(a), len(t)] == [int(v) for v in ds[f"audio_len_{n}"]]
+        idx = torch.from_numpy(ds[f"audio_idx_{n}"]).to(dev)
+        ad = torch.from_numpy(audio).to(dev)                       # un-padded: the kernel zero-fills the tail
+        f32, hi, _ = ops.frame_gather(ad, len(idx), 128, 1024, frame_idx=idx, out_bf16=True)
+        np.testing.assert_array_equal(f32.cpu().numpy(), ds[f"audio_frames_{n}"])
+        assert torch.equal(hi.cpu(), torch.from_numpy(ds[f"audio_frames_{n}"]).to(torch.bfloat16))
+        tf, _, _ = ops.frame_gather(ad, len(t), 1024, 1024)
+        np.testing.assert_array_equal(tf.cpu().numpy(), ds[f"test_frames_{n}"])
+
+
+def test_gpu_stream_matches_reference_stream(dev, golden_dir, tmp_path):
+    """GpuFrameStream over the same three wavs reproduces the reference IterableAudioDataset stream bit-exactly
+    (stereo -> channel 0, zero padding, batches straddling files, endless cycling)."""
+    import scipy.io.wavfile as wavfile
+    from rawvae.dataset import IterableAudioDataset
+    from rawaudiovae_kelsey_b200 import ops
+    ds = np.load(golden_dir / "dataset.npz")
+    order = [str(s) for s in ds["stream_order"]]
+    for name in order:
+        wavfile.write(str(tmp_path / name), 44100, ds["stream_pcm_" + name])
+    it = IterableAudioDataset(tmp_path, 44100, 128, torch.float32, dev, shuffle=False)
+    it.audio_file_list = [tmp_path / n for n in order]             # glob order is filesystem dependent
+    got = []
+    for runs in it.gpu_stream(batch_size=50):
+        for r in runs:
+            got.append(r.materialize())
+        if sum(len(g) for g in got) >= 150:
+            break
+    got = torch.cat(got)[:150].cpu().numpy()
+    np.testing.assert_array_equal(got, ds["stream_frames"])
+    # PCM16-resident variant decodes to the same floats
+    got16 = []
+    for runs in it.gpu_stream(batch_size=50, pcm16=True):
+        got16 += [r.materialize() for r in runs]
+        if sum(len(g) for g in got16) >= 150:
+            break
+    np.testing.assert_array_equal(torch.cat(got16)[:150].cpu().numpy(), ds["stream_frames"])
+
+
+def test_full_size_framing_roundtrip_and_checksum(dev):
+    """Config-sized property test: 60 s of 44.1 kHz audio -> 20 657 overlapping frames -> overlap-add == padded
+    input; concat of TestDataset frames == padded input; checksum of frames == weighted checksum of samples."""
+    from rawaudiovae_kelsey_b200 import ops
+    from oracle.rawvae_oracle import audio_dataset_len
+    n, S, hop = 44100 * 60 + 77, 1024, 128
+    gen = torch.Generator().manual_seed(9)
+    audio = (torch.rand(n, generator=gen) * 2 - 1).to(dev)
+    N = audio_dataset_len(n, S, hop)
+    frames, _, _ = ops.frame_gather(audio, N, hop, S)
+    P = -(-n // hop) * hop
+    pad = torch.cat([audio, torch.zeros(P - n, device=dev)])
+    assert torch.equal(frames, pad.unfold(0, S, hop))
+    ola = ops.overlap_add(frames, hop)
+    assert ola.numel() == P and float((ola - pad).abs().max()) < 1e-6
+    cnt = torch.ones(P, dtype=torch.float64, device=dev)
+    cover = torch.minimum(torch.arange(P, device=dev) // hop, torch.tensor(N - 1, device=dev)) - \
+        torch.clamp((torch.arange(P, device=dev) - S + hop) // hop, min=0) + 1
+    assert abs(float(frames.double().sum()) - float((pad.double() * cover.double() * cnt).sum())) < 1e-6 * N
+    PT = -(-n // S) * S
+    tf, _, _ = ops.frame_gather(audio, PT // S, S, S)
+    assert torch.equal(tf.view(-1), torch.cat([audio, torch.zeros(PT - n, device=dev)]))
+    assert torch.equal(ops.overlap_add(tf, S), tf.view(-1))
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_gradient_additivity_and_api_agreement(dev):
+    """BASELINE config (default.ini dims, 8192 frames): size-independent properties instead of an 8192-row oracle run.
+    (1) fused step gradients == autograd-API gradients (two different kernel routes to the same numbers);
+    (2) with global-batch normalisation, grad(batch) == grad(first half) + grad(second half): the identity data
+        parallelism relies on."""
+    from rawvae.model import VAE, loss_function
+    S, H, L, B, beta = 1024, 2048, 256, 8192, 1e-4
+    torch.manual_seed(0)
+    model = VAE(S, H, L).to(dev)
+    gen = torch.Generator().manual_seed(2)
+    x = (torch.rand(B, S, generator=gen) * 2 - 1).to(dev)
+    eps = torch.randn(B, L, generator=gen).to(dev)
+    xh, mu, lv = model(x, eps=eps)
+    loss = loss_function(xh, x, mu, lv, beta, S)
+    loss.backward()
+    g_api = model._flat.grads.clone()
+    api_loss = loss.item()
+
+    plan = model._plan_for(B)
+
+    def fused(xs, es, global_batch):
+        plan.load_batch(xs)
+        plan.set_eps(es)
+        plan.set_global_batch(global_batch)
+        plan.forward(beta, fused_loss=True, want_xhat=False)
+        out = torch.zeros(1, device=dev)
+        plan.finish_loss(beta, out)
+        plan.backward(-1)
+        plan.set_global_batch(0)
+        return model._flat.grads.clone(), out.item()
+
+    step0 = float(model._flat.step)
+    g_full, l_full = fused(x, eps, 0)
+    assert abs(l_full - api_loss) < 1e-3 * api_loss
+    assert rel(g_full, g_api) < 5e-3          # same bf16 operands; differs only by bf16 rounding of g_xhat staging
+    g_a, l_a = fused(x[: B // 2], eps[: B // 2], B)
+    g_b, l_b = fused(x[B // 2:], eps[B // 2:], B)
+    assert abs((l_a + l_b) - l_full) < 1e-5 * l_full
+    assert rel(g_a + g_b, g_full) < 1e-3
+    model._flat.step.fill_(step0)             # finish_loss bumps the Adam step counter; restore
+    assert 0.2 < api_loss < 0.6               # init-time loss on U(-1,1) input is ~0.3855
+
+
+def test_cpu_tensors_fail_loudly(dev):
+    from rawvae.model import VAE, loss_function
+    from rawaudiovae_kelsey_b200._lib import RvaeError
+    m = VAE(128, 128, 64)
+    with pytest.raises(RvaeError):
+        m(torch.zeros(4, 128))                 # CPU model + CPU input: no fallback
+    m = m.to(dev)
+    with pytest.raises(RvaeError):
+        m(torch.zeros(4, 128))                 # CPU input on a CUDA model
+    with pytest.raises(RvaeError):
+        loss_function(torch.zeros(4, 128), torch.zeros(4, 128), torch.zeros(4, 64), torch.zeros(4, 64), 1e-4, 128)
+
+
+def test_inference_api_encode_reparameterize_decode(dev, small):
+    """tutorial.ipynb pattern: encode -> lerp of (mu, logvar) in float64 -> reparameterize -> decode -> view(-1)."""
+    from oracle import rawvae_oracle as O
+    model = make_model(small, "init", dev, "fp32").eval()
+    S, H, L, B, _ = (int(v) for v in small["meta"])
+    x = torch.from_numpy(small["x"]).to(dev)
+    with torch.no_grad():
+        mu, lv = model.encode(x)
+        assert rel(mu, small["mu"]) < FP32_TOL and rel(lv, small["logvar"]) < FP32_TOL
+        a = 0.25
+        mu_i = (1 - a) * mu[: B // 2].double() + a * mu[B // 2:].double()
+        lv_i = (1 - a) * lv[: B // 2].double() + a * lv[B // 2:].double()
+        eps = torch.randn(B // 2, L, device=dev)
+        z = model.reparameterize(mu_i, lv_i, eps=eps)
+        assert z.dtype == torch.float64
+        assert rel(z, mu_i + eps.double() * torch.exp(0.5 * lv_i)) < 1e-6
+        z2 = model.reparameterize(mu_i, lv_i)                  # internal Philox noise
+        assert z2.shape == z.shape and not torch.equal(z2, z)
+        xh = model.decode(z.float())
+        p = {k: torch.from_numpy(small["init/" + k]).double() for k in O.PARAM_NAMES}
+        zc = z.cpu().double()
+        ref = torch.tanh(torch.clamp_min(zc @ p["fc3.weight"].T + p["fc3.bias"], 0) @ p["fc4.weight"].T + p["fc4.bias"])
+        assert rel(xh, ref) < FP32_TOL
+        assert xh.view(-1).numel() == (B // 2) * S
+        x1d = model(x[0])[0]                                   # 1-D [S] input, as export-onnx.ipynb feeds
+        assert x1d.shape == (1, S)
+
+
+def test_checkpoint_roundtrip_with_reference_format(dev, small, tmp_path):
+    """ckpt dict {state_dict, optimizer} (train_iterable.py:222-226) and whole-module pickles reload; the
+    state_dict is plain fp32 tensors with the reference's keys/shapes."""
+    from rawvae.model import VAE, loss_function
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L, B, _ = (int(v) for v in small["meta"])
+    model = make_model(small, "init", dev, "bf16")
+    opt = Adam(model.parameters(), lr=1e-3)
+    x = torch.from_numpy(small["x"]).to(dev)
+    xh, mu, lv = model(x)
+    loss_function(xh, x, mu, lv, 1e-4, S).backward()
+    opt.step()
+    state = {"batch_id": 1, "state_dict": model.state_dict(), "optimizer": opt.state_dict()}
+    torch.save(state, tmp_path / "ckpt_00001")
+    torch.save(model, tmp_path / "last_model.pt")
+    ck = torch.load(tmp_path / "ckpt_00001", weights_only=False)
+    assert list(ck["state_dict"].keys()) == [k for k, _ in model.named_parameters()]
+    assert ck["state_dict"]["fc21.weight"].shape == (L, H) and ck["state_dict"]["fc21.weight"].dtype == torch.float32
+    assert len(ck["optimizer"]["state"]) == 10 and ck["optimizer"]["param_groups"][0]["params"] == list(range(10))
+    m2 = VAE(S, H, L).to(dev)
+    m2.load_state_dict(ck["state_dict"])
+    o2 = Adam(m2.parameters(), lr=1e-3)
+    o2.load_state_dict(ck["optimizer"])
+    eps = torch.randn(B, L, device=dev)
+    a = model(x, eps=eps)[0]
+    b = m2(x, eps=eps)[0]
+    assert torch.equal(a, b)
+    m3 = torch.load(tmp_path / "last_model.pt", weights_only=False)
+    assert torch.equal(m3(x, eps=eps)[0], a)
+    assert float(o2.state_dict()["state"][0]["step"]) == 1.0
