@@ -51,20 +51,32 @@ def init_params(segment_length: int, n_units: int, latent_dim: int, seed: int = 
     return params
 
 
-def forward(params: Dict[str, torch.Tensor], x: torch.Tensor, eps: torch.Tensor) -> Dict[str, torch.Tensor]:
+def bf16_operands(t: torch.Tensor) -> torch.Tensor:
+    """Round to bfloat16 and back: models the "bf16 mode" of BASELINE.json, in which every GEMM operand (inputs,
+    weights, activations and activation gradients) is carried as bf16 while accumulation, biases, the elementwise
+    math and the master weights stay in higher precision."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _ident(t: torch.Tensor) -> torch.Tensor:
+    return t
+
+
+def forward(params: Dict[str, torch.Tensor], x: torch.Tensor, eps: torch.Tensor, q=_ident) -> Dict[str, torch.Tensor]:
     """VAE.forward with the noise made explicit (rawvae/model.py:19-35).
-    encode :19-21, reparameterize :23-26 (eps replaces torch.randn_like), decode :28-30, view(-1, S) :33."""
+    encode :19-21, reparameterize :23-26 (eps replaces torch.randn_like), decode :28-30, view(-1, S) :33.
+    `q` is applied to every GEMM operand: identity = the reference's arithmetic; bf16_operands = bf16 mode."""
     S = params["fc1.weight"].shape[1]
-    x = x.reshape(-1, S)
-    a1 = x @ params["fc1.weight"].T + params["fc1.bias"]              # model.py:20  fc1
-    h1 = torch.clamp_min(a1, 0)                                       # model.py:20  relu
-    mu = h1 @ params["fc21.weight"].T + params["fc21.bias"]           # model.py:21
-    logvar = h1 @ params["fc22.weight"].T + params["fc22.bias"]       # model.py:21
+    x = q(x.reshape(-1, S))
+    a1 = x @ q(params["fc1.weight"]).T + params["fc1.bias"]           # model.py:20  fc1
+    h1 = q(torch.clamp_min(a1, 0))                                    # model.py:20  relu
+    mu = h1 @ q(params["fc21.weight"]).T + params["fc21.bias"]        # model.py:21
+    logvar = h1 @ q(params["fc22.weight"]).T + params["fc22.bias"]    # model.py:21
     std = torch.exp(0.5 * logvar)                                     # model.py:24
-    z = mu + eps * std                                                # model.py:26
-    a3 = z @ params["fc3.weight"].T + params["fc3.bias"]              # model.py:29
-    h3 = torch.clamp_min(a3, 0)
-    x_hat = torch.tanh(h3 @ params["fc4.weight"].T + params["fc4.bias"])  # model.py:30
+    z = q(mu + eps * std)                                             # model.py:26
+    a3 = z @ q(params["fc3.weight"]).T + params["fc3.bias"]           # model.py:29
+    h3 = q(torch.clamp_min(a3, 0))
+    x_hat = torch.tanh(h3 @ q(params["fc4.weight"]).T + params["fc4.bias"])  # model.py:30
     return dict(x=x, h1=h1, mu=mu, logvar=logvar, std=std, eps=eps, z=z, h3=h3, x_hat=x_hat)
 
 
@@ -77,31 +89,31 @@ def loss_function(x_hat, x, mu, logvar, kl_beta: float, segment_length: int) -> 
 
 
 def backward(params: Dict[str, torch.Tensor], act: Dict[str, torch.Tensor], kl_beta: float,
-             grad_out: float = 1.0) -> Dict[str, torch.Tensor]:
+             grad_out: float = 1.0, q=_ident) -> Dict[str, torch.Tensor]:
     """What loss.backward() (train.py:191, train_iterable.py:208) computes for the graph above, written out
     (SURVEY.md Appendix A): 5 weight gradients, 5 bias gradients, no gradient for x. Also returns the
-    activation gradients the kernels materialise (da4, da3, dmu, dlv, da1)."""
+    activation gradients the kernels materialise (da4, da3, dmu, dlv, da1). `q` as in forward()."""
     x, h1, mu, lv, std, eps, z, h3, xh = (act[k] for k in ("x", "h1", "mu", "logvar", "std", "eps", "z", "h3", "x_hat"))
     B, S = xh.shape
     L = mu.shape[1]
     dxh = grad_out * 2.0 * (xh - x) / (B * S)                         # MseLossBackward
-    da4 = dxh * (1 - xh * xh)                                         # TanhBackward
+    da4 = q(dxh * (1 - xh * xh))                                      # TanhBackward
     g = {}
     g["fc4.weight"] = da4.T @ h3                                      # AddmmBackward (wgrad)
     g["fc4.bias"] = da4.sum(0)
-    dh3 = da4 @ params["fc4.weight"]                                  # AddmmBackward (dgrad)
-    da3 = dh3 * (h3 > 0)                                              # ReluBackward (threshold_backward)
+    dh3 = da4 @ q(params["fc4.weight"])                               # AddmmBackward (dgrad)
+    da3 = q(dh3 * (h3 > 0))                                           # ReluBackward (threshold_backward)
     g["fc3.weight"] = da3.T @ z
     g["fc3.bias"] = da3.sum(0)
-    dz = da3 @ params["fc3.weight"]
-    dmu = dz + grad_out * kl_beta * mu / (B * L)                      # reparam + KL branch
-    dlv = dz * eps * std * 0.5 + grad_out * kl_beta * (torch.exp(lv) - 1) / (2 * B * L)
+    dz = da3 @ q(params["fc3.weight"])
+    dmu = q(dz + grad_out * kl_beta * mu / (B * L))                   # reparam + KL branch
+    dlv = q(dz * eps * std * 0.5 + grad_out * kl_beta * (torch.exp(lv) - 1) / (2 * B * L))
     g["fc21.weight"] = dmu.T @ h1
     g["fc21.bias"] = dmu.sum(0)
     g["fc22.weight"] = dlv.T @ h1
     g["fc22.bias"] = dlv.sum(0)
-    dh1 = dmu @ params["fc21.weight"] + dlv @ params["fc22.weight"]
-    da1 = dh1 * (h1 > 0)
+    dh1 = dmu @ q(params["fc21.weight"]) + dlv @ q(params["fc22.weight"])
+    da1 = q(dh1 * (h1 > 0))
     g["fc1.weight"] = da1.T @ x
     g["fc1.bias"] = da1.sum(0)
     g["_act"] = dict(da4=da4, da3=da3, dmu=dmu, dlv=dlv, da1=da1)
@@ -128,12 +140,12 @@ def adam_step(params, grads, state, lr: float, betas=(0.9, 0.999), eps: float = 
         p -= (lr / bc1) * st["exp_avg"] / denom                       # addcdiv_
 
 
-def train_step(params, state, x, eps, kl_beta: float, lr: float) -> float:
+def train_step(params, state, x, eps, kl_beta: float, lr: float, q=_ident) -> float:
     """One iteration of the training-loop body (train_iterable.py:200-210): forward, loss, backward, Adam."""
-    act = forward(params, x, eps)
+    act = forward(params, x, eps, q)
     S = params["fc1.weight"].shape[1]
     loss = loss_function(act["x_hat"], act["x"], act["mu"], act["logvar"], kl_beta, S)
-    grads = backward(params, act, kl_beta)
+    grads = backward(params, act, kl_beta, 1.0, q)
     adam_step(params, grads, state, lr)
     return float(loss)
 

@@ -46,6 +46,8 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   ctx->c.launches = 0;
   ctx->c.force_block_n = 0;
   if (const char* e = getenv("RVAE_BLOCK_N")) ctx->c.force_block_n = atoi(e);
+  ctx->c.force_cta_group = 0;
+  if (const char* e = getenv("RVAE_CTA_GROUP")) ctx->c.force_cta_group = atoi(e);
   *out = ctx;
   return RVAE_OK;
 }

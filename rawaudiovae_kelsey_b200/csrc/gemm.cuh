@@ -73,19 +73,22 @@ struct alignas(64) GemmParams {
   CUtensorMap tmB[kMaxPasses];
   int M, N, K;
   int num_passes;
-  int m_blocks, n_blocks;
+  int m_blocks, n_blocks;  // m_blocks counts 128*CG-row tiles
   int k_splits, kb_per_split, kb_total;
   int b_tile_stride;  // K-major B: row advance per n-block
   int b_half_stride;  // K-major B: row offset of the second half-tile load
   EpiArgs epi;
 };
 
-template <int BLOCK_N>
+// CG = CTAs cooperating on one tile (tcgen05 cta_group): 1 -> 128 x BLOCK_N tile per CTA; 2 -> a CTA pair computes a
+// 256 x BLOCK_N tile, each CTA staging its own 128 rows of A and HALF of the B tile (the pair's tensor cores read
+// both halves), which cuts L2->smem traffic per FLOP by a third and doubles the MMA's M.
+template <int BLOCK_N, int CG>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = (210 * 1024) / kStageBytes > 8 ? 8 : (210 * 1024) / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (kAccStages * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int kBarrierBytes = 256;
@@ -158,11 +161,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI, int CG>
+__device__ __forceinline__ void gemm_body(const GemmParams& p) {
+  using Cfg = GemmCfg<BLOCK_N, CG>;
   constexpr int kStages = Cfg::kStages;
-  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM, BLOCK_N, A_MAJOR, B_MAJOR);
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM * CG, BLOCK_N, A_MAJOR, B_MAJOR);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -176,6 +179,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int group_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;       // tile-owning unit: CTA or CTA pair
+  const int num_groups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.num_passes; ++i) {
@@ -183,18 +190,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       ptx::prefetch_tensormap(&p.tmB[i]);
     }
     for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&full_bar[i], CG);   // leader's barrier: one arrive per producer of the pair
+      ptx::mbar_init(&empty_bar[i], 1);   // per CTA: tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
-      ptx::mbar_init(&tmem_full_bar[i], 1);
-      ptx::mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_full_bar[i], 1);        // per CTA: tcgen05.commit
+      ptx::mbar_init(&tmem_empty_bar[i], 4 * CG);  // leader's barrier: one arrive per epilogue warp of the pair
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -202,15 +209,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   const int total_units = tiles * p.k_splits;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = group_id; u < total_units; u += num_groups) {
         const int ks = u / tiles;
         const int tile = u - ks * tiles;
         const int n_blk = tile / p.m_blocks;
         const int m_blk = tile - n_blk * p.m_blocks;
-        const int m0 = m_blk * kBlockM;
+        const int m0 = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
         for (int pass = 0; pass < p.num_passes; ++pass) {
@@ -218,27 +225,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
           const CUtensorMap* tmB = &p.tmB[pass];
           for (int kb = kb_begin; kb < kb_begin + kb_count; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint64_t* fb = &full_bar[stage];
+            if constexpr (CG == 1) {
+              ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+            } else {
+              // both CTAs' loads complete on the LEADER's barrier; the leader announces the pair's bytes
+              if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
+              else ptx::mbar_arrive_cluster(fb, 0);
+            }
             uint8_t* sA = smem + stage * Cfg::kStageBytes;
             uint8_t* sB = sA + Cfg::kABytes;
             const int k0 = kb * kBlockK;
             if constexpr (A_MAJOR == MAJOR_K) {
-              ptx::tma_load_2d(sA, tmA, &full_bar[stage], k0, m0);
+              ptx::tma_load_2d_cg<CG>(sA, tmA, fb, k0, m0);
             } else {
 #pragma unroll
               for (int i = 0; i < kBlockM / 64; ++i)
-                ptx::tma_load_2d(sA + i * (kBlockK * 128), tmA, &full_bar[stage], m0 + i * 64, k0);
+                ptx::tma_load_2d_cg<CG>(sA + i * (kBlockK * 128), tmA, fb, m0 + i * 64, k0);
             }
             if constexpr (B_MAJOR == MAJOR_K) {
+              // the B tile is staged as two boxes of BLOCK_N/2 rows: CG == 1 loads both, CG == 2 one per CTA
               const int r0 = n_blk * p.b_tile_stride;
+              if constexpr (CG == 1) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
-                ptx::tma_load_2d(sB + h * (Cfg::kBBytes / 2), tmB, &full_bar[stage], k0, r0 + h * p.b_half_stride);
+                for (int h = 0; h < 2; ++h)
+                  ptx::tma_load_2d_cg<1>(sB + h * (Cfg::kBBytes / 2), tmB, fb, k0, r0 + h * p.b_half_stride);
+              } else {
+                ptx::tma_load_2d_cg<2>(sB, tmB, fb, k0, r0 + static_cast<int>(cta_rank) * p.b_half_stride);
+              }
             } else {
-              const int n0 = n_blk * BLOCK_N;
+              const int n0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
 #pragma unroll
-              for (int i = 0; i < BLOCK_N / 64; ++i)
-                ptx::tma_load_2d(sB + i * (kBlockK * 128), tmB, &full_bar[stage], n0 + i * 64, k0);
+              for (int i = 0; i < BLOCK_N / CG / 64; ++i)
+                ptx::tma_load_2d_cg<CG>(sB + i * (kBlockK * 128), tmB, fb, n0 + i * 64, k0);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -246,10 +265,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = group_id; u < total_units; u += num_groups) {
         const int ks = u / tiles;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
@@ -268,12 +287,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
                                                         : ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
             const uint64_t bdesc = (B_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 2), 0, 1024)
                                                         : ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
-            ptx::umma_bf16<1>(d_tmem, adesc, bdesc, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16<CG>(d_tmem, adesc, bdesc, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit<1>(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          ptx::umma_commit<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit<1>(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+        ptx::umma_commit<CG>(&tmem_full_bar[as]);  // accumulator complete -> epilogue (of both CTAs)
         if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
@@ -285,12 +304,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
     const EpiArgs& e = p.epi;
     float loss_local = 0.f;
     uint32_t as = 0, aphase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = group_id; u < total_units; u += num_groups) {
       const int ks = u / tiles;
       const int tile = u - ks * tiles;
       const int n_blk = tile / p.m_blocks;
       const int m_blk = tile - n_blk * p.m_blocks;
-      const int m = m_blk * kBlockM + row_in_tile;
+      const int m = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM + row_in_tile;
       const bool row_ok = m < p.M;
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
@@ -423,7 +442,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
       // release the accumulator back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if (CG == 1 || leader) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
     if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
@@ -433,12 +455,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_cons
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+    ptx::tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  gemm_body<BLOCK_N, A_MAJOR, B_MAJOR, EPI, 1>(p);
+}
+
+template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_kernel_2cta(const __grid_constant__ GemmParams p) {
+  gemm_body<BLOCK_N, A_MAJOR, B_MAJOR, EPI, 2>(p);
 }
 
 }  // namespace rvae

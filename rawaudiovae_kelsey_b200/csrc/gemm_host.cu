@@ -73,13 +73,14 @@ static int encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t dim0, uint
 typedef void (*GemmKernel)(const GemmParams);
 
 struct Variant {
-  int block_n, a_major, b_major, epi;
+  int block_n, a_major, b_major, epi, cg;
   GemmKernel fn;
   int smem;
 };
 
-#define RVAE_VARIANT(BN, AM, BM, EP) \
-  { BN, AM, BM, EP, gemm_kernel<BN, AM, BM, EP>, GemmCfg<BN>::kSmemBytes }
+#define RVAE_VARIANT(BN, AM, BM, EP)                                                          \
+  { BN, AM, BM, EP, 1, gemm_kernel<BN, AM, BM, EP>, GemmCfg<BN, 1>::kSmemBytes },             \
+  { BN, AM, BM, EP, 2, gemm_kernel_2cta<BN, AM, BM, EP>, GemmCfg<BN, 2>::kSmemBytes }
 
 static const Variant kVariants[] = {
     RVAE_VARIANT(256, MAJOR_K, MAJOR_K, EPI_LINEAR),  RVAE_VARIANT(128, MAJOR_K, MAJOR_K, EPI_LINEAR),
@@ -91,10 +92,10 @@ static const Variant kVariants[] = {
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-static int find_variant(int block_n, int a_major, int b_major, int epi) {
+static int find_variant(int block_n, int a_major, int b_major, int epi, int cg) {
   for (int i = 0; i < kNumVariants; ++i)
     if (kVariants[i].block_n == block_n && kVariants[i].a_major == a_major && kVariants[i].b_major == b_major &&
-        kVariants[i].epi == epi)
+        kVariants[i].epi == epi && kVariants[i].cg == cg)
       return i;
   return -1;
 }
@@ -118,16 +119,21 @@ static int configure_variants() {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Pick the N tile: fewer, fatter tiles are more efficient per FLOP, but whole waves over the SMs matter more.
-static int choose_block_n(const Ctx* ctx, int M, int N, bool allow128, bool allow256) {
-  if (ctx->force_block_n == 128 && allow128) return 128;
-  if (ctx->force_block_n == 256 && allow256) return 256;
-  if (!allow256) return 128;
-  if (!allow128) return 256;
-  const int mb = ceil_div(M, kBlockM);
-  const double c256 = 1.0 * ceil_div(mb * ceil_div(N, 256), ctx->num_sms);
-  const double c128 = 0.6 * ceil_div(mb * ceil_div(N, 128), ctx->num_sms);
-  return (c128 < c256) ? 128 : 256;
+// Pick the tile: cta_group 2 (256-row pair tiles) whenever there are at least two 128-row blocks; for N, fewer and
+// fatter tiles are more efficient per FLOP, but whole waves over the SMs (or SM pairs) matter more.
+static void choose_tile(const Ctx* ctx, int M, int N, bool allow128, bool allow256, int* block_n, int* cg) {
+  int g = (M > kBlockM) ? 2 : 1;
+  if (ctx->force_cta_group == 1 || ctx->force_cta_group == 2) g = ctx->force_cta_group;
+  *cg = g;
+  const int slots = ctx->num_sms / g;
+  const int mb = ceil_div(M, kBlockM * g);
+  if (ctx->force_block_n == 128 && allow128) { *block_n = 128; return; }
+  if (ctx->force_block_n == 256 && allow256) { *block_n = 256; return; }
+  if (!allow256) { *block_n = 128; return; }
+  if (!allow128) { *block_n = 256; return; }
+  const double c256 = 1.0 * ceil_div(mb * ceil_div(N, 256), slots);
+  const double c128 = 0.6 * ceil_div(mb * ceil_div(N, 128), slots);
+  *block_n = (c128 < c256) ? 128 : 256;
 }
 
 int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
@@ -142,23 +148,24 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = d.args;
 
-  int block_n;
+  int block_n, cg;
   if (d.epi == EPI_HEAD) {
     const int L = d.head_L;
     RVAE_REQUIRE(d.N == 2 * L && L % 64 == 0, RVAE_ERR_UNSUPPORTED, "head gemm: N=%d must be 2*L, L=%d %% 64 == 0",
                  d.N, L);
-    block_n = (L % 128 == 0) ? choose_block_n(ctx, d.M, d.N, true, true) : 128;
+    choose_tile(ctx, d.M, d.N, true, L % 128 == 0, &block_n, &cg);
     p.n_blocks = L / (block_n / 2);
     p.b_tile_stride = block_n / 2;
     p.b_half_stride = L;
     p.epi.L = L;
   } else {
-    block_n = choose_block_n(ctx, d.M, d.N, true, true);
+    choose_tile(ctx, d.M, d.N, true, true, &block_n, &cg);
     p.n_blocks = ceil_div(d.N, block_n);
     p.b_tile_stride = block_n;
     p.b_half_stride = block_n / 2;
   }
-  p.m_blocks = ceil_div(d.M, kBlockM);
+  p.m_blocks = ceil_div(d.M, kBlockM * cg);
+  const int slots = ctx->num_sms / cg;
   p.kb_total = ceil_div(d.K, kBlockK);
 
   // split-K only where the epilogue is a linear accumulation (weight gradients)
@@ -172,7 +179,7 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
       double best = 0.0;
       for (int s = 1; s <= 8 && p.kb_total / s >= 8; ++s) {
         const int units = tiles * s;
-        const double eff = (double)units / (ceil_div(units, ctx->num_sms) * (double)ctx->num_sms);
+        const double eff = (double)units / (ceil_div(units, slots) * (double)slots);
         if (eff > best + 1e-9) { best = eff; splits = s; }
         if (eff >= 0.90) break;
       }
@@ -213,11 +220,11 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   }
 
   g.block_n = block_n;
-  g.variant = find_variant(block_n, d.A.major, d.B.major, d.epi);
+  g.variant = find_variant(block_n, d.A.major, d.B.major, d.epi, cg);
   RVAE_REQUIRE(g.variant >= 0, RVAE_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d majors (%d,%d) epilogue %d",
                block_n, d.A.major, d.B.major, d.epi);
   const int units = p.m_blocks * p.n_blocks * p.k_splits;
-  g.grid = units < ctx->num_sms ? units : ctx->num_sms;
+  g.grid = cg * (units < slots ? units : slots);
   g.smem_bytes = kVariants[g.variant].smem;
   return RVAE_OK;
 }

@@ -99,12 +99,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // in the cluster's leader CTA (peer bit of the shared::cluster address cleared).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
                                                 int32_t c1) {
-  uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  uint32_t mbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(mbar) : "r"(smem_u32(bar)), "r"(0u));
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
       "%4}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar), "r"(c0), "r"(c1)
       : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
+                                               int32_t c1) {
+  if constexpr (CG == 1) tma_load_2d(smem_dst, tm, bar, c0, c1);
+  else tma_load_2d_2sm(smem_dst, tm, bar, c0, c1);
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

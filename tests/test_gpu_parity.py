@@ -9,14 +9,45 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-BF16_TOL = 2e-2
-FP32_TOL = 1e-4
+BF16_TOL = 2e-2        # vs the fp32 reference: activations, loss, and gradients not behind a ReLU mask
+FP32_TOL = 1e-4        # fp32 mode vs the reference: everything
+BF16_EMU_TOL = 5e-3    # bf16 mode vs the oracle run with bf16-rounded GEMM operands: everything
+BF16_DEEP_TOL = 6e-2   # bf16 mode vs the fp32 reference for gradients behind ReLU masks (see check_grads)
 
 
 def rel(a, b):
     a = torch.as_tensor(a).detach().double().cpu().flatten()
     b = torch.as_tensor(b).detach().double().cpu().flatten()
     return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def cosine(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().flatten()
+    b = torch.as_tensor(b).detach().double().cpu().flatten()
+    return float(a @ b / (a.norm() * b.norm() + 1e-300))
+
+
+def check_grads(named_grads, ref, precision, ref_bf16=None):
+    """fp32 mode: every gradient within 1e-4 of the reference. bf16 mode: every gradient within 5e-3 of the oracle
+    evaluated with bf16-rounded operands (same algorithm, same rounding points), and against the fp32 reference
+    2e-2 for fc4 (no ReLU between it and the loss) and 6e-2 / cosine >= 0.998 for the layers behind a ReLU:
+    rounding a pre-activation to bf16 flips the sign of ~0.03-0.1 % of the near-zero units, and each flipped mask
+    bit changes that unit's gradient by 100 % - inherent to bf16 operands, not to this implementation."""
+    for k, g in named_grads:
+        if precision == "fp32":
+            assert rel(g, ref[k]) < FP32_TOL, k
+            continue
+        if ref_bf16 is not None:
+            assert rel(g, ref_bf16[k]) < BF16_EMU_TOL, k
+        tol = BF16_TOL if k.startswith("fc4") else BF16_DEEP_TOL
+        assert rel(g, ref[k]) < tol, k
+        assert cosine(g, ref[k]) > 0.998, k
+
+
+def bf16_oracle_grads(params64, x, eps, beta):
+    from oracle import rawvae_oracle as O
+    act = O.forward(params64, x.double(), eps.double(), O.bf16_operands)
+    return O.backward(params64, act, beta, 1.0, O.bf16_operands), act
 
 
 @pytest.fixture(scope="module")
@@ -60,21 +91,28 @@ def test_forward_backward_vs_reference_golden(dev, small, precision, tol):
     assert loss.dim() == 0
     assert abs(loss.item() - float(small["losses"][0])) < tol * abs(float(small["losses"][0]))
     loss.backward()
-    for k, p in model.named_parameters():
-        assert p.grad is not None, k
-        assert rel(p.grad, small["grad/" + k]) < tol, k
+    assert all(p.grad is not None for p in model.parameters())
+    p64 = {k: torch.from_numpy(small["init/" + k]).double() for k in PARAM_NAMES}
+    emu, _ = bf16_oracle_grads(p64, torch.from_numpy(small["x"]), torch.from_numpy(small["eps"][0]), kl_beta)
+    check_grads([(k, p.grad) for k, p in model.named_parameters()], {k: small["grad/" + k] for k in PARAM_NAMES},
+                precision, emu)
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", FP32_TOL)])
 def test_three_adam_steps_vs_reference_golden(dev, small, precision, tol):
-    """The reference loop body (train_iterable.py:200-210) through the drop-in API, 3 steps."""
+    """The reference loop body (train_iterable.py:200-210) through the drop-in API, 3 steps: losses against the
+    reference's golden losses; Adam state against the reference's (fp32 mode) or the bf16-operand oracle's."""
     from rawvae.model import loss_function
     from rawaudiovae_kelsey_b200.optim import Adam
+    from oracle import rawvae_oracle as O
     S, H, L, B, steps = (int(v) for v in small["meta"])
     kl_beta, lr = (float(v) for v in small["hyper"])
     model = make_model(small, "init", dev, precision)
     opt = Adam(model.parameters(), lr=lr)
     x = torch.from_numpy(small["x"]).to(dev)
+    q = O.bf16_operands if precision == "bf16" else (lambda t: t)
+    p = {k: torch.from_numpy(small["init/" + k]).double() for k in O.PARAM_NAMES}
+    st = O.adam_init(p)
     for s in range(steps):
         opt.zero_grad()
         xh, mu, lv = model(x, eps=torch.from_numpy(small["eps"][s]).to(dev))
@@ -82,18 +120,26 @@ def test_three_adam_steps_vs_reference_golden(dev, small, precision, tol):
         loss.backward()
         opt.step()
         assert abs(loss.item() - float(small["losses"][s])) < tol * abs(float(small["losses"][s]))
-    sd = model.state_dict()
-    for k in sd:
-        # parameters move by ~lr per step: compare the UPDATE, not the weights, so the tolerance means something
-        upd = sd[k].cpu().double() - torch.from_numpy(small["init/" + k]).double()
-        ref = torch.from_numpy(small["final/" + k]).double() - torch.from_numpy(small["init/" + k]).double()
-        assert rel(upd, ref) < (0.1 if precision == "bf16" else 2e-3), k   # Adam's sign-like update amplifies noise
+        O.train_step(p, st, torch.from_numpy(small["x"]).double(), torch.from_numpy(small["eps"][s]).double(),
+                     kl_beta, lr, q)
     ost = opt.state_dict()
     assert sorted(ost["state"][0].keys()) == ["exp_avg", "exp_avg_sq", "step"]
     assert float(ost["state"][0]["step"]) == steps
     names = [k for k, _ in model.named_parameters()]
+    mtol = FP32_TOL * 3 if precision == "fp32" else BF16_EMU_TOL * 2
     for i, k in enumerate(names):
-        assert rel(ost["state"][i]["exp_avg"], small["exp_avg/" + k]) < tol * 2, k
+        assert rel(ost["state"][i]["exp_avg"], st[k]["exp_avg"]) < mtol, k
+        assert rel(ost["state"][i]["exp_avg_sq"], st[k]["exp_avg_sq"]) < 2 * mtol, k
+        if precision == "fp32":  # the reference's own optimizer state
+            assert rel(ost["state"][i]["exp_avg"], small["exp_avg/" + k]) < 3 * FP32_TOL, k
+    sd = model.state_dict()
+    for k in sd:
+        # parameters move by ~lr per step: compare the UPDATE, not the weights, so the tolerance means something.
+        # Adam's update is m/sqrt(v) ~ sign(g): entries whose gradient is near zero amplify any rounding.
+        upd = sd[k].cpu().double() - torch.from_numpy(small["init/" + k]).double()
+        ref = p[k] - torch.from_numpy(small["init/" + k]).double()
+        assert rel(upd, ref) < (5e-3 if precision == "fp32" else 5e-2), k
+        assert rel(sd[k], small["final/" + k]) < 1e-3, k
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("fp32", FP32_TOL)])
@@ -110,15 +156,16 @@ def test_fused_train_step_matches_oracle(dev, small, precision, tol):
     p = {k: torch.from_numpy(small["init/" + k]).double() for k in O.PARAM_NAMES}
     st = O.adam_init(p)
     x = torch.from_numpy(small["x"])
+    q = O.bf16_operands if precision == "bf16" else (lambda t: t)
     for s in range(steps):
         eps = torch.from_numpy(small["eps"][s])
         loss = step(x.to(dev), eps=eps.to(dev))
-        ref = O.train_step(p, st, x.double(), eps.double(), kl_beta, lr)
-        assert abs(loss.item() - ref) < tol * abs(ref)
-        assert abs(ref - float(small["losses"][s])) < 1e-5 * abs(ref)
+        O.train_step(p, st, x.double(), eps.double(), kl_beta, lr, q)
+        assert abs(loss.item() - float(small["losses"][s])) < tol * float(small["losses"][s])
     flat = model._flat
+    mtol = FP32_TOL * 3 if precision == "fp32" else BF16_EMU_TOL * 2
     for k in O.PARAM_NAMES:
-        assert rel(flat.view(flat.exp_avg, k), st[k]["exp_avg"]) < tol * 2, k
+        assert rel(flat.view(flat.exp_avg, k), st[k]["exp_avg"]) < mtol, k
     assert float(flat.step) == steps
     # bf16 shadow planes follow the fp32 master weights
     assert rel(flat.shadow_hi.float(), flat.params) < 4e-3
@@ -147,7 +194,8 @@ def test_default_ini_dims_fused_step(dev, golden_dir):
         for name, t in (("x_hat", xh), ("mu", mu), ("logvar", lv)):
             assert abs(float(t.double().norm()) - g[name]["norm"]) < tol * g[name]["norm"], name
         for k, p in model.named_parameters():
-            assert abs(float(p.grad.double().norm()) - g["grads"][k]["norm"]) < tol * g["grads"][k]["norm"], k
+            gtol = tol if (precision == "fp32" or k.startswith("fc4")) else BF16_DEEP_TOL
+            assert abs(float(p.grad.double().norm()) - g["grads"][k]["norm"]) < gtol * g["grads"][k]["norm"], k
 
 
 # ------------------------------------------------------------------------------------------------ larger, oracle on the fly
@@ -172,8 +220,10 @@ def test_activations_and_gradients_vs_oracle_ragged_batch(dev, precision, tol):
     gr = O.backward(p64, act, beta)
     assert rel(xh, act["x_hat"]) < tol and rel(mu, act["mu"]) < tol and rel(lv, act["logvar"]) < tol
     assert abs(loss.item() - float(ref_loss)) < tol * float(ref_loss)
-    for k, prm in model.named_parameters():
-        assert rel(prm.grad, gr[k]) < tol, k
+    emu, emu_act = bf16_oracle_grads(p64, x, eps, beta)
+    if precision == "bf16":
+        assert rel(xh, emu_act["x_hat"]) < BF16_EMU_TOL and rel(mu, emu_act["mu"]) < BF16_EMU_TOL
+    check_grads([(k, prm.grad) for k, prm in model.named_parameters()], gr, precision, emu)
 
 
 def test_loss_curve_1k_steps_within_one_percent(dev, small):

@@ -149,6 +149,42 @@ def main(case):
             opt.step()
             ops.adam_step(p, gr * (i + 1), m_, v_, st, 1e-3, shadow_hi=sh)
         print("adam", rel(p, pr.detach()), "step", float(st), "shadow", rel(sh, p.to(torch.bfloat16)))
+    elif case == "perf":
+        import os
+        tag = f"CG={os.environ.get('RVAE_CTA_GROUP','auto')} BN={os.environ.get('RVAE_BLOCK_N','auto')}"
+        B, S_, H_, L_ = 8192, 1024, 2048, 256
+        def timeit(fn, flops, name):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"{tag} {name:5s} {ms*1e3:7.1f} us {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+            return ms
+        x, h, z, ml = bf(g(B, S_)), bf(g(B, H_)), bf(g(B, L_)), bf(g(B, 2 * L_))
+        w1, w2, w3, w4 = bf(g(H_, S_)), bf(g(2 * L_, H_)), bf(g(H_, L_)), bf(g(S_, H_))
+        b1, b2, b4 = g(H_), g(2 * L_), g(S_)
+        eps, esh = g(B, L_), g(B, L_)
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        dw4 = torch.zeros(S_, H_, device=dev); dw3 = torch.zeros(H_, L_, device=dev)
+        dw2 = torch.zeros(2 * L_, H_, device=dev); dw1 = torch.zeros(H_, S_, device=dev)
+        tot = 0.0
+        tot += timeit(lambda: ops.linear_act_fwd(x, w1, b1, ops.ACT_RELU), 2 * B * H_ * S_, "F1")
+        tot += timeit(lambda: ops.encode_head_fwd(h, w2, b2, eps, want_bwd=True, kl_acc=acc[1:]), 2 * B * 2 * L_ * H_, "F2")
+        tot += timeit(lambda: ops.linear_act_fwd(z, w3, b1, ops.ACT_RELU), 2 * B * H_ * L_, "F3")
+        tot += timeit(lambda: ops.out_tanh_mse_fwd(h, w4, b4, x, grad_scale=1e-6, tanh_approx=True, want_xhat=False, mse_acc=acc[:1]), 2 * B * S_ * H_, "F4")
+        tot += timeit(lambda: ops.wgrad(x, h, out=dw4), 2 * B * S_ * H_, "B4w")
+        tot += timeit(lambda: ops.dgrad_relu(x, w4, h), 2 * B * S_ * H_, "B4d")
+        tot += timeit(lambda: ops.wgrad(h, z, out=dw3), 2 * B * H_ * L_, "B3w")
+        tot += timeit(lambda: ops.dgrad_latent(h, w3, esh, esh, esh), 2 * B * H_ * L_, "B3d")
+        tot += timeit(lambda: ops.wgrad(ml, h, out=dw2), 2 * B * 2 * L_ * H_, "B2w")
+        tot += timeit(lambda: ops.dgrad_relu(ml, w2, h), 2 * B * 2 * L_ * H_, "B2d")
+        tot += timeit(lambda: ops.wgrad(h, x, out=dw1), 2 * B * H_ * S_, "B1w")
+        print(f"{tag} TOTAL {tot*1e3:.1f} us -> {30408704*B/tot/1e9:.1f} TFLOP/s chain", flush=True)
     print("launches", ops.launch_count(), flush=True)
 
 
