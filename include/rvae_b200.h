@@ -236,6 +236,10 @@ const float* rvae_plan_mu(const rvae_plan* plan);
 const float* rvae_plan_logvar(const rvae_plan* plan);
 const float* rvae_plan_xhat(const rvae_plan* plan);
 const float* rvae_plan_eps(const rvae_plan* plan);
+/* Introspection (tests / debugging): device pointers to the bf16 planes of an intermediate of the current batch.
+ * which: 0 x [B,S], 1 h1 [B,H], 2 z [B,L], 3 h3 [B,H], 4 da4 [B,S], 5 da3 [B,H], 6 d_ml [B,2L], 7 da1 [B,H].
+ * *lo is NULL in bf16 mode. */
+int rvae_plan_activation(const rvae_plan* plan, int which, void** hi, void** lo, int* cols);
 /* gradient bucket s (see rvae_plan_backward): pointer into bufs.grads and element count. Buckets 0..3 are the
  * four weight matrices in backward-completion order; bucket 4 is the bias block. */
 int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count);

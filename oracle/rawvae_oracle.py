@@ -77,7 +77,7 @@ def forward(params: Dict[str, torch.Tensor], x: torch.Tensor, eps: torch.Tensor,
     a3 = z @ q(params["fc3.weight"]).T + params["fc3.bias"]           # model.py:29
     h3 = q(torch.clamp_min(a3, 0))
     x_hat = torch.tanh(h3 @ q(params["fc4.weight"]).T + params["fc4.bias"])  # model.py:30
-    return dict(x=x, h1=h1, mu=mu, logvar=logvar, std=std, eps=eps, z=z, h3=h3, x_hat=x_hat)
+    return dict(x=x, a1=a1, h1=h1, mu=mu, logvar=logvar, std=std, eps=eps, z=z, a3=a3, h3=h3, x_hat=x_hat)
 
 
 def loss_function(x_hat, x, mu, logvar, kl_beta: float, segment_length: int) -> torch.Tensor:
@@ -89,10 +89,15 @@ def loss_function(x_hat, x, mu, logvar, kl_beta: float, segment_length: int) -> 
 
 
 def backward(params: Dict[str, torch.Tensor], act: Dict[str, torch.Tensor], kl_beta: float,
-             grad_out: float = 1.0, q=_ident) -> Dict[str, torch.Tensor]:
+             grad_out: float = 1.0, q=_ident, masks=None) -> Dict[str, torch.Tensor]:
     """What loss.backward() (train.py:191, train_iterable.py:208) computes for the graph above, written out
     (SURVEY.md Appendix A): 5 weight gradients, 5 bias gradients, no gradient for x. Also returns the
-    activation gradients the kernels materialise (da4, da3, dmu, dlv, da1). `q` as in forward()."""
+    activation gradients the kernels materialise (da4, da3, dmu, dlv, da1). `q` as in forward().
+    `masks=(m1, m3)` overrides the ReLU gates [h1 > 0], [h3 > 0] - used by the parity tests to evaluate the reference
+    gradient at the implementation's gating pattern (the gate of a unit whose pre-activation is ~0 is ill-conditioned:
+    any rounding flips it, and a flipped gate changes that unit's gradient by 100 %)."""
+    m1 = (act["h1"] > 0) if masks is None else masks[0].to(act["h1"].dtype)
+    m3 = (act["h3"] > 0) if masks is None else masks[1].to(act["h3"].dtype)
     x, h1, mu, lv, std, eps, z, h3, xh = (act[k] for k in ("x", "h1", "mu", "logvar", "std", "eps", "z", "h3", "x_hat"))
     B, S = xh.shape
     L = mu.shape[1]
@@ -102,7 +107,7 @@ def backward(params: Dict[str, torch.Tensor], act: Dict[str, torch.Tensor], kl_b
     g["fc4.weight"] = da4.T @ h3                                      # AddmmBackward (wgrad)
     g["fc4.bias"] = da4.sum(0)
     dh3 = da4 @ q(params["fc4.weight"])                               # AddmmBackward (dgrad)
-    da3 = q(dh3 * (h3 > 0))                                           # ReluBackward (threshold_backward)
+    da3 = q(dh3 * m3)                                                 # ReluBackward (threshold_backward)
     g["fc3.weight"] = da3.T @ z
     g["fc3.bias"] = da3.sum(0)
     dz = da3 @ q(params["fc3.weight"])
@@ -113,7 +118,7 @@ def backward(params: Dict[str, torch.Tensor], act: Dict[str, torch.Tensor], kl_b
     g["fc22.weight"] = dlv.T @ h1
     g["fc22.bias"] = dlv.sum(0)
     dh1 = dmu @ q(params["fc21.weight"]) + dlv @ q(params["fc22.weight"])
-    da1 = q(dh1 * (h1 > 0))
+    da1 = q(dh1 * m1)
     g["fc1.weight"] = da1.T @ x
     g["fc1.bias"] = da1.sum(0)
     g["_act"] = dict(da4=da4, da3=da3, dmu=dmu, dlv=dlv, da1=da1)

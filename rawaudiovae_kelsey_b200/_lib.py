@@ -79,6 +79,7 @@ SIGNATURES = {
     "rvae_plan_logvar": (P, [P]),
     "rvae_plan_xhat": (P, [P]),
     "rvae_plan_eps": (P, [P]),
+    "rvae_plan_activation": (c_int, [P, c_int, C.POINTER(P), C.POINTER(P), C.POINTER(c_int)]),
     "rvae_plan_bucket": (c_int, [P, c_int, C.POINTER(P), C.POINTER(c_int64)]),
     "rvae_plan_enable_timing": (c_int, [P, c_int]),
     "rvae_plan_read_timing": (c_int, [P, P, P, P]),

@@ -736,6 +736,16 @@ const float* rvae_plan_logvar(const rvae_plan* plan) { return plan ? plan->lv : 
 const float* rvae_plan_xhat(const rvae_plan* plan) { return plan ? plan->xhat : nullptr; }
 const float* rvae_plan_eps(const rvae_plan* plan) { return plan ? plan->eps : nullptr; }
 
+int rvae_plan_activation(const rvae_plan* plan, int which, void** hi, void** lo, int* cols) {
+  RVAE_REQUIRE(plan && hi && lo && cols, RVAE_ERR_INVALID, "plan_activation: null argument");
+  RVAE_REQUIRE(plan->bound, RVAE_ERR_STATE, "plan_activation: plan not bound");
+  const Planes* t[8] = {&plan->x, &plan->h1, &plan->z, &plan->h3, &plan->da4, &plan->da3, &plan->dml, &plan->da1};
+  const int c[8] = {plan->S, plan->H, plan->L, plan->H, plan->S, plan->H, 2 * plan->L, plan->H};
+  RVAE_REQUIRE(which >= 0 && which < 8, RVAE_ERR_INVALID, "plan_activation: which=%d not in 0..7", which);
+  *hi = t[which]->hi; *lo = t[which]->lo; *cols = c[which];
+  return RVAE_OK;
+}
+
 int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count) {
   RVAE_REQUIRE(plan && ptr && count, RVAE_ERR_INVALID, "plan_bucket: null argument");
   RVAE_REQUIRE(plan->bound && plan->bufs.grads, RVAE_ERR_STATE, "plan_bucket: grads not bound");

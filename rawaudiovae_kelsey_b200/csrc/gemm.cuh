@@ -190,7 +190,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       ptx::prefetch_tensormap(&p.tmB[i]);
     }
     for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(&full_bar[i], CG);   // leader's barrier: one arrive per producer of the pair
+      ptx::mbar_init(&full_bar[i], 1);    // leader's barrier: its producer arrives once with the pair's byte count
       ptx::mbar_init(&empty_bar[i], 1);   // per CTA: tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
@@ -229,9 +229,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
             } else {
-              // both CTAs' loads complete on the LEADER's barrier; the leader announces the pair's bytes
+              // Both CTAs' loads complete_tx on the LEADER's barrier; the leader alone arrives, announcing the pair's
+              // bytes. The peer sends no arrive (a cluster-scope release per k-block would throttle its producer):
+              // it cannot run a phase ahead because its smem slot is only freed by the commit that follows the MMAs
+              // which consumed this phase, and a complete_tx that lands before the leader's expect_tx merely leaves
+              // the tx-count transiently negative while the leader's arrival is still pending.
               if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
-              else ptx::mbar_arrive_cluster(fb, 0);
             }
             uint8_t* sA = smem + stage * Cfg::kStageBytes;
             uint8_t* sB = sA + Cfg::kABytes;

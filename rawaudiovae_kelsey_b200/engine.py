@@ -194,6 +194,23 @@ class Plan:
         check(self.lib.rvae_plan_read_timing(self.handle, ms, cnt, fl))
         return {k: (float(ms[i]), int(cnt[i]), float(fl[i])) for i, k in enumerate(self.GEMM_SLOTS)}
 
+    ACTIVATIONS = ("x", "h1", "z", "h3", "da4", "da3", "d_ml", "da1")
+
+    def activation(self, name: str):
+        """(hi, lo) bf16 views [batch, cols] of an intermediate of the current batch (lo is None in bf16 mode).
+        Introspection for tests / debugging; the tensors alias the workspace and are overwritten by the next step."""
+        hi, lo, cols = C.c_void_p(), C.c_void_p(), C.c_int()
+        check(self.lib.rvae_plan_activation(self.handle, self.ACTIVATIONS.index(name), C.byref(hi), C.byref(lo),
+                                            C.byref(cols)))
+
+        def view(ptr):
+            if not ptr:
+                return None
+            off = ptr - self.workspace.data_ptr()
+            n = self.batch * cols.value
+            return self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.batch, cols.value)
+        return view(hi.value), view(lo.value)
+
     def bucket(self, s: int) -> torch.Tensor:
         """Gradient bucket s as a view of flat.grads (0..3 = W4, W3, W2, W1 in backward order; 4 = biases)."""
         ptr, cnt = C.c_void_p(), C.c_int64()
