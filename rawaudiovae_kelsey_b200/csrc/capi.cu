@@ -430,9 +430,9 @@ int get_set(rvae_plan* p, GemmSet** out) {
 int run_untimed(rvae_plan* p, GemmSet* gs, int id, cudaStream_t st, const EpiArgs* override_args) {
   if (override_args) {
     PreparedGemm g = gs->g[id];
-    const int L = g.params.epi.L;
-    g.params.epi = *override_args;
-    if (g.params.epi.L == 0) g.params.epi.L = L;
+    EpiArgs a = *override_args;
+    if (a.L == 0) a.L = g.params.epi.L;
+    RVAE_CHECK(gemm_bind_outputs(&g, a, false));  // re-encodes the TMA store maps of redirected outputs
     return gemm_run(&p->ctx->c, g, st);
   }
   return gemm_run(&p->ctx->c, gs->g[id], st);

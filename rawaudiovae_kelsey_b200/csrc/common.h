@@ -72,7 +72,12 @@ struct PreparedGemm {
   int variant;  // index into the kernel table
   int grid;
   int smem_bytes;
+  // geometry of the epilogue's output tensors (for re-binding output pointers)
+  int out_rows, out_cols_bf16, out_ld_bf16, out_cols_f32, out_ld_f32;
+  bool out_f32_tma;
 };
+
+int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& args, bool force);
 
 int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out);
 int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream);

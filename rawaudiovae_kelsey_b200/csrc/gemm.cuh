@@ -31,6 +31,8 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 192;
 constexpr int kMaxPasses = 3;
+constexpr int kOutSlotBytes = 128 * 128;  // one epilogue staging slot: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
+constexpr int kOutSlots = 2;
 
 enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
 enum : int { EPI_LINEAR = 0, EPI_HEAD = 1, EPI_OUT = 2, EPI_DRELU = 3, EPI_DZ = 4, EPI_WGRAD = 5 };
@@ -71,6 +73,9 @@ struct EpiArgs {
 struct alignas(64) GemmParams {
   CUtensorMap tmA[kMaxPasses];
   CUtensorMap tmB[kMaxPasses];
+  CUtensorMap tmOutHi;   // bf16 output plane (box 64 cols x 128 rows, 128B swizzle)
+  CUtensorMap tmOutLo;   // bf16 residual plane (fp32 emulation)
+  CUtensorMap tmOutF32;  // fp32 output (box 32 cols x 128 rows, 128B swizzle)
   int M, N, K;
   int num_passes;
   int m_blocks, n_blocks;  // m_blocks counts 128*CG-row tiles
@@ -88,11 +93,13 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (210 * 1024) / kStageBytes > 8 ? 8 : (210 * 1024) / kStageBytes;
+  static constexpr int kOutBytes = kOutSlots * kOutSlotBytes;  // epilogue staging for TMA stores
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBudget = 232448 - 1024 - kOutBytes - kBarrierBytes;  // 227 KB usable per CTA
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (kAccStages * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOutBytes + kBarrierBytes;
 };
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -161,6 +168,85 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue staging: the 4 epilogue warps (one output row per thread) write a 128-row x 128-byte sub-tile into a
+// 128B-swizzled smem slot (16-byte chunk c of row r lands at chunk c ^ (r & 7): conflict-free for row-per-thread
+// writes), then one thread issues a TMA store (or reduce-add) of the slot: full 128-byte coalesced lines to L2 instead
+// of 16-byte row-strided stores, and rows / columns beyond the tensor are clipped by the TMA unit.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void slot_write16(uint8_t* slot, int r, int c, uint4 v) {
+  *reinterpret_cast<uint4*>(slot + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+// 32 fp32 values -> bf16 into chunks [c0, c0 + 4) of row r
+__device__ __forceinline__ void stage_bf16(uint8_t* slot, int r, int c0, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    slot_write16(slot, r, c0 + i,
+                 make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                            ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7])));
+}
+__device__ __forceinline__ void stage_bf16_residual(uint8_t* slot, int r, int c0, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = v[8 * i + j] - __bfloat162float(__float2bfloat16_rn(v[8 * i + j]));
+    slot_write16(slot, r, c0 + i,
+                 make_uint4(ptx::pack_bf16x2(q[0], q[1]), ptx::pack_bf16x2(q[2], q[3]), ptx::pack_bf16x2(q[4], q[5]),
+                            ptx::pack_bf16x2(q[6], q[7])));
+  }
+}
+// 32 fp32 values -> the 8 chunks of row r
+__device__ __forceinline__ void stage_f32(uint8_t* slot, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    slot_write16(slot, r, i,
+                 make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                            __float_as_uint(v[4 * i + 3])));
+}
+
+struct OutRing {
+  uint8_t* base;
+  uint32_t n;
+  bool issuer;
+  // one slot: the store issued two uses ago must have finished READING smem
+  __device__ __forceinline__ uint8_t* acquire() {
+    if (issuer) ptx::tma_store_wait_read<1>();
+    epi_bar_sync();
+    return base + (n & 1) * kOutSlotBytes;
+  }
+  // both slots at once (hi + residual planes)
+  __device__ __forceinline__ void acquire_pair(uint8_t*& a, uint8_t*& b) {
+    if (issuer) ptx::tma_store_wait_read<0>();
+    epi_bar_sync();
+    a = base + (n & 1) * kOutSlotBytes;
+    b = base + ((n + 1) & 1) * kOutSlotBytes;
+  }
+  __device__ __forceinline__ void commit(const CUtensorMap* tm, const uint8_t* slot, int c0, int c1, bool reduce) {
+    ptx::fence_proxy_async_smem();
+    epi_bar_sync();
+    if (issuer) {
+      if (reduce) ptx::tma_reduce_add_2d(tm, slot, c0, c1);
+      else ptx::tma_store_2d(tm, slot, c0, c1);
+      ptx::tma_store_commit();
+    }
+    n += 1;
+  }
+  __device__ __forceinline__ void commit_pair(const CUtensorMap* tm_a, const uint8_t* a, const CUtensorMap* tm_b,
+                                              const uint8_t* b, int c0, int c1) {
+    ptx::fence_proxy_async_smem();
+    epi_bar_sync();
+    if (issuer) {
+      ptx::tma_store_2d(tm_a, a, c0, c1);
+      ptx::tma_store_2d(tm_b, b, c0, c1);
+      ptx::tma_store_commit();
+    }
+    n += 2;
+  }
+};
+
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI, int CG>
 __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -171,7 +257,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* out_slots = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_slots + Cfg::kOutBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
@@ -189,6 +276,9 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       ptx::prefetch_tensormap(&p.tmA[i]);
       ptx::prefetch_tensormap(&p.tmB[i]);
     }
+    ptx::prefetch_tensormap(&p.tmOutHi);
+    ptx::prefetch_tensormap(&p.tmOutLo);
+    ptx::prefetch_tensormap(&p.tmOutF32);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);    // leader's barrier: its producer arrives once with the pair's byte count
       ptx::mbar_init(&empty_bar[i], 1);   // per CTA: tcgen05.commit (multicast to both CTAs when CG == 2)
@@ -302,9 +392,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;  // tcgen05.ld: a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int row_in_tile = quarter * 32 + lane;
+    const int row = quarter * 32 + lane;  // row of the tile owned by this thread
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const EpiArgs& e = p.epi;
+    OutRing ring{out_slots, 0u, warp == 2 && lane == 0};
     float loss_local = 0.f;
     uint32_t as = 0, aphase = 0;
     for (int u = group_id; u < total_units; u += num_groups) {
@@ -312,134 +403,227 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       const int tile = u - ks * tiles;
       const int n_blk = tile / p.m_blocks;
       const int m_blk = tile - n_blk * p.m_blocks;
-      const int m = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM + row_in_tile;
+      const int m0 = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM;
+      const int m = m0 + row;
       const bool row_ok = m < p.M;
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + as * BLOCK_N;
+      const bool dual = e.out_lo != nullptr;
 
       if constexpr (EPI == EPI_HEAD) {
+        // tile columns [0, kHalf) = mu, [kHalf, BLOCK_N) = logvar of latent columns n_blk*kHalf ..
         constexpr int kHalf = BLOCK_N / 2;
         const int L = e.L;
-        for (int c = 0; c < kHalf; c += 16) {
-          __syncwarp();
-          uint32_t rm[16], rl[16];
-          ptx::tmem_ld_32x16(t_acc + c, rm);
-          ptx::tmem_ld_32x16(t_acc + kHalf + c, rl);
-          ptx::tmem_ld_wait();
-          const int col = n_blk * kHalf + c;
-          if (row_ok && col < L) {
+        for (int sub = 0; sub < kHalf / 64; ++sub) {
+          const int col0 = n_blk * kHalf + sub * 64;
+          uint8_t *s_hi = nullptr, *s_lo = nullptr;
+          if (e.out_hi) {
+            if (dual) ring.acquire_pair(s_hi, s_lo); else s_hi = ring.acquire();
+          }
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const int c = sub * 64 + h * 32;
+            const int col = col0 + h * 32;
+            __syncwarp();
+            uint32_t rm[32], rl[32];
+            ptx::tmem_ld_32x32(t_acc + c, rm);
+            ptx::tmem_ld_32x32(t_acc + kHalf + c, rl);
+            ptx::tmem_ld_wait();
+            float z[32];
             const size_t off = static_cast<size_t>(m) * L + col;
-            float eps[16], mu[16], lv[16], z[16], esh[16], gmu[16], glv[16];
-            if (e.in0) {
-              load_row_f32<16>(reinterpret_cast<const float*>(e.in0) + off, eps);
-            } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) eps[j] = 0.f;
-            }
+            for (int q = 0; q < 2; ++q) {  // 16 columns at a time keeps the side arrays small
+              float eps[16], mu[16], lv[16], esh[16], gmu[16], glv[16];
+              if (row_ok && e.in0) {
+                load_row_f32<16>(reinterpret_cast<const float*>(e.in0) + off + 16 * q, eps);
+              } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              mu[j] = __uint_as_float(rm[j]) + __ldg(e.bias + col + j);
-              lv[j] = __uint_as_float(rl[j]) + __ldg(e.bias + L + col + j);
-              const float sig = expf(0.5f * lv[j]);
-              const float var = sig * sig;
-              z[j] = fmaf(eps[j], sig, mu[j]);
-              esh[j] = 0.5f * eps[j] * sig;
-              gmu[j] = e.c0 * mu[j];
-              glv[j] = 0.5f * e.c0 * (var - 1.f);
-              loss_local += (1.f + lv[j]) - fmaf(mu[j], mu[j], var);
+                for (int j = 0; j < 16; ++j) eps[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int jj = 16 * q + j;
+                mu[j] = __uint_as_float(rm[jj]) + __ldg(e.bias + col + jj);
+                lv[j] = __uint_as_float(rl[jj]) + __ldg(e.bias + L + col + jj);
+                const float sig = expf(0.5f * lv[j]);
+                const float var = sig * sig;
+                z[jj] = fmaf(eps[j], sig, mu[j]);
+                esh[j] = 0.5f * eps[j] * sig;
+                gmu[j] = e.c0 * mu[j];
+                glv[j] = 0.5f * e.c0 * (var - 1.f);
+                if (row_ok) loss_local += (1.f + lv[j]) - fmaf(mu[j], mu[j], var);
+              }
+              if (row_ok) {
+                store_row_f32<16>(e.out_f32 + off + 16 * q, mu);
+                store_row_f32<16>(e.out_f32_b + off + 16 * q, lv);
+                if (e.aux0) store_row_f32<16>(e.aux0 + off + 16 * q, esh);
+                if (e.aux1) store_row_f32<16>(e.aux1 + off + 16 * q, gmu);
+                if (e.aux2) store_row_f32<16>(e.aux2 + off + 16 * q, glv);
+              }
             }
-            store_row_f32<16>(e.out_f32 + off, mu);
-            store_row_f32<16>(e.out_f32_b + off, lv);
-            if (e.out_hi) store_row_bf16<16>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, z);
-            if (e.aux0) store_row_f32<16>(e.aux0 + off, esh);
-            if (e.aux1) store_row_f32<16>(e.aux1 + off, gmu);
-            if (e.aux2) store_row_f32<16>(e.aux2 + off, glv);
+            if (e.out_hi) {
+              stage_bf16(s_hi, row, h * 4, z);
+              if (dual) stage_bf16_residual(s_lo, row, h * 4, z);
+            }
+          }
+          if (e.out_hi) {
+            if (dual) ring.commit_pair(&p.tmOutHi, s_hi, &p.tmOutLo, s_lo, col0, m0);
+            else ring.commit(&p.tmOutHi, s_hi, col0, m0, false);
           }
         }
-      } else {
+      } else if constexpr (EPI == EPI_WGRAD) {
         for (int c = 0; c < BLOCK_N; c += 32) {
+          const int n = n_blk * BLOCK_N + c;
+          if (n >= p.N) break;
+          uint8_t* slot = ring.acquire();
           __syncwarp();
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_acc + c, r);
           ptx::tmem_ld_wait();
-          const int n = n_blk * BLOCK_N + c;
-          if (row_ok && n < p.N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const size_t off = static_cast<size_t>(m) * e.ldo + n;
-
-          if constexpr (EPI == EPI_LINEAR) {
-            if (e.bias) {
+          stage_f32(slot, row, v);
+          ring.commit(&p.tmOutF32, slot, n, m0, e.accumulate != 0);
+        }
+      } else {
+        // ---- bf16 stream(s): LINEAR (act), DRELU (mask), OUT (da4), DZ (dmu then dlv)
+        constexpr int kStreams = (EPI == EPI_DZ) ? 2 : 1;
+        if (e.out_hi) {
+#pragma unroll 1
+          for (int stream = 0; stream < kStreams; ++stream) {
+            for (int sub = 0; sub < BLOCK_N / 64; ++sub) {
+              const int n0 = n_blk * BLOCK_N + sub * 64;
+              if (n0 >= p.N) break;
+              uint8_t *s_hi = nullptr, *s_lo = nullptr;
+              if (dual) ring.acquire_pair(s_hi, s_lo); else s_hi = ring.acquire();
+#pragma unroll 1
+              for (int h = 0; h < 2; ++h) {
+                const int n = n0 + h * 32;
+                __syncwarp();
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_acc + sub * 64 + h * 32, r);
+                ptx::tmem_ld_wait();
+                float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
-            }
-            if (e.act == ACT_RELU) {
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const size_t off = static_cast<size_t>(m) * e.ldo + n;
+                if constexpr (EPI == EPI_LINEAR) {
+                  if (e.bias) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (e.act == ACT_TANH) {
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
+                  }
+                  if (e.act == ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-            } else if (e.act == ACT_TANH_APPROX) {
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                  } else if (e.act == ACT_TANH) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = ptx::tanh_approx(v[j]);
-            }
-            if (e.out_hi) store_row_bf16<32>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, v);
-            if (e.out_f32) store_row_f32<32>(e.out_f32 + off, v);
-          } else if constexpr (EPI == EPI_OUT) {
-            float x[32];
-            load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, x);
-            if (e.in1) {
-              float xl[32];
-              load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
+                    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                  } else if (e.act == ACT_TANH_APPROX) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] += xl[j];
-            }
-            float da[32];
+                    for (int j = 0; j < 32; ++j) v[j] = ptx::tanh_approx(v[j]);
+                  }
+                } else if constexpr (EPI == EPI_DRELU) {
+                  if (e.in0 && row_ok) {
+                    float hm[32];
+                    load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, hm);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float a = v[j] + __ldg(e.bias + n + j);
-              const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
-              const float d = xh - x[j];
-              loss_local = fmaf(d, d, loss_local);
-              da[j] = e.c0 * d * (1.f - xh * xh);
-              v[j] = xh;
-            }
-            if (e.out_f32) store_row_f32<32>(e.out_f32 + off, v);
-            if (e.out_hi) store_row_bf16<32>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, da);
-          } else if constexpr (EPI == EPI_DRELU) {
-            if (e.in0) {
-              float h[32];
-              load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, h);
+                    for (int j = 0; j < 32; ++j) v[j] = (hm[j] > 0.f) ? v[j] : 0.f;
+                  }
+                } else if constexpr (EPI == EPI_OUT) {
+                  float x[32];
+                  if (row_ok) {
+                    load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, x);
+                    if (e.in1) {
+                      float xl[32];
+                      load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (h[j] > 0.f) ? v[j] : 0.f;
-            }
-            store_row_bf16<32>(e.out_hi + off, e.out_lo ? e.out_lo + off : nullptr, v);
-          } else if constexpr (EPI == EPI_DZ) {
-            const int L = e.L;
-            const size_t loff = static_cast<size_t>(m) * L + n;
-            float esh[32], g[32], dl[32];
-            load_row_f32<32>(reinterpret_cast<const float*>(e.in0) + loff, esh);
-            load_row_f32<32>(reinterpret_cast<const float*>(e.in2) + loff, g);
+                      for (int j = 0; j < 32; ++j) x[j] += xl[j];
+                    }
+                  } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dl[j] = fmaf(v[j], esh[j], g[j]);
-            load_row_f32<32>(reinterpret_cast<const float*>(e.in1) + loff, g);
+                    for (int j = 0; j < 32; ++j) x[j] = 0.f;
+                  }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += g[j];
-            const size_t ooff = static_cast<size_t>(m) * e.ldo + n;
-            store_row_bf16<32>(e.out_hi + ooff, e.out_lo ? e.out_lo + ooff : nullptr, v);
-            store_row_bf16<32>(e.out_hi + ooff + L, e.out_lo ? e.out_lo + ooff + L : nullptr, dl);
-          } else if constexpr (EPI == EPI_WGRAD) {
-            float* dst = e.out_f32 + off;
-            if (e.accumulate) {
+                  for (int j = 0; j < 32; ++j) {
+                    const float a = v[j] + __ldg(e.bias + n + j);
+                    const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
+                    const float d = xh - x[j];
+                    if (row_ok) loss_local = fmaf(d, d, loss_local);
+                    v[j] = e.c0 * d * (1.f - xh * xh);
+                  }
+                } else if constexpr (EPI == EPI_DZ) {
+                  const int L = e.L;
+                  const size_t loff = static_cast<size_t>(m) * L + n;
+                  if (row_ok) {
+                    float g[32];
+                    if (stream == 0) {  // dmu = dz + g_mu
+                      load_row_f32<32>(reinterpret_cast<const float*>(e.in1) + loff, g);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) ptx::red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              store_row_f32<32>(dst, v);
+                      for (int j = 0; j < 32; ++j) v[j] += g[j];
+                    } else {            // dlv = dz * (eps sigma / 2) + g_logvar
+                      float esh[32];
+                      load_row_f32<32>(reinterpret_cast<const float*>(e.in0) + loff, esh);
+                      load_row_f32<32>(reinterpret_cast<const float*>(e.in2) + loff, g);
+#pragma unroll
+                      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], esh[j], g[j]);
+                    }
+                  }
+                }
+                stage_bf16(s_hi, row, h * 4, v);
+                if (dual) stage_bf16_residual(s_lo, row, h * 4, v);
+              }
+              const int c_out = (EPI == EPI_DZ) ? stream * e.L + n0 : n0;
+              if (dual) ring.commit_pair(&p.tmOutHi, s_hi, &p.tmOutLo, s_lo, c_out, m0);
+              else ring.commit(&p.tmOutHi, s_hi, c_out, m0, false);
             }
           }
-          }  // row_ok && n < N
+        }
+        // ---- fp32 stream: LINEAR's fp32 copy / OUT's xhat
+        if constexpr (EPI == EPI_LINEAR || EPI == EPI_OUT) {
+          if (e.out_f32) {
+            for (int c = 0; c < BLOCK_N; c += 32) {
+              const int n = n_blk * BLOCK_N + c;
+              if (n >= p.N) break;
+              uint8_t* slot = ring.acquire();
+              __syncwarp();
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(t_acc + c, r);
+              ptx::tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+              const int act = (EPI == EPI_OUT && e.act != ACT_TANH_APPROX) ? ACT_TANH : e.act;
+              if (act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+              } else if (act == ACT_TANH_APPROX) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ptx::tanh_approx(v[j]);
+              }
+              if constexpr (EPI == EPI_OUT) {
+                if (!e.out_hi && row_ok) {  // loss-only forward: accumulate the MSE here
+                  const size_t off = static_cast<size_t>(m) * e.ldo + n;
+                  float x[32];
+                  load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, x);
+                  if (e.in1) {
+                    float xl[32];
+                    load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] += xl[j];
+                  }
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) loss_local = fmaf(v[j] - x[j], v[j] - x[j], loss_local);
+                }
+              }
+              stage_f32(slot, row, v);
+              ring.commit(&p.tmOutF32, slot, n, m0, false);
+            }
+          }
         }
       }
       // release the accumulator back to the MMA warp
@@ -451,6 +635,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       }
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
+    if (ring.issuer) ptx::tma_store_wait<0>();  // all bulk stores of this CTA have completed
     if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
       const float s = warp_sum(loss_local);
       if (lane == 0 && e.loss_acc) atomicAdd(e.loss_acc, static_cast<double>(s));

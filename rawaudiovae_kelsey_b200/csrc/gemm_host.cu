@@ -45,25 +45,46 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows with pitch `ld` elements; 128-byte swizzle; OOB reads zero.
-static int encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld,
-                          uint32_t box0, uint32_t box1) {
+// 2-D tensor map: dim0 (contiguous) x dim1 rows with pitch `ld` elements; 128-byte swizzle; OOB reads zero, OOB
+// writes are dropped.
+static int encode_2d(CUtensorMap* tm, const void* base, bool f32, uint64_t dim0, uint64_t dim1, uint64_t ld,
+                     uint32_t box0, uint32_t box1) {
   EncodeTiledFn fn = get_encode_fn();
+  const uint64_t esz = f32 ? 4 : 2;
   RVAE_REQUIRE(fn != nullptr, RVAE_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
-  RVAE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, RVAE_ERR_INVALID, "operand base %p not 16-byte aligned",
+  RVAE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, RVAE_ERR_INVALID, "tensor base %p not 16-byte aligned",
                base);
-  RVAE_REQUIRE((ld * 2) % 16 == 0, RVAE_ERR_UNSUPPORTED, "operand row pitch %llu elements not a multiple of 8",
+  RVAE_REQUIRE((ld * esz) % 16 == 0, RVAE_ERR_UNSUPPORTED, "row pitch %llu elements is not a multiple of 16 bytes",
                (unsigned long long)ld);
   cuuint64_t gdim[2] = {dim0, dim1};
-  cuuint64_t gstride[1] = {ld * 2};
+  cuuint64_t gstride[1] = {ld * esz};
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RVAE_REQUIRE(r == CUDA_SUCCESS, RVAE_ERR_DRIVER,
                "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu box %u x %u", (int)r,
                (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)ld, box0, box1);
+  return RVAE_OK;
+}
+static int encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld,
+                          uint32_t box0, uint32_t box1) {
+  return encode_2d(tm, base, false, dim0, dim1, ld, box0, box1);
+}
+
+// Output tensor maps of a prepared GEMM (epilogue TMA stores): bf16 planes in boxes of 64 columns, fp32 in boxes of
+// 32 columns, 128 rows each. Re-encodes only the maps whose base pointer changed.
+int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& a, bool force) {
+  GemmParams& p = g->params;
+  const EpiArgs old = p.epi;
+  p.epi = a;
+  if (a.out_hi && (force || a.out_hi != old.out_hi))
+    RVAE_CHECK(encode_2d(&p.tmOutHi, a.out_hi, false, g->out_cols_bf16, g->out_rows, g->out_ld_bf16, 64, 128));
+  if (a.out_lo && (force || a.out_lo != old.out_lo))
+    RVAE_CHECK(encode_2d(&p.tmOutLo, a.out_lo, false, g->out_cols_bf16, g->out_rows, g->out_ld_bf16, 64, 128));
+  if (a.out_f32 && g->out_f32_tma && (force || a.out_f32 != old.out_f32))
+    RVAE_CHECK(encode_2d(&p.tmOutF32, a.out_f32, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
   return RVAE_OK;
 }
 
@@ -218,6 +239,19 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
     else
       RVAE_CHECK(encode_bf16_2d(&p.tmB[i], b_ptr[i], d.N, d.K, d.B.ld, 64, kBlockK));
   }
+
+  // epilogue output tensors (what the TMA stores write)
+  g.out_rows = d.M;
+  g.out_f32_tma = (d.epi == EPI_LINEAR || d.epi == EPI_OUT || d.epi == EPI_WGRAD);
+  if (d.epi == EPI_HEAD) {            // z [M, L]
+    g.out_cols_bf16 = d.head_L; g.out_ld_bf16 = d.head_L;
+  } else if (d.epi == EPI_DZ) {       // d_ml [M, 2L]
+    g.out_cols_bf16 = 2 * d.args.L; g.out_ld_bf16 = d.args.ldo;
+  } else {
+    g.out_cols_bf16 = d.N; g.out_ld_bf16 = d.args.ldo;
+  }
+  g.out_cols_f32 = d.N; g.out_ld_f32 = d.args.ldo;
+  RVAE_CHECK(gemm_bind_outputs(&g, p.epi, true));
 
   g.block_n = block_n;
   g.variant = find_variant(block_n, d.A.major, d.B.major, d.epi, cg);

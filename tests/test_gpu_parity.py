@@ -142,7 +142,9 @@ def test_three_adam_steps_vs_reference_golden(dev, small, precision, tol):
     assert len(ost["state"]) == 10 and ost["param_groups"][0]["params"] == list(range(10))
     sd = model.state_dict()
     for i, k in enumerate(sd):
-        assert rel(sd[k], small["final/" + k]) < 1e-3, k                 # weights moved by ~3 lr
+        # weights moved by ~3 lr (~6 % of their norm); Adam's m/sqrt(v) ~ sign(g) amplifies rounding of near-zero
+        # gradient entries, so the bound is on the weights, not on the update
+        assert rel(sd[k], small["final/" + k]) < (1e-3 if precision == "fp32" else 1e-2), k
         # after 3 steps trajectories have separated by rounding noise (gates, bf16 weight shadows): loose bound
         assert rel(ost["state"][i]["exp_avg"], small["exp_avg/" + k]) < (1e-2 if precision == "fp32" else 8e-2), k
 
@@ -175,7 +177,7 @@ def test_fused_train_step_matches_oracle(dev, small, precision, tol):
     # bf16 shadow planes follow the fp32 master weights
     assert rel(flat.shadow_hi.float(), flat.params) < 4e-3
     for k in O.PARAM_NAMES:
-        assert rel(flat.view(flat.params, k), small["final/" + k]) < 1e-3, k
+        assert rel(flat.view(flat.params, k), small["final/" + k]) < (1e-3 if precision == "fp32" else 1e-2), k
 
 
 def test_default_ini_dims_fused_step(dev, golden_dir):
