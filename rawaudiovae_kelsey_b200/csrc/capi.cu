@@ -48,6 +48,8 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   if (const char* e = getenv("RVAE_BLOCK_N")) ctx->c.force_block_n = atoi(e);
   ctx->c.force_cta_group = 0;
   if (const char* e = getenv("RVAE_CTA_GROUP")) ctx->c.force_cta_group = atoi(e);
+  ctx->c.debug = 0;
+  if (const char* e = getenv("RVAE_DEBUG")) ctx->c.debug = atoi(e);
   *out = ctx;
   return RVAE_OK;
 }

@@ -46,6 +46,7 @@ struct Ctx {
   int num_sms;
   int force_block_n;  // 0 = heuristic, 128 / 256 = forced (env RVAE_BLOCK_N, for experiments)
   int force_cta_group;  // 0 = heuristic, 1 / 2 = forced (env RVAE_CTA_GROUP, for experiments)
+  int debug;            // env RVAE_DEBUG, experiments only (see GemmParams::debug)
   uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
 };
 

@@ -29,7 +29,8 @@ namespace rvae {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two teams of four)
+constexpr int kEpiTeams = 2;
 constexpr int kMaxPasses = 3;
 constexpr int kOutSlotBytes = 128 * 128;  // one epilogue staging slot: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
 constexpr int kOutSlots = 2;
@@ -82,6 +83,7 @@ struct alignas(64) GemmParams {
   int k_splits, kb_per_split, kb_total;
   int b_tile_stride;  // K-major B: row advance per n-block
   int b_half_stride;  // K-major B: row offset of the second half-tile load
+  int debug;          // experiments only (env RVAE_DEBUG, CG == 1): 1 = no MMA issue, 2 = no TMA loads
   EpiArgs epi;
 };
 
@@ -94,7 +96,7 @@ struct GemmCfg {
   static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = kOutSlots * kOutSlotBytes;  // epilogue staging for TMA stores
-  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBarrierBytes = 256 + kEpiTeams * 64 * 4;  // mbarriers + TMEM slot + per-team bias strips
   static constexpr int kBudget = 232448 - 1024 - kOutBytes - kBarrierBytes;  // 227 KB usable per CTA
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
@@ -169,25 +171,30 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Epilogue staging: the 4 epilogue warps (one output row per thread) write a 128-row x 128-byte sub-tile into a
-// 128B-swizzled smem slot (16-byte chunk c of row r lands at chunk c ^ (r & 7): conflict-free for row-per-thread
-// writes), then one thread issues a TMA store (or reduce-add) of the slot: full 128-byte coalesced lines to L2 instead
-// of 16-byte row-strided stores, and rows / columns beyond the tensor are clipped by the TMA unit.
+// Epilogue staging. Eight epilogue warps form two TEAMS of four (one warp per TMEM lane quarter, one output row per
+// thread). The work units of a tile (64-column bf16 sub-tiles, 32-column fp32 sub-tiles) alternate between the
+// teams, so one team's TMEM loads / global side loads / barrier waits overlap the other's math and smem writes.
+// A team stages a unit as 128 rows x 128 bytes in its own 128B-swizzled smem slot (16-byte chunk c of row r lands at
+// chunk c ^ (r & 7): conflict-free for row-per-thread writes); then one thread issues a TMA store (or reduce-add)
+// of the slot: full 128-byte coalesced lines to L2 instead of 16-byte row-strided stores, and rows / columns beyond
+// the tensor are clipped by the TMA unit.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void team_bar_sync(int team) {
+  asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");
+}
 
 __device__ __forceinline__ void slot_write16(uint8_t* slot, int r, int c, uint4 v) {
   *reinterpret_cast<uint4*>(slot + r * 128 + ((c ^ (r & 7)) << 4)) = v;
 }
 // 32 fp32 values -> bf16 into chunks [c0, c0 + 4) of row r
-__device__ __forceinline__ void stage_bf16(uint8_t* slot, int r, int c0, const float (&v)[32]) {
+__device__ __forceinline__ void stage_bf16(uint8_t* slot, int r, int c0, const float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     slot_write16(slot, r, c0 + i,
                  make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                             ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7])));
 }
-__device__ __forceinline__ void stage_bf16_residual(uint8_t* slot, int r, int c0, const float (&v)[32]) {
+__device__ __forceinline__ void stage_bf16_residual(uint8_t* slot, int r, int c0, const float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float q[8];
@@ -199,7 +206,7 @@ __device__ __forceinline__ void stage_bf16_residual(uint8_t* slot, int r, int c0
   }
 }
 // 32 fp32 values -> the 8 chunks of row r
-__device__ __forceinline__ void stage_f32(uint8_t* slot, int r, const float (&v)[32]) {
+__device__ __forceinline__ void stage_f32(uint8_t* slot, int r, const float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     slot_write16(slot, r, i,
@@ -207,43 +214,25 @@ __device__ __forceinline__ void stage_f32(uint8_t* slot, int r, const float (&v)
                             __float_as_uint(v[4 * i + 3])));
 }
 
-struct OutRing {
-  uint8_t* base;
-  uint32_t n;
+// One team's staging slot + bias strip. acquire(): the team's previous TMA store has finished reading the slot
+// (and, as a side effect of the barrier, the bias strip written before it is visible). commit(): hand the slot to TMA.
+struct TeamOut {
+  uint8_t* slot;
+  float* bias_s;   // 64 floats
+  int team;
   bool issuer;
-  // one slot: the store issued two uses ago must have finished READING smem
-  __device__ __forceinline__ uint8_t* acquire() {
-    if (issuer) ptx::tma_store_wait_read<1>();
-    epi_bar_sync();
-    return base + (n & 1) * kOutSlotBytes;
-  }
-  // both slots at once (hi + residual planes)
-  __device__ __forceinline__ void acquire_pair(uint8_t*& a, uint8_t*& b) {
+  __device__ __forceinline__ void acquire() {
     if (issuer) ptx::tma_store_wait_read<0>();
-    epi_bar_sync();
-    a = base + (n & 1) * kOutSlotBytes;
-    b = base + ((n + 1) & 1) * kOutSlotBytes;
+    team_bar_sync(team);
   }
-  __device__ __forceinline__ void commit(const CUtensorMap* tm, const uint8_t* slot, int c0, int c1, bool reduce) {
+  __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, bool reduce) {
     ptx::fence_proxy_async_smem();
-    epi_bar_sync();
+    team_bar_sync(team);
     if (issuer) {
       if (reduce) ptx::tma_reduce_add_2d(tm, slot, c0, c1);
       else ptx::tma_store_2d(tm, slot, c0, c1);
       ptx::tma_store_commit();
     }
-    n += 1;
-  }
-  __device__ __forceinline__ void commit_pair(const CUtensorMap* tm_a, const uint8_t* a, const CUtensorMap* tm_b,
-                                              const uint8_t* b, int c0, int c1) {
-    ptx::fence_proxy_async_smem();
-    epi_bar_sync();
-    if (issuer) {
-      ptx::tma_store_2d(tm_a, a, c0, c1);
-      ptx::tma_store_2d(tm_b, b, c0, c1);
-      ptx::tma_store_commit();
-    }
-    n += 2;
   }
 };
 
@@ -258,7 +247,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   uint8_t* out_slots = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_slots + Cfg::kOutBytes);
+  float* bias_strips = reinterpret_cast<float*>(out_slots + Cfg::kOutBytes);  // kEpiTeams x 64 floats
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_slots + Cfg::kOutBytes + kEpiTeams * 64 * 4);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
@@ -285,7 +275,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       ptx::mbar_init(&tmem_full_bar[i], 1);        // per CTA: tcgen05.commit
-      ptx::mbar_init(&tmem_empty_bar[i], 4 * CG);  // leader's barrier: one arrive per epilogue warp of the pair
+      ptx::mbar_init(&tmem_empty_bar[i], 8 * CG);  // leader's barrier: one arrive per epilogue warp of the pair
     }
     ptx::fence_barrier_init();
   }
@@ -316,6 +306,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           for (int kb = kb_begin; kb < kb_begin + kb_count; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint64_t* fb = &full_bar[stage];
+            if (CG == 1 && (p.debug & 2)) {  // experiment: measure the MMA side alone (operands are stale smem)
+              ptx::mbar_arrive(fb);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
             } else {
@@ -372,6 +367,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         for (int it = 0; it < iters; ++it) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
+          if (CG == 1 && (p.debug & 1)) {  // experiment: measure the TMA side alone
+            ptx::mbar_arrive(&empty_bar[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
@@ -385,17 +385,21 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           ptx::umma_commit<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit<CG>(&tmem_full_bar[as]);  // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 1 && (p.debug & 1)) ptx::mbar_arrive(&tmem_full_bar[as]);
+        else ptx::umma_commit<CG>(&tmem_full_bar[as]);  // accumulator complete -> epilogue (of both CTAs)
         if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
+    // ------------------------------------------------------------------ epilogue warps (2 teams x 4 warps)
+    const int team = (warp - 2) >> 2;
     const int quarter = warp & 3;  // tcgen05.ld: a warp may only touch TMEM lanes 32*(warp%4) .. +31
     const int row = quarter * 32 + lane;  // row of the tile owned by this thread
+    const int team_tid = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the team
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const EpiArgs& e = p.epi;
-    OutRing ring{out_slots, 0u, warp == 2 && lane == 0};
+    TeamOut out{out_slots + team * kOutSlotBytes, bias_strips + team * 64, team, team_tid == 0};
+    const bool dual = e.out_lo != nullptr;
     float loss_local = 0.f;
     uint32_t as = 0, aphase = 0;
     for (int u = group_id; u < total_units; u += num_groups) {
@@ -409,19 +413,16 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + as * BLOCK_N;
-      const bool dual = e.out_lo != nullptr;
 
       if constexpr (EPI == EPI_HEAD) {
         // tile columns [0, kHalf) = mu, [kHalf, BLOCK_N) = logvar of latent columns n_blk*kHalf ..
         constexpr int kHalf = BLOCK_N / 2;
         const int L = e.L;
-        for (int sub = 0; sub < kHalf / 64; ++sub) {
+        for (int sub = team; sub < kHalf / 64; sub += kEpiTeams) {
           const int col0 = n_blk * kHalf + sub * 64;
-          uint8_t *s_hi = nullptr, *s_lo = nullptr;
-          if (e.out_hi) {
-            if (dual) ring.acquire_pair(s_hi, s_lo); else s_hi = ring.acquire();
-          }
-#pragma unroll 1
+          if (e.out_hi) out.acquire();
+          float z[64];
+#pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = sub * 64 + h * 32;
             const int col = col0 + h * 32;
@@ -429,18 +430,18 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             uint32_t rm[32], rl[32];
             ptx::tmem_ld_32x32(t_acc + c, rm);
             ptx::tmem_ld_32x32(t_acc + kHalf + c, rl);
-            ptx::tmem_ld_wait();
-            float z[32];
             const size_t off = static_cast<size_t>(m) * L + col;
+            float eps[32];
+            if (row_ok && e.in0) {
+              load_row_f32<32>(reinterpret_cast<const float*>(e.in0) + off, eps);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) eps[j] = 0.f;
+            }
+            ptx::tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 2; ++q) {  // 16 columns at a time keeps the side arrays small
-              float eps[16], mu[16], lv[16], esh[16], gmu[16], glv[16];
-              if (row_ok && e.in0) {
-                load_row_f32<16>(reinterpret_cast<const float*>(e.in0) + off + 16 * q, eps);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) eps[j] = 0.f;
-              }
+              float mu[16], lv[16], esh[16], gmu[16], glv[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int jj = 16 * q + j;
@@ -448,8 +449,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 lv[j] = __uint_as_float(rl[jj]) + __ldg(e.bias + L + col + jj);
                 const float sig = expf(0.5f * lv[j]);
                 const float var = sig * sig;
-                z[jj] = fmaf(eps[j], sig, mu[j]);
-                esh[j] = 0.5f * eps[j] * sig;
+                z[h * 32 + jj] = fmaf(eps[jj], sig, mu[j]);
+                esh[j] = 0.5f * eps[jj] * sig;
                 gmu[j] = e.c0 * mu[j];
                 glv[j] = 0.5f * e.c0 * (var - 1.f);
                 if (row_ok) loss_local += (1.f + lv[j]) - fmaf(mu[j], mu[j], var);
@@ -462,138 +463,162 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 if (e.aux2) store_row_f32<16>(e.aux2 + off + 16 * q, glv);
               }
             }
-            if (e.out_hi) {
-              stage_bf16(s_hi, row, h * 4, z);
-              if (dual) stage_bf16_residual(s_lo, row, h * 4, z);
-            }
           }
           if (e.out_hi) {
-            if (dual) ring.commit_pair(&p.tmOutHi, s_hi, &p.tmOutLo, s_lo, col0, m0);
-            else ring.commit(&p.tmOutHi, s_hi, col0, m0, false);
+            stage_bf16(out.slot, row, 0, z);
+            stage_bf16(out.slot, row, 4, z + 32);
+            out.commit(&p.tmOutHi, col0, m0, false);
+            if (dual) {
+              out.acquire();
+              stage_bf16_residual(out.slot, row, 0, z);
+              stage_bf16_residual(out.slot, row, 4, z + 32);
+              out.commit(&p.tmOutLo, col0, m0, false);
+            }
           }
         }
       } else if constexpr (EPI == EPI_WGRAD) {
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          const int n = n_blk * BLOCK_N + c;
-          if (n >= p.N) break;
-          uint8_t* slot = ring.acquire();
+        for (int piece = team; piece < BLOCK_N / 32; piece += kEpiTeams) {
+          const int n = n_blk * BLOCK_N + piece * 32;
+          if (n >= p.N) continue;
           __syncwarp();
           uint32_t r[32];
-          ptx::tmem_ld_32x32(t_acc + c, r);
+          ptx::tmem_ld_32x32(t_acc + piece * 32, r);
+          out.acquire();
           ptx::tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          stage_f32(slot, row, v);
-          ring.commit(&p.tmOutF32, slot, n, m0, e.accumulate != 0);
+          stage_f32(out.slot, row, v);
+          out.commit(&p.tmOutF32, n, m0, e.accumulate != 0);
         }
       } else {
-        // ---- bf16 stream(s): LINEAR (act), DRELU (mask), OUT (da4), DZ (dmu then dlv)
+        // ---- bf16 stream(s): LINEAR (act), DRELU (mask), OUT (da4), DZ (dmu then dlv): 64-column units
         constexpr int kStreams = (EPI == EPI_DZ) ? 2 : 1;
+        constexpr int kSubs = BLOCK_N / 64;
         if (e.out_hi) {
-#pragma unroll 1
-          for (int stream = 0; stream < kStreams; ++stream) {
-            for (int sub = 0; sub < BLOCK_N / 64; ++sub) {
-              const int n0 = n_blk * BLOCK_N + sub * 64;
-              if (n0 >= p.N) break;
-              uint8_t *s_hi = nullptr, *s_lo = nullptr;
-              if (dual) ring.acquire_pair(s_hi, s_lo); else s_hi = ring.acquire();
-#pragma unroll 1
-              for (int h = 0; h < 2; ++h) {
-                const int n = n0 + h * 32;
-                __syncwarp();
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(t_acc + sub * 64 + h * 32, r);
-                ptx::tmem_ld_wait();
-                float v[32];
+          for (int unit = team; unit < kStreams * kSubs; unit += kEpiTeams) {
+            const int stream = unit / kSubs;
+            const int sub = unit - stream * kSubs;
+            const int n0 = n_blk * BLOCK_N + sub * 64;
+            if (n0 >= p.N) continue;
+            __syncwarp();
+            // 1) accumulator: both 32-column TMEM loads in flight
+            uint32_t r[64];
+            ptx::tmem_ld_32x32(t_acc + sub * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            ptx::tmem_ld_32x32(t_acc + sub * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            // 2) side inputs from global memory, issued before anything waits
+            const size_t off = static_cast<size_t>(m) * e.ldo + n0;
+            float side[64];
+            if constexpr (EPI == EPI_DRELU) {
+              if (e.in0 && row_ok) {
+                load_row_bf16<64>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, side);
+              } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const size_t off = static_cast<size_t>(m) * e.ldo + n;
-                if constexpr (EPI == EPI_LINEAR) {
-                  if (e.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
-                  }
-                  if (e.act == ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                  } else if (e.act == ACT_TANH) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-                  } else if (e.act == ACT_TANH_APPROX) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = ptx::tanh_approx(v[j]);
-                  }
-                } else if constexpr (EPI == EPI_DRELU) {
-                  if (e.in0 && row_ok) {
-                    float hm[32];
-                    load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, hm);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = (hm[j] > 0.f) ? v[j] : 0.f;
-                  }
-                } else if constexpr (EPI == EPI_OUT) {
-                  float x[32];
-                  if (row_ok) {
-                    load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, x);
-                    if (e.in1) {
-                      float xl[32];
-                      load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
-#pragma unroll
-                      for (int j = 0; j < 32; ++j) x[j] += xl[j];
-                    }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = 0.f;
-                  }
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    const float a = v[j] + __ldg(e.bias + n + j);
-                    const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
-                    const float d = xh - x[j];
-                    if (row_ok) loss_local = fmaf(d, d, loss_local);
-                    v[j] = e.c0 * d * (1.f - xh * xh);
-                  }
-                } else if constexpr (EPI == EPI_DZ) {
-                  const int L = e.L;
-                  const size_t loff = static_cast<size_t>(m) * L + n;
-                  if (row_ok) {
-                    float g[32];
-                    if (stream == 0) {  // dmu = dz + g_mu
-                      load_row_f32<32>(reinterpret_cast<const float*>(e.in1) + loff, g);
-#pragma unroll
-                      for (int j = 0; j < 32; ++j) v[j] += g[j];
-                    } else {            // dlv = dz * (eps sigma / 2) + g_logvar
-                      float esh[32];
-                      load_row_f32<32>(reinterpret_cast<const float*>(e.in0) + loff, esh);
-                      load_row_f32<32>(reinterpret_cast<const float*>(e.in2) + loff, g);
-#pragma unroll
-                      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], esh[j], g[j]);
-                    }
-                  }
-                }
-                stage_bf16(s_hi, row, h * 4, v);
-                if (dual) stage_bf16_residual(s_lo, row, h * 4, v);
+                for (int j = 0; j < 64; ++j) side[j] = 1.f;
               }
-              const int c_out = (EPI == EPI_DZ) ? stream * e.L + n0 : n0;
-              if (dual) ring.commit_pair(&p.tmOutHi, s_hi, &p.tmOutLo, s_lo, c_out, m0);
-              else ring.commit(&p.tmOutHi, s_hi, c_out, m0, false);
+            } else if constexpr (EPI == EPI_OUT) {
+              if (row_ok) {
+                load_row_bf16<64>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, side);
+                if (e.in1) {
+                  float xl[64];
+                  load_row_bf16<64>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
+#pragma unroll
+                  for (int j = 0; j < 64; ++j) side[j] += xl[j];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) side[j] = 0.f;
+              }
+            } else if constexpr (EPI == EPI_DZ) {
+              const size_t loff = static_cast<size_t>(m) * e.L + n0;
+              if (row_ok) {
+                load_row_f32<64>(reinterpret_cast<const float*>(stream == 0 ? e.in1 : e.in2) + loff, side);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) side[j] = 0.f;
+              }
+            }
+            // 3) bias strip of this unit -> smem (published by the barrier inside acquire())
+            if constexpr (EPI == EPI_LINEAR || EPI == EPI_OUT) {
+              if (team_tid < 64) out.bias_s[team_tid] = e.bias ? __ldg(e.bias + n0 + team_tid) : 0.f;
+            }
+            out.acquire();
+            ptx::tmem_ld_wait();
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+            if constexpr (EPI == EPI_LINEAR) {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(out.bias_s + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+              if (e.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (e.act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = tanhf(v[j]);
+              } else if (e.act == ACT_TANH_APPROX) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = ptx::tanh_approx(v[j]);
+              }
+            } else if constexpr (EPI == EPI_DRELU) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = (side[j] > 0.f) ? v[j] : 0.f;
+            } else if constexpr (EPI == EPI_OUT) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const float a = v[j] + out.bias_s[j];
+                const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
+                const float d = xh - side[j];
+                if (row_ok) loss_local = fmaf(d, d, loss_local);
+                v[j] = e.c0 * d * (1.f - xh * xh);
+              }
+            } else if constexpr (EPI == EPI_DZ) {
+              if (stream == 0) {  // dmu = dz + g_mu
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] += side[j];
+              } else {            // dlv = dz * (eps sigma / 2) + g_logvar
+                float esh[64];
+                const size_t loff = static_cast<size_t>(m) * e.L + n0;
+                if (row_ok) {
+                  load_row_f32<64>(reinterpret_cast<const float*>(e.in0) + loff, esh);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 64; ++j) esh[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = fmaf(v[j], esh[j], side[j]);
+              }
+            }
+            const int c_out = (EPI == EPI_DZ) ? stream * e.L + n0 : n0;
+            stage_bf16(out.slot, row, 0, v);
+            stage_bf16(out.slot, row, 4, v + 32);
+            out.commit(&p.tmOutHi, c_out, m0, false);
+            if (dual) {
+              out.acquire();
+              stage_bf16_residual(out.slot, row, 0, v);
+              stage_bf16_residual(out.slot, row, 4, v + 32);
+              out.commit(&p.tmOutLo, c_out, m0, false);
             }
           }
         }
-        // ---- fp32 stream: LINEAR's fp32 copy / OUT's xhat
+        // ---- fp32 stream: LINEAR's fp32 copy / OUT's xhat: 32-column units
         if constexpr (EPI == EPI_LINEAR || EPI == EPI_OUT) {
           if (e.out_f32) {
-            for (int c = 0; c < BLOCK_N; c += 32) {
-              const int n = n_blk * BLOCK_N + c;
-              if (n >= p.N) break;
-              uint8_t* slot = ring.acquire();
+            for (int piece = team; piece < BLOCK_N / 32; piece += kEpiTeams) {
+              const int n = n_blk * BLOCK_N + piece * 32;
+              if (n >= p.N) continue;
               __syncwarp();
               uint32_t r[32];
-              ptx::tmem_ld_32x32(t_acc + c, r);
+              ptx::tmem_ld_32x32(t_acc + piece * 32, r);
+              if (team_tid < 32) out.bias_s[team_tid] = e.bias ? __ldg(e.bias + n + team_tid) : 0.f;
+              out.acquire();
               ptx::tmem_ld_wait();
               float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + out.bias_s[j];
               const int act = (EPI == EPI_OUT && e.act != ACT_TANH_APPROX) ? ACT_TANH : e.act;
               if (act == ACT_RELU) {
 #pragma unroll
@@ -620,8 +645,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                   for (int j = 0; j < 32; ++j) loss_local = fmaf(v[j] - x[j], v[j] - x[j], loss_local);
                 }
               }
-              stage_f32(slot, row, v);
-              ring.commit(&p.tmOutF32, slot, n, m0, false);
+              stage_f32(out.slot, row, v);
+              out.commit(&p.tmOutF32, n, m0, false);
             }
           }
         }
@@ -635,7 +660,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       }
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
-    if (ring.issuer) ptx::tma_store_wait<0>();  // all bulk stores of this CTA have completed
+    if (out.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
     if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
       const float s = warp_sum(loss_local);
       if (lane == 0 && e.loss_acc) atomicAdd(e.loss_acc, static_cast<double>(s));

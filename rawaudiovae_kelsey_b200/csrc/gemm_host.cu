@@ -152,6 +152,7 @@ static void choose_tile(const Ctx* ctx, int M, int N, bool allow128, bool allow2
   if (ctx->force_block_n == 256 && allow256) { *block_n = 256; return; }
   if (!allow256) { *block_n = 128; return; }
   if (!allow128) { *block_n = 256; return; }
+  if (N % 256 != 0) { *block_n = 128; return; }
   const double c256 = 1.0 * ceil_div(mb * ceil_div(N, 256), slots);
   const double c128 = 0.6 * ceil_div(mb * ceil_div(N, 128), slots);
   *block_n = (c128 < c256) ? 128 : 256;
@@ -168,6 +169,7 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   GemmParams& p = g.params;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = d.args;
+  p.debug = ctx->debug;
 
   int block_n, cg;
   if (d.epi == EPI_HEAD) {
@@ -180,7 +182,8 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
     p.b_half_stride = L;
     p.epi.L = L;
   } else {
-    choose_tile(ctx, d.M, d.N, true, true, &block_n, &cg);
+    // weight gradients: 256-wide tiles, split-K fills the machine; others: by wave count
+    choose_tile(ctx, d.M, d.N, d.epi != EPI_WGRAD || d.N % 256 != 0, true, &block_n, &cg);
     p.n_blocks = ceil_div(d.N, block_n);
     p.b_tile_stride = block_n;
     p.b_half_stride = block_n / 2;
