@@ -224,12 +224,14 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
 int rvae_plan_backward(rvae_plan* plan, int stage, void* stream);
 /* loss -> *loss_out (device float, may be NULL), clears the loss sums, *step += 1. */
 int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream);
-/* Adam over the flat buffers (+ shadow refresh). grad_scale = 1/world_size under data parallelism. */
+/* Adam over the flat buffers (+ shadow refresh). grad_scale rescales the gradients (1 for SUM all-reduced,
+ * globally normalised gradients). zero_grads != 0: the kernel also clears bufs.grads after consuming it - the
+ * optimizer.zero_grad() of the next iteration (train.py:184) - which lets the next backward skip its memsets. */
 int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, void* stream);
+                   float grad_scale, int zero_grads, void* stream);
 /* forward + finish_loss + backward(-1) + adam in one call (single-GPU training step). */
 int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, float* loss_out, void* stream);
+                         float weight_decay, int zero_grads, float* loss_out, void* stream);
 
 /* Device pointers into the workspace for the current batch (valid after forward): fp32 [batch, ...]. */
 const float* rvae_plan_mu(const rvae_plan* plan);

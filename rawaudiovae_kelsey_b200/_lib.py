@@ -73,8 +73,8 @@ SIGNATURES = {
     "rvae_plan_backward": (c_int, [P, c_int, P]),
     "rvae_plan_backward_external": (c_int, [P, P, P, P, P, P]),
     "rvae_plan_finish_loss": (c_int, [P, c_float, P, P]),
-    "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, P]),
-    "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, P, P]),
+    "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, P]),
     "rvae_plan_mu": (P, [P]),
     "rvae_plan_logvar": (P, [P]),
     "rvae_plan_xhat": (P, [P]),

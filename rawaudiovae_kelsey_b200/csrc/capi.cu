@@ -50,6 +50,8 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   if (const char* e = getenv("RVAE_CTA_GROUP")) ctx->c.force_cta_group = atoi(e);
   ctx->c.debug = 0;
   if (const char* e = getenv("RVAE_DEBUG")) ctx->c.debug = atoi(e);
+  ctx->c.use_pdl = 1;
+  if (const char* e = getenv("RVAE_PDL")) ctx->c.use_pdl = atoi(e);
   *out = ctx;
   return RVAE_OK;
 }
@@ -113,8 +115,8 @@ int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, 
                    float beta2, float eps, float weight_decay, float grad_scale, const float* step, void* shadow_hi,
                    void* shadow_lo, void* stream) {
   CTX_OR_FAIL(ctx);
-  return launch_adam(&ctx->c, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step, BF(shadow_hi),
-                     BF(shadow_lo), S_(stream));
+  return launch_adam(&ctx->c, p, const_cast<float*>(g), m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
+                     BF(shadow_hi), BF(shadow_lo), 0, S_(stream));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -270,6 +272,7 @@ struct rvae_plan {
   float *out_mu, *out_lv, *out_xhat;
   int batch;        // current batch
   int64_t global_batch;  // loss normalisation under data parallelism (0 = local batch)
+  bool grads_zeroed[4];  // weight-gradient bucket s already holds zeros (left so by the fused Adam kernel)
   bool have_eps;
   std::map<int, GemmSet> sets;  // prepared GEMMs per batch size
   // optional per-GEMM timing
@@ -475,25 +478,29 @@ int backward_stage(rvae_plan* p, int stage, const EpiArgs* dz_override, cudaStre
   float* grads = p->bufs.grads;
   switch (stage) {
     case 0:
-      RVAE_CUDA(cudaMemsetAsync(grads + ly.w4, 0, sizeof(float) * (size_t)S * H, st));
+      if (!p->grads_zeroed[0]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w4, 0, sizeof(float) * (size_t)S * H, st));
+      p->grads_zeroed[0] = false;
       RVAE_CHECK(run(p, G_B4W, st));
       RVAE_CHECK(launch_colsum(c, p->da4.hi, p->da4.lo, B, S, S, grads + ly.b4, 0, st));
       return RVAE_OK;
     case 1:
       RVAE_CHECK(run(p, G_B4D, st));
-      RVAE_CUDA(cudaMemsetAsync(grads + ly.w3, 0, sizeof(float) * (size_t)H * L, st));
+      if (!p->grads_zeroed[1]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w3, 0, sizeof(float) * (size_t)H * L, st));
+      p->grads_zeroed[1] = false;
       RVAE_CHECK(run(p, G_B3W, st));
       RVAE_CHECK(launch_colsum(c, p->da3.hi, p->da3.lo, B, H, H, grads + ly.b3, 0, st));
       return RVAE_OK;
     case 2:
       RVAE_CHECK(run(p, G_B3D, st, dz_override));
-      RVAE_CUDA(cudaMemsetAsync(grads + ly.w2, 0, sizeof(float) * (size_t)2 * L * H, st));
+      if (!p->grads_zeroed[2]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w2, 0, sizeof(float) * (size_t)2 * L * H, st));
+      p->grads_zeroed[2] = false;
       RVAE_CHECK(run(p, G_B2W, st));
       RVAE_CHECK(launch_colsum(c, p->dml.hi, p->dml.lo, B, 2 * L, 2 * L, grads + ly.b2, 0, st));
       return RVAE_OK;
     case 3:
       RVAE_CHECK(run(p, G_B2D, st));
-      RVAE_CUDA(cudaMemsetAsync(grads + ly.w1, 0, sizeof(float) * (size_t)H * S, st));
+      if (!p->grads_zeroed[3]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w1, 0, sizeof(float) * (size_t)H * S, st));
+      p->grads_zeroed[3] = false;
       RVAE_CHECK(run(p, G_B1W, st));
       RVAE_CHECK(launch_colsum(c, p->da1.hi, p->da1.lo, B, H, H, grads + ly.b1, 0, st));
       return RVAE_OK;
@@ -519,6 +526,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
   p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
   p->timing = false;
+  for (int i = 0; i < 4; ++i) p->grads_zeroed[i] = false;
   for (int i = 0; i < G_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
   p->out_mu = p->out_lv = p->out_xhat = nullptr;
   memset(&p->bufs, 0, sizeof(p->bufs));
@@ -577,6 +585,7 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
   if (plan->precision == RVAE_PRECISION_BF16) plan->bufs.shadow_lo = nullptr;
   carve(plan, reinterpret_cast<uint8_t*>(b->workspace));
   plan->sets.clear();
+  for (int i = 0; i < 4; ++i) plan->grads_zeroed[i] = false;
   plan->bound = true;
   plan->batch = 0;
   return RVAE_OK;
@@ -716,21 +725,26 @@ int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void*
 }
 
 int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, void* stream) {
+                   float grad_scale, int zero_grads, void* stream) {
   RVAE_CHECK(check_ready(plan, false));
   const rvae_plan_buffers& b = plan->bufs;
   RVAE_REQUIRE(b.grads && b.exp_avg && b.exp_avg_sq && b.step, RVAE_ERR_STATE,
                "plan_adam: grads / exp_avg / exp_avg_sq / step not bound");
-  return launch_adam(&plan->ctx->c, b.params, b.grads, b.exp_avg, b.exp_avg_sq, plan->lay.total, lr, beta1, beta2, eps,
-                     weight_decay, grad_scale, b.step, BF(b.shadow_hi), BF(b.shadow_lo), S_(stream));
+  // zero_grads: the kernel clears the gradient buffer after consuming it (what optimizer.zero_grad() does at the top
+  // of the reference loop, train.py:184), so the next step's split-K weight gradients can reduce-add without memsets
+  RVAE_CHECK(launch_adam(&plan->ctx->c, b.params, b.grads, b.exp_avg, b.exp_avg_sq, plan->lay.total, lr, beta1, beta2,
+                         eps, weight_decay, grad_scale, b.step, BF(b.shadow_hi), BF(b.shadow_lo), zero_grads,
+                         S_(stream)));
+  for (int i = 0; i < 4; ++i) plan->grads_zeroed[i] = zero_grads != 0;
+  return RVAE_OK;
 }
 
 int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, float* loss_out, void* stream) {
+                         float weight_decay, int zero_grads, float* loss_out, void* stream) {
   RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, stream));
   RVAE_CHECK(rvae_plan_finish_loss(plan, kl_beta, loss_out, stream));
   RVAE_CHECK(rvae_plan_backward(plan, -1, stream));
-  return rvae_plan_adam(plan, lr, beta1, beta2, eps, weight_decay, 1.0f, stream);
+  return rvae_plan_adam(plan, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, stream);
 }
 
 const float* rvae_plan_mu(const rvae_plan* plan) { return plan ? plan->mu : nullptr; }

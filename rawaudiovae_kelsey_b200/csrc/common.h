@@ -47,8 +47,27 @@ struct Ctx {
   int force_block_n;  // 0 = heuristic, 128 / 256 = forced (env RVAE_BLOCK_N, for experiments)
   int force_cta_group;  // 0 = heuristic, 1 / 2 = forced (env RVAE_CTA_GROUP, for experiments)
   int debug;            // env RVAE_DEBUG, experiments only (see GemmParams::debug)
+  int use_pdl;          // programmatic dependent launch between consecutive kernels (env RVAE_PDL=0 disables)
   uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
 };
+
+// Launch with programmatic stream serialization: the kernel may start (and run its prologue) while the previous
+// kernel of the stream drains; every kernel of this library executes griddepcontrol.wait before touching memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(const Ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // A bf16 GEMM operand. K-major: storage [mn][k] (k contiguous, row pitch ld). MN-major: storage [k][mn].
 struct Operand {
@@ -106,9 +125,9 @@ int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps,
                    cudaStream_t stream);
 int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, float* step,
                          cudaStream_t stream);
-int launch_adam(Ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
-                __nv_bfloat16* shadow_lo, cudaStream_t stream);
+                __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream);
 int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream);
 
 }  // namespace rvae

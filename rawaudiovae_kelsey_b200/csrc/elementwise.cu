@@ -15,7 +15,6 @@ static inline int grid_for(const Ctx* ctx, int64_t work_items, int threads, int 
 
 #define RVAE_LAUNCH_CHECK(ctx)           \
   do {                                   \
-    RVAE_CUDA(cudaGetLastError());       \
     (ctx)->launches++;                   \
   } while (0)
 
@@ -47,6 +46,8 @@ __global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_sa
                                     const int64_t* __restrict__ frame_idx, int64_t first_frame, int64_t n_frames,
                                     int hop, int S, __nv_bfloat16* __restrict__ out_hi,
                                     __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int vec_per_frame = S >> 3;
   const int64_t total = n_frames * vec_per_frame;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -120,11 +121,11 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
   const int threads = 256;
   const int grid = grid_for(ctx, n_frames * (S / 8), threads, 16);
   if (audio_is_i16)
-    frame_gather_kernel<true><<<grid, threads, 0, stream>>>(audio, n_samples, frame_idx, first_frame, n_frames, hop, S,
-                                                            out_hi, out_lo, out_f32);
+    RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<true>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop, S,
+                                                            out_hi, out_lo, out_f32));
   else
-    frame_gather_kernel<false><<<grid, threads, 0, stream>>>(audio, n_samples, frame_idx, first_frame, n_frames, hop,
-                                                             S, out_hi, out_lo, out_f32);
+    RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<false>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop,
+                                                             S, out_hi, out_lo, out_f32));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -135,6 +136,8 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
 // ------------------------------------------------------------------------------------------------
 __global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_frames, int S, int hop,
                                    float* __restrict__ out, int64_t n_out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_out; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t i_hi = t / hop;
     if (i_hi > n_frames - 1) i_hi = n_frames - 1;
@@ -159,7 +162,7 @@ int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, i
   RVAE_REQUIRE(S > 0 && hop > 0 && hop <= S, RVAE_ERR_UNSUPPORTED, "overlap_add: need 0 < hop <= S");
   if (n_out <= 0) return RVAE_OK;
   const int threads = 256;
-  overlap_add_kernel<<<grid_for(ctx, n_out, threads, 16), threads, 0, stream>>>(frames, n_frames, S, hop, out, n_out);
+  RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel, dim3(grid_for(ctx, n_out, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, n_out));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -182,6 +185,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 }
 
 __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int64_t nvec = (n + 3) >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(offset),
@@ -211,7 +216,7 @@ int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset
   RVAE_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, RVAE_ERR_INVALID, "randn: bad output buffer");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  randn_kernel<<<grid_for(ctx, (n + 3) / 4, threads, 8), threads, 0, stream>>>(out, n, seed, offset);
+  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -221,6 +226,8 @@ int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset
 // ------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int64_t nvec = n >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
@@ -255,7 +262,7 @@ int launch_split_bf16(Ctx* ctx, const float* src, int64_t n, __nv_bfloat16* hi, 
                RVAE_ERR_INVALID, "split_bf16: buffers must be 16-byte aligned");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  split_bf16_kernel<<<grid_for(ctx, (n + 7) / 8, threads, 8), threads, 0, stream>>>(src, n, hi, lo);
+  RVAE_CUDA(launch_kernel(ctx, split_bf16_kernel, dim3(grid_for(ctx, (n + 7) / 8, threads, 8)), dim3(threads), (size_t)0, stream, src, n, hi, lo));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -269,6 +276,8 @@ constexpr int kColsumRowsPerBlock = 256;
 
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int64_t M,
                               int N, int ld, float* __restrict__ out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   __shared__ float part[8][64];
   const int strip = blockIdx.x;           // 64 columns
   const int lane = threadIdx.x & 31;      // 2 columns each
@@ -308,7 +317,7 @@ int launch_colsum(Ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, in
   if (!accumulate) RVAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, stream));
   if (M <= 0) return RVAE_OK;
   dim3 grid((N + 63) / 64, static_cast<unsigned>((M + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock));
-  colsum_kernel<<<grid, 256, 0, stream>>>(hi, lo, M, N, ld, out);
+  RVAE_CUDA(launch_kernel(ctx, colsum_kernel, dim3(grid), dim3(256), (size_t)0, stream, hi, lo, M, N, ld, out));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -321,6 +330,8 @@ int launch_colsum(Ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, in
 __global__ void loss_fwd_kernel(const float* __restrict__ xhat, const float* __restrict__ x,
                                 const float* __restrict__ mu, const float* __restrict__ lv, int64_t n_rec,
                                 int64_t n_lat, double* __restrict__ acc) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   __shared__ float red[32];
   float mse = 0.f, kl = 0.f;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -354,6 +365,8 @@ __global__ void loss_fwd_kernel(const float* __restrict__ xhat, const float* __r
 
 __global__ void loss_finalize_kernel(double* __restrict__ acc, double inv_rec, double kl_scale,
                                      float* __restrict__ loss_out, float* __restrict__ step) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const double loss = acc[0] * inv_rec + kl_scale * acc[1];
     if (loss_out) *loss_out = static_cast<float>(loss);
@@ -368,7 +381,7 @@ int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float b
   RVAE_REQUIRE(acc, RVAE_ERR_INVALID, "loss_finalize: null accumulator");
   const double inv_rec = 1.0 / (static_cast<double>(B) * S);
   const double kl_scale = -0.5 * static_cast<double>(beta) / (static_cast<double>(B) * L);
-  loss_finalize_kernel<<<1, 32, 0, stream>>>(acc, inv_rec, kl_scale, loss_out, step);
+  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, acc, inv_rec, kl_scale, loss_out, step));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -380,7 +393,7 @@ int launch_loss_fwd(Ctx* ctx, const float* xhat, const float* x, const float* mu
   RVAE_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), stream));
   const int threads = 256;
   const int grid = grid_for(ctx, B * S / 4, threads, 4);
-  loss_fwd_kernel<<<grid, threads, 0, stream>>>(xhat, x, mu, lv, B * S, B * L, acc);
+  RVAE_CUDA(launch_kernel(ctx, loss_fwd_kernel, dim3(grid), dim3(threads), (size_t)0, stream, xhat, x, mu, lv, B * S, B * L, acc));
   RVAE_LAUNCH_CHECK(ctx);
   return launch_loss_finalize(ctx, acc, B, S, L, beta, loss_out, nullptr, stream);
 }
@@ -390,6 +403,8 @@ __global__ void loss_bwd_kernel(const float* __restrict__ xhat, const float* __r
                                 const float* __restrict__ mu, const float* __restrict__ lv, int64_t n_rec,
                                 int64_t n_lat, float c_rec, float c_kl, const float* __restrict__ grad_out,
                                 float* __restrict__ g_xhat, float* __restrict__ g_mu, float* __restrict__ g_lv) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const float g = grad_out ? __ldg(grad_out) : 1.f;
   const float cr = c_rec * g, ck = c_kl * g;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -416,8 +431,8 @@ int launch_loss_bwd(Ctx* ctx, const float* xhat, const float* x, const float* mu
   const float c_rec = static_cast<float>(2.0 / (static_cast<double>(B) * S));
   const float c_kl = static_cast<float>(static_cast<double>(beta) / (static_cast<double>(B) * L));
   const int threads = 256;
-  loss_bwd_kernel<<<grid_for(ctx, B * S / 4, threads, 8), threads, 0, stream>>>(xhat, x, mu, lv, B * S, B * L, c_rec,
-                                                                              c_kl, grad_out, g_xhat, g_mu, g_lv);
+  RVAE_CUDA(launch_kernel(ctx, loss_bwd_kernel, dim3(grid_for(ctx, B * S / 4, threads, 8)), dim3(threads), (size_t)0, stream, xhat, x, mu, lv, B * S, B * L, c_rec,
+                                                                              c_kl, grad_out, g_xhat, g_mu, g_lv));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -425,6 +440,8 @@ int launch_loss_bwd(Ctx* ctx, const float* xhat, const float* x, const float* mu
 // da4 = g_xhat * (1 - xhat^2) as bf16 planes (operand of the fc4 dgrad / wgrad GEMMs).
 __global__ void tanh_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat, int64_t n,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int64_t nvec = n >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * i);
@@ -454,7 +471,7 @@ int launch_tanh_bwd(Ctx* ctx, const float* g_xhat, const float* xhat, int64_t n,
   RVAE_REQUIRE(n % 8 == 0, RVAE_ERR_UNSUPPORTED, "tanh_bwd: element count must be a multiple of 8");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  tanh_bwd_kernel<<<grid_for(ctx, n / 8, threads, 8), threads, 0, stream>>>(g_xhat, xhat, n, da_hi, da_lo);
+  RVAE_CUDA(launch_kernel(ctx, tanh_bwd_kernel, dim3(grid_for(ctx, n / 8, threads, 8)), dim3(threads), (size_t)0, stream, g_xhat, xhat, n, da_hi, da_lo));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -462,6 +479,8 @@ int launch_tanh_bwd(Ctx* ctx, const float* g_xhat, const float* xhat, int64_t n,
 // Standalone reparameterisation z = mu + eps * exp(logvar / 2) (rawvae/model.py:23-26) for the inference API.
 __global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
                                const float* __restrict__ eps, int64_t n, float* __restrict__ z) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
 }
@@ -471,7 +490,7 @@ int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps,
   RVAE_REQUIRE(mu && lv && eps && z, RVAE_ERR_INVALID, "reparam: null buffer");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  reparam_kernel<<<grid_for(ctx, n, threads, 8), threads, 0, stream>>>(mu, lv, eps, n, z);
+  RVAE_CUDA(launch_kernel(ctx, reparam_kernel, dim3(grid_for(ctx, n, threads, 8)), dim3(threads), (size_t)0, stream, mu, lv, eps, n, z));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -482,10 +501,12 @@ int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps,
 //   t = *step (already incremented); m = m + (1-b1)(g-m); v = b2 v + (1-b2) g^2;
 //   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // ------------------------------------------------------------------------------------------------
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
                             float weight_decay, float grad_scale, const float* __restrict__ step,
-                            __nv_bfloat16* __restrict__ sh_hi, __nv_bfloat16* __restrict__ sh_lo) {
+                            __nv_bfloat16* __restrict__ sh_hi, __nv_bfloat16* __restrict__ sh_lo, int zero_grads) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   // bias corrections in double, as torch computes them on the host (python floats)
   const double t = static_cast<double>(__ldg(step));
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
@@ -495,7 +516,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const int64_t nvec = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    // zero_grads: the next step's split-K weight gradients reduce-add into this buffer (saves 4 memsets / step)
+    if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pa = reinterpret_cast<float*>(&pp);
@@ -532,6 +555,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
       const float vj = beta2 * v[j] + (1.f - beta2) * gr * gr;
       const float pj = p[j] - step_size * (mj / (sqrtf(vj) / sqrt_bc2 + eps));
       m[j] = mj; v[j] = vj; p[j] = pj;
+      if (zero_grads) g[j] = 0.f;
       if (sh_hi) {
         const __nv_bfloat16 h = __float2bfloat16_rn(pj);
         sh_hi[j] = h;
@@ -541,9 +565,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-int launch_adam(Ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
-                __nv_bfloat16* shadow_lo, cudaStream_t stream) {
+                __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream) {
   RVAE_REQUIRE(p && g && m && v && step, RVAE_ERR_INVALID, "adam: null buffer");
   RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                  reinterpret_cast<uintptr_t>(v)) & 15) == 0,
@@ -552,19 +576,22 @@ int launch_adam(Ctx* ctx, float* p, const float* g, float* m, float* v, int64_t 
                RVAE_ERR_INVALID, "adam: shadow planes must be 8-byte aligned");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  adam_kernel<<<grid_for(ctx, (n + 3) / 4, threads, 8), threads, 0, stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step, shadow_hi, shadow_lo);
+  RVAE_CUDA(launch_kernel(ctx, adam_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream,
+                          p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step, shadow_hi, shadow_lo,
+                          zero_grads));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
 
 __global__ void step_inc_kernel(float* step) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1.0f;
 }
 
 int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream) {
   RVAE_REQUIRE(step, RVAE_ERR_INVALID, "step_inc: null step");
-  step_inc_kernel<<<1, 32, 0, stream>>>(step);
+  RVAE_CUDA(launch_kernel(ctx, step_inc_kernel, dim3(1), dim3(32), (size_t)0, stream, step));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }

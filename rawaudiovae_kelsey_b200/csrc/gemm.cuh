@@ -221,14 +221,15 @@ struct TeamOut {
   float* bias_s;   // 64 floats
   int team;
   bool issuer;
+  int debug;       // experiments: 4 = no TMA store, 16 = no team barriers
   __device__ __forceinline__ void acquire() {
     if (issuer) ptx::tma_store_wait_read<0>();
-    team_bar_sync(team);
+    if (!(debug & 16)) team_bar_sync(team);
   }
   __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, bool reduce) {
     ptx::fence_proxy_async_smem();
-    team_bar_sync(team);
-    if (issuer) {
+    if (!(debug & 16)) team_bar_sync(team);
+    if (issuer && !(debug & 4)) {
       if (reduce) ptx::tma_reduce_add_2d(tm, slot, c0, c1);
       else ptx::tma_store_2d(tm, slot, c0, c1);
       ptx::tma_store_commit();
@@ -284,6 +285,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous
+  // kernel of the stream; from here on we read what it wrote.
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   const int tiles = p.m_blocks * p.n_blocks;
   const int total_units = tiles * p.k_splits;
@@ -292,6 +297,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      bool slot_free = ptx::mbar_try_wait(&empty_bar[0], 1);
       for (int u = group_id; u < total_units; u += num_groups) {
         const int ks = u / tiles;
         const int tile = u - ks * tiles;
@@ -304,7 +310,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
           const CUtensorMap* tmA = &p.tmA[pass];
           const CUtensorMap* tmB = &p.tmB[pass];
           for (int kb = kb_begin; kb < kb_begin + kb_count; ++kb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_wait_probed(slot_free, &empty_bar[stage], phase ^ 1);
+            {  // probe the NEXT slot now: the probe's latency overlaps the TMA issue below
+              const uint32_t ns = (stage + 1 == kStages) ? 0u : stage + 1;
+              const uint32_t np = (stage + 1 == kStages) ? phase ^ 1u : phase;
+              slot_free = ptx::mbar_try_wait(&empty_bar[ns], np ^ 1);
+            }
             uint64_t* fb = &full_bar[stage];
             if (CG == 1 && (p.debug & 2)) {  // experiment: measure the MMA side alone (operands are stale smem)
               ptx::mbar_arrive(fb);
@@ -356,6 +367,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
     if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      bool data_ready = false;
       for (int u = group_id; u < total_units; u += num_groups) {
         const int ks = u / tiles;
         const int kb_begin = ks * p.kb_per_split;
@@ -365,7 +377,13 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int it = 0; it < iters; ++it) {
-          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::mbar_wait_probed(data_ready, &full_bar[stage], phase);
+          {  // probe the NEXT stage now: the MMA issue below hides the probe's latency, so the tensor pipe does not
+             // drain while this thread waits on a barrier that has long completed
+            const uint32_t ns = (stage + 1 == kStages) ? 0u : stage + 1;
+            const uint32_t np = (stage + 1 == kStages) ? phase ^ 1u : phase;
+            data_ready = ptx::mbar_try_wait(&full_bar[ns], np);
+          }
           ptx::tc_fence_after();
           if (CG == 1 && (p.debug & 1)) {  // experiment: measure the TMA side alone
             ptx::mbar_arrive(&empty_bar[stage]);
@@ -398,7 +416,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     const int team_tid = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the team
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const EpiArgs& e = p.epi;
-    TeamOut out{out_slots + team * kOutSlotBytes, bias_strips + team * 64, team, team_tid == 0};
+    TeamOut out{out_slots + team * kOutSlotBytes, bias_strips + team * 64, team, team_tid == 0, p.debug};
     const bool dual = e.out_lo != nullptr;
     float loss_local = 0.f;
     uint32_t as = 0, aphase = 0;
@@ -504,8 +522,13 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             __syncwarp();
             // 1) accumulator: both 32-column TMEM loads in flight
             uint32_t r[64];
-            ptx::tmem_ld_32x32(t_acc + sub * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-            ptx::tmem_ld_32x32(t_acc + sub * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            if (!(p.debug & 8)) {
+              ptx::tmem_ld_32x32(t_acc + sub * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+              ptx::tmem_ld_32x32(t_acc + sub * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) r[j] = 0x3f800000u + j;
+            }
             // 2) side inputs from global memory, issued before anything waits
             const size_t off = static_cast<size_t>(m) * e.ldo + n0;
             float side[64];
@@ -593,8 +616,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
               }
             }
             const int c_out = (EPI == EPI_DZ) ? stream * e.L + n0 : n0;
-            stage_bf16(out.slot, row, 0, v);
-            stage_bf16(out.slot, row, 4, v + 32);
+            if (!(p.debug & 32)) {
+              stage_bf16(out.slot, row, 0, v);
+              stage_bf16(out.slot, row, 4, v + 32);
+            } else if (v[0] == 12345.678f) {
+              out.slot[row] = 1;  // keep v live
+            }
             out.commit(&p.tmOutHi, c_out, m0, false);
             if (dual) {
               out.acquire();

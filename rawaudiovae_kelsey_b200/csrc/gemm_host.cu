@@ -267,8 +267,8 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
 }
 
 int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream) {
-  kVariants[g.variant].fn<<<g.grid, kGemmThreads, g.smem_bytes, stream>>>(g.params);
-  RVAE_CUDA(cudaGetLastError());
+  RVAE_CUDA(launch_kernel(ctx, kVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes, stream,
+                          g.params));
   ctx->launches++;
   return RVAE_OK;
 }

@@ -69,8 +69,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef RVAE_MBAR_TIMEOUT_CYCLES
 #define RVAE_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > RVAE_MBAR_TIMEOUT_CYCLES) {
@@ -80,6 +79,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;  // try_wait suspends in hardware: a second probe usually succeeds
+  mbar_wait_slow(bar, parity);
+}
+// finish a wait whose first probe (issued earlier, to overlap its latency with other work) returned `ready`
+__device__ __forceinline__ void mbar_wait_probed(bool ready, uint64_t* bar, uint32_t parity) {
+  if (!ready) mbar_wait(bar, parity);
+}
+
+// Programmatic dependent launch (PDL): let the next kernel of the stream start its prologue while this one runs /
+// wait until the previous kernel of the stream has completed and flushed its memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // TMA

@@ -101,5 +101,5 @@ class DataParallelTrainStep:
                 works += allreduce_buckets(buckets, self.group)   # overlaps with the next backward stage
         for w in works:
             w.wait()                                              # compute stream waits for NCCL's stream
-        plan.adam(g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), 1.0)
+        plan.adam(g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), 1.0, zero_grads=True)
         return slot[0]

@@ -166,12 +166,13 @@ class Plan:
         check(self.lib.rvae_plan_finish_loss(self.handle, kl_beta,
                                              loss_out.data_ptr() if loss_out is not None else None, self._stream()))
 
-    def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0) -> None:
-        check(self.lib.rvae_plan_adam(self.handle, lr, beta1, beta2, eps, weight_decay, grad_scale, self._stream()))
+    def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0, zero_grads=False) -> None:
+        check(self.lib.rvae_plan_adam(self.handle, lr, beta1, beta2, eps, weight_decay, grad_scale, int(zero_grads),
+                                      self._stream()))
 
     def train_step(self, kl_beta, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
-                   loss_out: Optional[torch.Tensor] = None) -> None:
-        check(self.lib.rvae_plan_train_step(self.handle, kl_beta, lr, beta1, beta2, eps, weight_decay,
+                   loss_out: Optional[torch.Tensor] = None, zero_grads: bool = True) -> None:
+        check(self.lib.rvae_plan_train_step(self.handle, kl_beta, lr, beta1, beta2, eps, weight_decay, int(zero_grads),
                                             loss_out.data_ptr() if loss_out is not None else None, self._stream()))
 
     def encode(self) -> None:

@@ -320,8 +320,12 @@ class FusedTrainStep:
         loss = step(data)            # 0-dim CUDA tensor (a slot of the ring); .item() only when you log
     """
 
-    def __init__(self, model: VAE, optimizer, kl_beta: float, ring: int = 64):
+    def __init__(self, model: VAE, optimizer, kl_beta: float, ring: int = 64, keep_grads: bool = False):
+        """keep_grads=False (default): the Adam kernel clears the flat gradient buffer after consuming it, exactly
+        what the reference's optimizer.zero_grad() does at the top of the next iteration; keep_grads=True leaves the
+        step's gradients in model._flat.grads for inspection (costs four memsets per step)."""
         self.model, self.optimizer, self.kl_beta = model, optimizer, float(kl_beta)
+        self.keep_grads = keep_grads
         self.ring = None
         self.ring_size = ring
         self.i = 0
@@ -338,5 +342,6 @@ class FusedTrainStep:
         if hasattr(self.optimizer, "bind_flat"):
             self.optimizer.bind_flat(model._flat)
         b1, b2 = g["betas"]
-        plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=slot)
+        plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=slot,
+                        zero_grads=not self.keep_grads)
         return slot

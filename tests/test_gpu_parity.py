@@ -160,7 +160,7 @@ def test_fused_train_step_matches_oracle(dev, small, precision, tol):
     kl_beta, lr = (float(v) for v in small["hyper"])
     model = make_model(small, "init", dev, precision)
     opt = Adam(model.parameters(), lr=lr)
-    step = FusedTrainStep(model, opt, kl_beta)
+    step = FusedTrainStep(model, opt, kl_beta, keep_grads=(precision == "fp32"))  # both gradient-buffer policies
     p64 = {k: torch.from_numpy(small["init/" + k]).double() for k in O.PARAM_NAMES}
     x = torch.from_numpy(small["x"])
     flat = model._flat
@@ -171,7 +171,10 @@ def test_fused_train_step_matches_oracle(dev, small, precision, tol):
         if s == 0:
             _, gref, _ = gated_reference(model, p64, x, eps, kl_beta, tol)
             for k in O.PARAM_NAMES:
-                assert rel(flat.view(flat.grads, k), gref[k]) < tol, k
+                if step.keep_grads:
+                    assert rel(flat.view(flat.grads, k), gref[k]) < tol, k
+                else:
+                    assert float(flat.view(flat.grads, k).abs().max()) == 0.0, k   # cleared by the Adam kernel
                 assert rel(flat.view(flat.exp_avg, k), 0.1 * gref[k]) < tol, k
     assert float(flat.step) == steps
     # bf16 shadow planes follow the fp32 master weights

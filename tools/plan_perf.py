@@ -1,0 +1,42 @@
+"""Per-GEMM device timing of one fused training step (default.ini dims, B=8192) through the plan (prepared GEMMs,
+CUDA events recorded in C around each launch) - no Python/ctypes/tensor-map-encode overhead in the numbers."""
+import os
+import sys
+import torch
+from rawvae.model import VAE, FusedTrainStep
+from rawaudiovae_kelsey_b200.optim import Adam
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+S, H, L = 1024, 2048, 256
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = VAE(S, H, L).to(dev)
+opt = Adam(model.parameters(), lr=1e-4)
+step = FusedTrainStep(model, opt, 1e-4)
+x = torch.rand(B, S, device=dev) * 2 - 1
+for _ in range(5):
+    step(x)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 50
+e0.record()
+for _ in range(n):
+    step(x)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+tag = " ".join(f"{k}={os.environ[k]}" for k in ("RVAE_CTA_GROUP", "RVAE_BLOCK_N", "RVAE_DEBUG") if k in os.environ)
+print(f"[{tag}] step {ms*1e3:.1f} us  -> {B/ms/1e3:.2f} M frames/s  ({30408704*B/ms/1e9:.0f} TFLOP/s whole step)")
+plan = model._plan_for(B)
+plan.enable_timing(True)
+for _ in range(20):
+    step(x)
+torch.cuda.synchronize()
+tm = plan.read_timing()
+tot = 0.0
+for k, (t, c, f) in tm.items():
+    if c:
+        us = 1e3 * t / c
+        tot += us
+        print(f"  {k:7s} {us:7.1f} us  {f/us/1e6:7.1f} TFLOP/s")
+print(f"  GEMM total {tot:.1f} us -> {30408704*B/tot/1e6:.0f} TFLOP/s chain; non-GEMM+gaps {ms*1e3-tot:.1f} us")
