@@ -69,7 +69,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef RVAE_MBAR_TIMEOUT_CYCLES
 #define RVAE_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > RVAE_MBAR_TIMEOUT_CYCLES) {
