@@ -269,8 +269,10 @@ def run_ours(args):
         for i in range(nroof):
             device_step(args.warmup + i)
         torch.cuda.synchronize()
-        tm = plan.read_timing()
+        tm_all = plan.read_timing()
         plan.enable_timing(False)
+        tm = {k: v for k, v in tm_all.items() if k in plan.GEMM_SLOTS}
+        aux = {k: 1e3 * v[0] / nroof for k, v in tm_all.items() if k in plan.AUX_SLOTS and v[1] > 0}
         gemm_ms = sum(v[0] for v in tm.values()) / nroof
         flops = sum(v[1] * v[2] for v in tm.values()) / nroof
         passes = 3 if args.precision == "fp32" else 1
@@ -283,6 +285,7 @@ def run_ours(args):
                     "tensor_passes": passes}
         breakdown = {k: {"us": 1e3 * v[0] / max(v[1], 1), "tflops": (v[2] / (v[0] / max(v[1], 1) * 1e-3) / 1e12)
                          if v[0] > 0 else None} for k, v in tm.items() if v[1] > 0}
+        breakdown["other_kernels_us_per_step"] = aux
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu_baseline = None

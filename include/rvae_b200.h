@@ -246,11 +246,15 @@ int rvae_plan_activation(const rvae_plan* plan, int which, void** hi, void** lo,
  * four weight matrices in backward-completion order; bucket 4 is the bias block. */
 int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count);
 
-/* Per-kernel device timing (bench.py roofline): when enabled, every tcgen05 GEMM launch of the plan is bracketed
- * by CUDA events on the launch stream. rvae_plan_read_timing synchronises those events and returns, per GEMM slot
- * g in [0, 12), the accumulated milliseconds, launch count and algorithmic FLOPs per launch (2*M*N*K); it then
- * clears the accumulators. Slot order: F1, F2, F3, F4(out), F4(linear), B4w, B4d, B3w, B3d, B2w, B2d, B1w. */
+/* Per-kernel device timing (bench.py roofline): when enabled, every launch of the plan is bracketed by CUDA events
+ * on the launch stream (this also disables the overlap of consecutive kernels, so use it for attribution, not for
+ * the headline number). rvae_plan_read_timing synchronises those events and returns, per slot, the accumulated
+ * milliseconds, launch count and - for the GEMM slots - algorithmic FLOPs per launch (2*M*N*K); it then clears the
+ * accumulators. Slots 0..11 are the tcgen05 GEMMs F1, F2, F3, F4(out), F4(linear), B4w, B4d, B3w, B3d, B2w, B2d, B1w;
+ * slots 12..17 the HBM-bound kernels: batch load (framing / split), eps, loss finalize, bias-gradient column sums,
+ * Adam, tanh backward. All three output arrays hold RVAE_NUM_TIMING_SLOTS entries. */
 #define RVAE_NUM_GEMM_SLOTS 12
+#define RVAE_NUM_TIMING_SLOTS 18
 int rvae_plan_enable_timing(rvae_plan* plan, int enable);
 int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double* flops_per_launch);
 

@@ -249,6 +249,8 @@ struct Planes {
 };
 
 enum GemmId { G_F1, G_F2, G_F3, G_F4_OUT, G_F4_LIN, G_B4W, G_B4D, G_B3W, G_B3D, G_B2W, G_B2D, G_B1W, G_COUNT };
+// timing slots of the non-GEMM kernels follow the GEMM slots
+enum AuxSlot { T_LOAD = G_COUNT, T_EPS, T_FINALIZE, T_COLSUM, T_ADAM, T_TANHBWD, T_COUNT };
 
 struct GemmSet {
   PreparedGemm g[G_COUNT];
@@ -279,9 +281,9 @@ struct rvae_plan {
   bool timing;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   std::vector<std::pair<int, int>> ev_used;  // (gemm id, pool index)
-  double t_ms[G_COUNT];
-  int64_t t_n[G_COUNT];
-  double t_flops[G_COUNT];
+  double t_ms[T_COUNT];
+  int64_t t_n[T_COUNT];
+  double t_flops[T_COUNT];
 };
 
 namespace {
@@ -443,6 +445,27 @@ int run_untimed(rvae_plan* p, GemmSet* gs, int id, cudaStream_t st, const EpiArg
   return gemm_run(&p->ctx->c, gs->g[id], st);
 }
 
+// Bracket a non-GEMM launch with timing events when timing is enabled.
+struct TimedScope {
+  rvae_plan* p; int slot; cudaStream_t st; int idx;
+  TimedScope(rvae_plan* p_, int slot_, cudaStream_t st_) : p(p_), slot(slot_), st(st_), idx(-1) {
+    if (!p->timing) return;
+    const size_t k = p->ev_used.size();
+    if (k >= p->ev_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      p->ev_pool.emplace_back(a, b);
+    }
+    idx = (int)k;
+    cudaEventRecord(p->ev_pool[k].first, st);
+  }
+  ~TimedScope() {
+    if (idx < 0) return;
+    cudaEventRecord(p->ev_pool[idx].second, st);
+    p->ev_used.emplace_back(slot, idx);
+  }
+};
+
 int run(rvae_plan* p, int id, cudaStream_t st, const EpiArgs* override_args = nullptr) {
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));
@@ -481,28 +504,28 @@ int backward_stage(rvae_plan* p, int stage, const EpiArgs* dz_override, cudaStre
       if (!p->grads_zeroed[0]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w4, 0, sizeof(float) * (size_t)S * H, st));
       p->grads_zeroed[0] = false;
       RVAE_CHECK(run(p, G_B4W, st));
-      RVAE_CHECK(launch_colsum(c, p->da4.hi, p->da4.lo, B, S, S, grads + ly.b4, 0, st));
+      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->da4.hi, p->da4.lo, B, S, S, grads + ly.b4, 0, st)); }
       return RVAE_OK;
     case 1:
       RVAE_CHECK(run(p, G_B4D, st));
       if (!p->grads_zeroed[1]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w3, 0, sizeof(float) * (size_t)H * L, st));
       p->grads_zeroed[1] = false;
       RVAE_CHECK(run(p, G_B3W, st));
-      RVAE_CHECK(launch_colsum(c, p->da3.hi, p->da3.lo, B, H, H, grads + ly.b3, 0, st));
+      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->da3.hi, p->da3.lo, B, H, H, grads + ly.b3, 0, st)); }
       return RVAE_OK;
     case 2:
       RVAE_CHECK(run(p, G_B3D, st, dz_override));
       if (!p->grads_zeroed[2]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w2, 0, sizeof(float) * (size_t)2 * L * H, st));
       p->grads_zeroed[2] = false;
       RVAE_CHECK(run(p, G_B2W, st));
-      RVAE_CHECK(launch_colsum(c, p->dml.hi, p->dml.lo, B, 2 * L, 2 * L, grads + ly.b2, 0, st));
+      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->dml.hi, p->dml.lo, B, 2 * L, 2 * L, grads + ly.b2, 0, st)); }
       return RVAE_OK;
     case 3:
       RVAE_CHECK(run(p, G_B2D, st));
       if (!p->grads_zeroed[3]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w1, 0, sizeof(float) * (size_t)H * S, st));
       p->grads_zeroed[3] = false;
       RVAE_CHECK(run(p, G_B1W, st));
-      RVAE_CHECK(launch_colsum(c, p->da1.hi, p->da1.lo, B, H, H, grads + ly.b1, 0, st));
+      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->da1.hi, p->da1.lo, B, H, H, grads + ly.b1, 0, st)); }
       return RVAE_OK;
     default:
       return set_error(RVAE_ERR_INVALID, "plan_backward: stage %d not in -1..3", stage);
@@ -527,7 +550,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
   p->timing = false;
   for (int i = 0; i < 4; ++i) p->grads_zeroed[i] = false;
-  for (int i = 0; i < G_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
+  for (int i = 0; i < T_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
   p->out_mu = p->out_lv = p->out_xhat = nullptr;
   memset(&p->bufs, 0, sizeof(p->bufs));
   p->ws_bytes = carve(p, nullptr);
@@ -552,7 +575,7 @@ int rvae_plan_enable_timing(rvae_plan* plan, int enable) {
 
 int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double* flops_per_launch) {
   RVAE_REQUIRE(plan && ms && launches && flops_per_launch, RVAE_ERR_INVALID, "plan_read_timing: null argument");
-  static_assert(G_COUNT == RVAE_NUM_GEMM_SLOTS, "slot count");
+  static_assert(G_COUNT == RVAE_NUM_GEMM_SLOTS && T_COUNT == RVAE_NUM_TIMING_SLOTS, "slot count");
   for (auto& u : plan->ev_used) {
     auto& e = plan->ev_pool[u.second];
     RVAE_CUDA(cudaEventSynchronize(e.second));
@@ -562,7 +585,7 @@ int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double*
     plan->t_n[u.first] += 1;
   }
   plan->ev_used.clear();
-  for (int i = 0; i < G_COUNT; ++i) {
+  for (int i = 0; i < T_COUNT; ++i) {
     ms[i] = (float)plan->t_ms[i];
     launches[i] = plan->t_n[i];
     flops_per_launch[i] = plan->t_flops[i];
@@ -609,6 +632,7 @@ int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, 
   plan->batch = row_offset + count;
   plan->have_eps = false;
   const size_t off = (size_t)row_offset * plan->S;
+  TimedScope ts(plan, T_LOAD, S_(stream));
   return launch_frame_gather(&plan->ctx->c, audio, audio_is_i16, n_samples, frame_idx, first_frame, count, hop,
                              plan->S, plan->x.hi + off, plan->x.lo ? plan->x.lo + off : nullptr, nullptr, S_(stream));
 }
@@ -620,6 +644,7 @@ int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* strea
                batch, plan->max_batch);
   plan->batch = batch;
   plan->have_eps = false;
+  TimedScope ts(plan, T_LOAD, S_(stream));
   return launch_split_bf16(&plan->ctx->c, x, (int64_t)batch * plan->S, plan->x.hi, plan->x.lo, S_(stream));
 }
 
@@ -635,6 +660,7 @@ int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream) {
 int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
   plan->have_eps = true;
+  TimedScope ts(plan, T_EPS, S_(stream));
   return launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset, S_(stream));
 }
 
@@ -706,7 +732,7 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
   RVAE_REQUIRE(g_xhat && xhat && g_mu && g_logvar, RVAE_ERR_INVALID, "plan_backward_external: null gradient");
   rvae_plan* p = plan;
   cudaStream_t st = S_(stream);
-  RVAE_CHECK(launch_tanh_bwd(&p->ctx->c, g_xhat, xhat, (int64_t)p->batch * p->S, p->da4.hi, p->da4.lo, st));
+  { TimedScope ts(p, T_TANHBWD, st); RVAE_CHECK(launch_tanh_bwd(&p->ctx->c, g_xhat, xhat, (int64_t)p->batch * p->S, p->da4.hi, p->da4.lo, st)); }
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));
   RVAE_CHECK(prepare(p, *gs, G_B3D));
@@ -720,6 +746,7 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
 int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
   const int64_t nb = plan->global_batch > 0 ? plan->global_batch : plan->batch;
+  TimedScope ts(plan, T_FINALIZE, S_(stream));
   return launch_loss_finalize(&plan->ctx->c, plan->loss_acc, nb, plan->S, plan->L, kl_beta, loss_out,
                               plan->bufs.step, S_(stream));
 }
@@ -732,6 +759,7 @@ int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float ep
                "plan_adam: grads / exp_avg / exp_avg_sq / step not bound");
   // zero_grads: the kernel clears the gradient buffer after consuming it (what optimizer.zero_grad() does at the top
   // of the reference loop, train.py:184), so the next step's split-K weight gradients can reduce-add without memsets
+  TimedScope ts(plan, T_ADAM, S_(stream));
   RVAE_CHECK(launch_adam(&plan->ctx->c, b.params, b.grads, b.exp_avg, b.exp_avg_sq, plan->lay.total, lr, beta1, beta2,
                          eps, weight_decay, grad_scale, b.step, BF(b.shadow_hi), BF(b.shadow_lo), zero_grads,
                          S_(stream)));

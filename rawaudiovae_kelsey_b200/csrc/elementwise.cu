@@ -507,12 +507,19 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
                             __nv_bfloat16* __restrict__ sh_hi, __nv_bfloat16* __restrict__ sh_lo, int zero_grads) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  // bias corrections in double, as torch computes them on the host (python floats)
-  const double t = static_cast<double>(__ldg(step));
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
-  const float sqrt_bc2 = static_cast<float>(sqrt(bc2));
+  // bias corrections in double, as torch computes them on the host (python floats); one thread per block does the
+  // fp64 pow()s and broadcasts the two scalars
+  __shared__ float s_consts[2];
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(__ldg(step));
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+    s_consts[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+    s_consts[1] = static_cast<float>(sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_consts[0];
+  const float sqrt_bc2 = s_consts[1];
   const int64_t nvec = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];

@@ -184,16 +184,18 @@ class Plan:
         self.token += 1
 
     GEMM_SLOTS = ("F1", "F2", "F3", "F4_out", "F4_lin", "B4w", "B4d", "B3w", "B3d", "B2w", "B2d", "B1w")
+    AUX_SLOTS = ("load", "eps", "finalize", "colsum", "adam", "tanh_bwd")
 
     def enable_timing(self, on: bool) -> None:
         check(self.lib.rvae_plan_enable_timing(self.handle, int(on)))
 
     def read_timing(self):
         """{slot: (total_ms, launches, flops_per_launch)} since the last read (synchronises the timing events)."""
-        n = len(self.GEMM_SLOTS)
+        names = self.GEMM_SLOTS + self.AUX_SLOTS
+        n = len(names)
         ms, cnt, fl = (C.c_float * n)(), (C.c_int64 * n)(), (C.c_double * n)()
         check(self.lib.rvae_plan_read_timing(self.handle, ms, cnt, fl))
-        return {k: (float(ms[i]), int(cnt[i]), float(fl[i])) for i, k in enumerate(self.GEMM_SLOTS)}
+        return {k: (float(ms[i]), int(cnt[i]), float(fl[i])) for i, k in enumerate(names)}
 
     ACTIVATIONS = ("x", "h1", "z", "h3", "da4", "da3", "d_ml", "da1")
 

@@ -33,10 +33,25 @@ for _ in range(20):
     step(x)
 torch.cuda.synchronize()
 tm = plan.read_timing()
-tot = 0.0
+tot, aux = 0.0, 0.0
 for k, (t, c, f) in tm.items():
-    if c:
-        us = 1e3 * t / c
+    if not c:
+        continue
+    us = 1e3 * t / 20          # per step
+    if f > 0:
         tot += us
-        print(f"  {k:7s} {us:7.1f} us  {f/us/1e6:7.1f} TFLOP/s")
-print(f"  GEMM total {tot:.1f} us -> {30408704*B/tot/1e6:.0f} TFLOP/s chain; non-GEMM+gaps {ms*1e3-tot:.1f} us")
+        print(f"  {k:8s} {us:7.1f} us  {f*c/20/us/1e6:7.1f} TFLOP/s")
+    else:
+        aux += us
+        print(f"  {k:8s} {us:7.1f} us  ({c//20} launches/step)")
+print(f"  GEMM total {tot:.1f} us -> {30408704*B/tot/1e6:.0f} TFLOP/s chain; other kernels {aux:.1f} us; "
+      f"untimed step {ms*1e3:.1f} us")
+# pure host cost of enqueueing a step (few enough launches not to fill the launch queue)
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(10):
+    step(x)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"  host enqueue {1e5*(t1-t0):.1f} us/step")
