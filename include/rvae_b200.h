@@ -134,21 +134,24 @@ int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, cons
 
 /* Decoder output + reconstruction loss + its gradient (model.py:30,39): xhat = tanh(h3 W4^T + b4) [M,S] (fp32,
  * optional); mse_acc[0] += sum((xhat-x)^2); da4 = grad_scale*(xhat-x)*(1-xhat^2) as bf16 planes (optional),
- * grad_scale = 2/(B*S). x is given as bf16 planes. */
+ * grad_scale = 2/(B*S). x is given as bf16 planes. bias_grad (optional, fp32 [S]) += column sums of da4 = db4. */
 int rvae_out_tanh_mse_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w4_hi, const void* w4_lo,
                           const float* b4, int M, int S, int K, const void* x_hi, const void* x_lo, int tanh_approx,
-                          float* xhat, void* da_hi, void* da_lo, float grad_scale, double* mse_acc, void* stream);
+                          float* xhat, void* da_hi, void* da_lo, float grad_scale, double* mse_acc, float* bias_grad,
+                          void* stream);
 
 /* dX = (dY W) * [mask > 0]: dY [M,Kd], W [Kd,N] row-major (the Linear weight [out=Kd, in=N]), mask bf16 [M,N]
- * (NULL = no mask). AddmmBackward dgrad + ReluBackward (threshold_backward) for fc4->h3 and fc21/fc22->h1. */
+ * (NULL = no mask). AddmmBackward dgrad + ReluBackward (threshold_backward) for fc4->h3 and fc21/fc22->h1.
+ * bias_grad (optional, fp32 [N]) += column sums of dX: the bias gradient of the layer that produced `mask`. */
 int rvae_dgrad_relu(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, int M,
-                    int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, void* stream);
+                    int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, float* bias_grad, void* stream);
 
 /* Latent backward: dz = da3 W3 (W3 [H,L]); d_ml[:, :L] = dz + g_mu; d_ml[:, L:] = dz*esh + g_logvar; d_ml is bf16
- * planes [M, 2L]. Backward of reparameterize (model.py:24-26) merged with the KL gradient. */
+ * planes [M, 2L]. Backward of reparameterize (model.py:24-26) merged with the KL gradient.
+ * bias_grad (optional, fp32 [2L]) += column sums of d_ml = [db21; db22]. */
 int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, const void* w3_hi, const void* w3_lo,
                       int M, int L, int H, const float* esh, const float* g_mu, const float* g_logvar, void* dml_hi,
-                      void* dml_lo, void* stream);
+                      void* dml_lo, float* bias_grad, void* stream);
 
 /* dW (+)= dY^T X: dY [B,M], X [B,N], dW fp32 [M,N]. accumulate = 0 overwrites (single split), 1 adds (red.add;
  * dW must hold the running sum, e.g. zeros). k_splits = 0 lets the library choose. AddmmBackward wgrad. */
@@ -219,8 +222,10 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
  * xhat = the forward's output. Runs tanh backward then all four stages. */
 int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const float* xhat, const float* g_mu,
                                 const float* g_logvar, void* stream);
-/* Backward stage s = 0..3 (fc4 | fc3 | fc21+fc22 | fc1 gradients complete after stage s - the allreduce buckets,
- * in backward-completion order); stage -1 runs all four. Gradients land in bufs.grads. */
+/* Backward stage s = 0..3 (fc4 | fc3 | fc21+fc22 | fc1 WEIGHT gradients complete after stage s - the allreduce
+ * buckets, in backward-completion order; the bias block is complete after stage 2); stage -1 runs all four.
+ * Within a stage the weight-gradient GEMM runs on an internal side stream concurrently with the dgrad GEMM and is
+ * joined back into `stream` before the call returns. Gradients land in bufs.grads. */
 int rvae_plan_backward(rvae_plan* plan, int stage, void* stream);
 /* loss -> *loss_out (device float, may be NULL), clears the loss sums, *step += 1. */
 int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream);

@@ -166,7 +166,8 @@ int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, cons
 
 int rvae_out_tanh_mse_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w4_hi, const void* w4_lo,
                           const float* b4, int M, int S, int K, const void* x_hi, const void* x_lo, int tanh_approx,
-                          float* xhat, void* da_hi, void* da_lo, float grad_scale, double* mse_acc, void* stream) {
+                          float* xhat, void* da_hi, void* da_lo, float grad_scale, double* mse_acc, float* bias_grad,
+                          void* stream) {
   CTX_OR_FAIL(ctx);
   RVAE_REQUIRE(b4 && x_hi, RVAE_ERR_INVALID, "out_tanh_mse_fwd: null buffer");
   GemmDesc d = desc_base(EPI_OUT, M, S, K);
@@ -175,24 +176,25 @@ int rvae_out_tanh_mse_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, con
   d.args.bias = b4; d.args.in0 = x_hi; d.args.in1 = x_lo; d.args.out_f32 = xhat;
   d.args.out_hi = BF(da_hi); d.args.out_lo = BF(da_lo);
   d.args.act = tanh_approx ? ACT_TANH_APPROX : ACT_TANH;
-  d.args.c0 = grad_scale; d.args.loss_acc = mse_acc; d.args.ldo = S;
+  d.args.c0 = grad_scale; d.args.loss_acc = mse_acc; d.args.ldo = S; d.args.colsum = bias_grad;
   return gemm_launch(&ctx->c, d, S_(stream));
 }
 
 int rvae_dgrad_relu(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, int M,
-                    int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, void* stream) {
+                    int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, float* bias_grad, void* stream) {
   CTX_OR_FAIL(ctx);
   RVAE_REQUIRE(dx_hi, RVAE_ERR_INVALID, "dgrad_relu: null output");
   GemmDesc d = desc_base(EPI_DRELU, M, N, Kd);
   d.A = op(dy_hi, dy_lo, MAJOR_K, Kd);
   d.B = op(w_hi, w_lo, MAJOR_MN, N);
   d.args.in0 = mask; d.args.out_hi = BF(dx_hi); d.args.out_lo = BF(dx_lo); d.args.ldo = N;
+  d.args.colsum = bias_grad;
   return gemm_launch(&ctx->c, d, S_(stream));
 }
 
 int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, const void* w3_hi, const void* w3_lo,
                       int M, int L, int H, const float* esh, const float* g_mu, const float* g_logvar, void* dml_hi,
-                      void* dml_lo, void* stream) {
+                      void* dml_lo, float* bias_grad, void* stream) {
   CTX_OR_FAIL(ctx);
   RVAE_REQUIRE(esh && g_mu && g_logvar && dml_hi, RVAE_ERR_INVALID, "dgrad_latent: null buffer");
   GemmDesc d = desc_base(EPI_DZ, M, L, H);
@@ -200,6 +202,7 @@ int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, con
   d.B = op(w3_hi, w3_lo, MAJOR_MN, L);
   d.args.in0 = esh; d.args.in1 = g_mu; d.args.in2 = g_logvar;
   d.args.out_hi = BF(dml_hi); d.args.out_lo = BF(dml_lo); d.args.ldo = 2 * L; d.args.L = L;
+  d.args.colsum = bias_grad;
   return gemm_launch(&ctx->c, d, S_(stream));
 }
 
@@ -274,7 +277,11 @@ struct rvae_plan {
   float *out_mu, *out_lv, *out_xhat;
   int batch;        // current batch
   int64_t global_batch;  // loss normalisation under data parallelism (0 = local batch)
-  bool grads_zeroed[4];  // weight-gradient bucket s already holds zeros (left so by the fused Adam kernel)
+  bool grads_zeroed[5];  // gradient bucket s (0..3 weights, 4 biases) already holds zeros (left so by the fused Adam)
+  // the weight-gradient GEMM of a backward stage runs on a side stream, concurrently with the stage's dgrad GEMM
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  bool two_streams;
   bool have_eps;
   std::map<int, GemmSet> sets;  // prepared GEMMs per batch size
   // optional per-GEMM timing
@@ -372,6 +379,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.args.out_hi = p->da4.hi; d.args.out_lo = p->da4.lo;
       d.args.act = bf16_mode ? ACT_TANH_APPROX : ACT_TANH;
       d.args.loss_acc = p->loss_acc; d.args.ldo = S;
+      d.args.colsum = grads ? grads + ly.b4 : nullptr;   // db4 = column sums of da4
       break;
     case G_F4_LIN:
       d.epi = EPI_LINEAR; d.M = B; d.N = S; d.K = H;
@@ -388,6 +396,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.epi = EPI_DRELU; d.M = B; d.N = H; d.K = S;
       d.A = opnd(p->da4, MAJOR_K, S); d.B = wopnd(p, ly.w4, MAJOR_MN, H);
       d.args.in0 = p->h3.hi; d.args.out_hi = p->da3.hi; d.args.out_lo = p->da3.lo; d.args.ldo = H;
+      d.args.colsum = grads + ly.b3;                     // db3 = column sums of da3
       break;
     case G_B3W:
       d.epi = EPI_WGRAD; d.M = H; d.N = L; d.K = B;
@@ -399,6 +408,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.A = opnd(p->da3, MAJOR_K, H); d.B = wopnd(p, ly.w3, MAJOR_MN, L);
       d.args.in0 = p->esh; d.args.in1 = p->gmu; d.args.in2 = p->glv;
       d.args.out_hi = p->dml.hi; d.args.out_lo = p->dml.lo; d.args.ldo = 2 * L; d.args.L = L;
+      d.args.colsum = grads + ly.b2;                     // [db21; db22] = column sums of [dmu | dlv]
       break;
     case G_B2W:
       d.epi = EPI_WGRAD; d.M = 2 * L; d.N = H; d.K = B;
@@ -409,6 +419,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.epi = EPI_DRELU; d.M = B; d.N = H; d.K = 2 * L;
       d.A = opnd(p->dml, MAJOR_K, 2 * L); d.B = wopnd(p, ly.w2, MAJOR_MN, H);
       d.args.in0 = p->h1.hi; d.args.out_hi = p->da1.hi; d.args.out_lo = p->da1.lo; d.args.ldo = H;
+      d.args.colsum = grads + ly.b1;                     // db1 = column sums of da1
       break;
     case G_B1W:
       d.epi = EPI_WGRAD; d.M = H; d.N = S; d.K = B;
@@ -494,42 +505,56 @@ int check_ready(const rvae_plan* p, bool need_batch) {
   return RVAE_OK;
 }
 
+// Bias gradients accumulate (atomicAdd) into the bias block from the epilogues that produce the pre-activation
+// gradients; make sure the block starts from zero.
+int ensure_bias_zeroed(rvae_plan* p, cudaStream_t st) {
+  if (p->grads_zeroed[4]) return RVAE_OK;
+  const rvae_layout& ly = p->lay;
+  RVAE_CUDA(cudaMemsetAsync(p->bufs.grads + ly.b1, 0, sizeof(float) * (size_t)(ly.total - ly.b1), st));
+  p->grads_zeroed[4] = true;
+  return RVAE_OK;
+}
+
+int ensure_side_stream(rvae_plan* p) {
+  if (p->side) return RVAE_OK;
+  RVAE_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  return RVAE_OK;
+}
+
+// Backward stage s: weight gradient of layer (4 - s) [side stream] || the dgrad GEMM that produces the next layer's
+// pre-activation gradient and, in its epilogue, that layer's bias gradient [main stream]; joined before returning,
+// so that after stage s gradient bucket s is complete on `st`. Both kernels are persistent and want every SM: run
+// concurrently, the CTAs of one fill the SMs the other leaves idle in its last partial wave.
+//   s=0: dW4 = da4^T h3        || da3 = (da4 W4) * [h3>0], db3
+//   s=1: dW3 = da3^T z         || d_ml = f(da3 W3),        db2
+//   s=2: dW2 = d_ml^T h1       || da1 = (d_ml W2) * [h1>0], db1
+//   s=3: dW1 = da1^T x
 int backward_stage(rvae_plan* p, int stage, const EpiArgs* dz_override, cudaStream_t st) {
-  Ctx* c = &p->ctx->c;
-  const int B = p->batch, S = p->S, H = p->H, L = p->L;
+  const int S = p->S, H = p->H, L = p->L;
   const rvae_layout& ly = p->lay;
   float* grads = p->bufs.grads;
-  switch (stage) {
-    case 0:
-      if (!p->grads_zeroed[0]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w4, 0, sizeof(float) * (size_t)S * H, st));
-      p->grads_zeroed[0] = false;
-      RVAE_CHECK(run(p, G_B4W, st));
-      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->da4.hi, p->da4.lo, B, S, S, grads + ly.b4, 0, st)); }
-      return RVAE_OK;
-    case 1:
-      RVAE_CHECK(run(p, G_B4D, st));
-      if (!p->grads_zeroed[1]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w3, 0, sizeof(float) * (size_t)H * L, st));
-      p->grads_zeroed[1] = false;
-      RVAE_CHECK(run(p, G_B3W, st));
-      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->da3.hi, p->da3.lo, B, H, H, grads + ly.b3, 0, st)); }
-      return RVAE_OK;
-    case 2:
-      RVAE_CHECK(run(p, G_B3D, st, dz_override));
-      if (!p->grads_zeroed[2]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w2, 0, sizeof(float) * (size_t)2 * L * H, st));
-      p->grads_zeroed[2] = false;
-      RVAE_CHECK(run(p, G_B2W, st));
-      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->dml.hi, p->dml.lo, B, 2 * L, 2 * L, grads + ly.b2, 0, st)); }
-      return RVAE_OK;
-    case 3:
-      RVAE_CHECK(run(p, G_B2D, st));
-      if (!p->grads_zeroed[3]) RVAE_CUDA(cudaMemsetAsync(grads + ly.w1, 0, sizeof(float) * (size_t)H * S, st));
-      p->grads_zeroed[3] = false;
-      RVAE_CHECK(run(p, G_B1W, st));
-      { TimedScope ts(p, T_COLSUM, st); RVAE_CHECK(launch_colsum(c, p->da1.hi, p->da1.lo, B, H, H, grads + ly.b1, 0, st)); }
-      return RVAE_OK;
-    default:
-      return set_error(RVAE_ERR_INVALID, "plan_backward: stage %d not in -1..3", stage);
+  static const int kWgrad[4] = {G_B4W, G_B3W, G_B2W, G_B1W};
+  static const int kDgrad[4] = {G_B4D, G_B3D, G_B2D, -1};
+  RVAE_REQUIRE(stage >= 0 && stage < 4, RVAE_ERR_INVALID, "plan_backward: stage %d not in -1..3", stage);
+  float* wptr[4] = {grads + ly.w4, grads + ly.w3, grads + ly.w2, grads + ly.w1};
+  const size_t wcount[4] = {(size_t)S * H, (size_t)H * L, (size_t)2 * L * H, (size_t)H * S};
+  if (!p->grads_zeroed[stage]) RVAE_CUDA(cudaMemsetAsync(wptr[stage], 0, sizeof(float) * wcount[stage], st));
+  p->grads_zeroed[stage] = false;
+  const bool fork = p->two_streams && kDgrad[stage] >= 0 && !p->timing;
+  if (fork) {
+    RVAE_CHECK(ensure_side_stream(p));
+    RVAE_CUDA(cudaEventRecord(p->ev_fork, st));
+    RVAE_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    RVAE_CHECK(run(p, kWgrad[stage], p->side));
+    RVAE_CUDA(cudaEventRecord(p->ev_join, p->side));
+  } else {
+    RVAE_CHECK(run(p, kWgrad[stage], st));
   }
+  if (kDgrad[stage] >= 0) RVAE_CHECK(run(p, kDgrad[stage], st, stage == 1 ? dz_override : nullptr));
+  if (fork) RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+  return RVAE_OK;
 }
 
 }  // namespace
@@ -549,7 +574,10 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
   p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
   p->timing = false;
-  for (int i = 0; i < 4; ++i) p->grads_zeroed[i] = false;
+  for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
+  p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
+  p->two_streams = true;
+  if (const char* e = getenv("RVAE_TWO_STREAMS")) p->two_streams = atoi(e) != 0;
   for (int i = 0; i < T_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
   p->out_mu = p->out_lv = p->out_xhat = nullptr;
   memset(&p->bufs, 0, sizeof(p->bufs));
@@ -563,6 +591,12 @@ void rvae_plan_destroy(rvae_plan* plan) {
   for (auto& e : plan->ev_pool) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
+  }
+  if (plan->side) {
+    cudaStreamSynchronize(plan->side);
+    cudaEventDestroy(plan->ev_fork);
+    cudaEventDestroy(plan->ev_join);
+    cudaStreamDestroy(plan->side);
   }
   delete plan;
 }
@@ -608,7 +642,7 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
   if (plan->precision == RVAE_PRECISION_BF16) plan->bufs.shadow_lo = nullptr;
   carve(plan, reinterpret_cast<uint8_t*>(b->workspace));
   plan->sets.clear();
-  for (int i = 0; i < 4; ++i) plan->grads_zeroed[i] = false;
+  for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = false;
   plan->bound = true;
   plan->batch = 0;
   return RVAE_OK;
@@ -701,6 +735,9 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
   }
   RVAE_CHECK(run(p, G_F3, st));
   if (fused_loss) {
+    RVAE_REQUIRE(p->bufs.grads, RVAE_ERR_STATE, "plan_forward(fused_loss): no grads buffer bound");
+    RVAE_CHECK(ensure_bias_zeroed(p, st));   // F4's epilogue accumulates db4, the backward epilogues db3, db2, db1
+    p->grads_zeroed[4] = false;              // ... so after this step the block is dirty again
     RVAE_CHECK(prepare(p, *gs, G_F4_OUT));
     EpiArgs a = gs->g[G_F4_OUT].params.epi;
     a.c0 = (float)(2.0 / BS);
@@ -732,14 +769,18 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
   RVAE_REQUIRE(g_xhat && xhat && g_mu && g_logvar, RVAE_ERR_INVALID, "plan_backward_external: null gradient");
   rvae_plan* p = plan;
   cudaStream_t st = S_(stream);
+  RVAE_CHECK(ensure_bias_zeroed(p, st));
+  p->grads_zeroed[4] = false;
   { TimedScope ts(p, T_TANHBWD, st); RVAE_CHECK(launch_tanh_bwd(&p->ctx->c, g_xhat, xhat, (int64_t)p->batch * p->S, p->da4.hi, p->da4.lo, st)); }
+  { TimedScope ts(p, T_COLSUM, st);
+    RVAE_CHECK(launch_colsum(&p->ctx->c, p->da4.hi, p->da4.lo, p->batch, p->S, p->S, p->bufs.grads + p->lay.b4, 1, st)); }
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));
   RVAE_CHECK(prepare(p, *gs, G_B3D));
   EpiArgs a = gs->g[G_B3D].params.epi;
   a.in1 = g_mu;
   a.in2 = g_logvar;
-  for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(p, s, s == 2 ? &a : nullptr, st));
+  for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(p, s, s == 1 ? &a : nullptr, st));
   return RVAE_OK;
 }
 
@@ -763,7 +804,7 @@ int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float ep
   RVAE_CHECK(launch_adam(&plan->ctx->c, b.params, b.grads, b.exp_avg, b.exp_avg_sq, plan->lay.total, lr, beta1, beta2,
                          eps, weight_decay, grad_scale, b.step, BF(b.shadow_hi), BF(b.shadow_lo), zero_grads,
                          S_(stream)));
-  for (int i = 0; i < 4; ++i) plan->grads_zeroed[i] = zero_grads != 0;
+  for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = zero_grads != 0;
   return RVAE_OK;
 }
 

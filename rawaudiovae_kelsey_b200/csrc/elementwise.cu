@@ -524,8 +524,6 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
-    // zero_grads: the next step's split-K weight gradients reduce-add into this buffer (saves 4 memsets / step)
-    if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* pa = reinterpret_cast<float*>(&pp);
@@ -544,6 +542,9 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    // zero_grads: the next step's split-K weight gradients reduce-add into this buffer (saves 4 memsets / step).
+    // Stored last: a store issued while the load of the same line is still in flight serialises the LSU.
+    if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sh_hi) {
       reinterpret_cast<uint2*>(sh_hi)[i] = make_uint2(pack2(pa[0], pa[1]), pack2(pa[2], pa[3]));
       if (sh_lo) {

@@ -51,6 +51,8 @@ enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_TANH_APPROX = 3 };
 //   DZ     : dz = acc; dmu = dz + in1[m,n]; dlv = dz*in0[m,n] + in2[m,n] (all f32 [M, L]);
 //            dmu -> out_hi[m, n], dlv -> out_hi[m, L + n] (ldo = 2L) [, out_lo likewise]
 //   WGRAD  : out_f32[m, n] (+)= acc   (red.add when accumulate != 0, plain store otherwise)
+//   OUT / DRELU / DZ additionally accumulate the column sums of what they emit into `colsum` (the bias gradient of
+//   the layer whose pre-activation gradient this is: db = sum_b da), so no separate reduction kernel is needed.
 struct EpiArgs {
   const float* bias;
   __nv_bfloat16* out_hi;
@@ -64,6 +66,7 @@ struct EpiArgs {
   float* aux1;
   float* aux2;
   double* loss_acc;
+  float* colsum;  // OUT / DRELU / DZ: colsum[c] += sum over rows of the bf16 stream's fp32 values (bias gradients)
   int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and of bf16 inputs in0/in1
   int act;   // LINEAR / OUT activation
   int L;     // HEAD / DZ latent width
@@ -96,7 +99,7 @@ struct GemmCfg {
   static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = kOutSlots * kOutSlotBytes;  // epilogue staging for TMA stores
-  static constexpr int kBarrierBytes = 256 + kEpiTeams * 64 * 4;  // mbarriers + TMEM slot + per-team bias strips
+  static constexpr int kBarrierBytes = 256 + kEpiTeams * 128 * 4;  // mbarriers + TMEM slot + per-team strips
   static constexpr int kBudget = 232448 - 1024 - kOutBytes - kBarrierBytes;  // 227 KB usable per CTA
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
@@ -214,11 +217,32 @@ __device__ __forceinline__ void stage_f32(uint8_t* slot, int r, const float* v) 
                             __float_as_uint(v[4 * i + 3])));
 }
 
+// Column sums of a [32 rows (lanes) x 64 columns] register tile: butterfly reduce-scatter over the lanes (62
+// shuffles); afterwards lane l holds the sums of columns 2l and 2l+1 in v[0], v[1]. Destroys v.
+__device__ __forceinline__ void warp_colsum64(float* v, int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = 32 >> step;          // values kept per lane after this step
+    const int mask = 16 >> step;
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < half) {
+        // keep columns [0, half) if the mask bit of this lane is clear, [half, 2*half) otherwise
+        const float send = upper ? v[j] : v[j + half];
+        const float keep = upper ? v[j + half] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    }
+  }
+}
+
 // One team's staging slot + bias strip. acquire(): the team's previous TMA store has finished reading the slot
 // (and, as a side effect of the barrier, the bias strip written before it is visible). commit(): hand the slot to TMA.
 struct TeamOut {
   uint8_t* slot;
   float* bias_s;   // 64 floats
+  float* csum_s;   // 64 floats: per-unit column sums, combined across the team's four warps
   int team;
   bool issuer;
   int debug;       // experiments: 4 = no TMA store, 16 = no team barriers
@@ -248,8 +272,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
   uint8_t* out_slots = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
-  float* bias_strips = reinterpret_cast<float*>(out_slots + Cfg::kOutBytes);  // kEpiTeams x 64 floats
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_slots + Cfg::kOutBytes + kEpiTeams * 64 * 4);
+  float* bias_strips = reinterpret_cast<float*>(out_slots + Cfg::kOutBytes);  // kEpiTeams x (64 bias + 64 colsum)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_slots + Cfg::kOutBytes + kEpiTeams * 128 * 4);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
@@ -416,7 +440,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     const int team_tid = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the team
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const EpiArgs& e = p.epi;
-    TeamOut out{out_slots + team * kOutSlotBytes, bias_strips + team * 64, team, team_tid == 0, p.debug};
+    TeamOut out{out_slots + team * kOutSlotBytes, bias_strips + team * 128, bias_strips + team * 128 + 64, team,
+                team_tid == 0, p.debug};
     const bool dual = e.out_lo != nullptr;
     float loss_local = 0.f;
     uint32_t as = 0, aphase = 0;
@@ -565,6 +590,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             if constexpr (EPI == EPI_LINEAR || EPI == EPI_OUT) {
               if (team_tid < 64) out.bias_s[team_tid] = e.bias ? __ldg(e.bias + n0 + team_tid) : 0.f;
             }
+            const bool do_colsum = (EPI == EPI_OUT || EPI == EPI_DRELU || EPI == EPI_DZ) && e.colsum != nullptr;
+            if (do_colsum && team_tid >= 64) out.csum_s[team_tid - 64] = 0.f;
             out.acquire();
             ptx::tmem_ld_wait();
             float v[64];
@@ -596,7 +623,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                 const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
                 const float d = xh - side[j];
                 if (row_ok) loss_local = fmaf(d, d, loss_local);
-                v[j] = e.c0 * d * (1.f - xh * xh);
+                v[j] = row_ok ? e.c0 * d * (1.f - xh * xh) : 0.f;
               }
             } else if constexpr (EPI == EPI_DZ) {
               if (stream == 0) {  // dmu = dz + g_mu
@@ -622,13 +649,21 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             } else if (v[0] == 12345.678f) {
               out.slot[row] = 1;  // keep v live
             }
-            out.commit(&p.tmOutHi, c_out, m0, false);
-            if (dual) {
+            if (dual) {  // residual plane (fp32 emulation): second pass through the same slot, before v is reduced
+              out.commit(&p.tmOutHi, c_out, m0, false);
               out.acquire();
               stage_bf16_residual(out.slot, row, 0, v);
               stage_bf16_residual(out.slot, row, 4, v + 32);
-              out.commit(&p.tmOutLo, c_out, m0, false);
             }
+            if (do_colsum) {
+              // bias gradient: column sums of this unit over the tile's 128 rows (rows >= M contribute zeros)
+              warp_colsum64(v, lane);
+              atomicAdd(out.csum_s + 2 * lane, v[0]);
+              atomicAdd(out.csum_s + 2 * lane + 1, v[1]);
+            }
+            out.commit(dual ? &p.tmOutLo : &p.tmOutHi, c_out, m0, false);
+            // (the barrier inside commit() ordered the four warps' smem atomics before this read)
+            if (do_colsum && team_tid < 64) atomicAdd(e.colsum + c_out + team_tid, out.csum_s[team_tid]);
           }
         }
         // ---- fp32 stream: LINEAR's fp32 copy / OUT's xhat: 32-column units

@@ -230,7 +230,7 @@ def encode_head_fwd(h, w2, b2, eps, *, kl_grad_scale: float = 0.0, want_lo=False
 
 
 def out_tanh_mse_fwd(h3, w4, b4, x, *, grad_scale: float, tanh_approx=False, want_xhat=True, want_da=True,
-                     want_lo=False, mse_acc=None):
+                     want_lo=False, mse_acc=None, bias_grad=None):
     lib = _lib.load()
     hh, hl = _planes(h3, "h3")
     wh, wl = _planes(w4, "w4")
@@ -245,11 +245,12 @@ def out_tanh_mse_fwd(h3, w4, b4, x, *, grad_scale: float, tanh_approx=False, wan
     da_lo = torch.empty_like(da_hi) if (want_da and want_lo) else None
     check(lib.rvae_out_tanh_mse_fwd(ctx(dev), hh, hl, wh, wl, _ptr(b4, torch.float32, "b4"), M, S, K, xh, xl,
                                     int(tanh_approx), _ptr(xhat), _ptr(da_hi), _ptr(da_lo), grad_scale,
-                                    _ptr(mse_acc, torch.float64, "mse_acc"), _stream()))
+                                    _ptr(mse_acc, torch.float64, "mse_acc"),
+                                    _ptr(bias_grad, torch.float32, "bias_grad"), _stream()))
     return xhat, (da_hi, da_lo)
 
 
-def dgrad_relu(dy, w, mask, *, want_lo=False):
+def dgrad_relu(dy, w, mask, *, want_lo=False, bias_grad=None):
     """dx = (dy @ w) * [mask > 0]; dy [M,Kd], w [Kd,N] (Linear weight, row-major), mask bf16 [M,N] or None."""
     lib = _lib.load()
     dh, dl = _planes(dy, "dy")
@@ -262,11 +263,11 @@ def dgrad_relu(dy, w, mask, *, want_lo=False):
     dx_hi = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
     dx_lo = torch.empty_like(dx_hi) if want_lo else None
     check(lib.rvae_dgrad_relu(ctx(dev), dh, dl, wh, wl, M, N, Kd, _ptr(mask, torch.bfloat16, "mask"), _ptr(dx_hi),
-                              _ptr(dx_lo), _stream()))
+                              _ptr(dx_lo), _ptr(bias_grad, torch.float32, "bias_grad"), _stream()))
     return dx_hi, dx_lo
 
 
-def dgrad_latent(da3, w3, esh, g_mu, g_lv, *, want_lo=False):
+def dgrad_latent(da3, w3, esh, g_mu, g_lv, *, want_lo=False, bias_grad=None):
     lib = _lib.load()
     dh, dl = _planes(da3, "da3")
     wh, wl = _planes(w3, "w3")
@@ -278,7 +279,8 @@ def dgrad_latent(da3, w3, esh, g_mu, g_lv, *, want_lo=False):
     hi = torch.empty((M, 2 * L), dtype=torch.bfloat16, device=dev)
     lo = torch.empty_like(hi) if want_lo else None
     check(lib.rvae_dgrad_latent(ctx(dev), dh, dl, wh, wl, M, L, H, _ptr(esh, torch.float32), _ptr(g_mu, torch.float32),
-                                _ptr(g_lv, torch.float32), _ptr(hi), _ptr(lo), _stream()))
+                                _ptr(g_lv, torch.float32), _ptr(hi), _ptr(lo),
+                                _ptr(bias_grad, torch.float32, "bias_grad"), _stream()))
     return hi, lo
 
 

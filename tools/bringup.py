@@ -70,28 +70,32 @@ def main(case):
             hb, wb, xb = bf(h), bf(w), bf(x)
             acc = torch.zeros(2, dtype=torch.float64, device=dev)
             c0 = 2.0 / (M * S)
-            xhat, (da, _) = ops.out_tanh_mse_fwd(hb, wb, b, xb, grad_scale=c0, mse_acc=acc[:1])
+            bg = torch.zeros(S, device=dev)
+            xhat, (da, _) = ops.out_tanh_mse_fwd(hb, wb, b, xb, grad_scale=c0, mse_acc=acc[:1], bias_grad=bg)
             torch.cuda.synchronize()
             r = torch.tanh(hb.double() @ wb.double().T + b.double())
             d = r - xb.double()
-            print("out", (M, S, K), "xhat", rel(xhat, r), "da", rel(da, c0 * d * (1 - r * r)), "mse", float(acc[0]), float((d * d).sum()), flush=True)
+            print("out", (M, S, K), "xhat", rel(xhat, r), "da", rel(da, c0 * d * (1 - r * r)), "mse", float(acc[0]), float((d * d).sum()),
+                  "db", rel(bg, (c0 * d * (1 - r * r)).sum(0)), flush=True)
     elif case == "dgrad":
         for (M, N, Kd) in [(8192, 2048, 1024), (8192, 2048, 512), (200, 128, 64)]:
             dy, w, h = g(M, Kd), g(Kd, N) * 0.05, g(M, N)
             dyb, wb, hb = bf(dy), bf(w), bf(h)
-            dx, _ = ops.dgrad_relu(dyb, wb, hb)
+            bg = torch.zeros(N, device=dev)
+            dx, _ = ops.dgrad_relu(dyb, wb, hb, bias_grad=bg)
             torch.cuda.synchronize()
             ref = (dyb.double() @ wb.double()) * (hb.double() > 0)
-            print("dgrad", (M, N, Kd), rel(dx, ref), flush=True)
+            print("dgrad", (M, N, Kd), rel(dx, ref), "db", rel(bg, ref.sum(0)), flush=True)
     elif case == "dz":
         for (M, L, H) in [(8192, 256, 2048), (200, 64, 128)]:
             da3, w3, esh, gmu, glv = g(M, H), g(H, L) * 0.05, g(M, L), g(M, L), g(M, L)
             db, wb = bf(da3), bf(w3)
-            dml, _ = ops.dgrad_latent(db, wb, esh, gmu, glv)
+            bg = torch.zeros(2 * L, device=dev)
+            dml, _ = ops.dgrad_latent(db, wb, esh, gmu, glv, bias_grad=bg)
             torch.cuda.synchronize()
             dz = db.double() @ wb.double()
             ref = torch.cat([dz + gmu.double(), dz * esh.double() + glv.double()], 1)
-            print("dz", (M, L, H), rel(dml, ref), flush=True)
+            print("dz", (M, L, H), rel(dml, ref), "db", rel(bg, ref.sum(0)), flush=True)
     elif case in ("wgrad", "wgrad_split"):
         for (B, M, N) in [(8192, 1024, 2048), (8192, 2048, 256), (8192, 512, 2048), (1000, 128, 64), (8192, 2048, 1024)]:
             dy, x = g(B, M), g(B, N)
