@@ -1,0 +1,64 @@
+"""torchrun --nproc-per-node W tools/dp_check.py : data-parallel step == single-process step on the concatenated batch.
+Every rank computes (a) the W-rank DataParallelTrainStep on its shard and (b) the single-process FusedTrainStep on the
+full global batch with identical weights / eps, and compares losses, updated weights and Adam moments."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from rawaudiovae_kelsey_b200 import dist as rdist
+from rawaudiovae_kelsey_b200.dataset import shard_bounds
+from rawaudiovae_kelsey_b200.optim import Adam
+from rawvae.model import VAE, FusedTrainStep
+
+rank, world, local = rdist.init_from_env("nccl")
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+S, H, L = 1024, 2048, 256
+B = int(os.environ.get("DP_BATCH", "1000"))      # global batch, deliberately not divisible into equal 128-row tiles
+torch.manual_seed(0)
+gen = torch.Generator().manual_seed(1)
+x = (torch.rand(B, S, generator=gen) * 2 - 1).to(dev)
+eps = torch.randn(3, B, L, generator=gen).to(dev)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+def make():
+    torch.manual_seed(0)
+    m = VAE(S, H, L).to(dev)
+    return m, Adam(m.parameters(), lr=1e-3)
+
+
+m_dp, o_dp = make()
+m_1, o_1 = make()
+step_dp = rdist.DataParallelTrainStep(m_dp, o_dp, 1e-4, global_batch=B)
+step_1 = FusedTrainStep(m_1, o_1, 1e-4)
+lo, hi = shard_bounds(B, rank, world)
+ok = True
+for s in range(3):
+    l_dp = step_dp(x[lo:hi].contiguous(), eps=eps[s, lo:hi].contiguous())
+    l_1 = step_1(x, eps=eps[s])
+    torch.cuda.synchronize()
+    dl = abs(float(l_dp) - float(l_1)) / float(l_1)
+    dw = rel(m_dp._flat.params, m_1._flat.params)
+    dm = rel(m_dp._flat.exp_avg, m_1._flat.exp_avg)
+    if rank == 0:
+        print(f"step {s}: loss dp {float(l_dp):.6f} single {float(l_1):.6f} rel {dl:.2e}; weights rel {dw:.2e}; exp_avg rel {dm:.2e}")
+    ok &= dl < 1e-4 and dw < 1e-4 and dm < 2e-2
+# replicas stay bit-identical to each other
+ref = m_dp._flat.params.clone()
+dist.broadcast(ref, src=0)
+same = bool(torch.equal(ref, m_dp._flat.params))
+flag = torch.tensor([int(ok and same)], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("replicas identical:", same, "| DP CHECK", "PASSED" if int(flag) else "FAILED")
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if int(flag) else 1)
