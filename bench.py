@@ -266,8 +266,9 @@ def run_ours(args):
         plan = model._plan_for(BATCH)
         plan.enable_timing(True)
         nroof = min(args.steps, 20)
+        local_step = FusedTrainStep(model, opt, KL_BETA)   # no collectives: only rank 0 runs this attribution pass
         for i in range(nroof):
-            device_step(args.warmup + i)
+            local_step(FrameBatch(audio, BATCH, HOP, S, frame_idx=frame_idx[args.warmup + i]))
         torch.cuda.synchronize()
         tm_all = plan.read_timing()
         plan.enable_timing(False)
