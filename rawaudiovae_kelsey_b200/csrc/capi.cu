@@ -43,6 +43,11 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   RVAE_REQUIRE(ctx != nullptr, RVAE_ERR_INVALID, "ctx_create: out of host memory");
   ctx->c.device = device;
   ctx->c.num_sms = prop.multiProcessorCount;
+  // RVAE_NUM_SMS caps the SMs the persistent GEMM grids occupy (leaves the rest to concurrent kernels, e.g. NCCL)
+  if (const char* e = getenv("RVAE_NUM_SMS")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= prop.multiProcessorCount) ctx->c.num_sms = v & ~1;
+  }
   ctx->c.launches = 0;
   ctx->c.force_block_n = 0;
   if (const char* e = getenv("RVAE_BLOCK_N")) ctx->c.force_block_n = atoi(e);

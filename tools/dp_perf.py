@@ -1,0 +1,30 @@
+"""torchrun --nproc-per-node W tools/dp_perf.py : DP step timing + host enqueue cost."""
+import os, sys, time
+from pathlib import Path
+import torch, torch.distributed as dist
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from rawaudiovae_kelsey_b200 import dist as rdist
+from rawaudiovae_kelsey_b200.optim import Adam
+from rawvae.model import VAE, FusedTrainStep
+rank, world, local = rdist.init_from_env("nccl")
+dev = torch.device("cuda", local); torch.cuda.set_device(dev)
+S, H, L, B = 1024, 2048, 256, 8192
+torch.manual_seed(0)
+model = VAE(S, H, L).to(dev); opt = Adam(model.parameters(), lr=1e-4)
+step = rdist.DataParallelTrainStep(model, opt, 1e-4, global_batch=B * world, reduce_loss=os.environ.get("DP_REDUCE_LOSS", "1") == "1")
+x = torch.rand(B, S, device=dev) * 2 - 1
+for _ in range(10): step(x)
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 100
+e0.record()
+for _ in range(n): step(x)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+torch.cuda.synchronize(); dist.barrier()
+t0 = time.perf_counter()
+for _ in range(10): step(x)
+t1 = time.perf_counter(); torch.cuda.synchronize()
+if rank == 0:
+    print(f"W={world} NUM_SMS={os.environ.get('RVAE_NUM_SMS','all')} step {ms*1e3:.1f} us -> {B*world/ms/1e3:.2f} M frames/s; host enqueue {(t1-t0)*1e5:.1f} us/step")
+dist.barrier(); dist.destroy_process_group()
