@@ -177,9 +177,9 @@ def run_ours(args):
     model.eps_seed = 1 + rank
     opt = Adam(model.parameters(), lr=LR)
     if world > 1:
-        step_fn = rdist.DataParallelTrainStep(model, opt, KL_BETA, global_batch=BATCH * world)
+        step_fn = rdist.DataParallelTrainStep(model, opt, KL_BETA, global_batch=BATCH * world, graph=args.graph)
     else:
-        step_fn = FusedTrainStep(model, opt, KL_BETA)
+        step_fn = FusedTrainStep(model, opt, KL_BETA, graph=args.graph)
 
     # synthetic corpus resident in HBM (every rank holds it; rank r draws its own frame indices)
     corpus = synth_corpus(args.files, args.seconds)
@@ -308,7 +308,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "hop": HOP,
-                       "precision": args.precision, "parallelism": f"dp{world}",
+                       "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
                        "l2": "per-step working set ~330 MB (activations + weights + moments) exceeds the 126 MB L2; "
                              "a different random 8192-frame gather from a %.0f MB corpus every step" % (corpus.nbytes / 1e6),
                        "corpus": f"{args.files} files x {args.seconds:.0f} s, 0.5*sin+0.05*noise, rng 1234"},
@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--files", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every step eagerly (no CUDA graph)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

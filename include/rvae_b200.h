@@ -200,9 +200,11 @@ int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, 
 /* ... or an fp32 [batch, S] matrix already on the device. */
 int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* stream);
 
-/* eps for the loaded batch: copy from a caller tensor (parity runs) or generate with Philox (seed, offset). */
+/* eps for the loaded batch: copy from a caller tensor (parity runs) or generate with Philox (seed, offset).
+ * add_step != 0 adds the device-side Adam step counter (*bufs.step) to the offset inside the kernel, so a captured
+ * CUDA graph draws fresh noise on every replay. */
 int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream);
-int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, void* stream);
+int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_step, void* stream);
 
 /* Redirect the fp32 results of the next forward calls into caller tensors ([batch,L], [batch,L], [batch,S]);
  * NULL = keep them in the workspace. Used by the autograd wrapper so returned tensors outlive the step. */
@@ -227,8 +229,9 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
  * Within a stage the weight-gradient GEMM runs on an internal side stream concurrently with the dgrad GEMM and is
  * joined back into `stream` before the call returns. Gradients land in bufs.grads. */
 int rvae_plan_backward(rvae_plan* plan, int stage, void* stream);
-/* loss -> *loss_out (device float, may be NULL), clears the loss sums, *step += 1. */
-int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream);
+/* loss -> loss_out[t mod ring_size] (device floats, may be NULL; t = *step before the call), clears the loss sums,
+ * *step += 1. ring_size = 1 writes *loss_out. The value is the mean loss over this rank's frames. */
+int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, int ring_size, void* stream);
 /* Adam over the flat buffers (+ shadow refresh). grad_scale rescales the gradients (1 for SUM all-reduced,
  * globally normalised gradients). zero_grads != 0: the kernel also clears bufs.grads after consuming it - the
  * optimizer.zero_grad() of the next iteration (train.py:184) - which lets the next backward skip its memsets. */
@@ -236,7 +239,7 @@ int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float ep
                    float grad_scale, int zero_grads, void* stream);
 /* forward + finish_loss + backward(-1) + adam in one call (single-GPU training step). */
 int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, int zero_grads, float* loss_out, void* stream);
+                         float weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream);
 
 /* Device pointers into the workspace for the current batch (valid after forward): fp32 [batch, ...]. */
 const float* rvae_plan_mu(const rvae_plan* plan);

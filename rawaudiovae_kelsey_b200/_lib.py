@@ -66,15 +66,15 @@ SIGNATURES = {
     "rvae_plan_load_frames": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, c_int, P]),
     "rvae_plan_load_batch": (c_int, [P, P, c_int, P]),
     "rvae_plan_set_eps": (c_int, [P, P, P]),
-    "rvae_plan_gen_eps": (c_int, [P, c_uint64, c_uint64, P]),
+    "rvae_plan_gen_eps": (c_int, [P, c_uint64, c_uint64, c_int, P]),
     "rvae_plan_set_outputs": (c_int, [P, P, P, P]),
     "rvae_plan_set_global_batch": (c_int, [P, c_int64]),
     "rvae_plan_forward": (c_int, [P, c_float, c_int, c_int, P]),
     "rvae_plan_backward": (c_int, [P, c_int, P]),
     "rvae_plan_backward_external": (c_int, [P, P, P, P, P, P]),
-    "rvae_plan_finish_loss": (c_int, [P, c_float, P, P]),
+    "rvae_plan_finish_loss": (c_int, [P, c_float, P, c_int, P]),
     "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
-    "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, P]),
+    "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, c_int, P]),
     "rvae_plan_mu": (P, [P]),
     "rvae_plan_logvar": (P, [P]),
     "rvae_plan_xhat": (P, [P]),

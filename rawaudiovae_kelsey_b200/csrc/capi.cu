@@ -80,7 +80,7 @@ int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S
 }
 int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
   CTX_OR_FAIL(ctx);
-  return launch_randn(&ctx->c, out, n, seed, offset, S_(stream));
+  return launch_randn(&ctx->c, out, n, seed, offset, nullptr, S_(stream));
 }
 int rvae_split_bf16(rvae_ctx* ctx, const float* src, int64_t n, void* hi, void* lo, void* stream) {
   CTX_OR_FAIL(ctx);
@@ -648,6 +648,7 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
   carve(plan, reinterpret_cast<uint8_t*>(b->workspace));
   plan->sets.clear();
   for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = false;
+  if (plan->two_streams) RVAE_CHECK(ensure_side_stream(plan));
   plan->bound = true;
   plan->batch = 0;
   return RVAE_OK;
@@ -696,11 +697,13 @@ int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream) {
   return RVAE_OK;
 }
 
-int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, void* stream) {
+int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_step, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
+  RVAE_REQUIRE(!add_step || plan->bufs.step, RVAE_ERR_STATE, "plan_gen_eps(add_step): no step counter bound");
   plan->have_eps = true;
   TimedScope ts(plan, T_EPS, S_(stream));
-  return launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset, S_(stream));
+  return launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset,
+                      add_step ? plan->bufs.step : nullptr, S_(stream));
 }
 
 int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat) {
@@ -789,11 +792,13 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
   return RVAE_OK;
 }
 
-int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, void* stream) {
+int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, int ring_size, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
-  const int64_t nb = plan->global_batch > 0 ? plan->global_batch : plan->batch;
+  RVAE_REQUIRE(ring_size >= 1, RVAE_ERR_INVALID, "plan_finish_loss: ring_size %d", ring_size);
+  // The reported loss is the mean over THIS rank's frames (under data parallelism: an unbiased estimate of the
+  // global mean that needs no collective); the gradients use the global-batch normalisation set on the plan.
   TimedScope ts(plan, T_FINALIZE, S_(stream));
-  return launch_loss_finalize(&plan->ctx->c, plan->loss_acc, nb, plan->S, plan->L, kl_beta, loss_out,
+  return launch_loss_finalize(&plan->ctx->c, plan->loss_acc, plan->batch, plan->S, plan->L, kl_beta, loss_out, ring_size,
                               plan->bufs.step, S_(stream));
 }
 
@@ -814,9 +819,9 @@ int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float ep
 }
 
 int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, int zero_grads, float* loss_out, void* stream) {
+                         float weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream) {
   RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, stream));
-  RVAE_CHECK(rvae_plan_finish_loss(plan, kl_beta, loss_out, stream));
+  RVAE_CHECK(rvae_plan_finish_loss(plan, kl_beta, loss_out, ring_size, stream));
   RVAE_CHECK(rvae_plan_backward(plan, -1, stream));
   return rvae_plan_adam(plan, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, stream);
 }

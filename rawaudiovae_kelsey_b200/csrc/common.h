@@ -109,7 +109,8 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
                         __nv_bfloat16* out_lo, float* out_f32, cudaStream_t stream);
 int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
                        cudaStream_t stream);
-int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t stream);
+int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, const float* offset_src,
+                 cudaStream_t stream);
 int launch_split_bf16(Ctx* ctx, const float* src, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
                       cudaStream_t stream);
 int launch_colsum(Ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t M, int N, int ld, float* out,
@@ -123,8 +124,8 @@ int launch_tanh_bwd(Ctx* ctx, const float* g_xhat, const float* xhat, int64_t n,
                     __nv_bfloat16* da_lo, cudaStream_t stream);
 int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps, int64_t n, float* z,
                    cudaStream_t stream);
-int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, float* step,
-                         cudaStream_t stream);
+int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
+                         float* step, cudaStream_t stream);
 int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
                 __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream);

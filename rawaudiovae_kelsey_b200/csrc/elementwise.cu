@@ -184,9 +184,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
   }
 }
 
-__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
+                             const float* __restrict__ offset_src) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
+  // offset_src: a device-side counter (the Adam step) added to the offset, so that a CUDA graph replays fresh noise
+  if (offset_src) offset += static_cast<uint64_t>(__ldg(offset_src));
   const int64_t nvec = (n + 3) >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(offset),
@@ -197,9 +200,9 @@ __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, 
     for (int h = 0; h < 2; ++h) {
       const float u1 = (static_cast<float>(c[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
       const float u2 = (static_cast<float>(c[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-      const float r = sqrtf(-2.0f * logf(u1));
+      const float r = sqrtf(-2.0f * __logf(u1));
       float s, co;
-      sincospif(2.0f * u2, &s, &co);
+      __sincosf(6.283185307179586f * u2, &s, &co);
       z[2 * h] = r * co;
       z[2 * h + 1] = r * s;
     }
@@ -212,11 +215,12 @@ __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, 
   }
 }
 
-int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t stream) {
+int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, const float* offset_src,
+                 cudaStream_t stream) {
   RVAE_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, RVAE_ERR_INVALID, "randn: bad output buffer");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset));
+  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset, offset_src));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -364,24 +368,28 @@ __global__ void loss_fwd_kernel(const float* __restrict__ xhat, const float* __r
 }
 
 __global__ void loss_finalize_kernel(double* __restrict__ acc, double inv_rec, double kl_scale,
-                                     float* __restrict__ loss_out, float* __restrict__ step) {
+                                     float* __restrict__ loss_out, int ring_size, float* __restrict__ step) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const double loss = acc[0] * inv_rec + kl_scale * acc[1];
-    if (loss_out) *loss_out = static_cast<float>(loss);
+    // ring_size > 1: slot = (step count before this step) mod ring_size, so a replayed CUDA graph still lands every
+    // step's loss in its own slot without the host passing a new pointer
+    const int slot = (ring_size > 1 && step) ? static_cast<int>(static_cast<long long>(*step) % ring_size) : 0;
+    if (loss_out) loss_out[slot] = static_cast<float>(loss);
     acc[0] = 0.0;
     acc[1] = 0.0;
     if (step) *step += 1.0f;
   }
 }
 
-int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, float* step,
-                         cudaStream_t stream) {
+int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
+                         float* step, cudaStream_t stream) {
   RVAE_REQUIRE(acc, RVAE_ERR_INVALID, "loss_finalize: null accumulator");
   const double inv_rec = 1.0 / (static_cast<double>(B) * S);
   const double kl_scale = -0.5 * static_cast<double>(beta) / (static_cast<double>(B) * L);
-  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, acc, inv_rec, kl_scale, loss_out, step));
+  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, acc, inv_rec, kl_scale,
+                          loss_out, ring_size, step));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -395,7 +403,7 @@ int launch_loss_fwd(Ctx* ctx, const float* xhat, const float* x, const float* mu
   const int grid = grid_for(ctx, B * S / 4, threads, 4);
   RVAE_CUDA(launch_kernel(ctx, loss_fwd_kernel, dim3(grid), dim3(threads), (size_t)0, stream, xhat, x, mu, lv, B * S, B * L, acc));
   RVAE_LAUNCH_CHECK(ctx);
-  return launch_loss_finalize(ctx, acc, B, S, L, beta, loss_out, nullptr, stream);
+  return launch_loss_finalize(ctx, acc, B, S, L, beta, loss_out, 1, nullptr, stream);
 }
 
 // d loss / d xhat, mu, logvar scaled by the upstream gradient (a device scalar; nullptr = 1).

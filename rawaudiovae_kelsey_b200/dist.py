@@ -20,6 +20,8 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from .model import _StepBase
+
 
 def init_from_env(backend: Optional[str] = None) -> tuple:
     """Initialise torch.distributed from torchrun's environment. Returns (rank, world, local_rank)."""
@@ -55,45 +57,32 @@ def broadcast_parameters(flat_params: torch.Tensor, group=None, src: int = 0) ->
     dist.broadcast(flat_params, src=src, group=group)
 
 
-class DataParallelTrainStep:
+class DataParallelTrainStep(_StepBase):
     """FusedTrainStep for W ranks: forward (+fused loss) -> 4 backward stages, each followed by the asynchronous
-    all-reduce of the bucket it completed -> Adam. `data` is this rank's shard of the global batch."""
+    all-reduce of the bucket it completed -> Adam. `data` is this rank's shard of the global batch.
+
+    The returned loss is the mean over THIS rank's frames (an unbiased estimate of the global mean that needs no
+    collective); reduce_loss=True additionally averages it over the ranks (exact for equal shards).
+    graph=True captures the whole step, NCCL collectives included, into one CUDA graph per input signature."""
 
     def __init__(self, model, optimizer, kl_beta: float, global_batch: Optional[int] = None, group=None,
-                 ring: int = 64, reduce_loss: bool = True):
-        self.model, self.optimizer, self.kl_beta = model, optimizer, float(kl_beta)
+                 ring: int = 64, reduce_loss: bool = False, graph: bool = False):
+        super().__init__(model, optimizer, kl_beta, ring, graph)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.global_batch = global_batch
-        self.ring, self.ring_size, self.i = None, ring, 0
         self.reduce_loss = reduce_loss
         self._synced = False
 
-    def __call__(self, data, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
-        model = self.model
-        plan = model._load(data)
-        flat = model._flat
-        if not self._synced and self.world > 1:
-            broadcast_parameters(flat.params, self.group)
-            flat.sync_shadow()
-            self._synced = True
-        model._set_eps(plan, eps)
-        if self.ring is None:
-            self.ring = torch.zeros(self.ring_size, dtype=torch.float32, device=flat.device)
-        slot = self.ring[self.i % self.ring_size:self.i % self.ring_size + 1]
-        self.i += 1
+    def _enqueue(self, plan):
+        flat = self.model._flat
         gb = self.global_batch if self.global_batch is not None else plan.batch * self.world
         plan.set_global_batch(gb if self.world > 1 else 0)
-        if hasattr(self.optimizer, "bind_flat"):
-            self.optimizer.bind_flat(flat)
         g = self.optimizer.param_groups[0]
         b1, b2 = g["betas"]
-
         plan.forward(self.kl_beta, fused_loss=True, want_xhat=False)
-        plan.finish_loss(self.kl_beta, slot)
+        plan.finish_loss(self.kl_beta, self.ring, self.ring_size)
         works = []
-        if self.world > 1 and self.reduce_loss:
-            works += allreduce_buckets([slot], self.group)        # partial losses sum to the global loss
         for s in range(4):
             plan.backward(s)
             if self.world > 1:
@@ -102,4 +91,15 @@ class DataParallelTrainStep:
         for w in works:
             w.wait()                                              # compute stream waits for NCCL's stream
         plan.adam(g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), 1.0, zero_grads=True)
-        return slot[0]
+
+    def __call__(self, data, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        flat = self._prepare()
+        if not self._synced and self.world > 1:
+            broadcast_parameters(flat.params, self.group)
+            flat.sync_shadow()
+            self._synced = True
+        slot = self._run(data, eps)
+        if self.reduce_loss and self.world > 1:
+            dist.all_reduce(slot, op=dist.ReduceOp.SUM, group=self.group)
+            slot.div_(self.world)
+        return slot

@@ -141,8 +141,8 @@ class Plan:
             raise _lib.RvaeError(f"eps has {eps.numel()} elements, expected {self.batch}x{self.flat.L}")
         check(self.lib.rvae_plan_set_eps(self.handle, eps.data_ptr(), self._stream()))
 
-    def gen_eps(self, seed: int, offset: int) -> None:
-        check(self.lib.rvae_plan_gen_eps(self.handle, seed, offset, self._stream()))
+    def gen_eps(self, seed: int, offset: int, add_step: bool = False) -> None:
+        check(self.lib.rvae_plan_gen_eps(self.handle, seed, offset, int(add_step), self._stream()))
 
     def set_outputs(self, mu=None, logvar=None, xhat=None) -> None:
         p = lambda t: t.data_ptr() if t is not None else None
@@ -162,18 +162,20 @@ class Plan:
         check(self.lib.rvae_plan_backward_external(self.handle, g_xhat.data_ptr(), xhat.data_ptr(), g_mu.data_ptr(),
                                                    g_logvar.data_ptr(), self._stream()))
 
-    def finish_loss(self, kl_beta: float, loss_out: Optional[torch.Tensor]) -> None:
+    def finish_loss(self, kl_beta: float, loss_out: Optional[torch.Tensor], ring_size: int = 1) -> None:
         check(self.lib.rvae_plan_finish_loss(self.handle, kl_beta,
-                                             loss_out.data_ptr() if loss_out is not None else None, self._stream()))
+                                             loss_out.data_ptr() if loss_out is not None else None, ring_size,
+                                             self._stream()))
 
     def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0, zero_grads=False) -> None:
         check(self.lib.rvae_plan_adam(self.handle, lr, beta1, beta2, eps, weight_decay, grad_scale, int(zero_grads),
                                       self._stream()))
 
     def train_step(self, kl_beta, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
-                   loss_out: Optional[torch.Tensor] = None, zero_grads: bool = True) -> None:
+                   loss_out: Optional[torch.Tensor] = None, ring_size: int = 1, zero_grads: bool = True) -> None:
         check(self.lib.rvae_plan_train_step(self.handle, kl_beta, lr, beta1, beta2, eps, weight_decay, int(zero_grads),
-                                            loss_out.data_ptr() if loss_out is not None else None, self._stream()))
+                                            loss_out.data_ptr() if loss_out is not None else None, ring_size,
+                                            self._stream()))
 
     def encode(self) -> None:
         check(self.lib.rvae_plan_encode(self.handle, self._stream()))

@@ -311,37 +311,135 @@ def loss_function(recon_x, x, mu, logvar, kl_beta, segment_length):
     return _LossFunction.apply(c(recon_x), c(x), c(mu), c(logvar), float(kl_beta))
 
 
-class FusedTrainStep:
+class _StepBase:
+    """Shared machinery of FusedTrainStep / dist.DataParallelTrainStep: the device-side loss ring and the CUDA-graph
+    cache. A step is enqueued by `self._enqueue(plan)` (subclass); with graph=True the enqueue is captured once per
+    input signature (after `graph_warmup` eager steps) and replayed, so the host cost of a step drops from ~20
+    kernel launches to one graph launch. Replays stay correct because everything that changes from step to step is
+    read from device memory: frame indices from a static index buffer, the Philox offset and the loss-ring slot
+    from the optimizer's step counter."""
+
+    def __init__(self, model, optimizer, kl_beta, ring, graph, graph_warmup=3):
+        self.model, self.optimizer, self.kl_beta = model, optimizer, float(kl_beta)
+        self.ring_size = int(ring)
+        self.ring = None
+        self.i = None            # host mirror of the device step counter (slot = i % ring_size)
+        self.graph = bool(graph)
+        self.graph_warmup = graph_warmup
+        self._graphs = {}        # key -> dict(graph, static buffers, plan)
+        self._seen = {}          # key -> eager calls so far
+
+    # -- helpers
+    def _prepare(self):
+        model = self.model
+        flat = model._ensure_flat()
+        if self.ring is None:
+            self.ring = torch.zeros(self.ring_size, dtype=torch.float32, device=flat.device)
+        if self.i is None:
+            self.i = int(flat.step.item())          # one sync, first call only (resumed optimizers start at t0 > 0)
+        if hasattr(self.optimizer, "bind_flat"):
+            self.optimizer.bind_flat(flat)
+        return flat
+
+    def _slot(self):
+        return self.ring[self.i % self.ring_size]
+
+    def _eps(self, plan, eps):
+        model = self.model
+        if eps is not None:
+            plan.set_eps(eps)
+        elif model.eps_source == "torch":
+            plan.set_eps(torch.randn((plan.batch, model.latent_dim), device=model._flat.device))
+        else:
+            seed = model.eps_seed if model.eps_seed is not None else torch.initial_seed()
+            plan.gen_eps(int(seed) & 0xFFFFFFFFFFFFFFFF, 0, add_step=True)   # offset = device step counter
+
+    def _graph_key(self, data):
+        """Input signature for graph reuse, or None when the input cannot be served by a replay."""
+        if isinstance(data, FrameBatch):
+            return ("frames", data.audio.data_ptr(), data.n_frames, data.hop, data.segment_length)
+        if isinstance(data, torch.Tensor) and data.is_cuda:
+            return ("tensor", data.numel())
+        return None
+
+    def _load_static(self, key, data, st):
+        """Refresh the static input buffers of a captured graph from this call's input."""
+        if key[0] == "frames":
+            if data.frame_idx is not None:
+                st["idx"].copy_(data.frame_idx)
+            else:
+                torch.add(st["arange"], data.first_frame, out=st["idx"])
+        else:
+            st["x"].copy_(data.reshape(st["x"].shape))
+
+    def _run(self, data, eps):
+        flat = self._prepare()
+        model = self.model
+        key = self._graph_key(data) if (self.graph and eps is None and model.eps_source == "philox") else None
+        if key is not None and key in self._graphs:
+            st = self._graphs[key]
+            self._load_static(key, data, st)
+            st["graph"].replay()
+            st["plan"].token += 1
+        elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
+            self._capture(key, data)
+        else:
+            if key is not None:
+                self._seen[key] = self._seen.get(key, 0) + 1
+            plan = model._load(data)
+            self._eps(plan, eps)
+            self._enqueue(plan)
+        slot = self._slot()
+        self.i += 1
+        return slot
+
+    def _capture(self, key, data):
+        model = self.model
+        dev = model._flat.device
+        st = {}
+        if key[0] == "frames":
+            st["idx"] = torch.empty(data.n_frames, dtype=torch.int64, device=dev)
+            st["arange"] = torch.arange(data.n_frames, dtype=torch.int64, device=dev)
+            static_in = FrameBatch(data.audio, data.n_frames, data.hop, data.segment_length, frame_idx=st["idx"])
+        else:
+            st["x"] = torch.empty((data.numel() // model.segment_length, model.segment_length), dtype=torch.float32,
+                                  device=dev)
+            static_in = st["x"]
+        self._load_static(key, data, st)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            plan = model._load(static_in)
+            self._eps(plan, None)
+            self._enqueue(plan)
+        st["graph"], st["plan"] = g, plan
+        self._graphs[key] = st
+        g.replay()   # capture does not execute: this replay performs the step of the current call
+
+
+class FusedTrainStep(_StepBase):
     """zero_grad + forward + loss + backward + Adam (train_iterable.py:200-210) as ONE C call: every kernel of the
     step is enqueued by rvae_plan_train_step, the loss gradients are produced by the forward epilogues, and the
     loss lands in a device-side ring so the host never has to synchronise per step.
 
         step = FusedTrainStep(model, optimizer, kl_beta)
         loss = step(data)            # 0-dim CUDA tensor (a slot of the ring); .item() only when you log
-    """
 
-    def __init__(self, model: VAE, optimizer, kl_beta: float, ring: int = 64, keep_grads: bool = False):
-        """keep_grads=False (default): the Adam kernel clears the flat gradient buffer after consuming it, exactly
-        what the reference's optimizer.zero_grad() does at the top of the next iteration; keep_grads=True leaves the
-        step's gradients in model._flat.grads for inspection (costs four memsets per step)."""
-        self.model, self.optimizer, self.kl_beta = model, optimizer, float(kl_beta)
+    keep_grads=False (default): the Adam kernel clears the flat gradient buffer after consuming it, exactly what the
+    reference's optimizer.zero_grad() does at the top of the next iteration; keep_grads=True leaves the step's
+    gradients in model._flat.grads for inspection (costs memsets per step).
+    graph=True: replay a captured CUDA graph of the step (see _StepBase)."""
+
+    def __init__(self, model: VAE, optimizer, kl_beta: float, ring: int = 64, keep_grads: bool = False,
+                 graph: bool = False):
+        super().__init__(model, optimizer, kl_beta, ring, graph)
         self.keep_grads = keep_grads
-        self.ring = None
-        self.ring_size = ring
-        self.i = 0
+
+    def _enqueue(self, plan):
+        g = self.optimizer.param_groups[0]
+        b1, b2 = g["betas"]
+        plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=self.ring,
+                        ring_size=self.ring_size, zero_grads=not self.keep_grads)
 
     def __call__(self, data, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
-        model = self.model
-        plan = model._load(data)
-        model._set_eps(plan, eps)
-        if self.ring is None:
-            self.ring = torch.zeros(self.ring_size, dtype=torch.float32, device=model._flat.device)
-        slot = self.ring[self.i % self.ring_size]
-        self.i += 1
-        g = self.optimizer.param_groups[0]
-        if hasattr(self.optimizer, "bind_flat"):
-            self.optimizer.bind_flat(model._flat)
-        b1, b2 = g["betas"]
-        plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=slot,
-                        zero_grads=not self.keep_grads)
-        return slot
+        return self._run(data, eps)

@@ -194,10 +194,12 @@ def run_epoch_trainer(argv=None):
 
     model = VAE(segment_length, n_units, latent_dim, precision=_precision(config)).to(device)
     optimizer = Adam(model.parameters(), lr=learning_rate)
+    use_graph = config['training'].getboolean('cuda_graph', fallback=True)
+    ring = max(64, log_interval)
     if world > 1:
-        step = rdist.DataParallelTrainStep(model, optimizer, kl_beta)
+        step = rdist.DataParallelTrainStep(model, optimizer, kl_beta, ring=ring, graph=use_graph)
     else:
-        step = FusedTrainStep(model, optimizer, kl_beta)
+        step = FusedTrainStep(model, optimizer, kl_beta, ring=ring, graph=use_graph)
 
     train_loss_prev = 1000000
     best_loss = 1000000
@@ -339,10 +341,13 @@ def run_stream_trainer(argv=None):
 
         model = VAE(segment_length, n_units, latent_dim, precision=_precision(config)).to(device)
         optimizer = Adam(model.parameters(), lr=learning_rate)
+        use_graph = config['training'].getboolean('cuda_graph', fallback=True)
+        ring = max(64, log_interval)
         if world > 1:
-            step = rdist.DataParallelTrainStep(model, optimizer, kl_beta, global_batch=batch_size)
+            step = rdist.DataParallelTrainStep(model, optimizer, kl_beta, global_batch=batch_size, ring=ring,
+                                               graph=use_graph)
         else:
-            step = FusedTrainStep(model, optimizer, kl_beta)
+            step = FusedTrainStep(model, optimizer, kl_beta, ring=ring, graph=use_graph)
 
         train_loss_prev = 1000000
         best_loss = 1000000

@@ -37,7 +37,7 @@ def make():
 
 m_dp, o_dp = make()
 m_1, o_1 = make()
-step_dp = rdist.DataParallelTrainStep(m_dp, o_dp, 1e-4, global_batch=B)
+step_dp = rdist.DataParallelTrainStep(m_dp, o_dp, 1e-4, global_batch=B, reduce_loss=True)
 step_1 = FusedTrainStep(m_1, o_1, 1e-4)
 lo, hi = shard_bounds(B, rank, world)
 ok = True

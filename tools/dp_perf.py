@@ -11,7 +11,7 @@ dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 S, H, L, B = 1024, 2048, 256, 8192
 torch.manual_seed(0)
 model = VAE(S, H, L).to(dev); opt = Adam(model.parameters(), lr=1e-4)
-step = rdist.DataParallelTrainStep(model, opt, 1e-4, global_batch=B * world, reduce_loss=os.environ.get("DP_REDUCE_LOSS", "1") == "1")
+step = rdist.DataParallelTrainStep(model, opt, 1e-4, global_batch=B * world, graph=os.environ.get("DP_GRAPH", "1") == "1")
 x = torch.rand(B, S, device=dev) * 2 - 1
 for _ in range(10): step(x)
 torch.cuda.synchronize(); dist.barrier()

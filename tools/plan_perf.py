@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = VAE(S, H, L).to(dev)
 opt = Adam(model.parameters(), lr=1e-4)
-step = FusedTrainStep(model, opt, 1e-4)
+step = FusedTrainStep(model, opt, 1e-4, graph=os.environ.get('STEP_GRAPH', '0') == '1')
 x = torch.rand(B, S, device=dev) * 2 - 1
 for _ in range(5):
     step(x)
