@@ -44,7 +44,7 @@ for k, (t, c, f) in tm.items():
     else:
         aux += us
         print(f"  {k:8s} {us:7.1f} us  ({c//20} launches/step)")
-print(f"  GEMM total {tot:.1f} us -> {30408704*B/tot/1e6:.0f} TFLOP/s chain; other kernels {aux:.1f} us; "
+print(f"  GEMM total {tot:.1f} us -> {30408704*B/max(tot,1e-9)/1e6:.0f} TFLOP/s chain; other kernels {aux:.1f} us; "
       f"untimed step {ms*1e3:.1f} us")
 # pure host cost of enqueueing a step (few enough launches not to fill the launch queue)
 import time
