@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RVAE_ABI_VERSION 1
+#define RVAE_ABI_VERSION 2
 
 typedef struct rvae_ctx rvae_ctx;   /* per-device context (SM count, launch counter) */
 typedef struct rvae_plan rvae_plan; /* a bound training / inference step for fixed shapes and buffers */
@@ -124,13 +124,11 @@ int rvae_linear_act_fwd(rvae_ctx* ctx, const void* x_hi, const void* x_lo, const
                         void* stream);
 
 /* Encoder head + reparameterisation + KL (model.py:21,23-26,45): W2 = [fc21.weight; fc22.weight] stacked [2L,K],
- * b2 = [fc21.bias; fc22.bias] [2L]; mu, logvar fp32 [M,L]; z = mu + eps*exp(logvar/2) as bf16 planes.
- * Optional extras for the backward pass: esh = eps*sigma/2, g_mu = kl_grad_scale*mu,
- * g_logvar = kl_grad_scale*(exp(logvar)-1)/2 (all fp32 [M,L]); kl_acc[0] += sum(1+logvar-mu^2-exp(logvar)). */
+ * b2 = [fc21.bias; fc22.bias] [2L]; mu, logvar fp32 [M,L]; eps fp32 [M,L] (NULL = 0);
+ * z = mu + eps*exp(logvar/2) as bf16 planes (optional); kl_acc[0] += sum(1+logvar-mu^2-exp(logvar)) (optional). */
 int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w2_hi, const void* w2_lo,
                          const float* b2, int M, int L, int K, const float* eps, float* mu, float* logvar,
-                         void* z_hi, void* z_lo, float* esh, float* g_mu, float* g_logvar, float kl_grad_scale,
-                         double* kl_acc, void* stream);
+                         void* z_hi, void* z_lo, double* kl_acc, void* stream);
 
 /* Decoder output + reconstruction loss + its gradient (model.py:30,39): xhat = tanh(h3 W4^T + b4) [M,S] (fp32,
  * optional); mse_acc[0] += sum((xhat-x)^2); da4 = grad_scale*(xhat-x)*(1-xhat^2) as bf16 planes (optional),
@@ -146,12 +144,16 @@ int rvae_out_tanh_mse_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, con
 int rvae_dgrad_relu(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, int M,
                     int N, int Kd, const void* mask, void* dx_hi, void* dx_lo, float* bias_grad, void* stream);
 
-/* Latent backward: dz = da3 W3 (W3 [H,L]); d_ml[:, :L] = dz + g_mu; d_ml[:, L:] = dz*esh + g_logvar; d_ml is bf16
- * planes [M, 2L]. Backward of reparameterize (model.py:24-26) merged with the KL gradient.
+/* Latent backward: dz = da3 W3 (W3 [H,L]; split-K tcgen05 GEMM reduce-added into dz_scratch, fp32 [M,L]), then
+ *   sigma = exp(logvar/2);  d_ml[:, :L] = dz + g_mu;  d_ml[:, L:] = dz*eps*sigma/2 + g_logvar   (bf16 planes [M, 2L])
+ * with g_mu = kl_grad_scale*mu, g_logvar = kl_grad_scale*(sigma^2-1)/2 (the KL gradient, kl_grad_scale = beta/(B L))
+ * when g_mu_ext / g_logvar_ext are NULL, else those external upstream gradients (mu may then be NULL).
+ * Backward of reparameterize (model.py:24-26) merged with the KL gradient (model.py:45).
  * bias_grad (optional, fp32 [2L]) += column sums of d_ml = [db21; db22]. */
 int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, const void* w3_hi, const void* w3_lo,
-                      int M, int L, int H, const float* esh, const float* g_mu, const float* g_logvar, void* dml_hi,
-                      void* dml_lo, float* bias_grad, void* stream);
+                      int M, int L, int H, const float* eps, const float* logvar, const float* mu,
+                      const float* g_mu_ext, const float* g_logvar_ext, float kl_grad_scale, float* dz_scratch,
+                      void* dml_hi, void* dml_lo, float* bias_grad, void* stream);
 
 /* dW (+)= dY^T X: dY [B,M], X [B,N], dW fp32 [M,N]. accumulate = 0 overwrites (single split), 1 adds (red.add;
  * dW must hold the running sum, e.g. zeros). k_splits = 0 lets the library choose. AddmmBackward wgrad. */
@@ -221,9 +223,9 @@ int rvae_plan_set_global_batch(rvae_plan* plan, int64_t global_batch);
  * (+ what an external backward needs). want_xhat: materialise xhat fp32 (always done when fused_loss = 0). */
 int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_xhat, void* stream);
 /* Backward from external upstream gradients (autograd path): g_xhat [batch,S], g_mu, g_logvar [batch,L] fp32,
- * xhat = the forward's output. Runs tanh backward then all four stages. */
+ * xhat, logvar = the forward's outputs. Runs tanh backward then all four stages. */
 int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const float* xhat, const float* g_mu,
-                                const float* g_logvar, void* stream);
+                                const float* g_logvar, const float* logvar, void* stream);
 /* Backward stage s = 0..3 (fc4 | fc3 | fc21+fc22 | fc1 WEIGHT gradients complete after stage s - the allreduce
  * buckets, in backward-completion order; the bias block is complete after stage 2); stage -1 runs all four.
  * Within a stage the weight-gradient GEMM runs on an internal side stream concurrently with the dgrad GEMM and is
@@ -259,12 +261,22 @@ int rvae_plan_bucket(const rvae_plan* plan, int s, float** ptr, int64_t* count);
  * the headline number). rvae_plan_read_timing synchronises those events and returns, per slot, the accumulated
  * milliseconds, launch count and - for the GEMM slots - algorithmic FLOPs per launch (2*M*N*K); it then clears the
  * accumulators. Slots 0..11 are the tcgen05 GEMMs F1, F2, F3, F4(out), F4(linear), B4w, B4d, B3w, B3d, B2w, B2d, B1w;
- * slots 12..17 the HBM-bound kernels: batch load (framing / split), eps, loss finalize, bias-gradient column sums,
- * Adam, tanh backward. All three output arrays hold RVAE_NUM_TIMING_SLOTS entries. */
+ * slots 12..18 the HBM-bound kernels: batch load (framing / split), eps, loss finalize, bias-gradient column sums,
+ * Adam, tanh backward, latent backward. All three output arrays hold RVAE_NUM_TIMING_SLOTS entries. */
 #define RVAE_NUM_GEMM_SLOTS 12
-#define RVAE_NUM_TIMING_SLOTS 18
+#define RVAE_NUM_TIMING_SLOTS 19
 int rvae_plan_enable_timing(rvae_plan* plan, int enable);
 int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double* flops_per_launch);
+
+/* Debug / profiling aid: every tcgen05 GEMM prepared through `ctx` after this call writes a per-CTA, per-tile
+ * timeline (clock64 stamps of the TMA-producer, MMA-issuer and epilogue roles; layout in csrc/gemm.cuh, "Timeline
+ * trace") into `buf` (device memory, RVAE_TRACE_WORDS_PER_CTA * grid 64-bit words). NULL switches tracing off.
+ * Costs a few stores per tile; never enabled on the training path. */
+#define RVAE_TRACE_HEADER_WORDS 16
+#define RVAE_TRACE_TILES 24
+#define RVAE_TRACE_EVENTS 16
+#define RVAE_TRACE_WORDS_PER_CTA (RVAE_TRACE_HEADER_WORDS + RVAE_TRACE_TILES * RVAE_TRACE_EVENTS)
+int rvae_debug_set_trace(rvae_ctx* ctx, void* buf);
 
 /* Inference: decode latents z (fp32 [batch, L]) -> xhat fp32 [batch, S] (model.py:28-30). */
 int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out, void* stream);

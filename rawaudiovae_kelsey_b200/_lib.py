@@ -52,10 +52,10 @@ SIGNATURES = {
     "rvae_adam_step": (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P,
                                P]),
     "rvae_linear_act_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
-    "rvae_encode_head_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_float, P, P]),
+    "rvae_encode_head_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "rvae_out_tanh_mse_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, c_int, P, P, P, c_float, P, P, P]),
     "rvae_dgrad_relu": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
-    "rvae_dgrad_latent": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "rvae_dgrad_latent": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P]),
     "rvae_wgrad": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, c_int, c_int, P]),
     "rvae_param_layout": (c_int, [c_int, c_int, c_int, C.POINTER(Layout)]),
     "rvae_plan_create": (c_int, [P, c_int, c_int, c_int, c_int, c_int, C.POINTER(P)]),
@@ -71,7 +71,7 @@ SIGNATURES = {
     "rvae_plan_set_global_batch": (c_int, [P, c_int64]),
     "rvae_plan_forward": (c_int, [P, c_float, c_int, c_int, P]),
     "rvae_plan_backward": (c_int, [P, c_int, P]),
-    "rvae_plan_backward_external": (c_int, [P, P, P, P, P, P]),
+    "rvae_plan_backward_external": (c_int, [P, P, P, P, P, P, P]),
     "rvae_plan_finish_loss": (c_int, [P, c_float, P, c_int, P]),
     "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, c_int, P]),
@@ -83,6 +83,7 @@ SIGNATURES = {
     "rvae_plan_bucket": (c_int, [P, c_int, C.POINTER(P), C.POINTER(c_int64)]),
     "rvae_plan_enable_timing": (c_int, [P, c_int]),
     "rvae_plan_read_timing": (c_int, [P, P, P, P]),
+    "rvae_debug_set_trace": (c_int, [P, P]),
     "rvae_plan_decode": (c_int, [P, P, c_int, P, P]),
     "rvae_plan_encode": (c_int, [P, P]),
 }
@@ -111,8 +112,8 @@ def load(build_if_missing: bool = True):
             fn.restype = res
             fn.argtypes = args
         got = lib.rvae_abi_version()
-        if got != 1:
-            raise RvaeError(f"librvae_b200 ABI version {got}, expected 1")
+        if got != 2:
+            raise RvaeError(f"librvae_b200 ABI version {got}, expected 2")
         _LIB = lib
     return _LIB
 

@@ -49,6 +49,7 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
     if (v >= 2 && v <= prop.multiProcessorCount) ctx->c.num_sms = v & ~1;
   }
   ctx->c.launches = 0;
+  ctx->c.trace = nullptr;
   ctx->c.force_block_n = 0;
   if (const char* e = getenv("RVAE_BLOCK_N")) ctx->c.force_block_n = atoi(e);
   ctx->c.force_cta_group = 0;
@@ -65,6 +66,15 @@ int rvae_ctx_num_sms(const rvae_ctx* ctx) { return ctx ? ctx->c.num_sms : 0; }
 uint64_t rvae_ctx_launch_count(const rvae_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
 #define CTX_OR_FAIL(ctx) RVAE_REQUIRE((ctx) != nullptr, RVAE_ERR_INVALID, "null rvae_ctx")
+
+int rvae_debug_set_trace(rvae_ctx* ctx, void* buf) {
+  CTX_OR_FAIL(ctx);
+  static_assert(RVAE_TRACE_WORDS_PER_CTA == kTraceCtaWords && RVAE_TRACE_HEADER_WORDS == kTraceHeader &&
+                    RVAE_TRACE_TILES == kTraceTiles && RVAE_TRACE_EVENTS == kTraceEvents,
+                "trace layout");
+  ctx->c.trace = reinterpret_cast<unsigned long long*>(buf);
+  return RVAE_OK;
+}
 
 int rvae_frame_gather(rvae_ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples,
                       const int64_t* frame_idx, int64_t first_frame, int64_t n_frames, int hop, int S, void* out_hi,
@@ -154,8 +164,7 @@ int rvae_linear_act_fwd(rvae_ctx* ctx, const void* x_hi, const void* x_lo, const
 
 int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, const void* w2_hi, const void* w2_lo,
                          const float* b2, int M, int L, int K, const float* eps, float* mu, float* logvar, void* z_hi,
-                         void* z_lo, float* esh, float* g_mu, float* g_logvar, float kl_grad_scale, double* kl_acc,
-                         void* stream) {
+                         void* z_lo, double* kl_acc, void* stream) {
   CTX_OR_FAIL(ctx);
   RVAE_REQUIRE(b2 && mu && logvar, RVAE_ERR_INVALID, "encode_head_fwd: null buffer");
   GemmDesc d = desc_base(EPI_HEAD, M, 2 * L, K);
@@ -164,8 +173,7 @@ int rvae_encode_head_fwd(rvae_ctx* ctx, const void* h_hi, const void* h_lo, cons
   d.B = op(w2_hi, w2_lo, MAJOR_K, K);
   d.args.bias = b2; d.args.in0 = eps; d.args.out_f32 = mu; d.args.out_f32_b = logvar;
   d.args.out_hi = BF(z_hi); d.args.out_lo = BF(z_lo);
-  d.args.aux0 = esh; d.args.aux1 = g_mu; d.args.aux2 = g_logvar;
-  d.args.c0 = kl_grad_scale; d.args.loss_acc = kl_acc; d.args.L = L; d.args.ldo = L;
+  d.args.loss_acc = kl_acc; d.args.L = L; d.args.ldo = L;
   return gemm_launch(&ctx->c, d, S_(stream));
 }
 
@@ -198,17 +206,19 @@ int rvae_dgrad_relu(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const v
 }
 
 int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, const void* w3_hi, const void* w3_lo,
-                      int M, int L, int H, const float* esh, const float* g_mu, const float* g_logvar, void* dml_hi,
-                      void* dml_lo, float* bias_grad, void* stream) {
+                      int M, int L, int H, const float* eps, const float* logvar, const float* mu,
+                      const float* g_mu_ext, const float* g_logvar_ext, float kl_grad_scale, float* dz_scratch,
+                      void* dml_hi, void* dml_lo, float* bias_grad, void* stream) {
   CTX_OR_FAIL(ctx);
-  RVAE_REQUIRE(esh && g_mu && g_logvar && dml_hi, RVAE_ERR_INVALID, "dgrad_latent: null buffer");
-  GemmDesc d = desc_base(EPI_DZ, M, L, H);
+  RVAE_REQUIRE(eps && logvar && dz_scratch && dml_hi, RVAE_ERR_INVALID, "dgrad_latent: null buffer");
+  RVAE_CUDA(cudaMemsetAsync(dz_scratch, 0, sizeof(float) * (size_t)M * L, S_(stream)));
+  GemmDesc d = desc_base(EPI_REDUCE, M, L, H);
   d.A = op(da3_hi, da3_lo, MAJOR_K, H);
   d.B = op(w3_hi, w3_lo, MAJOR_MN, L);
-  d.args.in0 = esh; d.args.in1 = g_mu; d.args.in2 = g_logvar;
-  d.args.out_hi = BF(dml_hi); d.args.out_lo = BF(dml_lo); d.args.ldo = 2 * L; d.args.L = L;
-  d.args.colsum = bias_grad;
-  return gemm_launch(&ctx->c, d, S_(stream));
+  d.args.out_f32 = dz_scratch; d.args.ldo = L; d.args.accumulate = 1;
+  RVAE_CHECK(gemm_launch(&ctx->c, d, S_(stream)));
+  return launch_latent_bwd(&ctx->c, dz_scratch, eps, logvar, mu, g_mu_ext, g_logvar_ext, kl_grad_scale, M, L,
+                           BF(dml_hi), BF(dml_lo), bias_grad, 0, S_(stream));
 }
 
 int rvae_wgrad(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, int B, int M,
@@ -216,7 +226,7 @@ int rvae_wgrad(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* 
   CTX_OR_FAIL(ctx);
   RVAE_REQUIRE(dW, RVAE_ERR_INVALID, "wgrad: null output");
   RVAE_REQUIRE(M % 64 == 0, RVAE_ERR_UNSUPPORTED, "wgrad: M=%d must be a multiple of 64", M);
-  GemmDesc d = desc_base(EPI_WGRAD, M, N, B);
+  GemmDesc d = desc_base(EPI_REDUCE, M, N, B);
   d.A = op(dy_hi, dy_lo, MAJOR_MN, M);
   d.B = op(x_hi, x_lo, MAJOR_MN, N);
   d.args.out_f32 = dW; d.args.ldo = N; d.args.accumulate = accumulate;
@@ -258,7 +268,7 @@ struct Planes {
 
 enum GemmId { G_F1, G_F2, G_F3, G_F4_OUT, G_F4_LIN, G_B4W, G_B4D, G_B3W, G_B3D, G_B2W, G_B2D, G_B1W, G_COUNT };
 // timing slots of the non-GEMM kernels follow the GEMM slots
-enum AuxSlot { T_LOAD = G_COUNT, T_EPS, T_FINALIZE, T_COLSUM, T_ADAM, T_TANHBWD, T_COUNT };
+enum AuxSlot { T_LOAD = G_COUNT, T_EPS, T_FINALIZE, T_COLSUM, T_ADAM, T_TANHBWD, T_LATENT, T_COUNT };
 
 struct GemmSet {
   PreparedGemm g[G_COUNT];
@@ -276,12 +286,14 @@ struct rvae_plan {
   size_t ws_bytes;
   // workspace sections
   Planes x, h1, z, h3, da4, da3, dml, da1;
-  float *mu, *lv, *eps, *esh, *gmu, *glv, *xhat;
+  float *mu, *lv, *eps, *dz, *xhat;
   double* loss_acc;
   // redirected outputs
   float *out_mu, *out_lv, *out_xhat;
   int batch;        // current batch
   int64_t global_batch;  // loss normalisation under data parallelism (0 = local batch)
+  float kl_c0;           // kl_beta / (B L) of the last fused-loss forward (KL gradient scale of the latent backward)
+  bool dz_zeroed;        // the split-K latent dgrad accumulator holds zeros (left so by the latent backward kernel)
   bool grads_zeroed[5];  // gradient bucket s (0..3 weights, 4 biases) already holds zeros (left so by the fused Adam)
   // the weight-gradient GEMM of a backward stage runs on a side stream, concurrently with the stage's dgrad GEMM
   cudaStream_t side;
@@ -327,9 +339,7 @@ size_t carve(rvae_plan* p, uint8_t* base) {
   p->mu = reinterpret_cast<float*>(take(B * L * 4));
   p->lv = reinterpret_cast<float*>(take(B * L * 4));
   p->eps = reinterpret_cast<float*>(take(B * L * 4));
-  p->esh = reinterpret_cast<float*>(take(B * L * 4));
-  p->gmu = reinterpret_cast<float*>(take(B * L * 4));
-  p->glv = reinterpret_cast<float*>(take(B * L * 4));
+  p->dz = reinterpret_cast<float*>(take(B * L * 4));
   p->xhat = reinterpret_cast<float*>(take(B * S * 4));
   p->loss_acc = reinterpret_cast<double*>(take(2 * sizeof(double)));
   return off;
@@ -368,8 +378,8 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.epi = EPI_HEAD; d.M = B; d.N = 2 * L; d.K = H; d.head_L = L;
       d.A = opnd(p->h1, MAJOR_K, H); d.B = wopnd(p, ly.w2, MAJOR_K, H);
       d.args.bias = params + ly.b2; d.args.in0 = p->eps; d.args.out_f32 = p->mu; d.args.out_f32_b = p->lv;
-      d.args.out_hi = p->z.hi; d.args.out_lo = p->z.lo; d.args.aux0 = p->esh; d.args.aux1 = p->gmu;
-      d.args.aux2 = p->glv; d.args.loss_acc = p->loss_acc + 1; d.args.L = L; d.args.ldo = L;
+      d.args.out_hi = p->z.hi; d.args.out_lo = p->z.lo;
+      d.args.loss_acc = p->loss_acc + 1; d.args.L = L; d.args.ldo = L;
       break;
     case G_F3:
       d.epi = EPI_LINEAR; d.M = B; d.N = H; d.K = L;
@@ -393,7 +403,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.args.out_f32 = p->xhat;
       break;
     case G_B4W:
-      d.epi = EPI_WGRAD; d.M = S; d.N = H; d.K = B;
+      d.epi = EPI_REDUCE; d.M = S; d.N = H; d.K = B;
       d.A = opnd(p->da4, MAJOR_MN, S); d.B = opnd(p->h3, MAJOR_MN, H);
       d.args.out_f32 = grads + ly.w4; d.args.ldo = H; d.args.accumulate = 1;
       break;
@@ -404,19 +414,18 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.args.colsum = grads + ly.b3;                     // db3 = column sums of da3
       break;
     case G_B3W:
-      d.epi = EPI_WGRAD; d.M = H; d.N = L; d.K = B;
+      d.epi = EPI_REDUCE; d.M = H; d.N = L; d.K = B;
       d.A = opnd(p->da3, MAJOR_MN, H); d.B = opnd(p->z, MAJOR_MN, L);
       d.args.out_f32 = grads + ly.w3; d.args.ldo = L; d.args.accumulate = 1;
       break;
     case G_B3D:
-      d.epi = EPI_DZ; d.M = B; d.N = L; d.K = H;
+      // dz = da3 W3 as a split-K reduce-add GEMM into fp32; the latent backward kernel turns dz into d_ml and db2
+      d.epi = EPI_REDUCE; d.M = B; d.N = L; d.K = H;
       d.A = opnd(p->da3, MAJOR_K, H); d.B = wopnd(p, ly.w3, MAJOR_MN, L);
-      d.args.in0 = p->esh; d.args.in1 = p->gmu; d.args.in2 = p->glv;
-      d.args.out_hi = p->dml.hi; d.args.out_lo = p->dml.lo; d.args.ldo = 2 * L; d.args.L = L;
-      d.args.colsum = grads + ly.b2;                     // [db21; db22] = column sums of [dmu | dlv]
+      d.args.out_f32 = p->dz; d.args.ldo = L; d.args.accumulate = 1;
       break;
     case G_B2W:
-      d.epi = EPI_WGRAD; d.M = 2 * L; d.N = H; d.K = B;
+      d.epi = EPI_REDUCE; d.M = 2 * L; d.N = H; d.K = B;
       d.A = opnd(p->dml, MAJOR_MN, 2 * L); d.B = opnd(p->h1, MAJOR_MN, H);
       d.args.out_f32 = grads + ly.w2; d.args.ldo = H; d.args.accumulate = 1;
       break;
@@ -427,7 +436,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.args.colsum = grads + ly.b1;                     // db1 = column sums of da1
       break;
     case G_B1W:
-      d.epi = EPI_WGRAD; d.M = H; d.N = S; d.K = B;
+      d.epi = EPI_REDUCE; d.M = H; d.N = S; d.K = B;
       d.A = opnd(p->da1, MAJOR_MN, H); d.B = opnd(p->x, MAJOR_MN, S);
       d.args.out_f32 = grads + ly.w1; d.args.ldo = S; d.args.accumulate = 1;
       break;
@@ -533,10 +542,17 @@ int ensure_side_stream(rvae_plan* p) {
 // so that after stage s gradient bucket s is complete on `st`. Both kernels are persistent and want every SM: run
 // concurrently, the CTAs of one fill the SMs the other leaves idle in its last partial wave.
 //   s=0: dW4 = da4^T h3        || da3 = (da4 W4) * [h3>0], db3
-//   s=1: dW3 = da3^T z         || d_ml = f(da3 W3),        db2
+//   s=1: dW3 = da3^T z         || dz = da3 W3 (split-K, fp32) -> latent backward kernel: d_ml, db2
 //   s=2: dW2 = d_ml^T h1       || da1 = (d_ml W2) * [h1>0], db1
 //   s=3: dW1 = da1^T x
-int backward_stage(rvae_plan* p, int stage, const EpiArgs* dz_override, cudaStream_t st) {
+// External upstream gradients of (mu, logvar) for the autograd path, with the logvar tensor of that forward.
+struct LatentExt {
+  const float* g_mu;
+  const float* g_lv;
+  const float* lv;
+};
+
+int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t st) {
   const int S = p->S, H = p->H, L = p->L;
   const rvae_layout& ly = p->lay;
   float* grads = p->bufs.grads;
@@ -557,7 +573,16 @@ int backward_stage(rvae_plan* p, int stage, const EpiArgs* dz_override, cudaStre
   } else {
     RVAE_CHECK(run(p, kWgrad[stage], st));
   }
-  if (kDgrad[stage] >= 0) RVAE_CHECK(run(p, kDgrad[stage], st, stage == 1 ? dz_override : nullptr));
+  if (stage == 1 && !p->dz_zeroed)
+    RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
+  if (kDgrad[stage] >= 0) RVAE_CHECK(run(p, kDgrad[stage], st));
+  if (stage == 1) {
+    TimedScope ts(p, T_LATENT, st);
+    RVAE_CHECK(launch_latent_bwd(&p->ctx->c, p->dz, p->eps, ext ? ext->lv : p->lv, p->mu, ext ? ext->g_mu : nullptr,
+                                 ext ? ext->g_lv : nullptr, p->kl_c0, p->batch, L, p->dml.hi, p->dml.lo, grads + ly.b2, 1,
+                                 st));
+    p->dz_zeroed = true;
+  }
   if (fork) RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
   return RVAE_OK;
 }
@@ -579,6 +604,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
   p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
   p->timing = false;
+  p->kl_c0 = 0.f; p->dz_zeroed = false;
   for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
   p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
   p->two_streams = true;
@@ -648,6 +674,7 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
   carve(plan, reinterpret_cast<uint8_t*>(b->workspace));
   plan->sets.clear();
   for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = false;
+  plan->dz_zeroed = false;
   if (plan->two_streams) RVAE_CHECK(ensure_side_stream(plan));
   plan->bound = true;
   plan->batch = 0;
@@ -734,16 +761,15 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
     EpiArgs a = gs->g[G_F2].params.epi;
     if (p->out_mu) a.out_f32 = p->out_mu;
     if (p->out_lv) a.out_f32_b = p->out_lv;
-    if (fused_loss) {
-      a.c0 = (float)((double)kl_beta / BL);
-    } else {
-      a.aux1 = nullptr; a.aux2 = nullptr; a.loss_acc = nullptr; a.c0 = 0.f;
-    }
+    if (fused_loss) p->kl_c0 = (float)((double)kl_beta / BL);
+    else a.loss_acc = nullptr;
     RVAE_CHECK(run(p, G_F2, st, &a));
   }
   RVAE_CHECK(run(p, G_F3, st));
   if (fused_loss) {
     RVAE_REQUIRE(p->bufs.grads, RVAE_ERR_STATE, "plan_forward(fused_loss): no grads buffer bound");
+    RVAE_REQUIRE(!p->out_mu && !p->out_lv, RVAE_ERR_STATE,
+                 "plan_forward(fused_loss): mu / logvar must stay in the workspace (the fused backward reads them)");
     RVAE_CHECK(ensure_bias_zeroed(p, st));   // F4's epilogue accumulates db4, the backward epilogues db3, db2, db1
     p->grads_zeroed[4] = false;              // ... so after this step the block is dirty again
     RVAE_CHECK(prepare(p, *gs, G_F4_OUT));
@@ -771,10 +797,11 @@ int rvae_plan_backward(rvae_plan* plan, int stage, void* stream) {
 }
 
 int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const float* xhat, const float* g_mu,
-                                const float* g_logvar, void* stream) {
+                                const float* g_logvar, const float* logvar, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
   RVAE_REQUIRE(plan->bufs.grads, RVAE_ERR_STATE, "plan_backward_external: no grads buffer bound");
-  RVAE_REQUIRE(g_xhat && xhat && g_mu && g_logvar, RVAE_ERR_INVALID, "plan_backward_external: null gradient");
+  RVAE_REQUIRE(g_xhat && xhat && g_mu && g_logvar && logvar, RVAE_ERR_INVALID,
+               "plan_backward_external: null argument");
   rvae_plan* p = plan;
   cudaStream_t st = S_(stream);
   RVAE_CHECK(ensure_bias_zeroed(p, st));
@@ -782,13 +809,8 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
   { TimedScope ts(p, T_TANHBWD, st); RVAE_CHECK(launch_tanh_bwd(&p->ctx->c, g_xhat, xhat, (int64_t)p->batch * p->S, p->da4.hi, p->da4.lo, st)); }
   { TimedScope ts(p, T_COLSUM, st);
     RVAE_CHECK(launch_colsum(&p->ctx->c, p->da4.hi, p->da4.lo, p->batch, p->S, p->S, p->bufs.grads + p->lay.b4, 1, st)); }
-  GemmSet* gs;
-  RVAE_CHECK(get_set(p, &gs));
-  RVAE_CHECK(prepare(p, *gs, G_B3D));
-  EpiArgs a = gs->g[G_B3D].params.epi;
-  a.in1 = g_mu;
-  a.in2 = g_logvar;
-  for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(p, s, s == 1 ? &a : nullptr, st));
+  const LatentExt ext = {g_mu, g_logvar, logvar};
+  for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(p, s, &ext, st));
   return RVAE_OK;
 }
 
@@ -889,7 +911,7 @@ int rvae_plan_encode(rvae_plan* plan, void* stream) {
   if (p->out_mu) a.out_f32 = p->out_mu;
   if (p->out_lv) a.out_f32_b = p->out_lv;
   a.in0 = nullptr; a.out_hi = nullptr; a.out_lo = nullptr;
-  a.aux0 = nullptr; a.aux1 = nullptr; a.aux2 = nullptr; a.loss_acc = nullptr;
+  a.loss_acc = nullptr;
   return run(p, G_F2, st, &a);
 }
 

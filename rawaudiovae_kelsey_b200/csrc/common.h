@@ -48,6 +48,7 @@ struct Ctx {
   int force_cta_group;  // 0 = heuristic, 1 / 2 = forced (env RVAE_CTA_GROUP, for experiments)
   int debug;            // env RVAE_DEBUG, experiments only (see GemmParams::debug)
   int use_pdl;          // programmatic dependent launch between consecutive kernels (env RVAE_PDL=0 disables)
+  unsigned long long* trace;  // GEMM timeline trace buffer (rvae_debug_set_trace), nullptr = off
   uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
 };
 
@@ -93,8 +94,8 @@ struct PreparedGemm {
   int grid;
   int smem_bytes;
   // geometry of the epilogue's output tensors (for re-binding output pointers)
+  int epi;
   int out_rows, out_cols_bf16, out_ld_bf16, out_cols_f32, out_ld_f32;
-  bool out_f32_tma;
 };
 
 int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& args, bool force);
@@ -130,5 +131,8 @@ int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, flo
                 float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
                 __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream);
 int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream);
+int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, const float* mu, const float* g_mu_ext,
+                      const float* g_lv_ext, float kl_grad_scale, int64_t M, int L, __nv_bfloat16* dml_hi,
+                      __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, cudaStream_t stream);
 
 }  // namespace rvae

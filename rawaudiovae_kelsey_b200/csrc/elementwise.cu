@@ -599,6 +599,110 @@ int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, flo
   return RVAE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Latent backward (backward of reparameterize, rawvae/model.py:24-26, merged with the KL gradient of :45):
+//   sigma = exp(lv / 2)
+//   d_mu = dz + g_mu,  d_lv = dz * eps * sigma / 2 + g_lv        -> d_ml[:, :L], d_ml[:, L:]  (bf16 planes)
+//   g_mu = c * mu, g_lv = c * (sigma^2 - 1) / 2 (fused loss, c = kl_beta / (B L))   or external upstream gradients
+//   bias_grad[0:2L] += column sums of d_ml = [db21; db22];  dz is cleared for the next step's split-K reduce-add.
+// dz is the fp32 result of the split-K latent dgrad GEMM (da3 W3). One thread handles 4 adjacent latent columns of a
+// strided set of rows: float4 loads, 8-byte bf16 stores, column sums in registers -> smem -> one atomic per column
+// and block.
+// ------------------------------------------------------------------------------------------------
+__global__ void latent_bwd_kernel(float* __restrict__ dz, const float* __restrict__ eps, const float* __restrict__ lv,
+                                  const float* __restrict__ mu, const float* __restrict__ g_mu_ext,
+                                  const float* __restrict__ g_lv_ext, float c, int64_t M, int L,
+                                  __nv_bfloat16* __restrict__ dml_hi, __nv_bfloat16* __restrict__ dml_lo,
+                                  float* __restrict__ bias_grad, int clear_dz) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  extern __shared__ float s_sum[];  // [rows_per_pass][2L]
+  const int q = L >> 2;                    // float4 groups per row
+  const int rpp = blockDim.x / q;          // rows per pass
+  const int cx = threadIdx.x % q;          // column group of this thread
+  const int ry = threadIdx.x / q;
+  float smu[4] = {0.f, 0.f, 0.f, 0.f}, slv[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = (int64_t)blockIdx.x * rpp + ry; r < M; r += (int64_t)gridDim.x * rpp) {
+    const size_t i = (size_t)r * q + cx;
+    const float4 d4 = reinterpret_cast<const float4*>(dz)[i];
+    const float4 e4 = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    const float4 l4 = __ldg(reinterpret_cast<const float4*>(lv) + i);
+    float4 a4, b4 = make_float4(0.f, 0.f, 0.f, 0.f);  // additive terms of d_mu, d_lv
+    if (g_lv_ext != nullptr) {
+      a4 = __ldg(reinterpret_cast<const float4*>(g_mu_ext) + i);
+      b4 = __ldg(reinterpret_cast<const float4*>(g_lv_ext) + i);
+    } else {
+      a4 = __ldg(reinterpret_cast<const float4*>(mu) + i);
+    }
+    const float* d = reinterpret_cast<const float*>(&d4);
+    const float* e = reinterpret_cast<const float*>(&e4);
+    const float* l = reinterpret_cast<const float*>(&l4);
+    const float* a = reinterpret_cast<const float*>(&a4);
+    const float* b = reinterpret_cast<const float*>(&b4);
+    float dmu[4], dlv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sig = expf(0.5f * l[j]);
+      const float gm = (g_lv_ext != nullptr) ? a[j] : c * a[j];
+      const float gl = (g_lv_ext != nullptr) ? b[j] : 0.5f * c * (sig * sig - 1.f);
+      dmu[j] = d[j] + gm;
+      dlv[j] = fmaf(d[j], 0.5f * e[j] * sig, gl);
+      smu[j] += dmu[j];
+      slv[j] += dlv[j];
+    }
+    if (clear_dz) reinterpret_cast<float4*>(dz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t o = (size_t)r * (2 * L) + 4 * cx;
+    *reinterpret_cast<uint2*>(dml_hi + o) = make_uint2(pack2(dmu[0], dmu[1]), pack2(dmu[2], dmu[3]));
+    *reinterpret_cast<uint2*>(dml_hi + o + L) = make_uint2(pack2(dlv[0], dlv[1]), pack2(dlv[2], dlv[3]));
+    if (dml_lo) {
+      float rm[4], rl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rm[j] = dmu[j] - __bfloat162float(__float2bfloat16_rn(dmu[j]));
+        rl[j] = dlv[j] - __bfloat162float(__float2bfloat16_rn(dlv[j]));
+      }
+      *reinterpret_cast<uint2*>(dml_lo + o) = make_uint2(pack2(rm[0], rm[1]), pack2(rm[2], rm[3]));
+      *reinterpret_cast<uint2*>(dml_lo + o + L) = make_uint2(pack2(rl[0], rl[1]), pack2(rl[2], rl[3]));
+    }
+  }
+  if (bias_grad != nullptr) {
+    float* mine = s_sum + (size_t)ry * 2 * L;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mine[4 * cx + j] = smu[j];
+      mine[L + 4 * cx + j] = slv[j];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < 2 * L; col += blockDim.x) {
+      float t = 0.f;
+      for (int y = 0; y < rpp; ++y) t += s_sum[(size_t)y * 2 * L + col];
+      atomicAdd(bias_grad + col, t);
+    }
+  }
+}
+
+int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, const float* mu, const float* g_mu_ext,
+                      const float* g_lv_ext, float kl_grad_scale, int64_t M, int L, __nv_bfloat16* dml_hi,
+                      __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, cudaStream_t stream) {
+  RVAE_REQUIRE(dz && eps && lv && dml_hi, RVAE_ERR_INVALID, "latent_bwd: null buffer");
+  RVAE_REQUIRE((g_mu_ext != nullptr) == (g_lv_ext != nullptr), RVAE_ERR_INVALID,
+               "latent_bwd: external gradients come in pairs");
+  RVAE_REQUIRE(g_lv_ext != nullptr || mu != nullptr, RVAE_ERR_INVALID, "latent_bwd: mu required for the fused KL gradient");
+  RVAE_REQUIRE(L > 0 && L % 4 == 0 && L / 4 <= 1024, RVAE_ERR_UNSUPPORTED, "latent_bwd: latent_dim=%d", L);
+  if (M <= 0) return RVAE_OK;
+  const int q = L / 4;
+  const int rpp = q >= 256 ? 1 : 256 / q;
+  const int threads = q * rpp;
+  const int64_t want = (M + rpp - 1) / rpp;
+  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  const size_t smem = bias_grad ? (size_t)rpp * 2 * L * sizeof(float) : 0;
+  RVAE_CUDA(launch_kernel(ctx, latent_bwd_kernel, dim3(grid), dim3(threads), smem, stream, dz, eps, lv, mu, g_mu_ext,
+                          g_lv_ext, kl_grad_scale, M, L, dml_hi, dml_lo, bias_grad, clear_dz));
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
 __global__ void step_inc_kernel(float* step) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();

@@ -2,12 +2,19 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]        (bf16 operands, fp32 accumulation in TMEM)
 //
-// One CTA per SM loops over 128 x BLOCK_N output tiles (x split-K slices for the weight-gradient GEMMs):
+// One CTA per SM loops over 128 x BLOCK_N output tiles (x split-K slices for the reduce-add GEMMs):
 //   warp 0 (one lane)  : TMA producer   - fills a STAGES-deep ring of {A tile, B tile} in 128B-swizzled smem
 //   warp 1 (one lane)  : UMMA issuer    - tcgen05.mma 128 x BLOCK_N x 16 into one of two TMEM accumulators
-//   warps 2..5         : epilogue       - tcgen05.ld the finished accumulator, apply the fused epilogue
-//                                         (bias/ReLU/tanh, reparameterisation+KL, tanh+MSE+dL/da, ReLU mask, ...)
+//   warps 2..9         : epilogue       - two teams of four warps: tcgen05.ld the finished accumulator, apply the
+//                                         fused epilogue (bias/ReLU/tanh, reparameterisation+KL, tanh+MSE+dL/da,
+//                                         ReLU mask, ...), stage the result in swizzled smem and TMA-store it
 // so the epilogue of tile i overlaps the MMAs of tile i+1 (double-buffered TMEM, 2 x BLOCK_N columns).
+//
+// Every byte the epilogue exchanges with global memory moves through TMA and 128B-swizzled smem slots: the side
+// inputs (ReLU mask, x for the MSE, eps for the reparameterisation) are prefetched by TMA loads while the tile's MMAs
+// still run, the thread that owns a row reads them from the slot, writes its result IN PLACE, and the slot is handed
+// to a TMA store (or reduce-add). Row-per-thread global loads / stores (32 cache lines per warp instruction) are
+// never issued.
 //
 // Operands may be K-major (row = m or n, K contiguous: activations / weights in the forward pass) or
 // MN-major (row = k, M or N contiguous: weights in dgrad, activations in wgrad) - no transposed copies are
@@ -32,27 +39,25 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two teams of four)
 constexpr int kEpiTeams = 2;
 constexpr int kMaxPasses = 3;
-constexpr int kOutSlotBytes = 128 * 128;  // one epilogue staging slot: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
-constexpr int kOutSlots = 2;
+constexpr int kSlotBytes = 128 * 128;  // one epilogue slot: 128 rows x 128 bytes (64 bf16 / 32 fp32 columns)
+constexpr int kSlotsPerTeam = 3;
 
 enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
-enum : int { EPI_LINEAR = 0, EPI_HEAD = 1, EPI_OUT = 2, EPI_DRELU = 3, EPI_DZ = 4, EPI_WGRAD = 5 };
+enum : int { EPI_LINEAR = 0, EPI_HEAD = 1, EPI_OUT = 2, EPI_DRELU = 3, EPI_REDUCE = 5 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_TANH_APPROX = 3 };
 
 // Epilogue arguments. Slot meaning per epilogue kind:
 //   LINEAR : v = acc + bias[n]; act(v) -> out_hi (bf16) [, out_lo (bf16 residual)] [, out_f32]
 //   HEAD   : tile columns [0,half) are mu, [half,BLOCK_N) are logvar of the same latent columns.
-//            mu -> out_f32, logvar -> out_f32_b, eps <- in0 (f32, NULL = 0), z = mu + eps*exp(lv/2) -> out_hi/out_lo,
-//            aux0 <- eps*sigma/2 (f32, for backward), aux1 <- c0*mu, aux2 <- c0*(e^lv-1)/2 (KL gradients),
-//            loss_acc[0] += sum(1 + lv - mu^2 - e^lv)
+//            mu -> out_f32, logvar -> out_f32_b, eps <- in0 (f32 [M, L], NULL = 0),
+//            z = mu + eps*exp(lv/2) -> out_hi/out_lo (optional), loss_acc[0] += sum(1 + lv - mu^2 - e^lv)
 //   OUT    : xh = tanh(acc + bias[n]) -> out_f32 (optional); x <- in0 (bf16 hi) [+ in1 (bf16 lo)];
 //            loss_acc[0] += sum((xh-x)^2); da = c0*(xh-x)*(1-xh^2) -> out_hi/out_lo
 //   DRELU  : v = acc * [in0[m,n] > 0] (in0 bf16, optional) -> out_hi/out_lo
-//   DZ     : dz = acc; dmu = dz + in1[m,n]; dlv = dz*in0[m,n] + in2[m,n] (all f32 [M, L]);
-//            dmu -> out_hi[m, n], dlv -> out_hi[m, L + n] (ldo = 2L) [, out_lo likewise]
-//   WGRAD  : out_f32[m, n] (+)= acc   (red.add when accumulate != 0, plain store otherwise)
-//   OUT / DRELU / DZ additionally accumulate the column sums of what they emit into `colsum` (the bias gradient of
-//   the layer whose pre-activation gradient this is: db = sum_b da), so no separate reduction kernel is needed.
+//   REDUCE : out_f32[m, n] (+)= acc   (TMA reduce-add when accumulate != 0, plain store otherwise): weight
+//            gradients and the split-K latent dgrad
+//   OUT / DRELU additionally accumulate the column sums of what they emit into `colsum` (the bias gradient of the
+//   layer whose pre-activation gradient this is: db = sum_b da), so no separate reduction kernel is needed.
 struct EpiArgs {
   const float* bias;
   __nv_bfloat16* out_hi;
@@ -61,15 +66,11 @@ struct EpiArgs {
   float* out_f32_b;
   const void* in0;
   const void* in1;
-  const void* in2;
-  float* aux0;
-  float* aux1;
-  float* aux2;
   double* loss_acc;
-  float* colsum;  // OUT / DRELU / DZ: colsum[c] += sum over rows of the bf16 stream's fp32 values (bias gradients)
-  int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and of bf16 inputs in0/in1
+  float* colsum;  // OUT / DRELU: colsum[c] += sum over rows of the emitted values (bias gradients)
+  int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and of the bf16 inputs in0/in1
   int act;   // LINEAR / OUT activation
-  int L;     // HEAD / DZ latent width
+  int L;     // HEAD latent width
   int accumulate;
   float c0;
 };
@@ -77,9 +78,11 @@ struct EpiArgs {
 struct alignas(64) GemmParams {
   CUtensorMap tmA[kMaxPasses];
   CUtensorMap tmB[kMaxPasses];
-  CUtensorMap tmOutHi;   // bf16 output plane (box 64 cols x 128 rows, 128B swizzle)
-  CUtensorMap tmOutLo;   // bf16 residual plane (fp32 emulation)
-  CUtensorMap tmOutF32;  // fp32 output (box 32 cols x 128 rows, 128B swizzle)
+  CUtensorMap tmOutHi;    // bf16 output plane (box 64 cols x 128 rows, 128B swizzle)
+  CUtensorMap tmOutLo;    // bf16 residual plane (fp32 emulation)
+  CUtensorMap tmOutF32;   // fp32 output (box 32 cols x 128 rows, 128B swizzle)
+  CUtensorMap tmOutF32b;  // HEAD: logvar
+  CUtensorMap tmSide;     // side input in0: bf16 (box 64 x 128) for OUT / DRELU, fp32 (box 32 x 128) for HEAD
   int M, N, K;
   int num_passes;
   int m_blocks, n_blocks;  // m_blocks counts 128*CG-row tiles
@@ -87,6 +90,7 @@ struct alignas(64) GemmParams {
   int b_tile_stride;  // K-major B: row advance per n-block
   int b_half_stride;  // K-major B: row offset of the second half-tile load
   int debug;          // experiments only (env RVAE_DEBUG, CG == 1): 1 = no MMA issue, 2 = no TMA loads
+  unsigned long long* trace;  // experiments only (rvae_debug_set_trace): per-CTA, per-tile role timestamps
   EpiArgs epi;
 };
 
@@ -98,57 +102,48 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutBytes = kOutSlots * kOutSlotBytes;  // epilogue staging for TMA stores
-  static constexpr int kBarrierBytes = 256 + kEpiTeams * 128 * 4;  // mbarriers + TMEM slot + per-team strips
-  static constexpr int kBudget = 232448 - 1024 - kOutBytes - kBarrierBytes;  // 227 KB usable per CTA
+  static constexpr int kSlotRegion = kEpiTeams * kSlotsPerTeam * kSlotBytes;  // 96 KB of epilogue slots
+  static constexpr int kBiasFloats = BLOCK_N / 2 > 128 ? BLOCK_N / 2 : 128;   // a team's own columns of the tile
+  static constexpr int kBiasBytes = kEpiTeams * kBiasFloats * 4;
+  static constexpr int kCsumBytes = kEpiTeams * 2 * 64 * 4;
+  static constexpr int kBarrierBytes = 256;                                   // <= 26 mbarriers + the TMEM slot
+  static constexpr int kBudget = 232448 - kSlotRegion - kBiasBytes - kCsumBytes - kBarrierBytes;  // 227 KB per CTA
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = (kAccStages * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOutBytes + kBarrierBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlotRegion + kBiasBytes + kCsumBytes + kBarrierBytes;
+  static_assert(kStages >= 2, "pipeline too shallow");
 };
 
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+// Timeline trace (debug): per CTA a 16-word header then kTraceTiles x kTraceEvents clock64() stamps.
+//   header: 0 globaltimer at entry, 1 clock at entry, 2 clock after setup, 3 clock after the PDL wait,
+//           4 clock when the producer finished, 5 clock at exit, 6 globaltimer at exit
+//   events: 0/1 producer tile begin / last load issued; 2/3 MMA before / after the accumulator-free wait,
+//           4 first operands landed, 5 tile committed; 6/7 epilogue team 0 accumulator ready / tile released,
+//           8/9 the same for team 1; 10..13 team 0's first unit: side input landed / accumulator in registers /
+//           staged / store issued; 14/15 its second unit: side input landed / store issued
+constexpr int kTraceHeader = 16;
+constexpr int kTraceTiles = 24;
+constexpr int kTraceEvents = 16;
+constexpr int kTraceCtaWords = kTraceHeader + kTraceTiles * kTraceEvents;
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_hdr(const unsigned long long* trace, int word, unsigned long long v) {
+  if (trace) const_cast<unsigned long long*>(trace)[static_cast<size_t>(blockIdx.x) * kTraceCtaWords + word] = v;
+}
+__device__ __forceinline__ void trace_ev(const unsigned long long* trace, int tile_iter, int ev) {
+  if (trace && tile_iter < kTraceTiles)
+    const_cast<unsigned long long*>(trace)[static_cast<size_t>(blockIdx.x) * kTraceCtaWords + kTraceHeader +
+                                           tile_iter * kTraceEvents + ev] = clock64();
 }
 
-// Store COUNT consecutive fp32 values of one output row as bf16 (hi plane and optional residual plane).
-template <int COUNT>
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* hi_row, __nv_bfloat16* lo_row, const float (&v)[COUNT]) {
-  uint4* dh = reinterpret_cast<uint4*>(hi_row);
+__device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
-  for (int i = 0; i < COUNT / 8; ++i) {
-    dh[i] = make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                       ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-  }
-  if (lo_row != nullptr) {
-    uint4* dl = reinterpret_cast<uint4*>(lo_row);
-#pragma unroll
-    for (int i = 0; i < COUNT / 8; ++i) {
-      float r[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = v[8 * i + j] - __bfloat162float(__float2bfloat16_rn(v[8 * i + j]));
-      dl[i] = make_uint4(ptx::pack_bf16x2(r[0], r[1]), ptx::pack_bf16x2(r[2], r[3]), ptx::pack_bf16x2(r[4], r[5]),
-                         ptx::pack_bf16x2(r[6], r[7]));
-    }
-  }
-}
-
-template <int COUNT>
-__device__ __forceinline__ void store_row_f32(float* row, const float (&v)[COUNT]) {
-  float4* d = reinterpret_cast<float4*>(row);
-#pragma unroll
-  for (int i = 0; i < COUNT / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-
-template <int COUNT>
-__device__ __forceinline__ void load_row_f32(const float* row, float (&v)[COUNT]) {
-  const float4* s = reinterpret_cast<const float4*>(row);
-#pragma unroll
-  for (int i = 0; i < COUNT / 4; ++i) {
-    float4 t = __ldg(s + i);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 template <int COUNT>
@@ -167,54 +162,72 @@ __device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* row, float (&
   }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Epilogue staging. Eight epilogue warps form two TEAMS of four (one warp per TMEM lane quarter, one output row per
+// Epilogue slots. Eight epilogue warps form two TEAMS of four (one warp per TMEM lane quarter, one output row per
 // thread). The work units of a tile (64-column bf16 sub-tiles, 32-column fp32 sub-tiles) alternate between the
-// teams, so one team's TMEM loads / global side loads / barrier waits overlap the other's math and smem writes.
-// A team stages a unit as 128 rows x 128 bytes in its own 128B-swizzled smem slot (16-byte chunk c of row r lands at
-// chunk c ^ (r & 7): conflict-free for row-per-thread writes); then one thread issues a TMA store (or reduce-add)
-// of the slot: full 128-byte coalesced lines to L2 instead of 16-byte row-strided stores, and rows / columns beyond
-// the tensor are clipped by the TMA unit.
+// teams. A team owns three 16 KB slots (128 rows x 128 bytes, 128B-swizzled: 16-byte chunk c of row r lives at chunk
+// c ^ (r & 7), conflict-free for row-per-thread accesses) and uses them round-robin, one slot per unit:
+//   [TMA load of the unit's side input, issued at the start of the tile] -> row owners read it, compute, write the
+//   result in place -> fence.proxy.async -> team barrier -> one thread issues the TMA store (reduce-add) and then
+//   waits until at most ONE store is still reading smem (cp.async.bulk.wait_group.read 1).
+// Invariant: whenever the issuer passes a team barrier, every store but the most recent one has released its slot.
+// A unit writes the slot used three units earlier, whose store was the most recent one two barriers ago - so by
+// the time a thread has passed the previous unit's barrier that slot is free, and no store-read latency is ever on
+// the critical path.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void team_bar_sync(int team) {
   asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");
 }
-
-__device__ __forceinline__ void slot_write16(uint8_t* slot, int r, int c, uint4 v) {
-  *reinterpret_cast<uint4*>(slot + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+__device__ __forceinline__ uint4* slot_chunk(uint8_t* slot, int r, int c) {
+  return reinterpret_cast<uint4*>(slot + r * 128 + ((c ^ (r & 7)) << 4));
 }
-// 32 fp32 values -> bf16 into chunks [c0, c0 + 4) of row r
-__device__ __forceinline__ void stage_bf16(uint8_t* slot, int r, int c0, const float* v) {
+// 64 fp32 values -> bf16 into the 8 chunks of row r
+__device__ __forceinline__ void stage_bf16(uint8_t* slot, int r, const float* v) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    slot_write16(slot, r, c0 + i,
-                 make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                            ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7])));
+  for (int i = 0; i < 8; ++i)
+    *slot_chunk(slot, r, i) =
+        make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                   ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
 }
-__device__ __forceinline__ void stage_bf16_residual(uint8_t* slot, int r, int c0, const float* v) {
+__device__ __forceinline__ float bf16_residual(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void stage_bf16_residual(uint8_t* slot, int r, const float* v) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     float q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q[j] = v[8 * i + j] - __bfloat162float(__float2bfloat16_rn(v[8 * i + j]));
-    slot_write16(slot, r, c0 + i,
-                 make_uint4(ptx::pack_bf16x2(q[0], q[1]), ptx::pack_bf16x2(q[2], q[3]), ptx::pack_bf16x2(q[4], q[5]),
-                            ptx::pack_bf16x2(q[6], q[7])));
+    for (int j = 0; j < 8; ++j) q[j] = bf16_residual(v[8 * i + j]);
+    *slot_chunk(slot, r, i) = make_uint4(ptx::pack_bf16x2(q[0], q[1]), ptx::pack_bf16x2(q[2], q[3]),
+                                         ptx::pack_bf16x2(q[4], q[5]), ptx::pack_bf16x2(q[6], q[7]));
   }
 }
 // 32 fp32 values -> the 8 chunks of row r
 __device__ __forceinline__ void stage_f32(uint8_t* slot, int r, const float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    slot_write16(slot, r, i,
-                 make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
-                            __float_as_uint(v[4 * i + 3])));
+    *slot_chunk(slot, r, i) = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                                         __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+}
+// row r of a bf16 slot (64 values) / an fp32 slot (32 values) -> registers
+__device__ __forceinline__ void unstage_bf16(uint8_t* slot, int r, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 t = *slot_chunk(slot, r, i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      v[8 * i + 2 * j] = f.x;
+      v[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void unstage_f32(uint8_t* slot, int r, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 t = *slot_chunk(slot, r, i);
+    v[4 * i] = __uint_as_float(t.x); v[4 * i + 1] = __uint_as_float(t.y);
+    v[4 * i + 2] = __uint_as_float(t.z); v[4 * i + 3] = __uint_as_float(t.w);
+  }
 }
 
 // Column sums of a [32 rows (lanes) x 64 columns] register tile: butterfly reduce-scatter over the lanes (62
@@ -237,27 +250,65 @@ __device__ __forceinline__ void warp_colsum64(float* v, int lane) {
   }
 }
 
-// One team's staging slot + bias strip. acquire(): the team's previous TMA store has finished reading the slot
-// (and, as a side effect of the barrier, the bias strip written before it is visible). commit(): hand the slot to TMA.
-struct TeamOut {
-  uint8_t* slot;
-  float* bias_s;   // 64 floats
-  float* csum_s;   // 64 floats: per-unit column sums, combined across the team's four warps
+// Accurate tanh is only used by the fp32-emulation path; kept out of line so the hot epilogues stay small enough for
+// the instruction cache.
+static __device__ __noinline__ float tanh_accurate(float x) { return tanhf(x); }
+
+template <int COUNT>
+__device__ __forceinline__ void apply_act(float (&v)[COUNT], int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int q = 0; q < COUNT; ++q) v[q] = fmaxf(v[q], 0.f);
+  } else if (act == ACT_TANH_APPROX) {
+#pragma unroll
+    for (int q = 0; q < COUNT; ++q) v[q] = ptx::tanh_approx(v[q]);
+  } else if (act == ACT_TANH) {
+#pragma unroll
+    for (int q = 0; q < COUNT; ++q) v[q] = tanh_accurate(v[q]);
+  }
+}
+
+// One epilogue team's view of its slots.
+struct Team {
+  uint8_t* slots;     // kSlotsPerTeam x kSlotBytes
+  uint64_t* in_bar;   // one mbarrier per slot: completion of the TMA load of a side input
+  float* bias_s;      // bias strip of the team's own columns of the current tile
+  float* csum_s;      // 2 x 64 floats: per-unit column sums, combined across the team's four warps (double-buffered)
+  uint32_t use;       // running slot-use counter (identical in all threads of the team)
+  uint32_t in_phase;  // bit s: parity of in_bar[s]
+  uint32_t cs_par;    // which of the two column-sum strips the next unit uses
   int team;
   bool issuer;
-  int debug;       // experiments: 4 = no TMA store, 16 = no team barriers
-  __device__ __forceinline__ void acquire() {
-    if (issuer) ptx::tma_store_wait_read<0>();
-    if (!(debug & 16)) team_bar_sync(team);
+
+  __device__ __forceinline__ uint8_t* slot(uint32_t u) const { return slots + (u % kSlotsPerTeam) * kSlotBytes; }
+  __device__ __forceinline__ void sync() const { team_bar_sync(team); }
+  // issuer only: start the TMA load of a side tile into the slot of use u
+  __device__ __forceinline__ void load(uint32_t u, const CUtensorMap* tm, int c0, int c1) const {
+    uint64_t* bar = &in_bar[u % kSlotsPerTeam];
+    ptx::mbar_arrive_expect_tx(bar, kSlotBytes);
+    ptx::tma_load_2d(slot(u), tm, bar, c0, c1);
   }
-  __device__ __forceinline__ void commit(const CUtensorMap* tm, int c0, int c1, bool reduce) {
+  // all threads: wait for the side tile of use u
+  __device__ __forceinline__ void wait_load(uint32_t u) {
+    const uint32_t s = u % kSlotsPerTeam;
+    ptx::mbar_wait(&in_bar[s], (in_phase >> s) & 1u);
+    in_phase ^= 1u << s;
+  }
+  // all threads, after writing their row of the slot of use u: publish it and hand it to the TMA unit
+  __device__ __forceinline__ void store(uint32_t u, const CUtensorMap* tm, int c0, int c1, bool reduce) const {
     ptx::fence_proxy_async_smem();
-    if (!(debug & 16)) team_bar_sync(team);
-    if (issuer && !(debug & 4)) {
-      if (reduce) ptx::tma_reduce_add_2d(tm, slot, c0, c1);
-      else ptx::tma_store_2d(tm, slot, c0, c1);
+    sync();
+    if (issuer) {
+      if (reduce) ptx::tma_reduce_add_2d(tm, slot(u), c0, c1);
+      else ptx::tma_store_2d(tm, slot(u), c0, c1);
       ptx::tma_store_commit();
+      ptx::tma_store_wait_read<1>();
     }
+  }
+  // slow paths (fp32 emulation): every slot is free and every thread knows it
+  __device__ __forceinline__ void drain() const {
+    if (issuer) ptx::tma_store_wait_read<0>();
+    sync();
   }
 };
 
@@ -267,17 +318,17 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM * CG, BLOCK_N, A_MAJOR, B_MAJOR);
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-
-  uint8_t* out_slots = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
-  float* bias_strips = reinterpret_cast<float*>(out_slots + Cfg::kOutBytes);  // kEpiTeams x (64 bias + 64 colsum)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_slots + Cfg::kOutBytes + kEpiTeams * 128 * 4);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* slot_base = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  float* bias_strips = reinterpret_cast<float*>(slot_base + Cfg::kSlotRegion);
+  float* csum_strips = bias_strips + kEpiTeams * Cfg::kBiasFloats;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(csum_strips + kEpiTeams * 128);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::kAccStages);
+  uint64_t* in_bars = tmem_empty_bar + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + kEpiTeams * kSlotsPerTeam);
+  static_assert((2 * 8 + 2 * 2 + kEpiTeams * kSlotsPerTeam) * 8 + 4 <= Cfg::kBarrierBytes, "barrier region");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,6 +337,14 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   const int group_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;       // tile-owning unit: CTA or CTA pair
   const int num_groups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
 
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {  // swizzled tiles need the declared 1 KB alignment
+      printf("rvae: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    trace_hdr(p.trace, 0, global_timer());
+    trace_hdr(p.trace, 1, clock64());
+  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.num_passes; ++i) {
       ptx::prefetch_tensormap(&p.tmA[i]);
@@ -294,6 +353,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     ptx::prefetch_tensormap(&p.tmOutHi);
     ptx::prefetch_tensormap(&p.tmOutLo);
     ptx::prefetch_tensormap(&p.tmOutF32);
+    ptx::prefetch_tensormap(&p.tmOutF32b);
+    ptx::prefetch_tensormap(&p.tmSide);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);    // leader's barrier: its producer arrives once with the pair's byte count
       ptx::mbar_init(&empty_bar[i], 1);   // per CTA: tcgen05.commit (multicast to both CTAs when CG == 2)
@@ -302,17 +363,21 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       ptx::mbar_init(&tmem_full_bar[i], 1);        // per CTA: tcgen05.commit
       ptx::mbar_init(&tmem_empty_bar[i], 8 * CG);  // leader's barrier: one arrive per epilogue warp of the pair
     }
+    for (int i = 0; i < kEpiTeams * kSlotsPerTeam; ++i) ptx::mbar_init(&in_bars[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kEpiTeams * 128) csum_strips[threadIdx.x - 64] = 0.f;
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous
   // kernel of the stream; from here on we read what it wrote.
+  if (threadIdx.x == 0) trace_hdr(p.trace, 2, clock64());
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
+  if (threadIdx.x == 0) trace_hdr(p.trace, 3, clock64());
 
   const int tiles = p.m_blocks * p.n_blocks;
   const int total_units = tiles * p.k_splits;
@@ -322,7 +387,9 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool slot_free = ptx::mbar_try_wait(&empty_bar[0], 1);
-      for (int u = group_id; u < total_units; u += num_groups) {
+      int titer = 0;
+      for (int u = group_id; u < total_units; u += num_groups, ++titer) {
+        trace_ev(p.trace, titer, 0);
         const int ks = u / tiles;
         const int tile = u - ks * tiles;
         const int n_blk = tile / p.m_blocks;
@@ -385,20 +452,25 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
+        trace_ev(p.trace, titer, 1);
       }
+      trace_hdr(p.trace, 4, clock64());
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
     if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       bool data_ready = false;
-      for (int u = group_id; u < total_units; u += num_groups) {
+      int titer = 0;
+      for (int u = group_id; u < total_units; u += num_groups, ++titer) {
         const int ks = u / tiles;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
         const int iters = kb_count * p.num_passes;
+        trace_ev(p.trace, titer, 2);
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         ptx::tc_fence_after();
+        trace_ev(p.trace, titer, 3);
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int it = 0; it < iters; ++it) {
           ptx::mbar_wait_probed(data_ready, &full_bar[stage], phase);
@@ -409,6 +481,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
             data_ready = ptx::mbar_try_wait(&full_bar[ns], np);
           }
           ptx::tc_fence_after();
+          if (it == 0) trace_ev(p.trace, titer, 4);
           if (CG == 1 && (p.debug & 1)) {  // experiment: measure the TMA side alone
             ptx::mbar_arrive(&empty_bar[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -429,6 +502,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         }
         if (CG == 1 && (p.debug & 1)) ptx::mbar_arrive(&tmem_full_bar[as]);
         else ptx::umma_commit<CG>(&tmem_full_bar[as]);  // accumulator complete -> epilogue (of both CTAs)
+        trace_ev(p.trace, titer, 5);
         if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
@@ -440,12 +514,14 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     const int team_tid = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the team
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const EpiArgs& e = p.epi;
-    TeamOut out{out_slots + team * kOutSlotBytes, bias_strips + team * 128, bias_strips + team * 128 + 64, team,
-                team_tid == 0, p.debug};
+    Team tm{slot_base + team * (kSlotsPerTeam * kSlotBytes), in_bars + team * kSlotsPerTeam,
+            bias_strips + team * Cfg::kBiasFloats, csum_strips + team * 128, 0u, 0u, 0u, team, team_tid == 0};
     const bool dual = e.out_lo != nullptr;
+    const bool tr = team_tid == 0 && team == 0;
     float loss_local = 0.f;
     uint32_t as = 0, aphase = 0;
-    for (int u = group_id; u < total_units; u += num_groups) {
+    int titer = 0;
+    for (int u = group_id; u < total_units; u += num_groups, ++titer) {
       const int ks = u / tiles;
       const int tile = u - ks * tiles;
       const int n_blk = tile / p.m_blocks;
@@ -453,245 +529,285 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       const int m0 = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM;
       const int m = m0 + row;
       const bool row_ok = m < p.M;
-      ptx::mbar_wait(&tmem_full_bar[as], aphase);
-      ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + as * BLOCK_N;
 
       if constexpr (EPI == EPI_HEAD) {
-        // tile columns [0, kHalf) = mu, [kHalf, BLOCK_N) = logvar of latent columns n_blk*kHalf ..
+        // ---- tile columns [0, kHalf) = mu, [kHalf, BLOCK_N) = logvar of latent columns n_blk*kHalf ..; a team owns
+        //      64 latent columns (BLOCK_N = 128: team 0 only). Slots A = 0, B = 1, C = 2 (drained once per tile):
+        //        eps[0:32] -> A, eps[32:64] -> B (TMA loads, issued before the accumulator is ready)
+        //        mu[0:32] in place in A, lv[0:32] -> C, stored; mu[32:64] in place in B, stored;
+        //        then lv[32:64] -> A and z[0:64] (bf16) -> C, stored.
         constexpr int kHalf = BLOCK_N / 2;
+        static_assert(kHalf / 64 <= kEpiTeams, "one HEAD unit per team per tile");
         const int L = e.L;
-        for (int sub = team; sub < kHalf / 64; sub += kEpiTeams) {
-          const int col0 = n_blk * kHalf + sub * 64;
-          if (e.out_hi) out.acquire();
+        const bool active = team < kHalf / 64;
+        const int col0 = n_blk * kHalf + team * 64;  // latent column of this team's unit
+        const bool has_eps = e.in0 != nullptr;
+        if (active && team_tid < 128) {
+          const int i = team_tid;  // strip: [0,64) mu bias, [64,128) logvar bias of the team's 64 latent columns
+          tm.bias_s[i] = (i < 64) ? __ldg(e.bias + col0 + i) : __ldg(e.bias + L + col0 + i - 64);
+        }
+        if (tm.issuer && active) {
+          ptx::tma_store_wait_read<0>();  // the previous tile's stores have released all three slots
+          if (has_eps) {
+            tm.load(0, &p.tmSide, col0, m0);
+            tm.load(1, &p.tmSide, col0 + 32, m0);
+          }
+        }
+        ptx::mbar_wait(&tmem_full_bar[as], aphase);
+        ptx::tc_fence_after();
+        if (team_tid == 0) trace_ev(p.trace, titer, 6 + 2 * team);
+        tm.sync();  // bias strip visible; slots known to be free
+        if (active) {
           float z[64];
+          float lv1[32];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int c = sub * 64 + h * 32;
-            const int col = col0 + h * 32;
-            __syncwarp();
+            const int c = team * 64 + h * 32;  // accumulator column of mu; logvar sits kHalf further
             uint32_t rm[32], rl[32];
             ptx::tmem_ld_32x32(t_acc + c, rm);
             ptx::tmem_ld_32x32(t_acc + kHalf + c, rl);
-            const size_t off = static_cast<size_t>(m) * L + col;
-            float eps[32];
-            if (row_ok && e.in0) {
-              load_row_f32<32>(reinterpret_cast<const float*>(e.in0) + off, eps);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) eps[j] = 0.f;
-            }
+            if (has_eps) tm.wait_load(h);
             ptx::tmem_ld_wait();
+            uint8_t* s_mu = tm.slot(h);        // eps in, mu out (in place)
+            uint8_t* s_lv = tm.slot(2);        // h == 0 only
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {  // 16 columns at a time keeps the side arrays small
-              float mu[16], lv[16], esh[16], gmu[16], glv[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int jj = 16 * q + j;
-                mu[j] = __uint_as_float(rm[jj]) + __ldg(e.bias + col + jj);
-                lv[j] = __uint_as_float(rl[jj]) + __ldg(e.bias + L + col + jj);
-                const float sig = expf(0.5f * lv[j]);
-                const float var = sig * sig;
-                z[h * 32 + jj] = fmaf(eps[jj], sig, mu[j]);
-                esh[j] = 0.5f * eps[jj] * sig;
-                gmu[j] = e.c0 * mu[j];
-                glv[j] = 0.5f * e.c0 * (var - 1.f);
-                if (row_ok) loss_local += (1.f + lv[j]) - fmaf(mu[j], mu[j], var);
+            for (int i = 0; i < 8; ++i) {      // one 16-byte chunk (4 columns) at a time keeps the register count low
+              float eps[4] = {0.f, 0.f, 0.f, 0.f};
+              if (has_eps) {
+                const uint4 t = *slot_chunk(s_mu, row, i);
+                eps[0] = __uint_as_float(t.x); eps[1] = __uint_as_float(t.y);
+                eps[2] = __uint_as_float(t.z); eps[3] = __uint_as_float(t.w);
               }
-              if (row_ok) {
-                store_row_f32<16>(e.out_f32 + off + 16 * q, mu);
-                store_row_f32<16>(e.out_f32_b + off + 16 * q, lv);
-                if (e.aux0) store_row_f32<16>(e.aux0 + off + 16 * q, esh);
-                if (e.aux1) store_row_f32<16>(e.aux1 + off + 16 * q, gmu);
-                if (e.aux2) store_row_f32<16>(e.aux2 + off + 16 * q, glv);
+              float mu[4], lv[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int jj = 4 * i + q;
+                mu[q] = __uint_as_float(rm[jj]) + tm.bias_s[h * 32 + jj];
+                lv[q] = __uint_as_float(rl[jj]) + tm.bias_s[64 + h * 32 + jj];
+                const float sig = expf(0.5f * lv[q]);
+                z[h * 32 + jj] = fmaf(eps[q], sig, mu[q]);
+                if (row_ok) loss_local += (1.f + lv[q]) - fmaf(mu[q], mu[q], sig * sig);
+                if (h == 1) lv1[jj] = lv[q];
+              }
+              *slot_chunk(s_mu, row, i) = make_uint4(__float_as_uint(mu[0]), __float_as_uint(mu[1]),
+                                                     __float_as_uint(mu[2]), __float_as_uint(mu[3]));
+              if (h == 0)
+                *slot_chunk(s_lv, row, i) = make_uint4(__float_as_uint(lv[0]), __float_as_uint(lv[1]),
+                                                       __float_as_uint(lv[2]), __float_as_uint(lv[3]));
+            }
+            ptx::fence_proxy_async_smem();
+            if (h == 0) {
+              tm.sync();
+              if (tm.issuer) {
+                ptx::tma_store_2d(&p.tmOutF32, tm.slot(0), col0, m0);
+                ptx::tma_store_2d(&p.tmOutF32b, tm.slot(2), col0, m0);
+                ptx::tma_store_commit();
+              }
+            } else {
+              if (tm.issuer) ptx::tma_store_wait_read<0>();  // slots A and C are free again ...
+              tm.sync();                                      // ... and everyone knows
+              if (tm.issuer) {
+                ptx::tma_store_2d(&p.tmOutF32, tm.slot(1), col0 + 32, m0);
+                ptx::tma_store_commit();
+              }
+              stage_f32(tm.slot(0), row, lv1);
+              if (e.out_hi) stage_bf16(tm.slot(2), row, z);
+              ptx::fence_proxy_async_smem();
+              tm.sync();
+              if (tm.issuer) {
+                ptx::tma_store_2d(&p.tmOutF32b, tm.slot(0), col0 + 32, m0);
+                if (e.out_hi) ptx::tma_store_2d(&p.tmOutHi, tm.slot(2), col0, m0);
+                ptx::tma_store_commit();
               }
             }
           }
-          if (e.out_hi) {
-            stage_bf16(out.slot, row, 0, z);
-            stage_bf16(out.slot, row, 4, z + 32);
-            out.commit(&p.tmOutHi, col0, m0, false);
-            if (dual) {
-              out.acquire();
-              stage_bf16_residual(out.slot, row, 0, z);
-              stage_bf16_residual(out.slot, row, 4, z + 32);
-              out.commit(&p.tmOutLo, col0, m0, false);
+          if (e.out_hi && dual) {
+            tm.drain();
+            stage_bf16_residual(tm.slot(0), row, z);
+            ptx::fence_proxy_async_smem();
+            tm.sync();
+            if (tm.issuer) {
+              ptx::tma_store_2d(&p.tmOutLo, tm.slot(0), col0, m0);
+              ptx::tma_store_commit();
             }
           }
         }
-      } else if constexpr (EPI == EPI_WGRAD) {
+      } else if constexpr (EPI == EPI_REDUCE) {
+        ptx::mbar_wait(&tmem_full_bar[as], aphase);
+        ptx::tc_fence_after();
+        if (team_tid == 0) trace_ev(p.trace, titer, 6 + 2 * team);
         for (int piece = team; piece < BLOCK_N / 32; piece += kEpiTeams) {
           const int n = n_blk * BLOCK_N + piece * 32;
           if (n >= p.N) continue;
-          __syncwarp();
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_acc + piece * 32, r);
-          out.acquire();
           ptx::tmem_ld_wait();
-          float v[32];
+          uint8_t* sl = tm.slot(tm.use);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          stage_f32(out.slot, row, v);
-          out.commit(&p.tmOutF32, n, m0, e.accumulate != 0);
+          for (int i = 0; i < 8; ++i) *slot_chunk(sl, row, i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          tm.store(tm.use, &p.tmOutF32, n, m0, e.accumulate != 0);
+          ++tm.use;
         }
       } else {
-        // ---- bf16 stream(s): LINEAR (act), DRELU (mask), OUT (da4), DZ (dmu then dlv): 64-column units
-        constexpr int kStreams = (EPI == EPI_DZ) ? 2 : 1;
+        // ---- bf16 stream: LINEAR (act), DRELU (mask), OUT (da4): 64-column units, side input prefetched by TMA.
+        //      Team t owns the 64-column groups t, t + 2 of the tile (bias strip: its own columns only).
         constexpr int kSubs = BLOCK_N / 64;
-        if (e.out_hi) {
-          for (int unit = team; unit < kStreams * kSubs; unit += kEpiTeams) {
-            const int stream = unit / kSubs;
-            const int sub = unit - stream * kSubs;
+        constexpr int kUnitsPerTeam = (kSubs + kEpiTeams - 1) / kEpiTeams;
+        static_assert(kUnitsPerTeam <= 2, "side-input prefetch covers at most two units per team and tile");
+        constexpr bool kSide = (EPI == EPI_OUT || EPI == EPI_DRELU);
+        constexpr bool kBias = (EPI == EPI_LINEAR || EPI == EPI_OUT);
+        const bool side = kSide && e.in0 != nullptr && e.out_hi != nullptr;
+        const bool do_colsum = kSide && e.colsum != nullptr;
+        if constexpr (kBias) {
+          if (team_tid < kUnitsPerTeam * 64) {
+            const int n = n_blk * BLOCK_N + (team + (team_tid >> 6) * kEpiTeams) * 64 + (team_tid & 63);
+            tm.bias_s[team_tid] = (e.bias && n < p.N) ? __ldg(e.bias + n) : 0.f;
+          }
+        }
+        if (side && !dual && tm.issuer) {
+          // the slots of the next two uses are free (see the invariant above): start this tile's side loads now,
+          // while its MMAs are still running
+#pragma unroll
+          for (int j = 0; j < kUnitsPerTeam; ++j) {
+            const int sub = team + j * kEpiTeams;
             const int n0 = n_blk * BLOCK_N + sub * 64;
-            if (n0 >= p.N) continue;
-            __syncwarp();
+            if (sub < kSubs && n0 < p.N) tm.load(tm.use + j, &p.tmSide, n0, m0);
+          }
+        }
+        ptx::mbar_wait(&tmem_full_bar[as], aphase);
+        ptx::tc_fence_after();
+        if (team_tid == 0) trace_ev(p.trace, titer, 6 + 2 * team);
+        if constexpr (kBias) tm.sync();  // bias strip visible
+        if (e.out_hi) {
+#pragma unroll 1
+          for (int j = 0; j < kUnitsPerTeam; ++j) {
+            const int sub = team + j * kEpiTeams;
+            const int n0 = n_blk * BLOCK_N + sub * 64;
+            if (sub >= kSubs || n0 >= p.N) continue;
             // 1) accumulator: both 32-column TMEM loads in flight
             uint32_t r[64];
-            if (!(p.debug & 8)) {
-              ptx::tmem_ld_32x32(t_acc + sub * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-              ptx::tmem_ld_32x32(t_acc + sub * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 64; ++j) r[j] = 0x3f800000u + j;
+            ptx::tmem_ld_32x32(t_acc + sub * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            ptx::tmem_ld_32x32(t_acc + sub * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            // 2) side input of this unit
+            if (dual) {  // fp32 emulation: no prefetch, slots 0 (hi, in place) and 1 (residual plane)
+              tm.drain();
+              tm.use = 0;
+              if (side && tm.issuer) tm.load(0, &p.tmSide, n0, m0);
             }
-            // 2) side inputs from global memory, issued before anything waits
-            const size_t off = static_cast<size_t>(m) * e.ldo + n0;
-            float side[64];
-            if constexpr (EPI == EPI_DRELU) {
-              if (e.in0 && row_ok) {
-                load_row_bf16<64>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, side);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) side[j] = 1.f;
-              }
-            } else if constexpr (EPI == EPI_OUT) {
-              if (row_ok) {
-                load_row_bf16<64>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, side);
-                if (e.in1) {
-                  float xl[64];
-                  load_row_bf16<64>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
-#pragma unroll
-                  for (int j = 0; j < 64; ++j) side[j] += xl[j];
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) side[j] = 0.f;
-              }
-            } else if constexpr (EPI == EPI_DZ) {
-              const size_t loff = static_cast<size_t>(m) * e.L + n0;
-              if (row_ok) {
-                load_row_f32<64>(reinterpret_cast<const float*>(stream == 0 ? e.in1 : e.in2) + loff, side);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) side[j] = 0.f;
-              }
-            }
-            // 3) bias strip of this unit -> smem (published by the barrier inside acquire())
-            if constexpr (EPI == EPI_LINEAR || EPI == EPI_OUT) {
-              if (team_tid < 64) out.bias_s[team_tid] = e.bias ? __ldg(e.bias + n0 + team_tid) : 0.f;
-            }
-            const bool do_colsum = (EPI == EPI_OUT || EPI == EPI_DRELU || EPI == EPI_DZ) && e.colsum != nullptr;
-            if (do_colsum && team_tid >= 64) out.csum_s[team_tid - 64] = 0.f;
-            out.acquire();
+            if (side) tm.wait_load(tm.use);
+            if (tr) trace_ev(p.trace, titer, j == 0 ? 10 : 14);
             ptx::tmem_ld_wait();
+            if (tr && j == 0) trace_ev(p.trace, titer, 11);
+            uint8_t* sl = tm.slot(tm.use);
             float v[64];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+            for (int q = 0; q < 64; ++q) v[q] = __uint_as_float(r[q]);
+            if constexpr (kBias) {
+#pragma unroll
+              for (int q = 0; q < 64; q += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(tm.bias_s + j * 64 + q);
+                v[q] += b.x; v[q + 1] += b.y; v[q + 2] += b.z; v[q + 3] += b.w;
+              }
+            }
             if constexpr (EPI == EPI_LINEAR) {
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(out.bias_s + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-              if (e.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
-              } else if (e.act == ACT_TANH) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = tanhf(v[j]);
-              } else if (e.act == ACT_TANH_APPROX) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = ptx::tanh_approx(v[j]);
-              }
+              apply_act<64>(v, e.act);
             } else if constexpr (EPI == EPI_DRELU) {
+              if (side) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) v[j] = (side[j] > 0.f) ? v[j] : 0.f;
-            } else if constexpr (EPI == EPI_OUT) {
+                for (int i = 0; i < 8; ++i) {  // ReLU mask: keep the gradient where the forward activation was > 0
+                  const uint4 t = *slot_chunk(sl, row, i);
+                  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-              for (int j = 0; j < 64; ++j) {
-                const float a = v[j] + out.bias_s[j];
-                const float xh = (e.act == ACT_TANH_APPROX) ? ptx::tanh_approx(a) : tanhf(a);
-                const float d = xh - side[j];
-                if (row_ok) loss_local = fmaf(d, d, loss_local);
-                v[j] = row_ok ? e.c0 * d * (1.f - xh * xh) : 0.f;
+                  for (int q = 0; q < 4; ++q) {
+                    // bf16 > 0  <=>  sign clear and magnitude non-zero (per 16-bit half of the word)
+                    const uint32_t lo16 = w[q] & 0xffffu, hi16 = w[q] >> 16;
+                    if (!(lo16 != 0u && lo16 < 0x8000u)) v[8 * i + 2 * q] = 0.f;
+                    if (!(hi16 != 0u && hi16 < 0x8000u)) v[8 * i + 2 * q + 1] = 0.f;
+                  }
+                }
               }
-            } else if constexpr (EPI == EPI_DZ) {
-              if (stream == 0) {  // dmu = dz + g_mu
+            } else {  // OUT: xh = tanh(a); d = xh - x; loss += d^2; da = c0 * d * (1 - xh^2)
+              apply_act<64>(v, e.act == ACT_TANH_APPROX ? ACT_TANH_APPROX : ACT_TANH);
 #pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] += side[j];
-              } else {            // dlv = dz * (eps sigma / 2) + g_logvar
-                float esh[64];
-                const size_t loff = static_cast<size_t>(m) * e.L + n0;
-                if (row_ok) {
-                  load_row_f32<64>(reinterpret_cast<const float*>(e.in0) + loff, esh);
+              for (int i = 0; i < 8; ++i) {
+                float x[8];
+                if (side) {
+                  const uint4 t = *slot_chunk(sl, row, i);
+                  const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(hh[q]);
+                    x[2 * q] = f.x; x[2 * q + 1] = f.y;
+                  }
+                  if (e.in1 && row_ok) {  // x = hi + lo (fp32 emulation): the residual comes straight from global
+                    const uint4 t2 = __ldg(reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const __nv_bfloat16*>(e.in1) + static_cast<size_t>(m) * e.ldo + n0 + 8 * i));
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t2);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float2 f = __bfloat1622float2(h2[q]);
+                      x[2 * q] += f.x; x[2 * q + 1] += f.y;
+                    }
+                  }
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 64; ++j) esh[j] = 0.f;
+                  for (int q = 0; q < 8; ++q) x[q] = 0.f;
                 }
 #pragma unroll
-                for (int j = 0; j < 64; ++j) v[j] = fmaf(v[j], esh[j], side[j]);
+                for (int q = 0; q < 8; ++q) {
+                  const float xh = v[8 * i + q];
+                  const float d = xh - x[q];
+                  if (row_ok) loss_local = fmaf(d, d, loss_local);
+                  v[8 * i + q] = row_ok ? e.c0 * d * (1.f - xh * xh) : 0.f;
+                }
               }
             }
-            const int c_out = (EPI == EPI_DZ) ? stream * e.L + n0 : n0;
-            if (!(p.debug & 32)) {
-              stage_bf16(out.slot, row, 0, v);
-              stage_bf16(out.slot, row, 4, v + 32);
-            } else if (v[0] == 12345.678f) {
-              out.slot[row] = 1;  // keep v live
-            }
-            if (dual) {  // residual plane (fp32 emulation): second pass through the same slot, before v is reduced
-              out.commit(&p.tmOutHi, c_out, m0, false);
-              out.acquire();
-              stage_bf16_residual(out.slot, row, 0, v);
-              stage_bf16_residual(out.slot, row, 4, v + 32);
-            }
+            stage_bf16(sl, row, v);
+            if (dual) stage_bf16_residual(tm.slot(tm.use + 1), row, v);
+            if (tr && j == 0) trace_ev(p.trace, titer, 12);
+            float* cs = tm.csum_s + (tm.cs_par << 6);
             if (do_colsum) {
               // bias gradient: column sums of this unit over the tile's 128 rows (rows >= M contribute zeros)
               warp_colsum64(v, lane);
-              atomicAdd(out.csum_s + 2 * lane, v[0]);
-              atomicAdd(out.csum_s + 2 * lane + 1, v[1]);
+              atomicAdd(cs + 2 * lane, v[0]);
+              atomicAdd(cs + 2 * lane + 1, v[1]);
             }
-            out.commit(dual ? &p.tmOutLo : &p.tmOutHi, c_out, m0, false);
-            // (the barrier inside commit() ordered the four warps' smem atomics before this read)
-            if (do_colsum && team_tid < 64) atomicAdd(e.colsum + c_out + team_tid, out.csum_s[team_tid]);
+            tm.store(tm.use, &p.tmOutHi, n0, m0, false);
+            if (dual && tm.issuer) {
+              ptx::tma_store_2d(&p.tmOutLo, tm.slot(tm.use + 1), n0, m0);
+              ptx::tma_store_commit();
+            }
+            if (tr) trace_ev(p.trace, titer, j == 0 ? 13 : 15);
+            if (do_colsum) {
+              // the barrier inside store() ordered the four warps' smem atomics before this read; the strip is
+              // cleared for its next use two units from now (the other strip serves the unit in between)
+              if (team_tid < 64) {
+                atomicAdd(e.colsum + n0 + team_tid, cs[team_tid]);
+                cs[team_tid] = 0.f;
+              }
+              tm.cs_par ^= 1u;
+            }
+            ++tm.use;
           }
         }
-        // ---- fp32 stream: LINEAR's fp32 copy / OUT's xhat: 32-column units
-        if constexpr (EPI == EPI_LINEAR || EPI == EPI_OUT) {
+        // ---- fp32 stream: LINEAR's fp32 copy / OUT's xhat: 32-column pieces of the team's own column groups
+        if constexpr (kBias) {
           if (e.out_f32) {
-            for (int piece = team; piece < BLOCK_N / 32; piece += kEpiTeams) {
-              const int n = n_blk * BLOCK_N + piece * 32;
-              if (n >= p.N) continue;
-              __syncwarp();
+            if (dual) { tm.drain(); tm.use = 0; }
+#pragma unroll 1
+            for (int jp = 0; jp < 2 * kUnitsPerTeam; ++jp) {
+              const int j = jp >> 1, hf = jp & 1;
+              const int sub = team + j * kEpiTeams;
+              const int n = n_blk * BLOCK_N + sub * 64 + hf * 32;
+              if (sub >= kSubs || n >= p.N) continue;
               uint32_t r[32];
-              ptx::tmem_ld_32x32(t_acc + piece * 32, r);
-              if (team_tid < 32) out.bias_s[team_tid] = e.bias ? __ldg(e.bias + n + team_tid) : 0.f;
-              out.acquire();
+              ptx::tmem_ld_32x32(t_acc + sub * 64 + hf * 32, r);
               ptx::tmem_ld_wait();
               float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + out.bias_s[j];
-              const int act = (EPI == EPI_OUT && e.act != ACT_TANH_APPROX) ? ACT_TANH : e.act;
-              if (act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              } else if (act == ACT_TANH) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-              } else if (act == ACT_TANH_APPROX) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ptx::tanh_approx(v[j]);
-              }
+              for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]) + tm.bias_s[j * 64 + hf * 32 + q];
+              apply_act<32>(v, (EPI == EPI_OUT && e.act != ACT_TANH_APPROX) ? ACT_TANH : e.act);
               if constexpr (EPI == EPI_OUT) {
                 if (!e.out_hi && row_ok) {  // loss-only forward: accumulate the MSE here
                   const size_t off = static_cast<size_t>(m) * e.ldo + n;
@@ -701,14 +817,15 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
                     float xl[32];
                     load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in1) + off, xl);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] += xl[j];
+                    for (int q = 0; q < 32; ++q) x[q] += xl[q];
                   }
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) loss_local = fmaf(v[j] - x[j], v[j] - x[j], loss_local);
+                  for (int q = 0; q < 32; ++q) loss_local = fmaf(v[q] - x[q], v[q] - x[q], loss_local);
                 }
               }
-              stage_f32(out.slot, row, v);
-              out.commit(&p.tmOutF32, n, m0, false);
+              stage_f32(tm.slot(tm.use), row, v);
+              tm.store(tm.use, &p.tmOutF32, n, m0, false);
+              ++tm.use;
             }
           }
         }
@@ -718,11 +835,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       __syncwarp();
       if (lane == 0) {
         if (CG == 1 || leader) ptx::mbar_arrive(&tmem_empty_bar[as]);
-        else ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+        else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
       }
+      if (team_tid == 0) trace_ev(p.trace, titer, 7 + 2 * team);
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
-    if (out.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
+    if (tm.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
     if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
       const float s = warp_sum(loss_local);
       if (lane == 0 && e.loss_acc) atomicAdd(e.loss_acc, static_cast<double>(s));
@@ -735,6 +853,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
     __syncwarp();
     ptx::tc_fence_after();
     ptx::tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
+  }
+  if (threadIdx.x == 0) {
+    trace_hdr(p.trace, 5, clock64());
+    trace_hdr(p.trace, 6, global_timer());
   }
 }
 

@@ -73,8 +73,8 @@ static int encode_bf16_2d(CUtensorMap* tm, const void* base, uint64_t dim0, uint
   return encode_2d(tm, base, false, dim0, dim1, ld, box0, box1);
 }
 
-// Output tensor maps of a prepared GEMM (epilogue TMA stores): bf16 planes in boxes of 64 columns, fp32 in boxes of
-// 32 columns, 128 rows each. Re-encodes only the maps whose base pointer changed.
+// Tensor maps of a prepared GEMM's epilogue (TMA stores and side-input loads): bf16 planes in boxes of 64 columns,
+// fp32 in boxes of 32 columns, 128 rows each. Re-encodes only the maps whose base pointer changed.
 int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& a, bool force) {
   GemmParams& p = g->params;
   const EpiArgs old = p.epi;
@@ -83,8 +83,16 @@ int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& a, bool force) {
     RVAE_CHECK(encode_2d(&p.tmOutHi, a.out_hi, false, g->out_cols_bf16, g->out_rows, g->out_ld_bf16, 64, 128));
   if (a.out_lo && (force || a.out_lo != old.out_lo))
     RVAE_CHECK(encode_2d(&p.tmOutLo, a.out_lo, false, g->out_cols_bf16, g->out_rows, g->out_ld_bf16, 64, 128));
-  if (a.out_f32 && g->out_f32_tma && (force || a.out_f32 != old.out_f32))
+  if (a.out_f32 && (force || a.out_f32 != old.out_f32))
     RVAE_CHECK(encode_2d(&p.tmOutF32, a.out_f32, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
+  if (a.out_f32_b && g->epi == EPI_HEAD && (force || a.out_f32_b != old.out_f32_b))
+    RVAE_CHECK(encode_2d(&p.tmOutF32b, a.out_f32_b, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
+  if (a.in0 && (force || a.in0 != old.in0)) {
+    if (g->epi == EPI_HEAD)  // eps, fp32 [M, L]
+      RVAE_CHECK(encode_2d(&p.tmSide, a.in0, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
+    else if (g->epi == EPI_OUT || g->epi == EPI_DRELU)  // x / ReLU mask, bf16 [M, N]
+      RVAE_CHECK(encode_2d(&p.tmSide, a.in0, false, g->out_cols_bf16, g->out_rows, g->out_ld_bf16, 64, 128));
+  }
   return RVAE_OK;
 }
 
@@ -108,8 +116,8 @@ static const Variant kVariants[] = {
     RVAE_VARIANT(256, MAJOR_K, MAJOR_K, EPI_HEAD),    RVAE_VARIANT(128, MAJOR_K, MAJOR_K, EPI_HEAD),
     RVAE_VARIANT(256, MAJOR_K, MAJOR_K, EPI_OUT),     RVAE_VARIANT(128, MAJOR_K, MAJOR_K, EPI_OUT),
     RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_DRELU),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_DRELU),
-    RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_DZ),     RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_DZ),
-    RVAE_VARIANT(256, MAJOR_MN, MAJOR_MN, EPI_WGRAD), RVAE_VARIANT(128, MAJOR_MN, MAJOR_MN, EPI_WGRAD),
+    RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_REDUCE),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_REDUCE),
+    RVAE_VARIANT(256, MAJOR_MN, MAJOR_MN, EPI_REDUCE), RVAE_VARIANT(128, MAJOR_MN, MAJOR_MN, EPI_REDUCE),
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -170,6 +178,7 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = d.args;
   p.debug = ctx->debug;
+  p.trace = ctx->trace;
 
   int block_n, cg;
   if (d.epi == EPI_HEAD) {
@@ -182,8 +191,9 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
     p.b_half_stride = L;
     p.epi.L = L;
   } else {
-    // weight gradients: 256-wide tiles, split-K fills the machine; others: by wave count
-    choose_tile(ctx, d.M, d.N, d.epi != EPI_WGRAD || d.N % 256 != 0, true, &block_n, &cg);
+    // reduce-add GEMMs (weight gradients, latent dgrad): 256-wide tiles, split-K fills the machine; others: by
+    // wave count
+    choose_tile(ctx, d.M, d.N, d.epi != EPI_REDUCE || d.N % 256 != 0, true, &block_n, &cg);
     p.n_blocks = ceil_div(d.N, block_n);
     p.b_tile_stride = block_n;
     p.b_half_stride = block_n / 2;
@@ -192,9 +202,9 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   const int slots = ctx->num_sms / cg;
   p.kb_total = ceil_div(d.K, kBlockK);
 
-  // split-K only where the epilogue is a linear accumulation (weight gradients)
+  // split-K only where the epilogue is a linear accumulation
   int splits = 1;
-  if (d.epi == EPI_WGRAD) {
+  if (d.epi == EPI_REDUCE) {
     const int tiles = p.m_blocks * p.n_blocks;
     if (d.k_splits > 0) {
       splits = d.k_splits;
@@ -209,7 +219,7 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
       }
     }
     if (splits > p.kb_total) splits = p.kb_total;
-    RVAE_REQUIRE(splits == 1 || d.args.accumulate, RVAE_ERR_INVALID, "wgrad: split-K needs accumulate=1");
+    RVAE_REQUIRE(splits == 1 || d.args.accumulate, RVAE_ERR_INVALID, "reduce gemm: split-K needs accumulate=1");
   }
   p.kb_per_split = ceil_div(p.kb_total, splits);
   p.k_splits = ceil_div(p.kb_total, p.kb_per_split);  // every split owns >= 1 k-block
@@ -243,17 +253,16 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
       RVAE_CHECK(encode_bf16_2d(&p.tmB[i], b_ptr[i], d.N, d.K, d.B.ld, 64, kBlockK));
   }
 
-  // epilogue output tensors (what the TMA stores write)
+  // epilogue tensors (what the TMA stores write and the side-input loads read)
+  g.epi = d.epi;
   g.out_rows = d.M;
-  g.out_f32_tma = (d.epi == EPI_LINEAR || d.epi == EPI_OUT || d.epi == EPI_WGRAD);
-  if (d.epi == EPI_HEAD) {            // z [M, L]
+  if (d.epi == EPI_HEAD) {            // z [M, L] bf16; mu, logvar, eps [M, L] fp32
     g.out_cols_bf16 = d.head_L; g.out_ld_bf16 = d.head_L;
-  } else if (d.epi == EPI_DZ) {       // d_ml [M, 2L]
-    g.out_cols_bf16 = 2 * d.args.L; g.out_ld_bf16 = d.args.ldo;
+    g.out_cols_f32 = d.head_L; g.out_ld_f32 = d.head_L;
   } else {
     g.out_cols_bf16 = d.N; g.out_ld_bf16 = d.args.ldo;
+    g.out_cols_f32 = d.N; g.out_ld_f32 = d.args.ldo;
   }
-  g.out_cols_f32 = d.N; g.out_ld_f32 = d.args.ldo;
   RVAE_CHECK(gemm_bind_outputs(&g, p.epi, true));
 
   g.block_n = block_n;

@@ -158,9 +158,9 @@ class Plan:
     def backward(self, stage: int = -1) -> None:
         check(self.lib.rvae_plan_backward(self.handle, stage, self._stream()))
 
-    def backward_external(self, g_xhat, xhat, g_mu, g_logvar) -> None:
+    def backward_external(self, g_xhat, xhat, g_mu, g_logvar, logvar) -> None:
         check(self.lib.rvae_plan_backward_external(self.handle, g_xhat.data_ptr(), xhat.data_ptr(), g_mu.data_ptr(),
-                                                   g_logvar.data_ptr(), self._stream()))
+                                                   g_logvar.data_ptr(), logvar.data_ptr(), self._stream()))
 
     def finish_loss(self, kl_beta: float, loss_out: Optional[torch.Tensor], ring_size: int = 1) -> None:
         check(self.lib.rvae_plan_finish_loss(self.handle, kl_beta,
@@ -186,7 +186,7 @@ class Plan:
         self.token += 1
 
     GEMM_SLOTS = ("F1", "F2", "F3", "F4_out", "F4_lin", "B4w", "B4d", "B3w", "B3d", "B2w", "B2d", "B1w")
-    AUX_SLOTS = ("load", "eps", "finalize", "colsum", "adam", "tanh_bwd")
+    AUX_SLOTS = ("load", "eps", "finalize", "colsum", "adam", "tanh_bwd", "latent_bwd")
 
     def enable_timing(self, on: bool) -> None:
         check(self.lib.rvae_plan_enable_timing(self.handle, int(on)))

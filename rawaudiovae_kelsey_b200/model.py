@@ -258,13 +258,13 @@ class _VAEForward(torch.autograd.Function):
         plan.forward(0.0, fused_loss=False, want_xhat=True)
         plan.set_outputs(None, None, None)
         ctx.model, ctx.plan, ctx.token = model, plan, plan.token
-        ctx.save_for_backward(xhat)
+        ctx.save_for_backward(xhat, lv)
         return xhat, mu, lv
 
     @staticmethod
     def backward(ctx, g_xhat, g_mu, g_lv):
         model, plan = ctx.model, ctx.plan
-        (xhat,) = ctx.saved_tensors
+        xhat, lv = ctx.saved_tensors
         if plan.token != ctx.token:
             raise RuntimeError("the activations of this forward pass were overwritten by a later forward on the "
                                "same model; call backward() before running the model again")
@@ -280,7 +280,7 @@ class _VAEForward(torch.autograd.Function):
         for _, p in named:
             if p.grad is not None and g0 <= p.grad.data_ptr() < g1:
                 p.grad = p.grad.clone()
-        plan.backward_external(g_xhat, xhat, g_mu, g_lv)
+        plan.backward_external(g_xhat, xhat, g_mu, g_lv, lv)
         grads = tuple(flat.view(flat.grads, n) for n, _ in named)
         return (None, None, None) + grads
 

@@ -48,6 +48,18 @@ def num_sms(device: Optional[torch.device] = None) -> int:
     return int(_lib.load().rvae_ctx_num_sms(ctx(device)))
 
 
+TRACE_HEADER, TRACE_TILES, TRACE_EVENTS = 16, 24, 16
+TRACE_WORDS_PER_CTA = TRACE_HEADER + TRACE_TILES * TRACE_EVENTS
+
+
+def set_trace(buf: Optional[torch.Tensor]) -> None:
+    """Debug: direct the GEMM timeline trace (csrc/gemm.cuh) into an int64 CUDA tensor of
+    TRACE_WORDS_PER_CTA * grid words, or switch it off with None."""
+    if buf is not None and (buf.dtype != torch.int64 or not buf.is_cuda or not buf.is_contiguous()):
+        raise _lib.RvaeError("trace buffer must be a contiguous int64 CUDA tensor")
+    check(_lib.load().rvae_debug_set_trace(ctx(None if buf is None else buf.device), None if buf is None else buf.data_ptr()))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -207,8 +219,9 @@ def linear_act_fwd(x, w, bias, act: int, *, out_bf16=True, out_lo=False, out_f32
     return y_hi, y_lo, y_f
 
 
-def encode_head_fwd(h, w2, b2, eps, *, kl_grad_scale: float = 0.0, want_lo=False, want_bwd=False, kl_acc=None):
-    """mu, logvar, z (+ esh, g_mu, g_logvar when want_bwd) from h [M,K], stacked W2 [2L,K], b2 [2L], eps [M,L]."""
+def encode_head_fwd(h, w2, b2, eps, *, want_lo=False, want_z=True, kl_acc=None):
+    """mu, logvar (fp32) and z = mu + eps*exp(logvar/2) (bf16 planes) from h [M,K], stacked W2 [2L,K], b2 [2L],
+    eps [M,L] (None = 0)."""
     lib = _lib.load()
     hh, hl = _planes(h, "h")
     wh, wl = _planes(w2, "w2")
@@ -219,14 +232,12 @@ def encode_head_fwd(h, w2, b2, eps, *, kl_grad_scale: float = 0.0, want_lo=False
     dev = ht.device
     f = lambda: torch.empty((M, L), dtype=torch.float32, device=dev)
     mu, lv = f(), f()
-    z_hi = torch.empty((M, L), dtype=torch.bfloat16, device=dev)
-    z_lo = torch.empty_like(z_hi) if want_lo else None
-    esh, gmu, glv = (f(), f(), f()) if want_bwd else (None, None, None)
+    z_hi = torch.empty((M, L), dtype=torch.bfloat16, device=dev) if want_z else None
+    z_lo = torch.empty_like(z_hi) if (want_z and want_lo) else None
     check(lib.rvae_encode_head_fwd(ctx(dev), hh, hl, wh, wl, _ptr(b2, torch.float32, "b2"), M, L, K,
                                    _ptr(eps, torch.float32, "eps"), _ptr(mu), _ptr(lv), _ptr(z_hi), _ptr(z_lo),
-                                   _ptr(esh), _ptr(gmu), _ptr(glv), kl_grad_scale,
                                    _ptr(kl_acc, torch.float64, "kl_acc"), _stream()))
-    return mu, lv, (z_hi, z_lo), esh, gmu, glv
+    return mu, lv, (z_hi, z_lo)
 
 
 def out_tanh_mse_fwd(h3, w4, b4, x, *, grad_scale: float, tanh_approx=False, want_xhat=True, want_da=True,
@@ -267,7 +278,10 @@ def dgrad_relu(dy, w, mask, *, want_lo=False, bias_grad=None):
     return dx_hi, dx_lo
 
 
-def dgrad_latent(da3, w3, esh, g_mu, g_lv, *, want_lo=False, bias_grad=None):
+def dgrad_latent(da3, w3, eps, logvar, mu=None, *, g_mu=None, g_logvar=None, kl_grad_scale: float = 0.0,
+                 want_lo=False, bias_grad=None):
+    """d_ml = [dz + g_mu | dz*eps*exp(logvar/2)/2 + g_logvar] with dz = da3 @ w3; the additive terms are the KL
+    gradient computed from (mu, logvar, kl_grad_scale) unless external g_mu / g_logvar are given."""
     lib = _lib.load()
     dh, dl = _planes(da3, "da3")
     wh, wl = _planes(w3, "w3")
@@ -278,8 +292,11 @@ def dgrad_latent(da3, w3, esh, g_mu, g_lv, *, want_lo=False, bias_grad=None):
     dev = dt.device
     hi = torch.empty((M, 2 * L), dtype=torch.bfloat16, device=dev)
     lo = torch.empty_like(hi) if want_lo else None
-    check(lib.rvae_dgrad_latent(ctx(dev), dh, dl, wh, wl, M, L, H, _ptr(esh, torch.float32), _ptr(g_mu, torch.float32),
-                                _ptr(g_lv, torch.float32), _ptr(hi), _ptr(lo),
+    dz = torch.empty((M, L), dtype=torch.float32, device=dev)
+    check(lib.rvae_dgrad_latent(ctx(dev), dh, dl, wh, wl, M, L, H, _ptr(eps, torch.float32, "eps"),
+                                _ptr(logvar, torch.float32, "logvar"), _ptr(mu, torch.float32, "mu"),
+                                _ptr(g_mu, torch.float32, "g_mu"), _ptr(g_logvar, torch.float32, "g_logvar"),
+                                kl_grad_scale, _ptr(dz), _ptr(hi), _ptr(lo),
                                 _ptr(bias_grad, torch.float32, "bias_grad"), _stream()))
     return hi, lo
 

@@ -33,8 +33,10 @@ def main(case):
                 ref = torch.relu(x.double() @ w.double().T + b.double())
             else:
                 xb, wb = bf(x), bf(w)
-                _, _, y = ops.linear_act_fwd(xb, wb, b, ops.ACT_RELU, out_bf16=False, out_f32=True)
+                yb, _, y = ops.linear_act_fwd(xb, wb, b, ops.ACT_RELU, out_bf16=True, out_f32=True)
                 ref = torch.relu(xb.double() @ wb.double().T + b.double())
+                torch.cuda.synchronize()
+                print(case, (M, N, K), "bf16 stream rel/maxabs", rel(yb, ref), flush=True)
             torch.cuda.synchronize()
             print(case, (M, N, K), "rel/maxabs", rel(y, ref), flush=True)
         # timing
@@ -55,15 +57,15 @@ def main(case):
             h, w2, b2, eps = g(M, K), g(2 * L, K) * 0.02, g(2 * L) * 0.1, g(M, L)
             hb, wb = bf(h), bf(w2)
             acc = torch.zeros(2, dtype=torch.float64, device=dev)
-            c0 = 1e-4 / (M * L)
-            mu, lv, (z, _), esh, gmu, glv = ops.encode_head_fwd(hb, wb, b2, eps, kl_grad_scale=c0, want_bwd=True, kl_acc=acc[1:])
+            mu, lv, (z, _) = ops.encode_head_fwd(hb, wb, b2, eps, kl_acc=acc[1:])
             torch.cuda.synchronize()
             ml = hb.double() @ wb.double().T + b2.double()
             rmu, rlv = ml[:, :L], ml[:, L:]
             sig = torch.exp(0.5 * rlv)
             print("head", (M, L, K), "mu", rel(mu, rmu), "lv", rel(lv, rlv), "z", rel(z, rmu + eps.double() * sig),
-                  "esh", rel(esh, 0.5 * eps.double() * sig), "gmu", rel(gmu, c0 * rmu), "glv", rel(glv, 0.5 * c0 * (torch.exp(rlv) - 1)),
                   "kl", float(acc[1]), float((1 + rlv - rmu ** 2 - torch.exp(rlv)).sum()), flush=True)
+            mu2, lv2, _ = ops.encode_head_fwd(hb, wb, b2, None, want_z=False)
+            print("head (encode only)", rel(mu2, rmu), rel(lv2, rlv), flush=True)
     elif case == "out":
         for (M, S, K) in [(8192, 1024, 2048), (200, 128, 64)]:
             h, w, b, x = g(M, K), g(S, K) * 0.02, g(S) * 0.1, torch.rand(M, S, device=dev) * 2 - 1
@@ -88,14 +90,22 @@ def main(case):
             print("dgrad", (M, N, Kd), rel(dx, ref), "db", rel(bg, ref.sum(0)), flush=True)
     elif case == "dz":
         for (M, L, H) in [(8192, 256, 2048), (200, 64, 128)]:
-            da3, w3, esh, gmu, glv = g(M, H), g(H, L) * 0.05, g(M, L), g(M, L), g(M, L)
+            da3, w3, eps, lv, mu = g(M, H), g(H, L) * 0.05, g(M, L), g(M, L) * 0.3, g(M, L)
             db, wb = bf(da3), bf(w3)
-            bg = torch.zeros(2 * L, device=dev)
-            dml, _ = ops.dgrad_latent(db, wb, esh, gmu, glv, bias_grad=bg)
-            torch.cuda.synchronize()
+            c0 = 1e-2
             dz = db.double() @ wb.double()
-            ref = torch.cat([dz + gmu.double(), dz * esh.double() + glv.double()], 1)
-            print("dz", (M, L, H), rel(dml, ref), "db", rel(bg, ref.sum(0)), flush=True)
+            sig = torch.exp(0.5 * lv.double())
+            esh = 0.5 * eps.double() * sig
+            bg = torch.zeros(2 * L, device=dev)
+            dml, _ = ops.dgrad_latent(db, wb, eps, lv, mu, kl_grad_scale=c0, bias_grad=bg)
+            torch.cuda.synchronize()
+            ref = torch.cat([dz + c0 * mu.double(), dz * esh + 0.5 * c0 * (sig * sig - 1)], 1)
+            print("dz fused", (M, L, H), rel(dml, ref), "db", rel(bg, ref.sum(0)), flush=True)
+            gmu, glv = g(M, L), g(M, L)
+            dml, _ = ops.dgrad_latent(db, wb, eps, lv, None, g_mu=gmu, g_logvar=glv)
+            torch.cuda.synchronize()
+            ref = torch.cat([dz + gmu.double(), dz * esh + glv.double()], 1)
+            print("dz external", (M, L, H), rel(dml, ref), flush=True)
     elif case in ("wgrad", "wgrad_split"):
         for (B, M, N) in [(8192, 1024, 2048), (8192, 2048, 256), (8192, 512, 2048), (1000, 128, 64), (8192, 2048, 1024)]:
             dy, x = g(B, M), g(B, N)
@@ -172,19 +182,19 @@ def main(case):
         x, h, z, ml = bf(g(B, S_)), bf(g(B, H_)), bf(g(B, L_)), bf(g(B, 2 * L_))
         w1, w2, w3, w4 = bf(g(H_, S_)), bf(g(2 * L_, H_)), bf(g(H_, L_)), bf(g(S_, H_))
         b1, b2, b4 = g(H_), g(2 * L_), g(S_)
-        eps, esh = g(B, L_), g(B, L_)
+        eps, esh = g(B, L_), g(B, L_) * 0.3
         acc = torch.zeros(2, dtype=torch.float64, device=dev)
         dw4 = torch.zeros(S_, H_, device=dev); dw3 = torch.zeros(H_, L_, device=dev)
         dw2 = torch.zeros(2 * L_, H_, device=dev); dw1 = torch.zeros(H_, S_, device=dev)
         tot = 0.0
         tot += timeit(lambda: ops.linear_act_fwd(x, w1, b1, ops.ACT_RELU), 2 * B * H_ * S_, "F1")
-        tot += timeit(lambda: ops.encode_head_fwd(h, w2, b2, eps, want_bwd=True, kl_acc=acc[1:]), 2 * B * 2 * L_ * H_, "F2")
+        tot += timeit(lambda: ops.encode_head_fwd(h, w2, b2, eps, kl_acc=acc[1:]), 2 * B * 2 * L_ * H_, "F2")
         tot += timeit(lambda: ops.linear_act_fwd(z, w3, b1, ops.ACT_RELU), 2 * B * H_ * L_, "F3")
         tot += timeit(lambda: ops.out_tanh_mse_fwd(h, w4, b4, x, grad_scale=1e-6, tanh_approx=True, want_xhat=False, mse_acc=acc[:1]), 2 * B * S_ * H_, "F4")
         tot += timeit(lambda: ops.wgrad(x, h, out=dw4), 2 * B * S_ * H_, "B4w")
         tot += timeit(lambda: ops.dgrad_relu(x, w4, h), 2 * B * S_ * H_, "B4d")
         tot += timeit(lambda: ops.wgrad(h, z, out=dw3), 2 * B * H_ * L_, "B3w")
-        tot += timeit(lambda: ops.dgrad_latent(h, w3, esh, esh, esh), 2 * B * H_ * L_, "B3d")
+        tot += timeit(lambda: ops.dgrad_latent(h, w3, eps, esh, esh), 2 * B * H_ * L_, "B3d")
         tot += timeit(lambda: ops.wgrad(ml, h, out=dw2), 2 * B * 2 * L_ * H_, "B2w")
         tot += timeit(lambda: ops.dgrad_relu(ml, w2, h), 2 * B * 2 * L_ * H_, "B2d")
         tot += timeit(lambda: ops.wgrad(h, x, out=dw1), 2 * B * H_ * S_, "B1w")
@@ -199,7 +209,7 @@ if __name__ == "__main__":
         for c in CASES:
             t0 = time.time()
             try:
-                r = subprocess.run([sys.executable, __file__, c], timeout=240)
+                r = subprocess.run([sys.executable, __file__, c], timeout=90)
                 code = r.returncode
             except subprocess.TimeoutExpired:
                 code = "TIMEOUT"
