@@ -228,18 +228,44 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
                                 const float* g_logvar, const float* logvar, void* stream);
 /* Backward stage s = 0..3 (fc4 | fc3 | fc21+fc22 | fc1 WEIGHT gradients complete after stage s - the allreduce
  * buckets, in backward-completion order; the bias block is complete after stage 2); stage -1 runs all four.
- * Within a stage the weight-gradient GEMM runs on an internal side stream concurrently with the dgrad GEMM and is
- * joined back into `stream` before the call returns. Gradients land in bufs.grads. */
+ * Within a stage the dgrad GEMM (the critical dependency chain) is issued before the weight-gradient GEMM, both on
+ * `stream`. Gradients land in bufs.grads. */
 int rvae_plan_backward(rvae_plan* plan, int stage, void* stream);
 /* loss -> loss_out[t mod ring_size] (device floats, may be NULL; t = *step before the call), clears the loss sums,
  * *step += 1. ring_size = 1 writes *loss_out. The value is the mean loss over this rank's frames. */
 int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, int ring_size, void* stream);
+/* Same, but without a kernel of its own: the finalisation is carried out by the latent backward kernel of the next
+ * rvae_plan_backward stage 1 (or -1) of this plan, which MUST follow on the same stream before loss_out is read, the
+ * next forward is issued or Adam runs. Saves one dependent launch per training step. */
+int rvae_plan_finish_loss_deferred(rvae_plan* plan, float kl_beta, float* loss_out, int ring_size);
+/* Input prefetch: describe the NEXT step's batch (same arguments as rvae_plan_load_frames with row_offset 0, plus
+ * the rvae_plan_gen_eps arguments for its noise). The next rvae_plan_train_step gathers it into the plan's alternate
+ * input buffers on a low-priority background stream while its own GEMMs run (the reference's DataLoader prefetches
+ * the next batch the same way, on the host); rvae_plan_swap_prefetched then makes it current instead of
+ * rvae_plan_load_frames + rvae_plan_gen_eps. rvae_plan_prefetched_batch: frames waiting in the alternate set (0 = none). */
+int rvae_plan_prefetch_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                              const int64_t* frame_idx, int64_t first_frame, int count, int hop, uint64_t seed,
+                              uint64_t offset, int add_step);
+int rvae_plan_swap_prefetched(rvae_plan* plan);
+int rvae_plan_prefetched_batch(const rvae_plan* plan);
+/* Make `stream` wait for background work of earlier calls that a later call would otherwise join (the noise of
+ * rvae_plan_gen_eps). Needed before a CUDA-graph capture starts: a captured stream must not wait on uncaptured work. */
+int rvae_plan_join_background(rvae_plan* plan, void* stream);
+/* Host-side bookkeeping for CUDA-graph replays: a replayed rvae_plan_train_step performed the prefetch on the device
+ * without running this library's host code; tell the plan that `count` frames wait in the alternate input set. */
+int rvae_plan_note_prefetched(rvae_plan* plan, int count);
 /* Adam over the flat buffers (+ shadow refresh). grad_scale rescales the gradients (1 for SUM all-reduced,
  * globally normalised gradients). zero_grads != 0: the kernel also clears bufs.grads after consuming it - the
  * optimizer.zero_grad() of the next iteration (train.py:184) - which lets the next backward skip its memsets. */
 int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
                    float grad_scale, int zero_grads, void* stream);
-/* forward + finish_loss + backward(-1) + adam in one call (single-GPU training step). */
+/* Adam restricted to the gradient buckets in bucket_mask (bit s = bucket s of rvae_plan_bucket): lets a caller update
+ * a bucket as soon as its gradient (and, under data parallelism, its all-reduce) is complete. The caller orders the
+ * launch after the backward stage that completes the bucket: that stage's dgrad GEMM reads the bucket's bf16 shadow. */
+int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, float grad_scale, int zero_grads, void* stream);
+/* forward + loss + backward + Adam in one call (single-GPU training step). Adam runs per bucket on an internal
+ * stream underneath the later backward stages; everything is joined back into `stream` before the call returns. */
 int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
                          float weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream);
 
@@ -270,13 +296,18 @@ int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double*
 
 /* Debug / profiling aid: every tcgen05 GEMM prepared through `ctx` after this call writes a per-CTA, per-tile
  * timeline (clock64 stamps of the TMA-producer, MMA-issuer and epilogue roles; layout in csrc/gemm.cuh, "Timeline
- * trace") into `buf` (device memory, RVAE_TRACE_WORDS_PER_CTA * grid 64-bit words). NULL switches tracing off.
- * Costs a few stores per tile; never enabled on the training path. */
+ * trace") into `buf` (device memory, `launches` slabs of RVAE_TRACE_WORDS_PER_CTA * SM-count 64-bit words; successive
+ * GEMM launches use successive slabs, wrapping around). NULL switches tracing off. Costs a few stores per tile;
+ * never enabled on the training path. */
 #define RVAE_TRACE_HEADER_WORDS 16
 #define RVAE_TRACE_TILES 24
 #define RVAE_TRACE_EVENTS 16
 #define RVAE_TRACE_WORDS_PER_CTA (RVAE_TRACE_HEADER_WORDS + RVAE_TRACE_TILES * RVAE_TRACE_EVENTS)
-int rvae_debug_set_trace(rvae_ctx* ctx, void* buf);
+int rvae_debug_set_trace(rvae_ctx* ctx, void* buf, int launches);
+/* Same idea for the HBM-bound kernels (gather, randn, latent backward, Adam): launch i writes 4 words at buf + 4*i
+ * (wrapping at `launches`): globaltimer of the first block's start (initialise to ~0ull) and the last block's end,
+ * kind (1 gather, 2 randn, 3 latent backward, 4 Adam), grid size. */
+int rvae_debug_set_aux_trace(rvae_ctx* ctx, void* buf, int launches);
 
 /* Inference: decode latents z (fp32 [batch, L]) -> xhat fp32 [batch, S] (model.py:28-30). */
 int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out, void* stream);

@@ -73,6 +73,13 @@ SIGNATURES = {
     "rvae_plan_backward": (c_int, [P, c_int, P]),
     "rvae_plan_backward_external": (c_int, [P, P, P, P, P, P, P]),
     "rvae_plan_finish_loss": (c_int, [P, c_float, P, c_int, P]),
+    "rvae_plan_finish_loss_deferred": (c_int, [P, c_float, P, c_int]),
+    "rvae_plan_prefetch_frames": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, c_uint64, c_uint64, c_int]),
+    "rvae_plan_swap_prefetched": (c_int, [P]),
+    "rvae_plan_prefetched_batch": (c_int, [P]),
+    "rvae_plan_note_prefetched": (c_int, [P, c_int]),
+    "rvae_plan_join_background": (c_int, [P, P]),
+    "rvae_plan_adam_buckets": (c_int, [P, C.c_uint, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, c_int, P]),
     "rvae_plan_mu": (P, [P]),
@@ -83,7 +90,8 @@ SIGNATURES = {
     "rvae_plan_bucket": (c_int, [P, c_int, C.POINTER(P), C.POINTER(c_int64)]),
     "rvae_plan_enable_timing": (c_int, [P, c_int]),
     "rvae_plan_read_timing": (c_int, [P, P, P, P]),
-    "rvae_debug_set_trace": (c_int, [P, P]),
+    "rvae_debug_set_trace": (c_int, [P, P, c_int]),
+    "rvae_debug_set_aux_trace": (c_int, [P, P, c_int]),
     "rvae_plan_decode": (c_int, [P, P, c_int, P, P]),
     "rvae_plan_encode": (c_int, [P, P]),
 }

@@ -43,6 +43,7 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   RVAE_REQUIRE(ctx != nullptr, RVAE_ERR_INVALID, "ctx_create: out of host memory");
   ctx->c.device = device;
   ctx->c.num_sms = prop.multiProcessorCount;
+  ctx->c.num_sms_total = prop.multiProcessorCount;
   // RVAE_NUM_SMS caps the SMs the persistent GEMM grids occupy (leaves the rest to concurrent kernels, e.g. NCCL)
   if (const char* e = getenv("RVAE_NUM_SMS")) {
     const int v = atoi(e);
@@ -50,6 +51,9 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   }
   ctx->c.launches = 0;
   ctx->c.trace = nullptr;
+  ctx->c.trace_launches = 1;
+  ctx->c.trace_seq = 0;
+  ctx->c.aux_trace = nullptr; ctx->c.aux_cap = 0; ctx->c.aux_seq = 0;
   ctx->c.force_block_n = 0;
   if (const char* e = getenv("RVAE_BLOCK_N")) ctx->c.force_block_n = atoi(e);
   ctx->c.force_cta_group = 0;
@@ -67,8 +71,19 @@ uint64_t rvae_ctx_launch_count(const rvae_ctx* ctx) { return ctx ? ctx->c.launch
 
 #define CTX_OR_FAIL(ctx) RVAE_REQUIRE((ctx) != nullptr, RVAE_ERR_INVALID, "null rvae_ctx")
 
-int rvae_debug_set_trace(rvae_ctx* ctx, void* buf) {
+int rvae_debug_set_aux_trace(rvae_ctx* ctx, void* buf, int launches) {
   CTX_OR_FAIL(ctx);
+  ctx->c.aux_trace = reinterpret_cast<unsigned long long*>(buf);
+  ctx->c.aux_cap = buf ? launches : 0;
+  ctx->c.aux_seq = 0;
+  return RVAE_OK;
+}
+
+int rvae_debug_set_trace(rvae_ctx* ctx, void* buf, int launches) {
+  CTX_OR_FAIL(ctx);
+  RVAE_REQUIRE(launches >= 1, RVAE_ERR_INVALID, "debug_set_trace: launches=%d", launches);
+  ctx->c.trace_launches = launches;
+  ctx->c.trace_seq = 0;
   static_assert(RVAE_TRACE_WORDS_PER_CTA == kTraceCtaWords && RVAE_TRACE_HEADER_WORDS == kTraceHeader &&
                     RVAE_TRACE_TILES == kTraceTiles && RVAE_TRACE_EVENTS == kTraceEvents,
                 "trace layout");
@@ -218,7 +233,7 @@ int rvae_dgrad_latent(rvae_ctx* ctx, const void* da3_hi, const void* da3_lo, con
   d.args.out_f32 = dz_scratch; d.args.ldo = L; d.args.accumulate = 1;
   RVAE_CHECK(gemm_launch(&ctx->c, d, S_(stream)));
   return launch_latent_bwd(&ctx->c, dz_scratch, eps, logvar, mu, g_mu_ext, g_logvar_ext, kl_grad_scale, M, L,
-                           BF(dml_hi), BF(dml_lo), bias_grad, 0, S_(stream));
+                           BF(dml_hi), BF(dml_lo), bias_grad, 0, nullptr, S_(stream));
 }
 
 int rvae_wgrad(rvae_ctx* ctx, const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, int B, int M,
@@ -287,6 +302,18 @@ struct rvae_plan {
   // workspace sections
   Planes x, h1, z, h3, da4, da3, dml, da1;
   float *mu, *lv, *eps, *dz, *xhat;
+  // second input set (frames + noise) the background stream fills for the NEXT step while this one runs
+  Planes x_alt;
+  float* eps_alt;
+  int cur;                 // which input set is current (GEMM tensor maps are prepared per set)
+  unsigned int* ticket;    // last-block ticket of the step's final Adam launch (advances the step counter)
+  bool ticket_zeroed;
+  struct Prefetch {
+    bool registered;       // rvae_plan_prefetch_frames called; consumed by the next rvae_plan_train_step
+    int ready_batch;       // > 0: the alternate set holds this many frames (+ their noise), enqueued by a train step
+    const void* audio; int audio_is_i16; int64_t n_samples; const int64_t* frame_idx; int64_t first_frame;
+    int count, hop; uint64_t seed, offset; int add_step;
+  } pf;
   double* loss_acc;
   // redirected outputs
   float *out_mu, *out_lv, *out_xhat;
@@ -300,7 +327,19 @@ struct rvae_plan {
   cudaEvent_t ev_fork, ev_join;
   bool two_streams;
   bool have_eps;
-  std::map<int, GemmSet> sets;  // prepared GEMMs per batch size
+  // eps is generated on the side stream, concurrently with the batch load and fc1; F2 waits for ev_eps
+  cudaEvent_t ev_eps;
+  bool eps_pending;
+  // per-bucket Adam launches of rvae_plan_train_step run on their own stream, under the remaining backward GEMMs
+  cudaStream_t adam_stream;   // lowest priority: background work never takes an SM a pending GEMM CTA could use
+  cudaEvent_t ev_adam_fork, ev_adam_join;
+  // rvae_plan_train_step runs its critical chain on a highest-priority stream forked from the caller's stream
+  cudaStream_t hp;
+  cudaEvent_t ev_hp_fork, ev_hp_join;
+  // loss finalisation deferred into the latent backward kernel (rvae_plan_finish_loss_deferred)
+  LossFinalize fin;
+  bool fin_pending;
+  std::map<int, GemmSet> sets;  // prepared GEMMs per (batch size, input set)
   // optional per-GEMM timing
   bool timing;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -329,6 +368,7 @@ size_t carve(rvae_plan* p, uint8_t* base) {
     pl.lo = lo ? reinterpret_cast<__nv_bfloat16*>(take(elems * 2)) : nullptr;
   };
   planes(p->x, B * S);
+  planes(p->x_alt, B * S);
   planes(p->h1, B * H);
   planes(p->z, B * L);
   planes(p->h3, B * H);
@@ -339,6 +379,8 @@ size_t carve(rvae_plan* p, uint8_t* base) {
   p->mu = reinterpret_cast<float*>(take(B * L * 4));
   p->lv = reinterpret_cast<float*>(take(B * L * 4));
   p->eps = reinterpret_cast<float*>(take(B * L * 4));
+  p->eps_alt = reinterpret_cast<float*>(take(B * L * 4));
+  p->ticket = reinterpret_cast<unsigned int*>(take(256));
   p->dz = reinterpret_cast<float*>(take(B * L * 4));
   p->xhat = reinterpret_cast<float*>(take(B * S * 4));
   p->loss_acc = reinterpret_cast<double*>(take(2 * sizeof(double)));
@@ -449,11 +491,12 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
 }
 
 int get_set(rvae_plan* p, GemmSet** out) {
-  auto it = p->sets.find(p->batch);
+  const int key = p->batch * 2 + p->cur;  // tensor maps bake in the addresses of the current input set
+  auto it = p->sets.find(key);
   if (it == p->sets.end()) {
     GemmSet gs;
     memset(&gs, 0, sizeof(gs));
-    it = p->sets.emplace(p->batch, gs).first;
+    it = p->sets.emplace(key, gs).first;
   }
   *out = &it->second;
   return RVAE_OK;
@@ -531,20 +574,65 @@ int ensure_bias_zeroed(rvae_plan* p, cudaStream_t st) {
 
 int ensure_side_stream(rvae_plan* p) {
   if (p->side) return RVAE_OK;
-  RVAE_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  int least = 0, greatest = 0;
+  RVAE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  RVAE_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, greatest));
+  RVAE_CUDA(cudaStreamCreateWithPriority(&p->hp, cudaStreamNonBlocking, greatest));
+  RVAE_CUDA(cudaStreamCreateWithPriority(&p->adam_stream, cudaStreamNonBlocking, least));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_fork, cudaEventDisableTiming));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_join, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_eps, cudaEventDisableTiming));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_adam_fork, cudaEventDisableTiming));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_adam_join, cudaEventDisableTiming));
   return RVAE_OK;
 }
 
-// Backward stage s: weight gradient of layer (4 - s) [side stream] || the dgrad GEMM that produces the next layer's
-// pre-activation gradient and, in its epilogue, that layer's bias gradient [main stream]; joined before returning,
-// so that after stage s gradient bucket s is complete on `st`. Both kernels are persistent and want every SM: run
-// concurrently, the CTAs of one fill the SMs the other leaves idle in its last partial wave.
-//   s=0: dW4 = da4^T h3        || da3 = (da4 W4) * [h3>0], db3
-//   s=1: dW3 = da3^T z         || dz = da3 W3 (split-K, fp32) -> latent backward kernel: d_ml, db2
-//   s=2: dW2 = d_ml^T h1       || da1 = (d_ml W2) * [h1>0], db1
-//   s=3: dW1 = da1^T x
+// Adam over the gradient buckets selected by `mask` (bit s = bucket s of rvae_plan_bucket): the selected buckets are
+// merged into contiguous segments of the flat buffer and updated with one launch per pair of segments.
+int adam_buckets(rvae_plan* p, unsigned mask, float lr, float beta1, float beta2, float eps, float weight_decay,
+                 float grad_scale, int zero_grads, int step_bias, bool advance_step, cudaStream_t st) {
+  const rvae_layout& ly = p->lay;
+  const rvae_plan_buffers& b = p->bufs;
+  // flat order: W1 (bucket 3) | W2 (2) | W3 (1) | W4 (0) | biases (4)
+  const int order[5] = {3, 2, 1, 0, 4};
+  const int64_t begin[6] = {ly.w1, ly.w2, ly.w3, ly.w4, ly.b1, ly.total};
+  int64_t seg_off[5], seg_n[5];
+  int nseg = 0;
+  for (int i = 0; i < 5; ++i) {
+    if (!(mask & (1u << order[i]))) continue;
+    if (nseg > 0 && seg_off[nseg - 1] + seg_n[nseg - 1] == begin[i]) seg_n[nseg - 1] += begin[i + 1] - begin[i];
+    else { seg_off[nseg] = begin[i]; seg_n[nseg] = begin[i + 1] - begin[i]; ++nseg; }
+  }
+  if (advance_step && !p->ticket_zeroed) {
+    RVAE_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), st));
+    p->ticket_zeroed = true;
+  }
+  for (int i = 0; i < nseg; i += 2) {
+    const int64_t o = seg_off[i];
+    const bool pair = i + 1 < nseg;
+    const bool last = i + 2 >= nseg;
+    RVAE_CHECK(launch_adam2(&p->ctx->c, b.params + o, b.grads + o, b.exp_avg + o, b.exp_avg_sq + o, seg_n[i],
+                            pair ? seg_off[i + 1] - o : 0, pair ? seg_n[i + 1] : 0, lr, beta1, beta2, eps, weight_decay,
+                            grad_scale, b.step, step_bias, (advance_step && last) ? p->ticket : nullptr,
+                            BF(b.shadow_hi) + o, b.shadow_lo ? BF(b.shadow_lo) + o : nullptr, zero_grads, st));
+  }
+  for (int s = 0; s < 5; ++s)
+    if (mask & (1u << s)) p->grads_zeroed[s] = zero_grads != 0;
+  return RVAE_OK;
+}
+
+// Backward stage s, in one stream: the dgrad GEMM that produces the next layer's pre-activation gradient (and, in its
+// epilogue, that layer's bias gradient) first - it is the critical dependency chain - then the weight gradient of
+// layer (4 - s). After stage s gradient bucket s is complete on `st`.
+//   s=0: da3 = (da4 W4) * [h3>0], db3                                   ; dW4 = da4^T h3
+//   s=1: dz = da3 W3 (split-K, fp32) -> latent backward kernel: d_ml, db2 ; dW3 = da3^T z
+//   s=2: da1 = (d_ml W2) * [h1>0], db1                                  ; dW2 = d_ml^T h1
+//   s=3:                                                                  dW1 = da1^T x
+// The GEMMs are persistent on the fewest SMs that keep their wave count (gemm_prepare); running the two GEMMs of a
+// stage concurrently only makes them share those SMs, so they are not forked - the SMs left over belong to the
+// background stream (noise, Adam per bucket, all-reduce).
 // External upstream gradients of (mu, logvar) for the autograd path, with the logvar tensor of that forward.
 struct LatentExt {
   const float* g_mu;
@@ -563,16 +651,6 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   const size_t wcount[4] = {(size_t)S * H, (size_t)H * L, (size_t)2 * L * H, (size_t)H * S};
   if (!p->grads_zeroed[stage]) RVAE_CUDA(cudaMemsetAsync(wptr[stage], 0, sizeof(float) * wcount[stage], st));
   p->grads_zeroed[stage] = false;
-  const bool fork = p->two_streams && kDgrad[stage] >= 0 && !p->timing;
-  if (fork) {
-    RVAE_CHECK(ensure_side_stream(p));
-    RVAE_CUDA(cudaEventRecord(p->ev_fork, st));
-    RVAE_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-    RVAE_CHECK(run(p, kWgrad[stage], p->side));
-    RVAE_CUDA(cudaEventRecord(p->ev_join, p->side));
-  } else {
-    RVAE_CHECK(run(p, kWgrad[stage], st));
-  }
   if (stage == 1 && !p->dz_zeroed)
     RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
   if (kDgrad[stage] >= 0) RVAE_CHECK(run(p, kDgrad[stage], st));
@@ -580,11 +658,11 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
     TimedScope ts(p, T_LATENT, st);
     RVAE_CHECK(launch_latent_bwd(&p->ctx->c, p->dz, p->eps, ext ? ext->lv : p->lv, p->mu, ext ? ext->g_mu : nullptr,
                                  ext ? ext->g_lv : nullptr, p->kl_c0, p->batch, L, p->dml.hi, p->dml.lo, grads + ly.b2, 1,
-                                 st));
+                                 p->fin_pending ? &p->fin : nullptr, st));
+    p->fin_pending = false;
     p->dz_zeroed = true;
   }
-  if (fork) RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
-  return RVAE_OK;
+  return run(p, kWgrad[stage], st);
 }
 
 }  // namespace
@@ -605,8 +683,13 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
   p->timing = false;
   p->kl_c0 = 0.f; p->dz_zeroed = false;
+  p->cur = 0; p->ticket_zeroed = false; p->ticket = nullptr;
+  memset(&p->pf, 0, sizeof(p->pf));
   for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
   p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
+  p->hp = nullptr; p->ev_hp_fork = nullptr; p->ev_hp_join = nullptr;
+  p->adam_stream = nullptr; p->ev_eps = nullptr; p->ev_adam_fork = nullptr; p->ev_adam_join = nullptr;
+  p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
   if (const char* e = getenv("RVAE_TWO_STREAMS")) p->two_streams = atoi(e) != 0;
   for (int i = 0; i < T_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
@@ -625,9 +708,18 @@ void rvae_plan_destroy(rvae_plan* plan) {
   }
   if (plan->side) {
     cudaStreamSynchronize(plan->side);
+    cudaStreamSynchronize(plan->adam_stream);
+    cudaStreamSynchronize(plan->hp);
+    cudaEventDestroy(plan->ev_hp_fork);
+    cudaEventDestroy(plan->ev_hp_join);
+    cudaStreamDestroy(plan->hp);
     cudaEventDestroy(plan->ev_fork);
     cudaEventDestroy(plan->ev_join);
+    cudaEventDestroy(plan->ev_eps);
+    cudaEventDestroy(plan->ev_adam_fork);
+    cudaEventDestroy(plan->ev_adam_join);
     cudaStreamDestroy(plan->side);
+    cudaStreamDestroy(plan->adam_stream);
   }
   delete plan;
 }
@@ -675,6 +767,8 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
   plan->sets.clear();
   for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = false;
   plan->dz_zeroed = false;
+  plan->cur = 0; plan->ticket_zeroed = false;
+  memset(&plan->pf, 0, sizeof(plan->pf));
   if (plan->two_streams) RVAE_CHECK(ensure_side_stream(plan));
   plan->bound = true;
   plan->batch = 0;
@@ -728,9 +822,22 @@ int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_s
   RVAE_CHECK(check_ready(plan, true));
   RVAE_REQUIRE(!add_step || plan->bufs.step, RVAE_ERR_STATE, "plan_gen_eps(add_step): no step counter bound");
   plan->have_eps = true;
-  TimedScope ts(plan, T_EPS, S_(stream));
+  cudaStream_t st = S_(stream);
+  if (plan->two_streams && !plan->timing) {
+    // fork: the noise does not depend on the batch load or fc1, so it is drawn on the background stream meanwhile;
+    // rvae_plan_forward joins before the encoder head
+    RVAE_CHECK(ensure_side_stream(plan));
+    RVAE_CUDA(cudaEventRecord(plan->ev_fork, st));
+    RVAE_CUDA(cudaStreamWaitEvent(plan->adam_stream, plan->ev_fork, 0));
+    RVAE_CHECK(launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset,
+                            add_step ? plan->bufs.step : nullptr, plan->adam_stream));
+    RVAE_CUDA(cudaEventRecord(plan->ev_eps, plan->adam_stream));
+    plan->eps_pending = true;
+    return RVAE_OK;
+  }
+  TimedScope ts(plan, T_EPS, st);
   return launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset,
-                      add_step ? plan->bufs.step : nullptr, S_(stream));
+                      add_step ? plan->bufs.step : nullptr, st);
 }
 
 int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat) {
@@ -756,6 +863,10 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
   RVAE_CHECK(get_set(p, &gs));
 
   RVAE_CHECK(run(p, G_F1, st));
+  if (p->eps_pending) {
+    RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_eps, 0));
+    p->eps_pending = false;
+  }
   {
     RVAE_CHECK(prepare(p, *gs, G_F2));
     EpiArgs a = gs->g[G_F2].params.epi;
@@ -824,28 +935,135 @@ int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, int r
                               plan->bufs.step, S_(stream));
 }
 
+int rvae_plan_finish_loss_deferred(rvae_plan* plan, float kl_beta, float* loss_out, int ring_size) {
+  RVAE_CHECK(check_ready(plan, true));
+  RVAE_REQUIRE(ring_size >= 1, RVAE_ERR_INVALID, "plan_finish_loss_deferred: ring_size %d", ring_size);
+  plan->fin = make_loss_finalize(plan->loss_acc, plan->batch, plan->S, plan->L, kl_beta, loss_out, ring_size,
+                                 plan->bufs.step);
+  plan->fin_pending = true;
+  return RVAE_OK;
+}
+
+int rvae_plan_prefetch_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                              const int64_t* frame_idx, int64_t first_frame, int count, int hop, uint64_t seed,
+                              uint64_t offset, int add_step) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(audio && count > 0 && count <= plan->max_batch && hop > 0, RVAE_ERR_INVALID,
+               "plan_prefetch_frames: bad arguments (count %d of max %d)", count, plan->max_batch);
+  rvae_plan::Prefetch& f = plan->pf;
+  f.audio = audio; f.audio_is_i16 = audio_is_i16; f.n_samples = n_samples; f.frame_idx = frame_idx;
+  f.first_frame = first_frame; f.count = count; f.hop = hop; f.seed = seed; f.offset = offset; f.add_step = add_step;
+  f.registered = true;
+  return RVAE_OK;
+}
+
+int rvae_plan_swap_prefetched(rvae_plan* plan) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(plan->pf.ready_batch > 0, RVAE_ERR_STATE, "plan_swap_prefetched: no prefetched batch");
+  std::swap(plan->x, plan->x_alt);
+  std::swap(plan->eps, plan->eps_alt);
+  plan->cur ^= 1;
+  plan->batch = plan->pf.ready_batch;
+  plan->pf.ready_batch = 0;
+  plan->have_eps = true;
+  plan->eps_pending = false;
+  return RVAE_OK;
+}
+
+int rvae_plan_prefetched_batch(const rvae_plan* plan) { return plan ? plan->pf.ready_batch : 0; }
+
+int rvae_plan_join_background(rvae_plan* plan, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  if (plan->eps_pending) {
+    RVAE_CUDA(cudaStreamWaitEvent(S_(stream), plan->ev_eps, 0));
+    plan->eps_pending = false;
+  }
+  return RVAE_OK;
+}
+
+int rvae_plan_note_prefetched(rvae_plan* plan, int count) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(count > 0 && count <= plan->max_batch, RVAE_ERR_INVALID, "plan_note_prefetched: count %d", count);
+  plan->pf.ready_batch = count;
+  return RVAE_OK;
+}
+
 int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
                    float grad_scale, int zero_grads, void* stream) {
+  return rvae_plan_adam_buckets(plan, 0x1f, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grads, stream);
+}
+
+int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, float grad_scale, int zero_grads, void* stream) {
   RVAE_CHECK(check_ready(plan, false));
   const rvae_plan_buffers& b = plan->bufs;
   RVAE_REQUIRE(b.grads && b.exp_avg && b.exp_avg_sq && b.step, RVAE_ERR_STATE,
                "plan_adam: grads / exp_avg / exp_avg_sq / step not bound");
+  RVAE_REQUIRE(bucket_mask != 0 && bucket_mask <= 0x1f, RVAE_ERR_INVALID, "plan_adam_buckets: mask %#x", bucket_mask);
   // zero_grads: the kernel clears the gradient buffer after consuming it (what optimizer.zero_grad() does at the top
   // of the reference loop, train.py:184), so the next step's split-K weight gradients can reduce-add without memsets
   TimedScope ts(plan, T_ADAM, S_(stream));
-  RVAE_CHECK(launch_adam(&plan->ctx->c, b.params, b.grads, b.exp_avg, b.exp_avg_sq, plan->lay.total, lr, beta1, beta2,
-                         eps, weight_decay, grad_scale, b.step, BF(b.shadow_hi), BF(b.shadow_lo), zero_grads,
-                         S_(stream)));
-  for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = zero_grads != 0;
-  return RVAE_OK;
+  return adam_buckets(plan, bucket_mask, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grads, 0, false,
+                      S_(stream));
 }
 
 int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
                          float weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream) {
-  RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, stream));
-  RVAE_CHECK(rvae_plan_finish_loss(plan, kl_beta, loss_out, ring_size, stream));
-  RVAE_CHECK(rvae_plan_backward(plan, -1, stream));
-  return rvae_plan_adam(plan, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, stream);
+  RVAE_CHECK(check_ready(plan, true));
+  const rvae_plan_buffers& b = plan->bufs;
+  RVAE_REQUIRE(b.grads && b.exp_avg && b.exp_avg_sq && b.step, RVAE_ERR_STATE,
+               "plan_train_step: grads / exp_avg / exp_avg_sq / step not bound");
+  rvae_plan* p = plan;
+  // The step counter t (Adam's bias correction, the loss-ring slot, the Philox offset) stays at its old value for
+  // the whole step: every Adam launch uses t + 1, and the last block of the final launch advances it.
+  const bool fork = plan->two_streams && !plan->timing;
+  if (!fork) {
+    RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, stream));
+    RVAE_CHECK(rvae_plan_finish_loss_deferred(plan, kl_beta, loss_out, ring_size));  // runs inside stage 1
+    plan->fin.inc_step = 0;
+    RVAE_CHECK(rvae_plan_backward(plan, -1, stream));
+    TimedScope ts(plan, T_ADAM, S_(stream));
+    return adam_buckets(plan, 0x1f, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, true, S_(stream));
+  }
+  // The critical chain (GEMMs) runs on a highest-priority stream; the HBM-bound side work (next batch + its noise,
+  // Adam per bucket) on a lowest-priority background stream. The persistent GEMM grids leave the SMs that wave
+  // quantisation would idle anyway to that background work (gemm_prepare), and at kernel boundaries a pending GEMM
+  // CTA always wins the SM.
+  RVAE_CHECK(ensure_side_stream(plan));
+  cudaStream_t st = plan->hp, bg = plan->adam_stream;
+  RVAE_CUDA(cudaEventRecord(plan->ev_hp_fork, S_(stream)));
+  RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_hp_fork, 0));
+  if (p->pf.registered) {
+    // next step's inputs: frames gathered into the alternate x planes, noise drawn into the alternate eps buffer
+    const rvae_plan::Prefetch& f = p->pf;
+    RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_hp_fork, 0));
+    RVAE_CHECK(launch_frame_gather(&p->ctx->c, f.audio, f.audio_is_i16, f.n_samples, f.frame_idx, f.first_frame, f.count,
+                                   f.hop, p->S, p->x_alt.hi, p->x_alt.lo, nullptr, bg));
+    // the consumer sees a step counter advanced by one
+    RVAE_CHECK(launch_randn(&p->ctx->c, p->eps_alt, (int64_t)f.count * p->L, f.seed, f.offset + (f.add_step ? 1 : 0),
+                            f.add_step ? b.step : nullptr, bg));
+    p->pf.ready_batch = f.count;
+    p->pf.registered = false;
+  }
+  RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, st));
+  RVAE_CHECK(rvae_plan_finish_loss_deferred(plan, kl_beta, loss_out, ring_size));  // runs inside stage 1
+  plan->fin.inc_step = 0;
+  // Adam per bucket as soon as the bucket's gradient is complete; the dgrad GEMM that reads the bucket's bf16
+  // shadow weights runs before the weight-gradient GEMM of the same stage, so nothing of this step reads them again.
+  static const unsigned kBucketMask[3] = {0x1, 0x2, 0x4};
+  for (int s = 0; s < 3; ++s) {
+    RVAE_CHECK(rvae_plan_backward(plan, s, st));
+    RVAE_CUDA(cudaEventRecord(plan->ev_adam_fork, st));
+    RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_adam_fork, 0));
+    RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
+  }
+  RVAE_CUDA(cudaEventRecord(plan->ev_adam_join, bg));
+  RVAE_CHECK(rvae_plan_backward(plan, 3, st));
+  RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_adam_join, 0));  // every earlier Adam launch has read the step counter
+  RVAE_CHECK(adam_buckets(plan, 0x18, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, true, st));
+  RVAE_CUDA(cudaEventRecord(plan->ev_hp_join, st));
+  RVAE_CUDA(cudaStreamWaitEvent(S_(stream), plan->ev_hp_join, 0));
+  return RVAE_OK;
 }
 
 const float* rvae_plan_mu(const rvae_plan* plan) { return plan ? plan->mu : nullptr; }

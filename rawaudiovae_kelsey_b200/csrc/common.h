@@ -44,11 +44,17 @@ int cuda_error(cudaError_t err, const char* what);
 struct Ctx {
   int device;
   int num_sms;
+  int num_sms_total;  // SMs of the device (num_sms may be capped by RVAE_NUM_SMS)
   int force_block_n;  // 0 = heuristic, 128 / 256 = forced (env RVAE_BLOCK_N, for experiments)
   int force_cta_group;  // 0 = heuristic, 1 / 2 = forced (env RVAE_CTA_GROUP, for experiments)
   int debug;            // env RVAE_DEBUG, experiments only (see GemmParams::debug)
   int use_pdl;          // programmatic dependent launch between consecutive kernels (env RVAE_PDL=0 disables)
   unsigned long long* trace;  // GEMM timeline trace buffer (rvae_debug_set_trace), nullptr = off
+  int trace_launches;         // capacity of the trace buffer in launches (successive launches use successive slabs)
+  uint64_t trace_seq;         // GEMM launches since the trace was set
+  unsigned long long* aux_trace;  // elementwise-kernel trace: [aux_cap][4] = {first start, last end, kind, blocks}
+  int aux_cap;
+  uint64_t aux_seq;
   uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
 };
 
@@ -68,6 +74,22 @@ inline cudaError_t launch_kernel(const Ctx* ctx, void (*kernel)(KArgs...), dim3 
   cfg.attrs = attr;
   cfg.numAttrs = ctx->use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Debug trace of an elementwise launch (rvae_debug_set_aux_trace): globaltimer of the first block start / last block
+// end. kind: 1 gather, 2 randn, 3 latent_bwd, 4 adam.
+struct AuxTrace {
+  unsigned long long* slot;  // nullptr = off
+};
+inline AuxTrace next_aux(Ctx* ctx, int kind) {
+  AuxTrace t;
+  t.slot = nullptr;
+  if (ctx->aux_trace != nullptr && ctx->aux_cap > 0) {
+    t.slot = ctx->aux_trace + (ctx->aux_seq % (uint64_t)ctx->aux_cap) * 4;
+    ctx->aux_seq++;
+    (void)kind;
+  }
+  return t;
 }
 
 // A bf16 GEMM operand. K-major: storage [mn][k] (k contiguous, row pitch ld). MN-major: storage [k][mn].
@@ -130,9 +152,25 @@ int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float b
 int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
                 __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream);
+int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, int64_t off_b, int64_t n_b, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, float* step, int step_bias,
+                 unsigned int* ticket, __nv_bfloat16* shadow_hi, __nv_bfloat16* shadow_lo, int zero_grads,
+                 cudaStream_t stream);
 int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream);
+// loss = acc[0]*inv_rec + kl_scale*acc[1] -> loss_out[step mod ring_size]; acc cleared; *step += 1
+struct LossFinalize {
+  double* acc;
+  double inv_rec, kl_scale;
+  float* loss_out;
+  int ring_size;
+  float* step;
+  int inc_step;  // 0: the step counter is advanced elsewhere (by the last Adam launch of the step)
+};
+LossFinalize make_loss_finalize(double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
+                                float* step);
 int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, const float* mu, const float* g_mu_ext,
                       const float* g_lv_ext, float kl_grad_scale, int64_t M, int L, __nv_bfloat16* dml_hi,
-                      __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, cudaStream_t stream);
+                      __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, const LossFinalize* fin,
+                      cudaStream_t stream);
 
 }  // namespace rvae

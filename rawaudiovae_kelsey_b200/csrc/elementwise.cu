@@ -20,6 +20,16 @@ static inline int grid_for(const Ctx* ctx, int64_t work_items, int threads, int 
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return ptx::pack_bf16x2(a, b); }
 
+__device__ __forceinline__ void aux_begin(const AuxTrace& t, int kind) {
+  if (t.slot != nullptr && threadIdx.x == 0) {
+    atomicMin(t.slot, global_timer());
+    if (blockIdx.x == 0) { t.slot[2] = kind; t.slot[3] = gridDim.x; }
+  }
+}
+__device__ __forceinline__ void aux_end(const AuxTrace& t) {
+  if (t.slot != nullptr && threadIdx.x == 0) atomicMax(t.slot + 1, global_timer());
+}
+
 __device__ __forceinline__ float block_sum_to_warp0(float v, float* smem) {
   // returns the block total in every thread of warp 0
   v = warp_sum(v);
@@ -45,9 +55,10 @@ template <bool I16>
 __global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_samples,
                                     const int64_t* __restrict__ frame_idx, int64_t first_frame, int64_t n_frames,
                                     int hop, int S, __nv_bfloat16* __restrict__ out_hi,
-                                    __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32) {
+                                    __nv_bfloat16* __restrict__ out_lo, float* __restrict__ out_f32, AuxTrace tr) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
+  aux_begin(tr, 1);
   const int vec_per_frame = S >> 3;
   const int64_t total = n_frames * vec_per_frame;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -110,6 +121,7 @@ __global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_sa
       d[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
+  aux_end(tr);
 }
 
 int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples, const int64_t* frame_idx,
@@ -120,12 +132,13 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
   if (n_frames <= 0) return RVAE_OK;
   const int threads = 256;
   const int grid = grid_for(ctx, n_frames * (S / 8), threads, 16);
+  const AuxTrace tr = next_aux(ctx, 1);
   if (audio_is_i16)
     RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<true>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop, S,
-                                                            out_hi, out_lo, out_f32));
+                                                            out_hi, out_lo, out_f32, tr));
   else
     RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<false>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop,
-                                                             S, out_hi, out_lo, out_f32));
+                                                             S, out_hi, out_lo, out_f32, tr));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -185,9 +198,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 }
 
 __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
-                             const float* __restrict__ offset_src) {
+                             const float* __restrict__ offset_src, AuxTrace tr) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
+  aux_begin(tr, 2);
   // offset_src: a device-side counter (the Adam step) added to the offset, so that a CUDA graph replays fresh noise
   if (offset_src) offset += static_cast<uint64_t>(__ldg(offset_src));
   const int64_t nvec = (n + 3) >> 2;
@@ -213,6 +227,7 @@ __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, 
       for (int j = 0; j < 4 && o + j < n; ++j) out[o + j] = z[j];
     }
   }
+  aux_end(tr);
 }
 
 int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, const float* offset_src,
@@ -220,7 +235,7 @@ int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset
   RVAE_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, RVAE_ERR_INVALID, "randn: bad output buffer");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset, offset_src));
+  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset, offset_src, next_aux(ctx, 2)));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -367,28 +382,43 @@ __global__ void loss_fwd_kernel(const float* __restrict__ xhat, const float* __r
   }
 }
 
+__device__ __forceinline__ void loss_finalize_body(double* acc, double inv_rec, double kl_scale, float* loss_out,
+                                                   int ring_size, float* step, int inc_step) {
+  const double loss = acc[0] * inv_rec + kl_scale * acc[1];
+  // ring_size > 1: slot = (step count before this step) mod ring_size, so a replayed CUDA graph still lands every
+  // step's loss in its own slot without the host passing a new pointer
+  const int slot = (ring_size > 1 && step) ? static_cast<int>(static_cast<long long>(*step) % ring_size) : 0;
+  if (loss_out) loss_out[slot] = static_cast<float>(loss);
+  acc[0] = 0.0;
+  acc[1] = 0.0;
+  if (step && inc_step) *step += 1.0f;
+}
+
 __global__ void loss_finalize_kernel(double* __restrict__ acc, double inv_rec, double kl_scale,
                                      float* __restrict__ loss_out, int ring_size, float* __restrict__ step) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const double loss = acc[0] * inv_rec + kl_scale * acc[1];
-    // ring_size > 1: slot = (step count before this step) mod ring_size, so a replayed CUDA graph still lands every
-    // step's loss in its own slot without the host passing a new pointer
-    const int slot = (ring_size > 1 && step) ? static_cast<int>(static_cast<long long>(*step) % ring_size) : 0;
-    if (loss_out) loss_out[slot] = static_cast<float>(loss);
-    acc[0] = 0.0;
-    acc[1] = 0.0;
-    if (step) *step += 1.0f;
-  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) loss_finalize_body(acc, inv_rec, kl_scale, loss_out, ring_size, step, 1);
+}
+
+LossFinalize make_loss_finalize(double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
+                                float* step) {
+  LossFinalize f;
+  f.acc = acc;
+  f.inv_rec = 1.0 / (static_cast<double>(B) * S);
+  f.kl_scale = -0.5 * static_cast<double>(beta) / (static_cast<double>(B) * L);
+  f.loss_out = loss_out;
+  f.ring_size = ring_size;
+  f.step = step;
+  f.inc_step = 1;
+  return f;
 }
 
 int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
                          float* step, cudaStream_t stream) {
   RVAE_REQUIRE(acc, RVAE_ERR_INVALID, "loss_finalize: null accumulator");
-  const double inv_rec = 1.0 / (static_cast<double>(B) * S);
-  const double kl_scale = -0.5 * static_cast<double>(beta) / (static_cast<double>(B) * L);
-  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, acc, inv_rec, kl_scale,
+  const LossFinalize f = make_loss_finalize(acc, B, S, L, beta, loss_out, ring_size, step);
+  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, acc, f.inv_rec, f.kl_scale,
                           loss_out, ring_size, step));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
@@ -509,17 +539,22 @@ int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps,
 //   t = *step (already incremented); m = m + (1-b1)(g-m); v = b2 v + (1-b2) g^2;
 //   p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // ------------------------------------------------------------------------------------------------
+// A launch covers elements [0, n) and, optionally, a second segment [off_b, off_b + n_b) of the same buffers (both
+// multiples of 4 then): the per-bucket launches of a training step (W3|W4, W2, W1 + bias block).
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
-                            float weight_decay, float grad_scale, const float* __restrict__ step,
-                            __nv_bfloat16* __restrict__ sh_hi, __nv_bfloat16* __restrict__ sh_lo, int zero_grads) {
+                            float* __restrict__ v, int64_t n, int64_t off_b, int64_t n_b, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, float grad_scale, float* step,
+                            int step_bias, unsigned int* ticket, __nv_bfloat16* __restrict__ sh_hi,
+                            __nv_bfloat16* __restrict__ sh_lo, int zero_grads, AuxTrace tr) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
+  aux_begin(tr, 4);
   // bias corrections in double, as torch computes them on the host (python floats); one thread per block does the
   // fp64 pow()s and broadcasts the two scalars
   __shared__ float s_consts[2];
   if (threadIdx.x == 0) {
-    const double t = static_cast<double>(__ldg(step));
+    // t = *step + step_bias: step_bias = 1 when the step counter is advanced only at the end of the step (ticket)
+    const double t = static_cast<double>(*reinterpret_cast<volatile float*>(step)) + step_bias;
     const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
     const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
     s_consts[0] = static_cast<float>(static_cast<double>(lr) / bc1);
@@ -529,7 +564,10 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   const float step_size = s_consts[0];
   const float sqrt_bc2 = s_consts[1];
   const int64_t nvec = n >> 2;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t nvec_all = nvec + (n_b >> 2);
+  const int64_t shift_b = (off_b >> 2) - nvec;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nvec_all; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = w < nvec ? w : w + shift_b;
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -579,22 +617,46 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
       }
     }
   }
+  aux_end(tr);
+  if (ticket != nullptr) {
+    // the LAST block to finish advances the step counter: every block (of this and of the earlier per-bucket
+    // launches of the step, which the host joined before this launch) has read it by then
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int done = atomicAdd(ticket, 1u);
+      if (done == gridDim.x - 1) {
+        *ticket = 0u;
+        *step = *reinterpret_cast<volatile float*>(step) + 1.0f;
+      }
+    }
+  }
 }
 
 int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
                 __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream) {
+  return launch_adam2(ctx, p, g, m, v, n, 0, 0, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                      const_cast<float*>(step), 0, nullptr, shadow_hi, shadow_lo, zero_grads, stream);
+}
+
+int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, int64_t off_b, int64_t n_b, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, float* step, int step_bias,
+                 unsigned int* ticket, __nv_bfloat16* shadow_hi, __nv_bfloat16* shadow_lo, int zero_grads,
+                 cudaStream_t stream) {
   RVAE_REQUIRE(p && g && m && v && step, RVAE_ERR_INVALID, "adam: null buffer");
+  RVAE_REQUIRE(n_b == 0 || ((n & 3) == 0 && (off_b & 3) == 0 && (n_b & 3) == 0 && off_b >= n), RVAE_ERR_INVALID,
+               "adam: segments must be multiples of 4 elements");
   RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                  reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                RVAE_ERR_INVALID, "adam: p/g/m/v must be 16-byte aligned");
   RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(shadow_hi) | reinterpret_cast<uintptr_t>(shadow_lo)) & 7) == 0,
                RVAE_ERR_INVALID, "adam: shadow planes must be 8-byte aligned");
-  if (n <= 0) return RVAE_OK;
+  if (n + n_b <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, adam_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream,
-                          p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step, shadow_hi, shadow_lo,
-                          zero_grads));
+  RVAE_CUDA(launch_kernel(ctx, adam_kernel, dim3(grid_for(ctx, (n + n_b + 3) / 4, threads, 8)), dim3(threads), (size_t)0,
+                          stream, p, g, m, v, n, off_b, n_b, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
+                          step_bias, ticket, shadow_hi, shadow_lo, zero_grads, next_aux(ctx, 4)));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -613,9 +675,13 @@ __global__ void latent_bwd_kernel(float* __restrict__ dz, const float* __restric
                                   const float* __restrict__ mu, const float* __restrict__ g_mu_ext,
                                   const float* __restrict__ g_lv_ext, float c, int64_t M, int L,
                                   __nv_bfloat16* __restrict__ dml_hi, __nv_bfloat16* __restrict__ dml_lo,
-                                  float* __restrict__ bias_grad, int clear_dz) {
+                                  float* __restrict__ bias_grad, int clear_dz, LossFinalize fin, AuxTrace tr) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
+  aux_begin(tr, 3);
+  // the deferred loss finalisation of this step rides along (the forward that filled the sums is long complete)
+  if (fin.acc != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+    loss_finalize_body(fin.acc, fin.inv_rec, fin.kl_scale, fin.loss_out, fin.ring_size, fin.step, fin.inc_step);
   extern __shared__ float s_sum[];  // [rows_per_pass][2L]
   const int q = L >> 2;                    // float4 groups per row
   const int rpp = blockDim.x / q;          // rows per pass
@@ -679,11 +745,13 @@ __global__ void latent_bwd_kernel(float* __restrict__ dz, const float* __restric
       atomicAdd(bias_grad + col, t);
     }
   }
+  aux_end(tr);
 }
 
 int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, const float* mu, const float* g_mu_ext,
                       const float* g_lv_ext, float kl_grad_scale, int64_t M, int L, __nv_bfloat16* dml_hi,
-                      __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, cudaStream_t stream) {
+                      __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, const LossFinalize* fin,
+                      cudaStream_t stream) {
   RVAE_REQUIRE(dz && eps && lv && dml_hi, RVAE_ERR_INVALID, "latent_bwd: null buffer");
   RVAE_REQUIRE((g_mu_ext != nullptr) == (g_lv_ext != nullptr), RVAE_ERR_INVALID,
                "latent_bwd: external gradients come in pairs");
@@ -693,12 +761,16 @@ int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, co
   const int q = L / 4;
   const int rpp = q >= 256 ? 1 : 256 / q;
   const int threads = q * rpp;
+  // four blocks per SM: enough loads in flight for HBM, and only 4 x num_sms atomics per bias-gradient column
   const int64_t want = (M + rpp - 1) / rpp;
-  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  const int64_t cap = (int64_t)ctx->num_sms * 4;
   const int grid = (int)(want < cap ? want : cap);
   const size_t smem = bias_grad ? (size_t)rpp * 2 * L * sizeof(float) : 0;
+  LossFinalize f;
+  memset(&f, 0, sizeof(f));
+  if (fin) f = *fin;
   RVAE_CUDA(launch_kernel(ctx, latent_bwd_kernel, dim3(grid), dim3(threads), smem, stream, dz, eps, lv, mu, g_mu_ext,
-                          g_lv_ext, kl_grad_scale, M, L, dml_hi, dml_lo, bias_grad, clear_dz));
+                          g_lv_ext, kl_grad_scale, M, L, dml_hi, dml_lo, bias_grad, clear_dz, f, next_aux(ctx, 3)));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }

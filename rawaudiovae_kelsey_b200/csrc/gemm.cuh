@@ -375,7 +375,8 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous
   // kernel of the stream; from here on we read what it wrote.
   if (threadIdx.x == 0) trace_hdr(p.trace, 2, clock64());
-  ptx::pdl_launch_dependents();
+  // (the dependents are released late, by the epilogue after its last tile: released here, their CTAs would sit on
+  // the SMs this grid leaves to the step's background stream for the whole duration of this kernel)
   ptx::pdl_wait();
   if (threadIdx.x == 0) trace_hdr(p.trace, 3, clock64());
 
@@ -840,6 +841,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
       if (team_tid == 0) trace_ev(p.trace, titer, 7 + 2 * team);
       if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
+    ptx::pdl_launch_dependents();  // next kernel of the stream: its prologue overlaps our drain and teardown
     if (tm.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
     if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
       const float s = warp_sum(loss_local);

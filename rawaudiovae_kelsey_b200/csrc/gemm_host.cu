@@ -178,7 +178,7 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = d.args;
   p.debug = ctx->debug;
-  p.trace = ctx->trace;
+  p.trace = nullptr;
 
   int block_n, cg;
   if (d.epi == EPI_HEAD) {
@@ -269,13 +269,28 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   g.variant = find_variant(block_n, d.A.major, d.B.major, d.epi, cg);
   RVAE_REQUIRE(g.variant >= 0, RVAE_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d majors (%d,%d) epilogue %d",
                block_n, d.A.major, d.B.major, d.epi);
+  // Persistent grid: the fewest CTAs (pairs) that still finish in the same number of waves. What wave quantisation
+  // would leave idle in the last wave is left idle for the whole kernel instead - those SMs run the concurrent
+  // HBM-bound work of the step (noise, Adam, all-reduce) without taking anything from this GEMM.
   const int units = p.m_blocks * p.n_blocks * p.k_splits;
-  g.grid = cg * (units < slots ? units : slots);
+  const int waves = ceil_div(units, slots);
+  const int slots_eff = ceil_div(units, waves);
+  g.grid = cg * (units < slots_eff ? units : slots_eff);
   g.smem_bytes = kVariants[g.variant].smem;
   return RVAE_OK;
 }
 
 int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream) {
+  if (ctx->trace != nullptr) {  // debug: successive launches write successive slabs of the trace buffer
+    GemmParams p = g.params;
+    const uint64_t slab = ctx->trace_launches > 1 ? ctx->trace_seq % (uint64_t)ctx->trace_launches : 0;
+    p.trace = ctx->trace + slab * (uint64_t)ctx->num_sms_total * kTraceCtaWords;
+    ctx->trace_seq++;
+    RVAE_CUDA(launch_kernel(ctx, kVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
+                            stream, p));
+    ctx->launches++;
+    return RVAE_OK;
+  }
   RVAE_CUDA(launch_kernel(ctx, kVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes, stream,
                           g.params));
   ctx->launches++;

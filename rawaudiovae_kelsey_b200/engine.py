@@ -95,6 +95,7 @@ class Plan:
                                     flat.shadow_lo.data_ptr() if flat.shadow_lo is not None else None, aligned)
             check(lib.rvae_plan_bind(self.handle, C.byref(bufs)))
         self.batch = 0
+        self.cur = 0    # which of the two input sets is current (flips with every swap_prefetched)
         self.token = 0  # bumped whenever a new batch is loaded (activations of older forwards are gone)
 
     def __del__(self):
@@ -134,6 +135,37 @@ class Plan:
         if row_offset == 0:
             self.token += 1
 
+    def prefetch_frames(self, audio: torch.Tensor, count: int, hop: int, *, frame_idx: Optional[torch.Tensor] = None,
+                        first_frame: int = 0, seed: int = 0, offset: int = 0, add_step: bool = True) -> None:
+        """Describe the NEXT step's batch: the next train_step gathers it (and draws its noise) in the background."""
+        if audio.dtype not in (torch.float32, torch.int16) or not audio.is_cuda or not audio.is_contiguous():
+            raise _lib.RvaeError("audio must be a contiguous CUDA float32 / int16 tensor")
+        if frame_idx is not None and (frame_idx.dtype != torch.int64 or not frame_idx.is_cuda
+                                      or frame_idx.numel() != count or not frame_idx.is_contiguous()):
+            raise _lib.RvaeError("frame_idx must be a contiguous CUDA int64 tensor with `count` entries")
+        check(self.lib.rvae_plan_prefetch_frames(self.handle, audio.data_ptr(), int(audio.dtype == torch.int16),
+                                                 audio.numel(), frame_idx.data_ptr() if frame_idx is not None else None,
+                                                 first_frame, count, hop, seed, offset, int(add_step)))
+
+    def prefetched_batch(self) -> int:
+        return int(self.lib.rvae_plan_prefetched_batch(self.handle))
+
+    def swap_prefetched(self) -> None:
+        """Make the prefetched batch (and its noise) the current one - replaces load_frames + gen_eps."""
+        n = self.prefetched_batch()
+        check(self.lib.rvae_plan_swap_prefetched(self.handle))
+        self.batch = n
+        self.cur ^= 1
+        self.token += 1
+
+    def join_background(self) -> None:
+        """The current stream waits for pending background work of earlier calls (needed before a graph capture)."""
+        check(self.lib.rvae_plan_join_background(self.handle, self._stream()))
+
+    def note_prefetched(self, count: int) -> None:
+        """A replayed CUDA graph gathered `count` frames into the alternate input set: record it on the host side."""
+        check(self.lib.rvae_plan_note_prefetched(self.handle, count))
+
     def set_eps(self, eps: torch.Tensor) -> None:
         if eps.dtype != torch.float32 or not eps.is_cuda or not eps.is_contiguous():
             eps = eps.to(device=self.flat.device, dtype=torch.float32).contiguous()
@@ -166,6 +198,17 @@ class Plan:
         check(self.lib.rvae_plan_finish_loss(self.handle, kl_beta,
                                              loss_out.data_ptr() if loss_out is not None else None, ring_size,
                                              self._stream()))
+
+    def finish_loss_deferred(self, kl_beta: float, loss_out: Optional[torch.Tensor], ring_size: int = 1) -> None:
+        """Like finish_loss, but carried out by the latent backward kernel of the next backward stage 1 (no launch)."""
+        check(self.lib.rvae_plan_finish_loss_deferred(self.handle, kl_beta,
+                                                      loss_out.data_ptr() if loss_out is not None else None, ring_size))
+
+    def adam_buckets(self, mask: int, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0,
+                     zero_grads=False) -> None:
+        """Adam over the gradient buckets in `mask` (bit s = bucket s; 0..3 = W4, W3, W2, W1, 4 = biases)."""
+        check(self.lib.rvae_plan_adam_buckets(self.handle, mask, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                                              int(zero_grads), self._stream()))
 
     def adam(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0, zero_grads=False) -> None:
         check(self.lib.rvae_plan_adam(self.handle, lr, beta1, beta2, eps, weight_decay, grad_scale, int(zero_grads),

@@ -372,26 +372,115 @@ class _StepBase:
         else:
             st["x"].copy_(data.reshape(st["x"].shape))
 
-    def _run(self, data, eps):
+    def _seed(self):
+        model = self.model
+        seed = model.eps_seed if model.eps_seed is not None else torch.initial_seed()
+        return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+    def _can_prefetch(self, nxt, eps):
+        model = self.model
+        return (isinstance(nxt, FrameBatch) and eps is None and model.eps_source == "philox"
+                and nxt.segment_length == model.segment_length)
+
+    def _take_prefetched(self, data):
+        """If `data` is the batch the previous step prefetched, make it current and return its plan."""
+        pf = getattr(self, "_pf", None)
+        self._pf = None
+        if pf is None or pf[1] is not data:
+            return None
+        plan = pf[0]
+        if plan.prefetched_batch() != data.n_frames:
+            return None
+        plan.swap_prefetched()
+        return plan
+
+    def _run(self, data, eps, next_data=None):
+        """One step on `data`. `next_data` (optional FrameBatch): the batch of the NEXT call - it is gathered, and its
+        noise drawn, on a background stream while this step's GEMMs run (pass the same object as `data` next time)."""
         flat = self._prepare()
         model = self.model
-        key = self._graph_key(data) if (self.graph and eps is None and model.eps_source == "philox") else None
-        if key is not None and key in self._graphs:
-            st = self._graphs[key]
-            self._load_static(key, data, st)
-            st["graph"].replay()
-            st["plan"].token += 1
-        elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
-            self._capture(key, data)
+        graphable = self.graph and eps is None and model.eps_source == "philox"
+        plan = self._take_prefetched(data) if eps is None else None
+        prefetch = plan is not None or next_data is not None
+        if not prefetch:
+            # ---- plain path: load inside the step (captured graph: from static index / input buffers)
+            key = self._graph_key(data) if graphable else None
+            if key is not None and key in self._graphs:
+                st = self._graphs[key]
+                self._load_static(key, data, st)
+                st["graph"].replay()
+                st["plan"].token += 1
+            elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
+                self._capture(key, data)
+            else:
+                if key is not None:
+                    self._seen[key] = self._seen.get(key, 0) + 1
+                plan = model._load(data)
+                self._eps(plan, eps)
+                self._enqueue(plan)
         else:
-            if key is not None:
-                self._seen[key] = self._seen.get(key, 0) + 1
-            plan = model._load(data)
-            self._eps(plan, eps)
-            self._enqueue(plan)
+            # ---- pipelined path: the current batch is already in the plan (or loaded eagerly now), the next one is
+            #      prefetched by this step
+            if plan is None:
+                plan = model._load(data)
+                self._eps(plan, eps)
+            do_pf = self._can_prefetch(next_data, eps) and next_data.n_frames <= plan.max_batch
+            key = None
+            if graphable and do_pf and isinstance(data, FrameBatch):
+                key = ("pf", plan.handle.value, next_data.audio.data_ptr(), plan.batch, next_data.n_frames,
+                       next_data.hop, self._plan_cur(plan))
+            if key is not None and key in self._graphs:
+                st = self._graphs[key]
+                self._fill_idx(st, next_data)
+                st["graph"].replay()
+                self._mark_prefetched(plan, next_data)
+            elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
+                self._capture_pipelined(key, plan, next_data)
+            else:
+                if key is not None:
+                    self._seen[key] = self._seen.get(key, 0) + 1
+                if do_pf:
+                    plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop,
+                                         frame_idx=next_data.frame_idx, first_frame=next_data.first_frame,
+                                         seed=self._seed(), offset=0, add_step=True)
+                self._enqueue(plan)
+                if do_pf:
+                    self._pf = (plan, next_data)
         slot = self._slot()
         self.i += 1
         return slot
+
+    def _plan_cur(self, plan):
+        """Parity of the plan's current input set (captured graphs bake in its addresses): tracked on the host."""
+        return plan.cur
+
+    def _mark_prefetched(self, plan, next_data):
+        # a replayed graph performed the prefetch on the device; mirror it in the plan's host-side state
+        plan.note_prefetched(next_data.n_frames)
+        self._pf = (plan, next_data)
+
+    def _fill_idx(self, st, nxt):
+        if nxt.frame_idx is not None:
+            st["idx"].copy_(nxt.frame_idx)
+        else:
+            torch.add(st["arange"], nxt.first_frame, out=st["idx"])
+
+    def _capture_pipelined(self, key, plan, next_data):
+        dev = self.model._flat.device
+        st = {"idx": torch.empty(next_data.n_frames, dtype=torch.int64, device=dev),
+              "arange": torch.arange(next_data.n_frames, dtype=torch.int64, device=dev)}
+        self._fill_idx(st, next_data)
+        plan.join_background()
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop, frame_idx=st["idx"],
+                                 seed=self._seed(), offset=0, add_step=True)
+            self._enqueue(plan)
+        st["graph"], st["plan"] = g, plan
+        self._graphs[key] = st
+        g.replay()   # capture does not execute: this replay performs the step of the current call
+        self._pf = (plan, next_data)
 
     def _capture(self, key, data):
         model = self.model
@@ -441,5 +530,5 @@ class FusedTrainStep(_StepBase):
         plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=self.ring,
                         ring_size=self.ring_size, zero_grads=not self.keep_grads)
 
-    def __call__(self, data, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return self._run(data, eps)
+    def __call__(self, data, eps: Optional[torch.Tensor] = None, next_data=None) -> torch.Tensor:
+        return self._run(data, eps, next_data)

@@ -52,12 +52,23 @@ TRACE_HEADER, TRACE_TILES, TRACE_EVENTS = 16, 24, 16
 TRACE_WORDS_PER_CTA = TRACE_HEADER + TRACE_TILES * TRACE_EVENTS
 
 
-def set_trace(buf: Optional[torch.Tensor]) -> None:
+def set_trace(buf: Optional[torch.Tensor], launches: int = 1) -> None:
     """Debug: direct the GEMM timeline trace (csrc/gemm.cuh) into an int64 CUDA tensor of
-    TRACE_WORDS_PER_CTA * grid words, or switch it off with None."""
+    launches * TRACE_WORDS_PER_CTA * num_sms words (successive GEMM launches fill successive slabs), or switch it
+    off with None."""
     if buf is not None and (buf.dtype != torch.int64 or not buf.is_cuda or not buf.is_contiguous()):
         raise _lib.RvaeError("trace buffer must be a contiguous int64 CUDA tensor")
-    check(_lib.load().rvae_debug_set_trace(ctx(None if buf is None else buf.device), None if buf is None else buf.data_ptr()))
+    if buf is not None and buf.numel() < launches * TRACE_WORDS_PER_CTA * num_sms(buf.device):
+        raise _lib.RvaeError("trace buffer too small")
+    check(_lib.load().rvae_debug_set_trace(ctx(None if buf is None else buf.device),
+                                           None if buf is None else buf.data_ptr(), launches))
+
+
+def set_aux_trace(buf: Optional[torch.Tensor], launches: int = 0) -> None:
+    """Debug: trace of the HBM-bound kernels into an int64 CUDA tensor [launches, 4] (column 0 initialised to a large
+    value by the caller: it is reduced with atomicMin), or off with None."""
+    check(_lib.load().rvae_debug_set_aux_trace(ctx(None if buf is None else buf.device),
+                                               None if buf is None else buf.data_ptr(), launches))
 
 
 def _stream() -> int:

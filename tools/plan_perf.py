@@ -13,7 +13,22 @@ torch.manual_seed(0)
 model = VAE(S, H, L).to(dev)
 opt = Adam(model.parameters(), lr=1e-4)
 step = FusedTrainStep(model, opt, 1e-4, graph=os.environ.get('STEP_GRAPH', '0') == '1')
-x = torch.rand(B, S, device=dev) * 2 - 1
+PIPE = os.environ.get('STEP_PIPE', '0') == '1'
+if PIPE:   # frames gathered from a device-resident corpus; the next batch is prefetched by the current step
+    from rawvae.model import FrameBatch
+    audio = torch.rand(32 * 30 * 44100, device=dev) * 2 - 1
+    nfr = (audio.numel() - S) // 128 + 1
+    idx = torch.randint(0, nfr, (64, B), device=dev)
+    fbs = [FrameBatch(audio, B, 128, S, frame_idx=idx[i]) for i in range(64)]
+    k = [0]
+    _step = step
+    def step(_x=None):
+        i = k[0] % 64
+        k[0] += 1
+        return _step(fbs[i], next_data=fbs[(i + 1) % 64])
+    x = None
+else:
+    x = torch.rand(B, S, device=dev) * 2 - 1
 for _ in range(5):
     step(x)
 torch.cuda.synchronize()
@@ -25,7 +40,7 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-tag = " ".join(f"{k}={os.environ[k]}" for k in ("RVAE_CTA_GROUP", "RVAE_BLOCK_N", "RVAE_DEBUG") if k in os.environ)
+tag = " ".join(f"{k}={os.environ[k]}" for k in ("RVAE_CTA_GROUP", "RVAE_BLOCK_N", "RVAE_DEBUG", "STEP_PIPE", "STEP_GRAPH") if k in os.environ)
 print(f"[{tag}] step {ms*1e3:.1f} us  -> {B/ms/1e3:.2f} M frames/s  ({30408704*B/ms/1e9:.0f} TFLOP/s whole step)")
 plan = model._plan_for(B)
 plan.enable_timing(True)

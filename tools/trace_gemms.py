@@ -42,7 +42,7 @@ for name in names:
         fn()
     torch.cuda.synchronize()
     buf.zero_()
-    ops.set_trace(buf)
+    ops.set_trace(buf, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(); fn(); e1.record()

@@ -1,0 +1,88 @@
+"""Timeline of ONE fused training step (default.ini dims, B=8192): when each GEMM's CTAs enter / leave (globaltimer),
+so the gaps between kernels, the overlap of forked kernels and the cost of the non-GEMM kernels become visible.
+   python tools/trace_step.py      (needs a B200; debug aid, see rvae_debug_set_trace)"""
+import os
+import numpy as np
+import torch
+from rawvae.model import VAE, FusedTrainStep
+from rawaudiovae_kelsey_b200.optim import Adam
+from rawaudiovae_kelsey_b200 import ops
+
+B, S, H, L = 8192, 1024, 2048, 256
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = VAE(S, H, L).to(dev)
+opt = Adam(model.parameters(), lr=1e-4)
+step = FusedTrainStep(model, opt, 1e-4)
+if os.environ.get('STEP_PIPE', '0') == '1':
+    from rawvae.model import FrameBatch
+    audio = torch.rand(32 * 30 * 44100, device=dev) * 2 - 1
+    nfr = (audio.numel() - S) // 128 + 1
+    idx = torch.randint(0, nfr, (64, B), device=dev)
+    fbs = [FrameBatch(audio, B, 128, S, frame_idx=idx[i]) for i in range(64)]
+    k = [0]
+    _step = step
+    def step(_x=None):
+        i = k[0] % 64
+        k[0] += 1
+        return _step(fbs[i], next_data=fbs[(i + 1) % 64])
+    x = None
+else:
+    x = torch.rand(B, S, device=dev) * 2 - 1
+for _ in range(5):
+    step(x)
+torch.cuda.synchronize()
+NAMES = ["F1", "F2", "F3", "F4", "B4d", "B4w", "B3d", "B3w", "B2d", "B2w", "B1w"]
+NSTEP = 3
+W, HDR = ops.TRACE_WORDS_PER_CTA, ops.TRACE_HEADER
+nsm = ops.num_sms()
+nl = len(NAMES) * NSTEP
+buf = torch.zeros(nl * W * nsm, dtype=torch.int64, device=dev)
+AUXN = 16 * NSTEP
+aux = torch.zeros(AUXN, 4, dtype=torch.int64, device=dev)
+aux[:, 0] = 2 ** 62
+ops.set_aux_trace(aux, AUXN)
+ops.set_trace(buf, nl)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(NSTEP):
+    step(x)
+e1.record()
+torch.cuda.synchronize()
+ops.set_trace(None)
+ops.set_aux_trace(None)
+print(f"{NSTEP} traced steps: {1e3 * e0.elapsed_time(e1) / NSTEP:.1f} us/step")
+t = buf.cpu().numpy().reshape(nl, nsm, W)
+AUXK = {1: "gather", 2: "randn", 3: "latent", 4: "adam"}
+rows = []   # (start, text)
+a = aux.cpu().numpy()
+for j in range(AUXN):
+    if a[j, 1] > 0:
+        rows.append((float(a[j, 0]), float(a[j, 1]), f"{AUXK.get(int(a[j, 2]), '?'):6s} blocks {int(a[j, 3]):4d}"))
+t0 = None
+prev_end = None
+gemm_rows = []
+for i in range(nl):
+    hdr = t[i, :, :HDR].astype(np.float64)
+    live = hdr[:, 1] > 0
+    if not live.any():
+        continue
+    first, last_in = hdr[live, 0].min(), hdr[live, 0].max()
+    first_out, last = hdr[live, 6].min(), hdr[live, 6].max()
+    # time the CTAs spent waiting for the previous kernel (PDL wait) in cycles -> us using the CTA's own clock rate
+    ghz = np.median((hdr[live, 5] - hdr[live, 1]) / np.maximum(hdr[live, 6] - hdr[live, 0], 1))
+    pdl = np.median(hdr[live, 3] - hdr[live, 2]) / ghz / 1e3
+    if i % len(NAMES) == 0:
+        if t0 is not None:
+            print(f"   ---- step period {(first - t0) / 1e3:.1f} us")
+        t0 = first
+    gap = "" if prev_end is None else f" gap {((first - prev_end) / 1e3):6.1f}"
+    print(f"{NAMES[i % len(NAMES)]:4s} ctas {int(live.sum()):3d}  enter {((first - t0) / 1e3):7.1f}..{((last_in - t0) / 1e3):7.1f}  "
+          f"exit {((first_out - t0) / 1e3):7.1f}..{((last - t0) / 1e3):7.1f}  span {((last - first) / 1e3):6.1f}  pdl-wait {pdl:5.1f}{gap}")
+    prev_end = last
+    gemm_rows.append((first, last, NAMES[i % len(NAMES)]))
+base = gemm_rows[0][0]
+print("---- merged timeline (us since the first GEMM of the first traced step)")
+allr = [(f, l, f"GEMM {n}") for f, l, n in gemm_rows] + rows
+for f, l, name in sorted(allr):
+    print(f"  {(f - base) / 1e3:8.1f} -> {(l - base) / 1e3:8.1f}  ({(l - f) / 1e3:6.1f})  {name}")
