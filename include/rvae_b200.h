@@ -52,6 +52,31 @@ int rvae_ctx_num_sms(const rvae_ctx* ctx);
 uint64_t rvae_ctx_launch_count(const rvae_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Data parallelism (no counterpart in the reference, which is single-process: SURVEY.md 2b). One process per GPU;
+ * the host side (torch.distributed) only carries the 128-byte NCCL id from rank 0 to the others. Once a context
+ * has a communicator, rvae_plan_train_step all-reduces every gradient bucket (SUM, fp32) on a communication stream
+ * as soon as the backward stage that completes it is done, overlapped with the remaining stages, and each bucket's
+ * Adam launch waits for its reduced gradient. Use rvae_plan_set_global_batch so that the sum is the gradient of the
+ * concatenated batch. libnccl_path: the libnccl.so.2 to dlopen (NULL = the default search path).
+ * ------------------------------------------------------------------------------------------------------- */
+int rvae_dp_unique_id(rvae_ctx* ctx, const char* libnccl_path, void* out128);
+int rvae_dp_init(rvae_ctx* ctx, const char* libnccl_path, const void* id128, int rank, int world);
+int rvae_dp_world(const rvae_ctx* ctx);
+/* Peer-memory all-reduce (our own kernel instead of NCCL): rvae_dp_sym_alloc creates this rank's symmetric
+ * allocation (the library owns it - the one exception to "the caller owns every buffer", because it must be
+ * IPC-exportable) and returns the device pointer of its data area plus a 64-byte CUDA IPC handle; the host side
+ * gathers the handles of all ranks (torch.distributed) and passes them, indexed by rank, to rvae_dp_sym_open, which
+ * maps every peer's allocation. A plan whose bufs.grads lies in the data area then all-reduces its gradient
+ * buckets with a two-shot reduce-scatter / all-gather kernel that reads and writes NVLink peer memory directly
+ * (csrc/elementwise.cu "Gradient all-reduce over NVLink peer memory"); other gradients fall back to NCCL. */
+int rvae_dp_sym_alloc(rvae_ctx* ctx, size_t data_bytes, void** data_ptr, void* ipc_handle64);
+/* In-place SUM all-reduce of `count` floats (a multiple of 4) at ptr: the peer-memory kernel when ptr lies in the
+ * symmetric data area (bucket = 0..7 selects the flag set; concurrent all-reduces must use different buckets), NCCL
+ * otherwise. What rvae_plan_train_step issues per gradient bucket. */
+int rvae_dp_allreduce(rvae_ctx* ctx, float* ptr, int64_t count, int bucket, void* stream);
+int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Framing and resynthesis (rawvae/dataset.py)
  * ------------------------------------------------------------------------------------------------------- */
 
@@ -212,6 +237,9 @@ int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_s
  * NULL = keep them in the workspace. Used by the autograd wrapper so returned tensors outlive the step. */
 int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat);
 
+/* Data parallelism: make this plan's rvae_plan_train_step all-reduce its gradient buckets over the context's
+ * communicator (rvae_dp_init). Off by default, so other plans of the same device stay single-process. */
+int rvae_plan_enable_dp(rvae_plan* plan, int on);
 /* Data parallelism: normalise the loss (and therefore its gradients) by the GLOBAL batch size instead of the
  * local one, so that a plain SUM all-reduce over ranks yields exactly the single-process gradient of the
  * concatenated batch, also when shards are unequal. 0 (default) = use the local batch size. */
@@ -304,9 +332,9 @@ int rvae_plan_read_timing(rvae_plan* plan, float* ms, int64_t* launches, double*
 #define RVAE_TRACE_EVENTS 16
 #define RVAE_TRACE_WORDS_PER_CTA (RVAE_TRACE_HEADER_WORDS + RVAE_TRACE_TILES * RVAE_TRACE_EVENTS)
 int rvae_debug_set_trace(rvae_ctx* ctx, void* buf, int launches);
-/* Same idea for the HBM-bound kernels (gather, randn, latent backward, Adam): launch i writes 4 words at buf + 4*i
+/* Same idea for the HBM-bound kernels (gather, randn, latent backward, Adam): launch i writes 8 words at buf + 8*i
  * (wrapping at `launches`): globaltimer of the first block's start (initialise to ~0ull) and the last block's end,
- * kind (1 gather, 2 randn, 3 latent backward, 4 Adam), grid size. */
+ * kind (1 gather, 2 randn, 3 latent backward, 4 Adam, 5 all-reduce), grid size, 4 kernel-specific detail words. */
 int rvae_debug_set_aux_trace(rvae_ctx* ctx, void* buf, int launches);
 
 /* Inference: decode latents z (fp32 [batch, L]) -> xhat fp32 [batch, S] (model.py:28-30). */

@@ -39,6 +39,12 @@ SIGNATURES = {
     "rvae_ctx_destroy": (None, [P]),
     "rvae_ctx_num_sms": (c_int, [P]),
     "rvae_ctx_launch_count": (c_uint64, [P]),
+    "rvae_dp_unique_id": (c_int, [P, C.c_char_p, P]),
+    "rvae_dp_init": (c_int, [P, C.c_char_p, P, c_int, c_int]),
+    "rvae_dp_world": (c_int, [P]),
+    "rvae_dp_sym_alloc": (c_int, [P, c_size_t, C.POINTER(P), P]),
+    "rvae_dp_sym_open": (c_int, [P, P, c_int, c_int]),
+    "rvae_dp_allreduce": (c_int, [P, P, c_int64, c_int, P]),
     "rvae_frame_gather": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, P, P]),
     "rvae_overlap_add": (c_int, [P, P, c_int64, c_int, c_int, P, c_int64, P]),
     "rvae_randn": (c_int, [P, P, c_int64, c_uint64, c_uint64, P]),
@@ -68,6 +74,7 @@ SIGNATURES = {
     "rvae_plan_set_eps": (c_int, [P, P, P]),
     "rvae_plan_gen_eps": (c_int, [P, c_uint64, c_uint64, c_int, P]),
     "rvae_plan_set_outputs": (c_int, [P, P, P, P]),
+    "rvae_plan_enable_dp": (c_int, [P, c_int]),
     "rvae_plan_set_global_batch": (c_int, [P, c_int64]),
     "rvae_plan_forward": (c_int, [P, c_float, c_int, c_int, P]),
     "rvae_plan_backward": (c_int, [P, c_int, P]),

@@ -1,6 +1,7 @@
 // C ABI (include/rvae_b200.h): context, op-level entry points and the plan that issues a whole training or
 // inference step from C. No torch types cross this boundary.
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
 #include <map>
 #include <new>
@@ -16,8 +17,33 @@ const char* last_error();
 
 using namespace rvae;
 
+// NCCL entry points, resolved at run time from the libnccl the process already uses (torch's): no link-time
+// dependency, and the communicator is created from an id the host side exchanges over torch.distributed.
+struct NcclId {
+  char internal[128];  // ncclUniqueId
+};
+struct NcclApi {
+  void* handle;
+  int (*GetUniqueId)(NcclId*);
+  int (*CommInitRank)(void** comm, int nranks, NcclId id, int rank);
+  int (*AllReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t stream);
+  int (*CommDestroy)(void* comm);
+  const char* (*GetErrorString)(int);
+};
+
 struct rvae_ctx {
   Ctx c;
+  NcclApi nccl;
+  void* comm;      // ncclComm_t of the data-parallel group (nullptr = single process)
+  int dp_rank, dp_world;
+  // peer-memory all-reduce: this rank's symmetric allocation ([flags | gradient data]) and the peers' mappings
+  uint8_t* sym_base;
+  size_t sym_data_bytes;
+  void* peer_base[kP2PMaxWorld];
+  P2PArgs p2p;
+  bool p2p_ready;
+  int p2p_ctas;        // CTAs of an all-reduce that runs under the GEMMs (they live on the spare SMs)
+  int p2p_ctas_last;   // CTAs of the step's last, exposed all-reduce
 };
 
 static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -50,6 +76,19 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
     if (v >= 2 && v <= prop.multiProcessorCount) ctx->c.num_sms = v & ~1;
   }
   ctx->c.launches = 0;
+  memset(&ctx->nccl, 0, sizeof(ctx->nccl));
+  ctx->comm = nullptr; ctx->dp_rank = 0; ctx->dp_world = 1;
+  ctx->sym_base = nullptr; ctx->sym_data_bytes = 0; ctx->p2p_ready = false; ctx->p2p_ctas = 20; ctx->p2p_ctas_last = 48;
+  memset(ctx->peer_base, 0, sizeof(ctx->peer_base));
+  memset(&ctx->p2p, 0, sizeof(ctx->p2p));
+  if (const char* e = getenv("RVAE_P2P_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kP2PMaxCtas) ctx->p2p_ctas = v;
+  }
+  if (const char* e = getenv("RVAE_P2P_CTAS_LAST")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kP2PMaxCtas) ctx->p2p_ctas_last = v;
+  }
   ctx->c.trace = nullptr;
   ctx->c.trace_launches = 1;
   ctx->c.trace_seq = 0;
@@ -65,7 +104,126 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   *out = ctx;
   return RVAE_OK;
 }
-void rvae_ctx_destroy(rvae_ctx* ctx) { delete ctx; }
+void rvae_ctx_destroy(rvae_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+  for (int p = 0; p < kP2PMaxWorld; ++p)
+    if (ctx->peer_base[p] && p != ctx->dp_rank) cudaIpcCloseMemHandle(ctx->peer_base[p]);
+  if (ctx->sym_base) cudaFree(ctx->sym_base);
+  delete ctx;
+}
+
+static int nccl_load(rvae_ctx* ctx, const char* path) {
+  if (ctx->nccl.handle) return RVAE_OK;
+  void* h = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  RVAE_REQUIRE(h != nullptr, RVAE_ERR_DRIVER, "dlopen(%s) failed: %s", path && path[0] ? path : "libnccl.so.2", dlerror());
+  NcclApi a;
+  a.handle = h;
+  a.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(h, "ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(h, "ncclCommInitRank"));
+  a.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+  a.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+  a.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  RVAE_REQUIRE(a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString, RVAE_ERR_DRIVER,
+               "libnccl lacks a required symbol");
+  ctx->nccl = a;
+  return RVAE_OK;
+}
+#define RVAE_NCCL(ctx, expr)                                                                             \
+  do {                                                                                                   \
+    const int _r = (expr);                                                                               \
+    if (_r != 0) return set_error(RVAE_ERR_DRIVER, "NCCL error %d (%s) in %s", _r, (ctx)->nccl.GetErrorString(_r), #expr); \
+  } while (0)
+
+int rvae_dp_unique_id(rvae_ctx* ctx, const char* libnccl_path, void* out128) {
+  RVAE_REQUIRE(ctx != nullptr && out128 != nullptr, RVAE_ERR_INVALID, "dp_unique_id: null argument");
+  RVAE_CHECK(nccl_load(ctx, libnccl_path));
+  NcclId id;
+  RVAE_NCCL(ctx, ctx->nccl.GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return RVAE_OK;
+}
+
+int rvae_dp_init(rvae_ctx* ctx, const char* libnccl_path, const void* id128, int rank, int world) {
+  RVAE_REQUIRE(ctx != nullptr && id128 != nullptr, RVAE_ERR_INVALID, "dp_init: null argument");
+  RVAE_REQUIRE(world >= 1 && rank >= 0 && rank < world, RVAE_ERR_INVALID, "dp_init: rank %d of %d", rank, world);
+  RVAE_REQUIRE(ctx->comm == nullptr, RVAE_ERR_STATE, "dp_init: communicator already created");
+  RVAE_CHECK(nccl_load(ctx, libnccl_path));
+  NcclId id;
+  memcpy(&id, id128, sizeof(id));
+  RVAE_CUDA(cudaSetDevice(ctx->c.device));
+  RVAE_NCCL(ctx, ctx->nccl.CommInitRank(&ctx->comm, world, id, rank));
+  ctx->dp_rank = rank;
+  ctx->dp_world = world;
+  return RVAE_OK;
+}
+
+int rvae_dp_world(const rvae_ctx* ctx) { return ctx && ctx->comm ? ctx->dp_world : 1; }
+
+int rvae_dp_allreduce(rvae_ctx* ctx, float* ptr, int64_t count, int bucket, void* stream) {
+  RVAE_REQUIRE(ctx && ptr && count > 0, RVAE_ERR_INVALID, "dp_allreduce: bad argument");
+  const uint8_t* g0 = reinterpret_cast<const uint8_t*>(ptr);
+  if (ctx->p2p_ready && g0 >= ctx->sym_base + kP2PFlagBytes &&
+      g0 + sizeof(float) * (size_t)count <= ctx->sym_base + kP2PFlagBytes + ctx->sym_data_bytes) {
+    P2PSegs sg;
+    memset(&sg, 0, sizeof(sg));
+    sg.off[0] = ptr - ctx->p2p.data[ctx->p2p.rank];
+    sg.n[0] = count;
+    return launch_allreduce_p2p(&ctx->c, ctx->p2p, sg, bucket, ctx->p2p_ctas, S_(stream));
+  }
+  RVAE_REQUIRE(ctx->comm != nullptr, RVAE_ERR_STATE, "dp_allreduce: no communicator (rvae_dp_init / rvae_dp_sym_open)");
+  RVAE_NCCL(ctx, ctx->nccl.AllReduce(ptr, ptr, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ctx->comm, S_(stream)));
+  return RVAE_OK;
+}
+
+int rvae_dp_sym_alloc(rvae_ctx* ctx, size_t data_bytes, void** data_ptr, void* ipc_handle64) {
+  RVAE_REQUIRE(ctx && data_ptr && ipc_handle64 && data_bytes > 0, RVAE_ERR_INVALID, "dp_sym_alloc: bad argument");
+  RVAE_REQUIRE(ctx->sym_base == nullptr, RVAE_ERR_STATE, "dp_sym_alloc: already allocated");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  RVAE_CUDA(cudaSetDevice(ctx->c.device));
+  const size_t bytes = kP2PFlagBytes + ((data_bytes + 255) / 256) * 256;
+  void* base = nullptr;
+  RVAE_CUDA(cudaMalloc(&base, bytes));
+  RVAE_CUDA(cudaMemset(base, 0, bytes));
+  cudaIpcMemHandle_t h;
+  RVAE_CUDA(cudaIpcGetMemHandle(&h, base));
+  memcpy(ipc_handle64, &h, sizeof(h));
+  ctx->sym_base = reinterpret_cast<uint8_t*>(base);
+  ctx->sym_data_bytes = data_bytes;
+  *data_ptr = ctx->sym_base + kP2PFlagBytes;
+  return RVAE_OK;
+}
+
+int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world) {
+  RVAE_REQUIRE(ctx && handles && ctx->sym_base, RVAE_ERR_STATE, "dp_sym_open: call rvae_dp_sym_alloc first");
+  RVAE_REQUIRE(world >= 2 && world <= kP2PMaxWorld && rank >= 0 && rank < world, RVAE_ERR_INVALID,
+               "dp_sym_open: rank %d of %d (at most %d ranks)", rank, world, kP2PMaxWorld);
+  RVAE_CUDA(cudaSetDevice(ctx->c.device));
+  for (int p = 0; p < world; ++p) {
+    void* base = ctx->sym_base;
+    if (p != rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, reinterpret_cast<const uint8_t*>(handles) + 64 * p, sizeof(h));
+      RVAE_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->peer_base[p] = base;
+    ctx->p2p.flags[p] = reinterpret_cast<uint32_t*>(base);
+    ctx->p2p.data[p] = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + kP2PFlagBytes);
+  }
+  // local: epochs and tickets behind the flag table
+  static_assert(kP2PMaxBuckets * kP2PMaxCtas * kP2PMaxWorld * kP2PFlagStride * 4 + 2 * kP2PMaxBuckets * 4 <= kP2PFlagBytes,
+                "flag area");
+  ctx->p2p.epoch = reinterpret_cast<uint32_t*>(ctx->sym_base) + kP2PMaxBuckets * kP2PMaxCtas * kP2PMaxWorld * kP2PFlagStride;
+  ctx->p2p.ticket = ctx->p2p.epoch + kP2PMaxBuckets;
+  ctx->p2p.rank = rank;
+  ctx->p2p.world = world;
+  ctx->p2p.mode = 1;
+  if (const char* e = getenv("RVAE_P2P_MODE")) ctx->p2p.mode = atoi(e);
+  ctx->dp_rank = rank;
+  ctx->dp_world = world;
+  ctx->p2p_ready = true;
+  return RVAE_OK;
+}
 int rvae_ctx_num_sms(const rvae_ctx* ctx) { return ctx ? ctx->c.num_sms : 0; }
 uint64_t rvae_ctx_launch_count(const rvae_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
@@ -288,6 +446,8 @@ enum AuxSlot { T_LOAD = G_COUNT, T_EPS, T_FINALIZE, T_COLSUM, T_ADAM, T_TANHBWD,
 struct GemmSet {
   PreparedGemm g[G_COUNT];
   bool ready[G_COUNT];
+  PreparedDual dual[3];   // backward stage s: dgrad + weight gradient in one launch
+  int dual_state[3];      // 0 = not tried, 1 = ready, -1 = unsupported for these shapes (separate launches)
 };
 
 }  // namespace
@@ -306,6 +466,8 @@ struct rvae_plan {
   Planes x_alt;
   float* eps_alt;
   int cur;                 // which input set is current (GEMM tensor maps are prepared per set)
+  int* sched_dev;          // schedules of the fused backward-stage launches: [2 input sets][3 stages][pairs][kSchedMax]
+  int dual_pairs;          // CTA pairs a fused launch uses (0 = fused launches off)
   unsigned int* ticket;    // last-block ticket of the step's final Adam launch (advances the step counter)
   bool ticket_zeroed;
   struct Prefetch {
@@ -319,6 +481,7 @@ struct rvae_plan {
   float *out_mu, *out_lv, *out_xhat;
   int batch;        // current batch
   int64_t global_batch;  // loss normalisation under data parallelism (0 = local batch)
+  bool dp_enabled;       // rvae_plan_enable_dp: this plan's train steps all-reduce their gradients
   float kl_c0;           // kl_beta / (B L) of the last fused-loss forward (KL gradient scale of the latent backward)
   bool dz_zeroed;        // the split-K latent dgrad accumulator holds zeros (left so by the latent backward kernel)
   bool grads_zeroed[5];  // gradient bucket s (0..3 weights, 4 biases) already holds zeros (left so by the fused Adam)
@@ -336,6 +499,9 @@ struct rvae_plan {
   // rvae_plan_train_step runs its critical chain on a highest-priority stream forked from the caller's stream
   cudaStream_t hp;
   cudaEvent_t ev_hp_fork, ev_hp_join;
+  // data parallelism: gradient all-reduces run on their own stream, bucket by bucket as backward completes them
+  cudaStream_t comm_stream;
+  cudaEvent_t ev_comm_fork, ev_comm_done[5];
   // loss finalisation deferred into the latent backward kernel (rvae_plan_finish_loss_deferred)
   LossFinalize fin;
   bool fin_pending;
@@ -381,6 +547,7 @@ size_t carve(rvae_plan* p, uint8_t* base) {
   p->eps = reinterpret_cast<float*>(take(B * L * 4));
   p->eps_alt = reinterpret_cast<float*>(take(B * L * 4));
   p->ticket = reinterpret_cast<unsigned int*>(take(256));
+  p->sched_dev = reinterpret_cast<int*>(take(sizeof(int) * 2 * 3 * 128 * kSchedMax));
   p->dz = reinterpret_cast<float*>(take(B * L * 4));
   p->xhat = reinterpret_cast<float*>(take(B * S * 4));
   p->loss_acc = reinterpret_cast<double*>(take(2 * sizeof(double)));
@@ -581,6 +748,9 @@ int ensure_side_stream(rvae_plan* p) {
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->adam_stream, cudaStreamNonBlocking, least));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_fork, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_join, cudaEventDisableTiming));
+  RVAE_CUDA(cudaStreamCreateWithPriority(&p->comm_stream, cudaStreamNonBlocking, greatest));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_comm_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 5; ++i) RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_comm_done[i], cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_eps, cudaEventDisableTiming));
@@ -653,7 +823,29 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   p->grads_zeroed[stage] = false;
   if (stage == 1 && !p->dz_zeroed)
     RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
-  if (kDgrad[stage] >= 0) RVAE_CHECK(run(p, kDgrad[stage], st));
+  // dgrad and weight gradient of the stage as ONE persistent launch over a mixed, load-balanced tile list
+  bool fused = false;
+  if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && !p->timing) {
+    // under data parallelism the fused launches leave the same spare SMs as the single GEMMs do: NCCL's kernels
+    // run there
+    const int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
+    GemmSet* gs;
+    RVAE_CHECK(get_set(p, &gs));
+    if (gs->dual_state[stage] == 0) {
+      RVAE_CHECK(prepare(p, *gs, kDgrad[stage]));
+      RVAE_CHECK(prepare(p, *gs, kWgrad[stage]));
+      int* sched = p->sched_dev + ((size_t)p->cur * 3 + stage) * 128 * kSchedMax;
+      const int rc = gemm_prepare_dual(&p->ctx->c, gs->g[kDgrad[stage]], gs->g[kWgrad[stage]], pairs, sched,
+                                       &gs->dual[stage]);
+      gs->dual_state[stage] = rc == RVAE_OK ? 1 : -1;
+      if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+    }
+    if (gs->dual_state[stage] == 1) {
+      RVAE_CHECK(gemm_run_dual(&p->ctx->c, gs->dual[stage], st));
+      fused = true;
+    }
+  }
+  if (!fused && kDgrad[stage] >= 0) RVAE_CHECK(run(p, kDgrad[stage], st));
   if (stage == 1) {
     TimedScope ts(p, T_LATENT, st);
     RVAE_CHECK(launch_latent_bwd(&p->ctx->c, p->dz, p->eps, ext ? ext->lv : p->lv, p->mu, ext ? ext->g_mu : nullptr,
@@ -662,7 +854,7 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
     p->fin_pending = false;
     p->dz_zeroed = true;
   }
-  return run(p, kWgrad[stage], st);
+  return fused ? RVAE_OK : run(p, kWgrad[stage], st);
 }
 
 }  // namespace
@@ -682,15 +874,22 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
   p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
   p->timing = false;
-  p->kl_c0 = 0.f; p->dz_zeroed = false;
+  p->kl_c0 = 0.f; p->dz_zeroed = false; p->dp_enabled = false;
   p->cur = 0; p->ticket_zeroed = false; p->ticket = nullptr;
   memset(&p->pf, 0, sizeof(p->pf));
   for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
   p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
   p->hp = nullptr; p->ev_hp_fork = nullptr; p->ev_hp_join = nullptr;
+  p->comm_stream = nullptr; p->ev_comm_fork = nullptr;
+  for (int i = 0; i < 5; ++i) p->ev_comm_done[i] = nullptr;
   p->adam_stream = nullptr; p->ev_eps = nullptr; p->ev_adam_fork = nullptr; p->ev_adam_join = nullptr;
   p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
+  p->dual_pairs = ctx->c.num_sms / 2;
+  if (const char* e = getenv("RVAE_DUAL_PAIRS")) {
+    const int v = atoi(e);
+    if (v >= 0 && 2 * v <= ctx->c.num_sms_total) p->dual_pairs = v;
+  }
   if (const char* e = getenv("RVAE_TWO_STREAMS")) p->two_streams = atoi(e) != 0;
   for (int i = 0; i < T_COUNT; ++i) { p->t_ms[i] = 0; p->t_n[i] = 0; p->t_flops[i] = 0; }
   p->out_mu = p->out_lv = p->out_xhat = nullptr;
@@ -710,6 +909,10 @@ void rvae_plan_destroy(rvae_plan* plan) {
     cudaStreamSynchronize(plan->side);
     cudaStreamSynchronize(plan->adam_stream);
     cudaStreamSynchronize(plan->hp);
+    cudaStreamSynchronize(plan->comm_stream);
+    cudaEventDestroy(plan->ev_comm_fork);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(plan->ev_comm_done[i]);
+    cudaStreamDestroy(plan->comm_stream);
     cudaEventDestroy(plan->ev_hp_fork);
     cudaEventDestroy(plan->ev_hp_join);
     cudaStreamDestroy(plan->hp);
@@ -843,6 +1046,15 @@ int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_s
 int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat) {
   RVAE_REQUIRE(plan, RVAE_ERR_INVALID, "null rvae_plan");
   plan->out_mu = mu; plan->out_lv = logvar; plan->out_xhat = xhat;
+  return RVAE_OK;
+}
+
+int rvae_plan_enable_dp(rvae_plan* plan, int on) {
+  RVAE_REQUIRE(plan, RVAE_ERR_INVALID, "null rvae_plan");
+  RVAE_REQUIRE(!on || plan->ctx->comm != nullptr || plan->ctx->p2p_ready, RVAE_ERR_STATE,
+               "plan_enable_dp: call rvae_dp_init / rvae_dp_sym_open first");
+  if (plan->dp_enabled != (on != 0)) plan->sets.clear();   // fused-launch schedules depend on the SM budget
+  plan->dp_enabled = on != 0;
   return RVAE_OK;
 }
 
@@ -1018,6 +1230,8 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
   // the whole step: every Adam launch uses t + 1, and the last block of the final launch advances it.
   const bool fork = plan->two_streams && !plan->timing;
   if (!fork) {
+    // (per-kernel timing / RVAE_TWO_STREAMS=0: a LOCAL step - no collectives are issued even when the context has a
+    // communicator; bench.py's attribution pass runs this on rank 0 only)
     RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, stream));
     RVAE_CHECK(rvae_plan_finish_loss_deferred(plan, kl_beta, loss_out, ring_size));  // runs inside stage 1
     plan->fin.inc_step = 0;
@@ -1050,15 +1264,68 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
   plan->fin.inc_step = 0;
   // Adam per bucket as soon as the bucket's gradient is complete; the dgrad GEMM that reads the bucket's bf16
   // shadow weights runs before the weight-gradient GEMM of the same stage, so nothing of this step reads them again.
+  // Data parallelism: bucket s is SUM all-reduced (NCCL over NVLink / NVSwitch) on the communication stream as soon
+  // as stage s completes it, under the GEMMs of the later stages; its Adam launch waits for the reduced gradient.
+  // The loss was normalised by the global batch (rvae_plan_set_global_batch), so the sum IS the gradient.
+  rvae_ctx* cx = plan->ctx;
+  const bool dp = plan->dp_enabled && (cx->comm != nullptr || cx->p2p_ready) && cx->dp_world > 1;
+  cudaStream_t cs = plan->comm_stream;
+  // gradients that live in the symmetric allocation are reduced by our own peer-memory kernel; anything else by NCCL
+  const uint8_t* g0 = reinterpret_cast<const uint8_t*>(b.grads);
+  const bool use_p2p = cx->p2p_ready && cx->sym_base != nullptr && g0 >= cx->sym_base + kP2PFlagBytes &&
+                       g0 + sizeof(float) * (size_t)plan->lay.total <= cx->sym_base + kP2PFlagBytes + cx->sym_data_bytes;
+  RVAE_REQUIRE(!dp || use_p2p || cx->comm != nullptr, RVAE_ERR_STATE, "plan_train_step: no communicator for these gradients");
+  // all-reduce of the gradient buckets in `mask` as ONE operation (a flag hop between two GPUs costs ~5 us, so
+  // small buckets are merged): our kernel takes them as segments, NCCL gets one call per bucket
+  auto allreduce_buckets = [&](unsigned mask, int flag_set, int ctas) -> int {
+    P2PSegs sg;
+    memset(&sg, 0, sizeof(sg));
+    int ns = 0;
+    for (int bucket = 0; bucket < 5; ++bucket) {
+      if (!(mask & (1u << bucket))) continue;
+      float* ptr; int64_t cnt;
+      RVAE_CHECK(rvae_plan_bucket(plan, bucket, &ptr, &cnt));
+      if (use_p2p) {
+        RVAE_REQUIRE(ns < 3, RVAE_ERR_INVALID, "plan_train_step: too many segments in one all-reduce");
+        sg.off[ns] = ptr - cx->p2p.data[cx->p2p.rank];
+        sg.n[ns] = cnt;
+        ++ns;
+      } else {
+        RVAE_NCCL(cx, cx->nccl.AllReduce(ptr, ptr, (size_t)cnt, /*ncclFloat32*/ 7, /*ncclSum*/ 0, cx->comm, cs));
+      }
+    }
+    if (use_p2p) return launch_allreduce_p2p(&cx->c, cx->p2p, sg, flag_set, ctas, cs);
+    return RVAE_OK;
+  };
   static const unsigned kBucketMask[3] = {0x1, 0x2, 0x4};
   for (int s = 0; s < 3; ++s) {
     RVAE_CHECK(rvae_plan_backward(plan, s, st));
+    if (dp) {
+      // four exchanges per step: W4 after stage 0, W3 after stage 1, W2 + all biases after stage 2 (kept small: it
+      // must be out of the way when stage 3 ends), W1 after stage 3
+      static const unsigned kExchange[3] = {0x1u, 0x2u, 0x14u};
+      RVAE_CUDA(cudaEventRecord(plan->ev_comm_fork, st));
+      RVAE_CUDA(cudaStreamWaitEvent(cs, plan->ev_comm_fork, 0));
+      RVAE_CHECK(allreduce_buckets(kExchange[s], s, cx->p2p_ctas));
+      RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[s], cs));
+      RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_comm_done[s], 0));
+      RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
+      continue;
+    }
     RVAE_CUDA(cudaEventRecord(plan->ev_adam_fork, st));
     RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_adam_fork, 0));
     RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
   }
   RVAE_CUDA(cudaEventRecord(plan->ev_adam_join, bg));
   RVAE_CHECK(rvae_plan_backward(plan, 3, st));
+  if (dp) {
+    RVAE_CUDA(cudaEventRecord(plan->ev_comm_fork, st));
+    RVAE_CUDA(cudaStreamWaitEvent(cs, plan->ev_comm_fork, 0));
+    // the last exchange is exposed and has the machine to itself: more CTAs, more NVLink bytes in flight
+    RVAE_CHECK(allreduce_buckets(0x8u, 3, cx->p2p_ctas_last));
+    RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[3], cs));
+    RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_comm_done[3], 0));   // (the bias bucket precedes it on the same stream)
+  }
   RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_adam_join, 0));  // every earlier Adam launch has read the step counter
   RVAE_CHECK(adam_buckets(plan, 0x18, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, true, st));
   RVAE_CUDA(cudaEventRecord(plan->ev_hp_join, st));

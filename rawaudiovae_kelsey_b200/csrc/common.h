@@ -52,7 +52,7 @@ struct Ctx {
   unsigned long long* trace;  // GEMM timeline trace buffer (rvae_debug_set_trace), nullptr = off
   int trace_launches;         // capacity of the trace buffer in launches (successive launches use successive slabs)
   uint64_t trace_seq;         // GEMM launches since the trace was set
-  unsigned long long* aux_trace;  // elementwise-kernel trace: [aux_cap][4] = {first start, last end, kind, blocks}
+  unsigned long long* aux_trace;  // elementwise-kernel trace: [aux_cap][8] = {first start, last end, kind, blocks, 4 x detail}
   int aux_cap;
   uint64_t aux_seq;
   uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
@@ -85,7 +85,7 @@ inline AuxTrace next_aux(Ctx* ctx, int kind) {
   AuxTrace t;
   t.slot = nullptr;
   if (ctx->aux_trace != nullptr && ctx->aux_cap > 0) {
-    t.slot = ctx->aux_trace + (ctx->aux_seq % (uint64_t)ctx->aux_cap) * 4;
+    t.slot = ctx->aux_trace + (ctx->aux_seq % (uint64_t)ctx->aux_cap) * 8;
     ctx->aux_seq++;
     (void)kind;
   }
@@ -117,10 +117,24 @@ struct PreparedGemm {
   int smem_bytes;
   // geometry of the epilogue's output tensors (for re-binding output pointers)
   int epi;
+  int a_major, b_major, cg;
   int out_rows, out_cols_bf16, out_ld_bf16, out_cols_f32, out_ld_f32;
 };
 
 int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& args, bool force);
+
+// Two prepared GEMMs fused into one persistent launch (gemm_dual_kernel_2cta): units are assigned to CTA pairs by a
+// host-built longest-processing-time-first schedule stored in device memory.
+struct PreparedDual {
+  DualParams params;
+  int variant;  // index into the dual kernel table
+  int grid;
+  int smem_bytes;
+};
+// sched_dev: device buffer of at least pairs * kSchedMax ints (written here with a synchronous copy).
+int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm& g1, int pairs, int* sched_dev,
+                      PreparedDual* out);
+int gemm_run_dual(Ctx* ctx, const PreparedDual& g, cudaStream_t stream);
 
 int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out);
 int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream);
@@ -157,6 +171,26 @@ int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, in
                  unsigned int* ticket, __nv_bfloat16* shadow_hi, __nv_bfloat16* shadow_lo, int zero_grads,
                  cudaStream_t stream);
 int launch_step_inc(Ctx* ctx, float* step, cudaStream_t stream);
+
+// Peer-memory all-reduce (elementwise.cu): symmetric buffers of all ranks as mapped in THIS process.
+constexpr int kP2PMaxWorld = 8;
+constexpr int kP2PMaxBuckets = 8;
+constexpr int kP2PMaxCtas = 64;
+constexpr int kP2PFlagStride = 32;            // one 128-byte line per flag: no false sharing between CTAs / ranks
+constexpr size_t kP2PFlagBytes = 1024 * 1024;  // flags [bucket][cta][src rank] + epochs + tickets, at the start of the allocation
+struct P2PArgs {
+  float* data[kP2PMaxWorld];       // gradient buffer of rank p (peer-mapped; [rank] is local)
+  uint32_t* flags[kP2PMaxWorld];   // flag area of rank p
+  uint32_t* epoch;                 // local: [kP2PMaxBuckets]
+  unsigned int* ticket;            // local: [kP2PMaxBuckets]
+  int rank, world;
+  int mode;                        // barrier flavour (experiments: RVAE_P2P_MODE)
+};
+struct P2PSegs {   // a bucket = concatenation of up to three segments of the flat gradient buffer (float elements)
+  int64_t off[3];
+  int64_t n[3];
+};
+int launch_allreduce_p2p(Ctx* ctx, const P2PArgs& a, const P2PSegs& sg, int bucket, int ctas, cudaStream_t stream);
 // loss = acc[0]*inv_rec + kl_scale*acc[1] -> loss_out[step mod ring_size]; acc cleared; *step += 1
 struct LossFinalize {
   double* acc;

@@ -775,6 +775,168 @@ int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, co
   return RVAE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gradient all-reduce over NVLink peer memory (data parallelism). Every rank's flat gradient buffer lives in a
+// symmetric allocation that all peers map (CUDA IPC); the kernel reads and writes peer memory directly with 128-bit
+// loads - no staging copies, no NCCL. Two-shot, in place:
+//   barrier 1 : every peer's bucket gradient is complete (their kernel has started)
+//   reduce    : rank r sums slice r of the bucket over all ranks (W-1 peer reads + 1 local per element) and writes
+//               the sum into EVERY rank's buffer (local store + W-1 posted NVLink writes)   [reduce-scatter + push]
+//   barrier 2 : all slices have landed everywhere, and nobody reads this rank's buffer any more -> the caller may
+//               overwrite the gradient (Adam clears it)
+// A flag hop between two GPUs costs ~5 us on this fabric, so the protocol is built around the minimum of two hops.
+// Work is split by CTA index: CTA c of every rank owns chunk c of each slice and synchronises only with the CTAs c
+// of the other ranks (flags in the peers' symmetric memory, release / acquire at system scope), so no grid-wide
+// barrier is needed and a grid of a few CTAs lives on the SMs the persistent GEMMs leave free. Flag values are
+// monotonic (4 * epoch + phase); the epoch is a device counter, so CUDA-graph replays stay correct.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// MAXW: ranks the instantiation supports; U: float4 elements per thread and trip. All (MAXW - 1) * U peer loads of a
+// trip are issued before the first add, so ~16 x 16 bytes per thread are in flight (NVLink latency is ~1 us: a
+// few MB in flight are needed to fill it from 16 CTAs).
+template <int MAXW, int U>
+__global__ void __launch_bounds__(512, 1) allreduce_p2p_kernel(P2PArgs a, P2PSegs sg, int bucket, AuxTrace tr) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  aux_begin(tr, 5);
+  const int G = gridDim.x, c = blockIdx.x, W = a.world, me = a.rank;
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch + bucket) + 1u;
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  const int flag_row = (bucket * kP2PMaxCtas + c) * kP2PMaxWorld * kP2PFlagStride;
+
+  auto barrier = [&](uint32_t phase) {
+    __syncthreads();   // every thread's stores of the previous phase are ordered before the fence below
+    const uint32_t want = 4u * e + phase;
+    if (threadIdx.x < W && (int)threadIdx.x != me) {
+      const int p = threadIdx.x;
+      uint32_t* theirs = a.flags[p] + flag_row + me * kP2PFlagStride;
+      const uint32_t* mine = a.flags[me] + flag_row + p * kP2PFlagStride;
+      if (a.mode == 0) {
+        __threadfence_system();
+        st_release_sys(theirs, want);
+      } else if (a.mode == 1) {
+        st_release_sys(theirs, want);
+      } else if (a.mode == 3) {   // remote atomic: performed at the destination, cannot linger in a write buffer
+        __threadfence_system();
+        asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(theirs), "r"(want) : "memory");
+      } else if (a.mode == 4) {   // push the flag out with a trailing fence
+        st_release_sys(theirs, want);
+        __threadfence_system();
+      } else {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(theirs) = want;
+      }
+      const long long t0 = clock64();
+      while ((a.mode == 0 ? ld_acquire_sys(mine) : *reinterpret_cast<const volatile uint32_t*>(mine)) < want) {
+        if (clock64() - t0 > 4000000000ll) {
+          printf("rvae: all-reduce barrier timeout rank %d cta %d bucket %d phase %u peer %d\n", me, c, bucket, phase, p);
+          __trap();
+        }
+        if (a.mode >= 5) __nanosleep(40);
+      }
+      if (a.mode != 0) __threadfence_system();
+    }
+    __syncthreads();
+  };
+
+  // the bucket is the concatenation of up to three segments of the flat buffer (float4 units)
+  const int64_t n0 = sg.n[0] >> 2, n1 = sg.n[1] >> 2, n2 = sg.n[2] >> 2;
+  const int64_t o0 = sg.off[0] >> 2, o1 = sg.off[1] >> 2, o2 = sg.off[2] >> 2;
+  auto at = [&](int64_t i) -> int64_t { return i < n0 ? o0 + i : (i < n0 + n1 ? o1 + (i - n0) : o2 + (i - n0 - n1)); };
+  const int64_t n4 = n0 + n1 + n2;
+  const int64_t per_rank = (n4 + W - 1) / W;
+  const int64_t per_cta = (per_rank + G - 1) / G;
+  const int64_t T = blockDim.x;
+
+  const unsigned long long g0 = tr.slot ? global_timer() : 0ull;
+  barrier(1);
+  const unsigned long long g1 = tr.slot ? global_timer() : 0ull;
+  {  // my slice, my chunk: sum over all ranks, store locally AND push the result into every peer's buffer
+    const int64_t s0 = (int64_t)me * per_rank;
+    const int64_t s1 = min(s0 + per_rank, n4);
+    const int64_t b0 = min(s0 + (int64_t)c * per_cta, s1), b1 = min(b0 + per_cta, s1);
+    for (int64_t base = b0 + threadIdx.x; base < b1; base += T * U) {
+      float4 v[MAXW][U];
+#pragma unroll
+      for (int p = 0; p < MAXW; ++p) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = base + u * T;
+          v[p][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p < W && i < b1) {
+            const float4* src = reinterpret_cast<const float4*>(a.data[p]) + at(i);
+            v[p][u] = (p == me) ? *src : ld_peer(src);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = base + u * T;
+        if (i < b1) {
+          float4 acc = v[0][u];
+#pragma unroll
+          for (int p = 1; p < MAXW; ++p) { acc.x += v[p][u].x; acc.y += v[p][u].y; acc.z += v[p][u].z; acc.w += v[p][u].w; }
+#pragma unroll
+          for (int p = 0; p < MAXW; ++p)
+            if (p < W) reinterpret_cast<float4*>(a.data[p])[at(i)] = acc;   // p == me: local; else a posted NVLink write
+        }
+      }
+    }
+  }
+  const unsigned long long g2 = tr.slot ? global_timer() : 0ull;
+  // one more flag exchange ends the all-reduce: it publishes my pushes, tells me every peer's slice has landed in my
+  // buffer, and - because a peer signals only after it has read my contribution - that nobody reads my buffer any
+  // more, so the caller may overwrite it (Adam clears the gradient)
+  barrier(2);
+  if (tr.slot && threadIdx.x == 0) {  // detail words: the slowest CTA's barrier 1 / reduce+push / barrier 2
+    atomicMax(tr.slot + 4, g1 - g0);
+    atomicMax(tr.slot + 5, g2 - g1);
+    atomicMax(tr.slot + 6, global_timer() - g2);
+  }
+  aux_end(tr);
+  if (threadIdx.x == 0) {  // the last CTA advances the epoch of this bucket (every CTA has read it)
+    const unsigned int done = atomicAdd(a.ticket + bucket, 1u);
+    if (done == gridDim.x - 1) {
+      a.ticket[bucket] = 0u;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(a.epoch + bucket) = e;
+    }
+  }
+}
+
+int launch_allreduce_p2p(Ctx* ctx, const P2PArgs& a, const P2PSegs& sg, int bucket, int ctas, cudaStream_t stream) {
+  RVAE_REQUIRE(a.world >= 2 && a.world <= kP2PMaxWorld && bucket >= 0 && bucket < kP2PMaxBuckets, RVAE_ERR_INVALID,
+               "allreduce_p2p: world %d bucket %d", a.world, bucket);
+  RVAE_REQUIRE(ctas >= 1 && ctas <= kP2PMaxCtas, RVAE_ERR_INVALID, "allreduce_p2p: %d CTAs", ctas);
+  for (int i = 0; i < 3; ++i)
+    RVAE_REQUIRE((sg.n[i] & 3) == 0 && (sg.off[i] & 3) == 0 && sg.n[i] >= 0, RVAE_ERR_INVALID,
+                 "allreduce_p2p: segments must be multiples of 4 floats");
+  const AuxTrace tr = next_aux(ctx, 5);
+  if (a.world <= 2)
+    RVAE_CUDA(launch_kernel(ctx, allreduce_p2p_kernel<2, 12>, dim3(ctas), dim3(512), (size_t)0, stream, a, sg, bucket, tr));
+  else if (a.world <= 4)
+    RVAE_CUDA(launch_kernel(ctx, allreduce_p2p_kernel<4, 4>, dim3(ctas), dim3(512), (size_t)0, stream, a, sg, bucket, tr));
+  else
+    RVAE_CUDA(launch_kernel(ctx, allreduce_p2p_kernel<8, 2>, dim3(ctas), dim3(512), (size_t)0, stream, a, sg, bucket, tr));
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
 __global__ void step_inc_kernel(float* step) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();

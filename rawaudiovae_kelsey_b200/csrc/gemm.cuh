@@ -312,225 +312,234 @@ struct Team {
   }
 };
 
-template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI, int CG>
-__device__ __forceinline__ void gemm_body(const GemmParams& p) {
+// ---------------------------------------------------------------------------------------------------------------
+// A kernel runs one GEMM ("problem") or two independent ones fused into a single persistent launch (the dgrad and the
+// weight-gradient GEMM of a backward stage): the units of both share the CTAs' pipelines, so the machine is filled by
+// a mixed tile list instead of two partially filled waves and one kernel boundary disappears. Per-tile code is
+// templated on the problem's Kind; the role loops just dispatch.
+// ---------------------------------------------------------------------------------------------------------------
+template <int A_MAJOR_, int B_MAJOR_, int EPI_>
+struct Kind {
+  static constexpr int A = A_MAJOR_, B = B_MAJOR_, EPI = EPI_;
+};
+
+constexpr int kSchedMax = 16;  // units per CTA group in a host-built schedule (entries < 0 terminate the list)
+
+struct alignas(64) DualParams {
+  GemmParams p0, p1;
+  const int* sched;  // [groups][kSchedMax] unit indices in the combined space [0, units0) + [units0, units0 + units1)
+  int units0;
+};
+
+// Units of one CTA group: strided over a single problem's unit space, or read from the schedule table.
+struct UnitIter {
+  const int* sched;
+  int pos, u, stride, total;
+  __device__ __forceinline__ UnitIter(const int* sched_, int group_id, int num_groups, int total_)
+      : sched(sched_ ? sched_ + group_id * kSchedMax : nullptr), pos(0), u(group_id), stride(num_groups), total(total_) {}
+  __device__ __forceinline__ bool next(int& unit) {
+    if (sched) {
+      if (pos >= kSchedMax) return false;
+      unit = __ldg(sched + pos);
+      ++pos;
+      return unit >= 0;
+    }
+    if (u >= total) return false;
+    unit = u;
+    u += stride;
+    return true;
+  }
+};
+
+// smem carve-up and CTA identity shared by the three roles
+struct Shared {
+  uint8_t* smem;
+  uint8_t* slot_base;
+  float* bias_strips;
+  float* csum_strips;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  uint64_t* tmem_full_bar;
+  uint64_t* tmem_empty_bar;
+  uint64_t* in_bars;
+  uint32_t tmem_base;
+  uint32_t cta_rank;
+  bool leader;
+};
+
+struct TileCoord {
+  int ks, n_blk, m_blk, m0, kb_begin, kb_count;
+};
+template <int CG>
+__device__ __forceinline__ TileCoord decode_unit(const GemmParams& p, int u, uint32_t cta_rank) {
+  TileCoord t;
+  const int tiles = p.m_blocks * p.n_blocks;
+  t.ks = u / tiles;
+  const int tile = u - t.ks * tiles;
+  t.n_blk = tile / p.m_blocks;
+  t.m_blk = tile - t.n_blk * p.m_blocks;
+  t.m0 = (t.m_blk * CG + static_cast<int>(cta_rank)) * kBlockM;
+  t.kb_begin = t.ks * p.kb_per_split;
+  t.kb_count = min(p.kb_per_split, p.kb_total - t.kb_begin);
+  return t;
+}
+
+struct ProdState {
+  uint32_t stage, phase;
+  bool slot_free;
+};
+
+template <class KD, int BLOCK_N, int CG>
+__device__ __forceinline__ void produce_unit(const GemmParams& p, int u, ProdState& ps, const Shared& sh, int titer) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int A_MAJOR = KD::A, B_MAJOR = KD::B;
+  trace_ev(p.trace, titer, 0);
+  const TileCoord t = decode_unit<CG>(p, u, sh.cta_rank);
+  uint32_t stage = ps.stage, phase = ps.phase;
+  bool slot_free = ps.slot_free;
+  for (int pass = 0; pass < p.num_passes; ++pass) {
+    const CUtensorMap* tmA = &p.tmA[pass];
+    const CUtensorMap* tmB = &p.tmB[pass];
+    for (int kb = t.kb_begin; kb < t.kb_begin + t.kb_count; ++kb) {
+      ptx::mbar_wait_probed(slot_free, &sh.empty_bar[stage], phase ^ 1);
+      {  // probe the NEXT slot now: the probe's latency overlaps the TMA issue below
+        const uint32_t ns = (stage + 1 == kStages) ? 0u : stage + 1;
+        const uint32_t np = (stage + 1 == kStages) ? phase ^ 1u : phase;
+        slot_free = ptx::mbar_try_wait(&sh.empty_bar[ns], np ^ 1);
+      }
+      uint64_t* fb = &sh.full_bar[stage];
+      if (CG == 1 && (p.debug & 2)) {  // experiment: measure the MMA side alone (operands are stale smem)
+        ptx::mbar_arrive(fb);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        continue;
+      }
+      if constexpr (CG == 1) {
+        ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+      } else {
+        // Both CTAs' loads complete_tx on the LEADER's barrier; the leader alone arrives, announcing the pair's
+        // bytes. The peer sends no arrive (a cluster-scope release per k-block would throttle its producer):
+        // it cannot run a phase ahead because its smem slot is only freed by the commit that follows the MMAs
+        // which consumed this phase, and a complete_tx that lands before the leader's expect_tx merely leaves
+        // the tx-count transiently negative while the leader's arrival is still pending.
+        if (sh.leader) ptx::mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
+      }
+      uint8_t* sA = sh.smem + stage * Cfg::kStageBytes;
+      uint8_t* sB = sA + Cfg::kABytes;
+      const int k0 = kb * kBlockK;
+      if constexpr (A_MAJOR == MAJOR_K) {
+        ptx::tma_load_2d_cg<CG>(sA, tmA, fb, k0, t.m0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kBlockM / 64; ++i)
+          ptx::tma_load_2d_cg<CG>(sA + i * (kBlockK * 128), tmA, fb, t.m0 + i * 64, k0);
+      }
+      if constexpr (B_MAJOR == MAJOR_K) {
+        // the B tile is staged as two boxes of BLOCK_N/2 rows: CG == 1 loads both, CG == 2 one per CTA
+        const int r0 = t.n_blk * p.b_tile_stride;
+        if constexpr (CG == 1) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            ptx::tma_load_2d_cg<1>(sB + h * (Cfg::kBBytes / 2), tmB, fb, k0, r0 + h * p.b_half_stride);
+        } else {
+          ptx::tma_load_2d_cg<2>(sB, tmB, fb, k0, r0 + static_cast<int>(sh.cta_rank) * p.b_half_stride);
+        }
+      } else {
+        const int n0 = t.n_blk * BLOCK_N + static_cast<int>(sh.cta_rank) * (BLOCK_N / CG);
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / CG / 64; ++i)
+          ptx::tma_load_2d_cg<CG>(sB + i * (kBlockK * 128), tmB, fb, n0 + i * 64, k0);
+      }
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  }
+  ps.stage = stage; ps.phase = phase; ps.slot_free = slot_free;
+  trace_ev(p.trace, titer, 1);
+}
+
+struct MmaState {
+  uint32_t stage, phase, as, aphase;
+  bool data_ready;
+};
+
+template <class KD, int BLOCK_N, int CG>
+__device__ __forceinline__ void mma_unit(const GemmParams& p, int u, MmaState& ms, const Shared& sh, int titer) {
+  using Cfg = GemmCfg<BLOCK_N, CG>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int A_MAJOR = KD::A, B_MAJOR = KD::B;
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM * CG, BLOCK_N, A_MAJOR, B_MAJOR);
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* slot_base = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
-  float* bias_strips = reinterpret_cast<float*>(slot_base + Cfg::kSlotRegion);
-  float* csum_strips = bias_strips + kEpiTeams * Cfg::kBiasFloats;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(csum_strips + kEpiTeams * 128);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::kAccStages;
-  uint64_t* in_bars = tmem_empty_bar + Cfg::kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + kEpiTeams * kSlotsPerTeam);
-  static_assert((2 * 8 + 2 * 2 + kEpiTeams * kSlotsPerTeam) * 8 + 4 <= Cfg::kBarrierBytes, "barrier region");
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
-  const bool leader = cta_rank == 0;
-  const int group_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;       // tile-owning unit: CTA or CTA pair
-  const int num_groups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
-
-  if (threadIdx.x == 0) {
-    if ((ptx::smem_u32(smem) & 1023u) != 0) {  // swizzled tiles need the declared 1 KB alignment
-      printf("rvae: dynamic shared memory base is not 1024-byte aligned\n");
-      __trap();
-    }
-    trace_hdr(p.trace, 0, global_timer());
-    trace_hdr(p.trace, 1, clock64());
-  }
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.num_passes; ++i) {
-      ptx::prefetch_tensormap(&p.tmA[i]);
-      ptx::prefetch_tensormap(&p.tmB[i]);
-    }
-    ptx::prefetch_tensormap(&p.tmOutHi);
-    ptx::prefetch_tensormap(&p.tmOutLo);
-    ptx::prefetch_tensormap(&p.tmOutF32);
-    ptx::prefetch_tensormap(&p.tmOutF32b);
-    ptx::prefetch_tensormap(&p.tmSide);
-    for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);    // leader's barrier: its producer arrives once with the pair's byte count
-      ptx::mbar_init(&empty_bar[i], 1);   // per CTA: tcgen05.commit (multicast to both CTAs when CG == 2)
-    }
-    for (int i = 0; i < Cfg::kAccStages; ++i) {
-      ptx::mbar_init(&tmem_full_bar[i], 1);        // per CTA: tcgen05.commit
-      ptx::mbar_init(&tmem_empty_bar[i], 8 * CG);  // leader's barrier: one arrive per epilogue warp of the pair
-    }
-    for (int i = 0; i < kEpiTeams * kSlotsPerTeam; ++i) ptx::mbar_init(&in_bars[i], 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kEpiTeams * 128) csum_strips[threadIdx.x - 64] = 0.f;
-  ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  const TileCoord t = decode_unit<CG>(p, u, sh.cta_rank);
+  const int iters = t.kb_count * p.num_passes;
+  uint32_t stage = ms.stage, phase = ms.phase;
+  bool data_ready = ms.data_ready;
+  trace_ev(p.trace, titer, 2);
+  ptx::mbar_wait(&sh.tmem_empty_bar[ms.as], ms.aphase ^ 1);
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous
-  // kernel of the stream; from here on we read what it wrote.
-  if (threadIdx.x == 0) trace_hdr(p.trace, 2, clock64());
-  // (the dependents are released late, by the epilogue after its last tile: released here, their CTAs would sit on
-  // the SMs this grid leaves to the step's background stream for the whole duration of this kernel)
-  ptx::pdl_wait();
-  if (threadIdx.x == 0) trace_hdr(p.trace, 3, clock64());
-
-  const int tiles = p.m_blocks * p.n_blocks;
-  const int total_units = tiles * p.k_splits;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one per CTA)
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      bool slot_free = ptx::mbar_try_wait(&empty_bar[0], 1);
-      int titer = 0;
-      for (int u = group_id; u < total_units; u += num_groups, ++titer) {
-        trace_ev(p.trace, titer, 0);
-        const int ks = u / tiles;
-        const int tile = u - ks * tiles;
-        const int n_blk = tile / p.m_blocks;
-        const int m_blk = tile - n_blk * p.m_blocks;
-        const int m0 = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM;
-        const int kb_begin = ks * p.kb_per_split;
-        const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
-        for (int pass = 0; pass < p.num_passes; ++pass) {
-          const CUtensorMap* tmA = &p.tmA[pass];
-          const CUtensorMap* tmB = &p.tmB[pass];
-          for (int kb = kb_begin; kb < kb_begin + kb_count; ++kb) {
-            ptx::mbar_wait_probed(slot_free, &empty_bar[stage], phase ^ 1);
-            {  // probe the NEXT slot now: the probe's latency overlaps the TMA issue below
-              const uint32_t ns = (stage + 1 == kStages) ? 0u : stage + 1;
-              const uint32_t np = (stage + 1 == kStages) ? phase ^ 1u : phase;
-              slot_free = ptx::mbar_try_wait(&empty_bar[ns], np ^ 1);
-            }
-            uint64_t* fb = &full_bar[stage];
-            if (CG == 1 && (p.debug & 2)) {  // experiment: measure the MMA side alone (operands are stale smem)
-              ptx::mbar_arrive(fb);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-              continue;
-            }
-            if constexpr (CG == 1) {
-              ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
-            } else {
-              // Both CTAs' loads complete_tx on the LEADER's barrier; the leader alone arrives, announcing the pair's
-              // bytes. The peer sends no arrive (a cluster-scope release per k-block would throttle its producer):
-              // it cannot run a phase ahead because its smem slot is only freed by the commit that follows the MMAs
-              // which consumed this phase, and a complete_tx that lands before the leader's expect_tx merely leaves
-              // the tx-count transiently negative while the leader's arrival is still pending.
-              if (leader) ptx::mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
-            }
-            uint8_t* sA = smem + stage * Cfg::kStageBytes;
-            uint8_t* sB = sA + Cfg::kABytes;
-            const int k0 = kb * kBlockK;
-            if constexpr (A_MAJOR == MAJOR_K) {
-              ptx::tma_load_2d_cg<CG>(sA, tmA, fb, k0, m0);
-            } else {
-#pragma unroll
-              for (int i = 0; i < kBlockM / 64; ++i)
-                ptx::tma_load_2d_cg<CG>(sA + i * (kBlockK * 128), tmA, fb, m0 + i * 64, k0);
-            }
-            if constexpr (B_MAJOR == MAJOR_K) {
-              // the B tile is staged as two boxes of BLOCK_N/2 rows: CG == 1 loads both, CG == 2 one per CTA
-              const int r0 = n_blk * p.b_tile_stride;
-              if constexpr (CG == 1) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                  ptx::tma_load_2d_cg<1>(sB + h * (Cfg::kBBytes / 2), tmB, fb, k0, r0 + h * p.b_half_stride);
-              } else {
-                ptx::tma_load_2d_cg<2>(sB, tmB, fb, k0, r0 + static_cast<int>(cta_rank) * p.b_half_stride);
-              }
-            } else {
-              const int n0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / CG);
-#pragma unroll
-              for (int i = 0; i < BLOCK_N / CG / 64; ++i)
-                ptx::tma_load_2d_cg<CG>(sB + i * (kBlockK * 128), tmB, fb, n0 + i * 64, k0);
-            }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-        trace_ev(p.trace, titer, 1);
-      }
-      trace_hdr(p.trace, 4, clock64());
+  trace_ev(p.trace, titer, 3);
+  const uint32_t d_tmem = sh.tmem_base + ms.as * BLOCK_N;
+  for (int it = 0; it < iters; ++it) {
+    ptx::mbar_wait_probed(data_ready, &sh.full_bar[stage], phase);
+    {  // probe the NEXT stage now: the MMA issue below hides the probe's latency, so the tensor pipe does not
+       // drain while this thread waits on a barrier that has long completed
+      const uint32_t ns = (stage + 1 == kStages) ? 0u : stage + 1;
+      const uint32_t np = (stage + 1 == kStages) ? phase ^ 1u : phase;
+      data_ready = ptx::mbar_try_wait(&sh.full_bar[ns], np);
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      bool data_ready = false;
-      int titer = 0;
-      for (int u = group_id; u < total_units; u += num_groups, ++titer) {
-        const int ks = u / tiles;
-        const int kb_begin = ks * p.kb_per_split;
-        const int kb_count = min(p.kb_per_split, p.kb_total - kb_begin);
-        const int iters = kb_count * p.num_passes;
-        trace_ev(p.trace, titer, 2);
-        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        ptx::tc_fence_after();
-        trace_ev(p.trace, titer, 3);
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int it = 0; it < iters; ++it) {
-          ptx::mbar_wait_probed(data_ready, &full_bar[stage], phase);
-          {  // probe the NEXT stage now: the MMA issue below hides the probe's latency, so the tensor pipe does not
-             // drain while this thread waits on a barrier that has long completed
-            const uint32_t ns = (stage + 1 == kStages) ? 0u : stage + 1;
-            const uint32_t np = (stage + 1 == kStages) ? phase ^ 1u : phase;
-            data_ready = ptx::mbar_try_wait(&full_bar[ns], np);
-          }
-          ptx::tc_fence_after();
-          if (it == 0) trace_ev(p.trace, titer, 4);
-          if (CG == 1 && (p.debug & 1)) {  // experiment: measure the TMA side alone
-            ptx::mbar_arrive(&empty_bar[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          const uint32_t a_addr = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + Cfg::kABytes;
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t adesc = (A_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 2), 0, 1024)
-                                                        : ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
-            const uint64_t bdesc = (B_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 2), 0, 1024)
-                                                        : ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
-            ptx::umma_bf16<CG>(d_tmem, adesc, bdesc, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
-          ptx::umma_commit<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-        if (CG == 1 && (p.debug & 1)) ptx::mbar_arrive(&tmem_full_bar[as]);
-        else ptx::umma_commit<CG>(&tmem_full_bar[as]);  // accumulator complete -> epilogue (of both CTAs)
-        trace_ev(p.trace, titer, 5);
-        if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
-      }
+    ptx::tc_fence_after();
+    if (it == 0) trace_ev(p.trace, titer, 4);
+    if (CG == 1 && (p.debug & 1)) {  // experiment: measure the TMA side alone
+      ptx::mbar_arrive(&sh.empty_bar[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      continue;
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps (2 teams x 4 warps)
-    const int team = (warp - 2) >> 2;
-    const int quarter = warp & 3;  // tcgen05.ld: a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int row = quarter * 32 + lane;  // row of the tile owned by this thread
-    const int team_tid = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the team
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const EpiArgs& e = p.epi;
-    Team tm{slot_base + team * (kSlotsPerTeam * kSlotBytes), in_bars + team * kSlotsPerTeam,
-            bias_strips + team * Cfg::kBiasFloats, csum_strips + team * 128, 0u, 0u, 0u, team, team_tid == 0};
-    const bool dual = e.out_lo != nullptr;
-    const bool tr = team_tid == 0 && team == 0;
-    float loss_local = 0.f;
-    uint32_t as = 0, aphase = 0;
-    int titer = 0;
-    for (int u = group_id; u < total_units; u += num_groups, ++titer) {
-      const int ks = u / tiles;
-      const int tile = u - ks * tiles;
-      const int n_blk = tile / p.m_blocks;
-      const int m_blk = tile - n_blk * p.m_blocks;
-      const int m0 = (m_blk * CG + static_cast<int>(cta_rank)) * kBlockM;
-      const int m = m0 + row;
-      const bool row_ok = m < p.M;
-      const uint32_t t_acc = tmem_base + lane_base + as * BLOCK_N;
+    const uint32_t a_addr = ptx::smem_u32(sh.smem + stage * Cfg::kStageBytes);
+    const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+      const uint64_t adesc = (A_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 2), 0, 1024)
+                                                  : ptx::umma_desc_sw128(a_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
+      const uint64_t bdesc = (B_MAJOR == MAJOR_K) ? ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 2), 0, 1024)
+                                                  : ptx::umma_desc_sw128(b_addr + k * (kUmmaK * 128), kBlockK * 128, 1024);
+      ptx::umma_bf16<CG>(d_tmem, adesc, bdesc, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+    }
+    ptx::umma_commit<CG>(&sh.empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+  }
+  if (CG == 1 && (p.debug & 1)) ptx::mbar_arrive(&sh.tmem_full_bar[ms.as]);
+  else ptx::umma_commit<CG>(&sh.tmem_full_bar[ms.as]);  // accumulator complete -> epilogue (of both CTAs)
+  trace_ev(p.trace, titer, 5);
+  if (++ms.as == Cfg::kAccStages) { ms.as = 0; ms.aphase ^= 1; }
+  ms.stage = stage; ms.phase = phase; ms.data_ready = data_ready;
+}
+
+// Per-thread state of an epilogue warp
+struct EpiState {
+  Team tm;
+  uint32_t as, aphase;
+  float loss_local;
+  int team, quarter, row, team_tid, lane;
+  uint32_t lane_base;
+};
+
+template <class KD, int BLOCK_N, int CG>
+__device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiState& es, const Shared& sh, int titer) {
+  using Cfg = GemmCfg<BLOCK_N, CG>;
+  constexpr int EPI = KD::EPI;
+  const EpiArgs& e = p.epi;
+  Team& tm = es.tm;
+  const int team = es.team, row = es.row, team_tid = es.team_tid, lane = es.lane;
+  uint64_t* tmem_full_bar = sh.tmem_full_bar;
+  uint32_t& as = es.as;
+  uint32_t& aphase = es.aphase;
+  float& loss_local = es.loss_local;
+  const bool dual = e.out_lo != nullptr;
+  const bool tr = team_tid == 0 && team == 0;
+  const TileCoord tc = decode_unit<CG>(p, u, sh.cta_rank);
+  const int n_blk = tc.n_blk, m0 = tc.m0;
+  const int m = m0 + row;
+  const bool row_ok = m < p.M;
+  const uint32_t t_acc = sh.tmem_base + es.lane_base + as * BLOCK_N;
+  (void)lane; (void)tr; (void)dual; (void)row_ok; (void)m;
 
       if constexpr (EPI == EPI_HEAD) {
         // ---- tile columns [0, kHalf) = mu, [kHalf, BLOCK_N) = logvar of latent columns n_blk*kHalf ..; a team owns
@@ -832,20 +841,161 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
         }
       }
       // release the accumulator back to the MMA warp
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 1 || leader) ptx::mbar_arrive(&tmem_empty_bar[as]);
-        else ptx::mbar_arrive_remote(&tmem_empty_bar[as], 0);
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (CG == 1 || sh.leader) ptx::mbar_arrive(&sh.tmem_empty_bar[as]);
+    else ptx::mbar_arrive_remote(&sh.tmem_empty_bar[as], 0);
+  }
+  if (team_tid == 0) trace_ev(p.trace, titer, 7 + 2 * team);
+  if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
+}
+
+struct NoKind {};
+template <class K1>
+struct is_dual { static constexpr bool value = true; };
+template <>
+struct is_dual<NoKind> { static constexpr bool value = false; };
+
+// p1 / sched / units0 are only read when K1 is a real Kind.
+template <int BLOCK_N, int CG, class K0, class K1>
+__device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams& p1, const int* sched, int units0) {
+  using Cfg = GemmCfg<BLOCK_N, CG>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr bool kDual = is_dual<K1>::value;
+  const GemmParams& p = p0;  // trace / debug switches come from the first problem
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Shared sh;
+  sh.smem = smem;
+  sh.slot_base = smem + kStages * Cfg::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  sh.bias_strips = reinterpret_cast<float*>(sh.slot_base + Cfg::kSlotRegion);
+  sh.csum_strips = sh.bias_strips + kEpiTeams * Cfg::kBiasFloats;
+  sh.full_bar = reinterpret_cast<uint64_t*>(sh.csum_strips + kEpiTeams * 128);
+  sh.empty_bar = sh.full_bar + kStages;
+  sh.tmem_full_bar = sh.empty_bar + kStages;
+  sh.tmem_empty_bar = sh.tmem_full_bar + Cfg::kAccStages;
+  sh.in_bars = sh.tmem_empty_bar + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sh.in_bars + kEpiTeams * kSlotsPerTeam);
+  static_assert((2 * 8 + 2 * 2 + kEpiTeams * kSlotsPerTeam) * 8 + 4 <= Cfg::kBarrierBytes, "barrier region");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  sh.cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  sh.leader = sh.cta_rank == 0;
+  const int group_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;       // tile-owning unit: CTA or CTA pair
+  const int num_groups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {  // swizzled tiles need the declared 1 KB alignment
+      printf("rvae: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    trace_hdr(p.trace, 0, global_timer());
+    trace_hdr(p.trace, 1, clock64());
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p0.num_passes; ++i) {
+      ptx::prefetch_tensormap(&p0.tmA[i]);
+      ptx::prefetch_tensormap(&p0.tmB[i]);
+    }
+    ptx::prefetch_tensormap(&p0.tmOutHi);
+    ptx::prefetch_tensormap(&p0.tmOutLo);
+    ptx::prefetch_tensormap(&p0.tmOutF32);
+    ptx::prefetch_tensormap(&p0.tmOutF32b);
+    ptx::prefetch_tensormap(&p0.tmSide);
+    if constexpr (kDual) {
+      for (int i = 0; i < p1.num_passes; ++i) {
+        ptx::prefetch_tensormap(&p1.tmA[i]);
+        ptx::prefetch_tensormap(&p1.tmB[i]);
       }
-      if (team_tid == 0) trace_ev(p.trace, titer, 7 + 2 * team);
-      if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
+      ptx::prefetch_tensormap(&p1.tmOutHi);
+      ptx::prefetch_tensormap(&p1.tmOutLo);
+      ptx::prefetch_tensormap(&p1.tmOutF32);
+      ptx::prefetch_tensormap(&p1.tmSide);
+    }
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&sh.full_bar[i], 1);    // leader's barrier: its producer arrives once with the pair's byte count
+      ptx::mbar_init(&sh.empty_bar[i], 1);   // per CTA: tcgen05.commit (multicast to both CTAs when CG == 2)
+    }
+    for (int i = 0; i < Cfg::kAccStages; ++i) {
+      ptx::mbar_init(&sh.tmem_full_bar[i], 1);        // per CTA: tcgen05.commit
+      ptx::mbar_init(&sh.tmem_empty_bar[i], 8 * CG);  // leader's barrier: one arrive per epilogue warp of the pair
+    }
+    for (int i = 0; i < kEpiTeams * kSlotsPerTeam; ++i) ptx::mbar_init(&sh.in_bars[i], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kEpiTeams * 128) sh.csum_strips[threadIdx.x - 64] = 0.f;
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  sh.tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the previous
+  // kernel of the stream; from here on we read what it wrote.
+  if (threadIdx.x == 0) trace_hdr(p.trace, 2, clock64());
+  // (the dependents are released late, by the epilogue after its last tile: released here, their CTAs would sit on
+  // the SMs this grid leaves to the step's background stream for the whole duration of this kernel)
+  ptx::pdl_wait();
+  if (threadIdx.x == 0) trace_hdr(p.trace, 3, clock64());
+
+  const int total0 = p0.m_blocks * p0.n_blocks * p0.k_splits;
+  const int split = kDual ? units0 : total0;  // units below `split` belong to problem 0
+  UnitIter it(kDual ? sched : nullptr, group_id, num_groups, total0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one per CTA)
+    if (lane == 0) {
+      ProdState ps{0u, 0u, ptx::mbar_try_wait(&sh.empty_bar[0], 1)};
+      int titer = 0, u;
+      while (it.next(u)) {
+        if (!kDual || u < split) produce_unit<K0, BLOCK_N, CG>(p0, u, ps, sh, titer);
+        else if constexpr (kDual) produce_unit<K1, BLOCK_N, CG>(p1, u - split, ps, sh, titer);
+        ++titer;
+      }
+      trace_hdr(p.trace, 4, clock64());
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
+    if (lane == 0 && sh.leader) {
+      MmaState ms{0u, 0u, 0u, 0u, false};
+      int titer = 0, u;
+      while (it.next(u)) {
+        if (!kDual || u < split) mma_unit<K0, BLOCK_N, CG>(p0, u, ms, sh, titer);
+        else if constexpr (kDual) mma_unit<K1, BLOCK_N, CG>(p1, u - split, ms, sh, titer);
+        ++titer;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (2 teams x 4 warps)
+    EpiState es;
+    es.team = (warp - 2) >> 2;
+    es.quarter = warp & 3;  // tcgen05.ld: a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    es.lane = lane;
+    es.row = es.quarter * 32 + lane;  // row of the tile owned by this thread
+    es.team_tid = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the team
+    es.lane_base = static_cast<uint32_t>(es.quarter * 32) << 16;
+    es.tm = Team{sh.slot_base + es.team * (kSlotsPerTeam * kSlotBytes), sh.in_bars + es.team * kSlotsPerTeam,
+                 sh.bias_strips + es.team * Cfg::kBiasFloats, sh.csum_strips + es.team * 128, 0u, 0u, 0u, es.team,
+                 es.team_tid == 0};
+    es.as = 0; es.aphase = 0; es.loss_local = 0.f;
+    float loss0 = 0.f;
+    int titer = 0, u;
+    while (it.next(u)) {
+      if (!kDual || u < split) {
+        epilogue_unit<K0, BLOCK_N, CG>(p0, u, es, sh, titer);
+        loss0 += es.loss_local;
+        es.loss_local = 0.f;
+      } else if constexpr (kDual) {
+        epilogue_unit<K1, BLOCK_N, CG>(p1, u - split, es, sh, titer);
+      }
+      ++titer;
     }
     ptx::pdl_launch_dependents();  // next kernel of the stream: its prologue overlaps our drain and teardown
-    if (tm.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
-    if constexpr (EPI == EPI_HEAD || EPI == EPI_OUT) {
-      const float s = warp_sum(loss_local);
-      if (lane == 0 && e.loss_acc) atomicAdd(e.loss_acc, static_cast<double>(s));
+    if (es.tm.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
+    if constexpr (K0::EPI == EPI_HEAD || K0::EPI == EPI_OUT) {
+      const float s = warp_sum(loss0);
+      if (lane == 0 && p0.epi.loss_acc) atomicAdd(p0.epi.loss_acc, static_cast<double>(s));
     }
   }
 
@@ -854,7 +1004,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
   if (warp == 1) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
+    ptx::tmem_dealloc<CG>(sh.tmem_base, Cfg::kTmemCols);
   }
   if (threadIdx.x == 0) {
     trace_hdr(p.trace, 5, clock64());
@@ -864,13 +1014,21 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p) {
 
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BLOCK_N, A_MAJOR, B_MAJOR, EPI, 1>(p);
+  gemm_body<BLOCK_N, 1, Kind<A_MAJOR, B_MAJOR, EPI>, NoKind>(p, p, nullptr, 0);
 }
 
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_kernel_2cta(const __grid_constant__ GemmParams p) {
-  gemm_body<BLOCK_N, A_MAJOR, B_MAJOR, EPI, 2>(p);
+  gemm_body<BLOCK_N, 2, Kind<A_MAJOR, B_MAJOR, EPI>, NoKind>(p, p, nullptr, 0);
+}
+
+// Two independent GEMMs in one persistent launch (CTA pairs, 256-wide tiles); units are assigned by the host-built
+// schedule dp.sched.
+template <int BLOCK_N, class K0, class K1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_dual_kernel_2cta(const __grid_constant__ DualParams dp) {
+  gemm_body<BLOCK_N, 2, K0, K1>(dp.p0, dp.p1, dp.sched, dp.units0);
 }
 
 }  // namespace rvae

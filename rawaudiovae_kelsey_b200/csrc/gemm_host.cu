@@ -1,7 +1,9 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map encoding, tile/split-K selection, kernel table and launch.
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "common.h"
 
@@ -266,6 +268,7 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   RVAE_CHECK(gemm_bind_outputs(&g, p.epi, true));
 
   g.block_n = block_n;
+  g.a_major = d.A.major; g.b_major = d.B.major; g.cg = cg;
   g.variant = find_variant(block_n, d.A.major, d.B.major, d.epi, cg);
   RVAE_REQUIRE(g.variant >= 0, RVAE_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d majors (%d,%d) epilogue %d",
                block_n, d.A.major, d.B.major, d.epi);
@@ -293,6 +296,117 @@ int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream) {
   }
   RVAE_CUDA(launch_kernel(ctx, kVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes, stream,
                           g.params));
+  ctx->launches++;
+  return RVAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pairs of GEMMs
+// ------------------------------------------------------------------------------------------------
+typedef void (*DualKernel)(const DualParams);
+struct DualVariant {
+  int a0, b0, e0, a1, b1, e1;
+  DualKernel fn;
+};
+static const DualVariant kDualVariants[] = {
+    // dgrad + ReLU mask  |  weight gradient      (backward stages 0 and 2)
+    {MAJOR_K, MAJOR_MN, EPI_DRELU, MAJOR_MN, MAJOR_MN, EPI_REDUCE,
+     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_MN, EPI_DRELU>, Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>>},
+    // split-K latent dgrad |  weight gradient     (backward stage 1)
+    {MAJOR_K, MAJOR_MN, EPI_REDUCE, MAJOR_MN, MAJOR_MN, EPI_REDUCE,
+     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_MN, EPI_REDUCE>, Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>>},
+};
+static const int kNumDualVariants = sizeof(kDualVariants) / sizeof(kDualVariants[0]);
+
+static int configure_dual_variants() {
+  static int rc = -1;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    rc = RVAE_OK;
+    for (int i = 0; i < kNumDualVariants; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kDualVariants[i].fn),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 2>::kSmemBytes);
+      if (e != cudaSuccess) {
+        rc = cuda_error(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        break;
+      }
+    }
+  });
+  return rc;
+}
+
+// Estimated cost of one unit in k-block times: the MMA main loop, or the epilogue when that is longer (it overlaps
+// the next unit's main loop), plus a fixed hand-over cost.
+static double unit_cost(const PreparedGemm& g) {
+  const double mma = (double)g.params.kb_per_split * g.params.num_passes;
+  const double epi = (g.epi == EPI_DRELU || g.epi == EPI_OUT) ? 11.0 : 8.0;
+  return (mma > epi ? mma : epi) + 2.0;
+}
+
+int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm& g1, int pairs, int* sched_dev,
+                      PreparedDual* out) {
+  RVAE_REQUIRE(g0.block_n == 256 && g1.block_n == 256 && g0.cg == 2 && g1.cg == 2, RVAE_ERR_UNSUPPORTED,
+               "dual gemm: both problems must use 256-wide pair tiles");
+  RVAE_REQUIRE(sched_dev != nullptr && pairs >= 1 && 2 * pairs <= ctx->num_sms_total, RVAE_ERR_INVALID,
+               "dual gemm: bad schedule buffer / pair count %d", pairs);
+  RVAE_CHECK(configure_dual_variants());
+  int variant = -1;
+  for (int i = 0; i < kNumDualVariants; ++i) {
+    const DualVariant& v = kDualVariants[i];
+    if (v.a0 == g0.a_major && v.b0 == g0.b_major && v.e0 == g0.epi && v.a1 == g1.a_major && v.b1 == g1.b_major &&
+        v.e1 == g1.epi)
+      variant = i;
+  }
+  RVAE_REQUIRE(variant >= 0, RVAE_ERR_UNSUPPORTED, "dual gemm: no fused kernel for this pair of problems");
+  const int units0 = g0.params.m_blocks * g0.params.n_blocks * g0.params.k_splits;
+  const int units1 = g1.params.m_blocks * g1.params.n_blocks * g1.params.k_splits;
+  RVAE_REQUIRE(units0 + units1 <= pairs * kSchedMax, RVAE_ERR_UNSUPPORTED, "dual gemm: %d units exceed the schedule",
+               units0 + units1);
+  // longest-processing-time-first: units in descending cost, each to the least loaded pair
+  struct U { int id; double cost; };
+  std::vector<U> units;
+  units.reserve(units0 + units1);
+  const double c0 = unit_cost(g0), c1 = unit_cost(g1);
+  for (int i = 0; i < units0; ++i) units.push_back({i, c0});
+  for (int i = 0; i < units1; ++i) units.push_back({units0 + i, c1});
+  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  std::vector<double> load(pairs, 0.0);
+  std::vector<int> count(pairs, 0);
+  std::vector<int> sched((size_t)pairs * kSchedMax, -1);
+  for (const U& u : units) {
+    int best = -1;
+    for (int pidx = 0; pidx < pairs; ++pidx)
+      if (count[pidx] < kSchedMax && (best < 0 || load[pidx] < load[best] - 1e-9)) best = pidx;
+    RVAE_REQUIRE(best >= 0, RVAE_ERR_UNSUPPORTED, "dual gemm: schedule overflow");
+    sched[(size_t)best * kSchedMax + count[best]++] = u.id;
+    load[best] += u.cost;
+  }
+  RVAE_CUDA(cudaMemcpy(sched_dev, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice));
+  PreparedDual& d = *out;
+  memset(&d, 0, sizeof(d));
+  d.params.p0 = g0.params;
+  d.params.p1 = g1.params;
+  d.params.sched = sched_dev;
+  d.params.units0 = units0;
+  d.variant = variant;
+  d.grid = 2 * pairs;
+  d.smem_bytes = GemmCfg<256, 2>::kSmemBytes;
+  return RVAE_OK;
+}
+
+int gemm_run_dual(Ctx* ctx, const PreparedDual& g, cudaStream_t stream) {
+  if (ctx->trace != nullptr) {
+    DualParams p = g.params;
+    const uint64_t slab = ctx->trace_launches > 1 ? ctx->trace_seq % (uint64_t)ctx->trace_launches : 0;
+    p.p0.trace = ctx->trace + slab * (uint64_t)ctx->num_sms_total * kTraceCtaWords;
+    ctx->trace_seq++;
+    RVAE_CUDA(launch_kernel(ctx, kDualVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
+                            stream, p));
+    ctx->launches++;
+    return RVAE_OK;
+  }
+  RVAE_CUDA(launch_kernel(ctx, kDualVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
+                          stream, g.params));
   ctx->launches++;
   return RVAE_OK;
 }

@@ -8,9 +8,10 @@ independent units, so the path shards with exactly one exchange step per optimiz
   * the loss is normalised by the GLOBAL batch size inside the epilogues (rvae_plan_set_global_batch), so a plain
     SUM all-reduce of the gradients equals the single-process gradient of the concatenated batch exactly - also
     for unequal shards;
-  * gradients are all-reduced in 5 buckets in backward-completion order (W4, W3, W2, W1, biases); each all-reduce
-    is issued asynchronously right after the backward stage that completes it, so it runs on NCCL's stream while the
-    remaining dgrad / wgrad GEMMs run on the compute stream; Adam waits for all of them.
+  * gradients are all-reduced in 5 buckets in backward-completion order (W4, W3, W2 + biases, W1) by NCCL calls the
+    C library issues itself (rvae_plan_train_step, include/rvae_b200.h "Data parallelism"): each runs on a
+    communication stream right after the backward stage that completes it, on the SMs the persistent GEMM grids leave
+    free, while the remaining dgrad / wgrad GEMMs run; each bucket's Adam launch waits for its reduced gradient.
 """
 from __future__ import annotations
 
@@ -57,9 +58,95 @@ def broadcast_parameters(flat_params: torch.Tensor, group=None, src: int = 0) ->
     dist.broadcast(flat_params, src=src, group=group)
 
 
+def _libnccl_path() -> Optional[str]:
+    """The libnccl.so.2 torch itself uses (nvidia-nccl wheel), so both share one NCCL in the process."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+_COMM_READY = set()
+_SYM_READY = {}
+
+
+class _DevBuffer:
+    """A raw device allocation exposed through __cuda_array_interface__ (so torch can view it without copying)."""
+
+    def __init__(self, ptr: int, n_float32: int):
+        self.__cuda_array_interface__ = {"shape": (n_float32,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def adopt_symmetric_grads(model, group=None) -> bool:
+    """Move the model's flat gradient buffer into a symmetric allocation that every rank of the group maps over
+    CUDA IPC, so the gradient all-reduce can be done by librvae_b200's own NVLink peer-memory kernel instead of NCCL.
+    Returns False (and leaves NCCL in charge) when RVAE_DP_BACKEND=nccl or the group has more than 8 ranks."""
+    from . import _lib, ops
+    import ctypes as C
+    flat = model._ensure_flat()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if os.environ.get("RVAE_DP_BACKEND", "p2p") == "nccl" or world > 8:
+        return False
+    key = flat.device.index
+    if key in _SYM_READY:
+        if _SYM_READY[key][1] != flat.total:
+            return False               # one symmetric gradient buffer per device: other models use NCCL
+        grads = _SYM_READY[key][0]
+    else:
+        lib = _lib.load()
+        ptr, handle = C.c_void_p(), (C.c_char * 64)()
+        with torch.cuda.device(flat.device):
+            _lib.check(lib.rvae_dp_sym_alloc(ops.ctx(flat.device), flat.total * 4, C.byref(ptr), handle))
+            box = [None] * world
+            dist.all_gather_object(box, bytes(handle), group=group)
+            _lib.check(lib.rvae_dp_sym_open(ops.ctx(flat.device), b"".join(box), rank, world))
+        grads = torch.as_tensor(_DevBuffer(ptr.value, flat.total), device=flat.device)
+        _SYM_READY[key] = (grads, flat.total)
+    if flat.grads.data_ptr() != grads.data_ptr():
+        grads.copy_(flat.grads)
+        flat.grads = grads
+        model._plans = {}              # plans bind raw pointers: rebuild them on the new gradient buffer
+        for _, p in model._named():
+            p.grad = None
+    return True
+
+
+def init_native_comm(device: torch.device, group=None) -> None:
+    """Create librvae_b200's own NCCL communicator for `device`: rank 0 draws the 128-byte NCCL id, torch.distributed
+    carries it to the other ranks (plumbing only), every rank calls rvae_dp_init. Idempotent."""
+    from . import _lib, ops
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _COMM_READY:
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    os.environ.setdefault("NCCL_MAX_CTAS", "16")   # the all-reduce kernels live on the SMs the GEMM grids leave free
+    lib = _lib.load()
+    path = _libnccl_path()
+    cpath = path.encode() if path else None
+    import ctypes as C
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        _lib.check(lib.rvae_dp_unique_id(ops.ctx(device), cpath, buf))
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ident = (C.c_char * 128).from_buffer_copy(box[0])
+    with torch.cuda.device(idx):
+        _lib.check(lib.rvae_dp_init(ops.ctx(device), cpath, ident, rank, world))
+    _COMM_READY.add(idx)
+
+
 class DataParallelTrainStep(_StepBase):
-    """FusedTrainStep for W ranks: forward (+fused loss) -> 4 backward stages, each followed by the asynchronous
-    all-reduce of the bucket it completed -> Adam. `data` is this rank's shard of the global batch.
+    """FusedTrainStep for W ranks. The whole step, collectives included, is enqueued by ONE C call
+    (rvae_plan_train_step): forward (+fused loss) -> backward stages, each followed by the NCCL all-reduce of the
+    gradient bucket it completed on a communication stream, overlapped with the later stages -> Adam per bucket as its
+    reduced gradient arrives. `data` is this rank's shard of the global batch; `next_data` (optional) the shard of
+    the next call, prefetched in the background.
 
     The returned loss is the mean over THIS rank's frames (an unbiased estimate of the global mean that needs no
     collective); reduce_loss=True additionally averages it over the ranks (exact for equal shards).
@@ -75,30 +162,26 @@ class DataParallelTrainStep(_StepBase):
         self._synced = False
 
     def _enqueue(self, plan):
-        flat = self.model._flat
         gb = self.global_batch if self.global_batch is not None else plan.batch * self.world
         plan.set_global_batch(gb if self.world > 1 else 0)
+        if self.world > 1 and not getattr(plan, "_dp_on", False):
+            plan.enable_dp(True)
+            plan._dp_on = True
         g = self.optimizer.param_groups[0]
         b1, b2 = g["betas"]
-        plan.forward(self.kl_beta, fused_loss=True, want_xhat=False)
-        plan.finish_loss(self.kl_beta, self.ring, self.ring_size)
-        works = []
-        for s in range(4):
-            plan.backward(s)
-            if self.world > 1:
-                buckets = [plan.bucket(s)] + ([plan.bucket(4)] if s == 3 else [])
-                works += allreduce_buckets(buckets, self.group)   # overlaps with the next backward stage
-        for w in works:
-            w.wait()                                              # compute stream waits for NCCL's stream
-        plan.adam(g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), 1.0, zero_grads=True)
+        plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=self.ring,
+                        ring_size=self.ring_size, zero_grads=True)
 
-    def __call__(self, data, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, data, eps: Optional[torch.Tensor] = None, next_data=None) -> torch.Tensor:
         flat = self._prepare()
         if not self._synced and self.world > 1:
+            init_native_comm(flat.device, self.group)
+            adopt_symmetric_grads(self.model, self.group)
+            flat = self._prepare()
             broadcast_parameters(flat.params, self.group)
             flat.sync_shadow()
             self._synced = True
-        slot = self._run(data, eps)
+        slot = self._run(data, eps, next_data)
         if self.reduce_loss and self.world > 1:
             dist.all_reduce(slot, op=dist.ReduceOp.SUM, group=self.group)
             slot.div_(self.world)

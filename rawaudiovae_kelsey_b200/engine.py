@@ -180,6 +180,9 @@ class Plan:
         p = lambda t: t.data_ptr() if t is not None else None
         check(self.lib.rvae_plan_set_outputs(self.handle, p(mu), p(logvar), p(xhat)))
 
+    def enable_dp(self, on: bool = True) -> None:
+        check(self.lib.rvae_plan_enable_dp(self.handle, int(on)))
+
     def set_global_batch(self, global_batch: int) -> None:
         check(self.lib.rvae_plan_set_global_batch(self.handle, int(global_batch)))
 

@@ -327,6 +327,7 @@ class _StepBase:
         self.graph = bool(graph)
         self.graph_warmup = graph_warmup
         self._graphs = {}        # key -> dict(graph, static buffers, plan)
+        self.replayed_launches = 0   # kernels launched by graph replays (the library's launch counter only sees eager ones)
         self._seen = {}          # key -> eager calls so far
 
     # -- helpers
@@ -409,6 +410,7 @@ class _StepBase:
                 st = self._graphs[key]
                 self._load_static(key, data, st)
                 st["graph"].replay()
+                self.replayed_launches += st["launches"]
                 st["plan"].token += 1
             elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
                 self._capture(key, data)
@@ -433,6 +435,7 @@ class _StepBase:
                 st = self._graphs[key]
                 self._fill_idx(st, next_data)
                 st["graph"].replay()
+                self.replayed_launches += st["launches"]
                 self._mark_prefetched(plan, next_data)
             elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
                 self._capture_pipelined(key, plan, next_data)
@@ -473,11 +476,12 @@ class _StepBase:
         plan.join_background()
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count(dev)
         with torch.cuda.graph(g):
             plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop, frame_idx=st["idx"],
                                  seed=self._seed(), offset=0, add_step=True)
             self._enqueue(plan)
-        st["graph"], st["plan"] = g, plan
+        st["graph"], st["plan"], st["launches"] = g, plan, ops.launch_count(dev) - l0
         self._graphs[key] = st
         g.replay()   # capture does not execute: this replay performs the step of the current call
         self._pf = (plan, next_data)
@@ -497,11 +501,12 @@ class _StepBase:
         self._load_static(key, data, st)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count(dev)
         with torch.cuda.graph(g):
             plan = model._load(static_in)
             self._eps(plan, None)
             self._enqueue(plan)
-        st["graph"], st["plan"] = g, plan
+        st["graph"], st["plan"], st["launches"] = g, plan, ops.launch_count(dev) - l0
         self._graphs[key] = st
         g.replay()   # capture does not execute: this replay performs the step of the current call
 

@@ -65,7 +65,7 @@ def set_trace(buf: Optional[torch.Tensor], launches: int = 1) -> None:
 
 
 def set_aux_trace(buf: Optional[torch.Tensor], launches: int = 0) -> None:
-    """Debug: trace of the HBM-bound kernels into an int64 CUDA tensor [launches, 4] (column 0 initialised to a large
+    """Debug: trace of the HBM-bound kernels into an int64 CUDA tensor [launches, 8] (column 0 initialised to a large
     value by the caller: it is reduced with atomicMin), or off with None."""
     check(_lib.load().rvae_debug_set_aux_trace(ctx(None if buf is None else buf.device),
                                                None if buf is None else buf.data_ptr(), launches))

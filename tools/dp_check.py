@@ -51,7 +51,8 @@ for s in range(3):
     if rank == 0:
         print(f"step {s}: loss dp {float(l_dp):.6f} single {float(l_1):.6f} rel {dl:.2e}; weights rel {dw:.2e}; exp_avg rel {dm:.2e}")
     # step 0 is a pure reassociation difference; later steps inherit Adam's sign-like amplification of that noise
-    ok &= dl < 1e-5 and dw < (1e-6 if s == 0 else 2e-3) and dm < (1e-6 if s == 0 else 2e-2)
+    # (step 0: fp32 reassociation only - split-K reduce-adds, bias-gradient atomics, the all-reduce's summation order)
+    ok &= dl < 1e-5 and dw < (5e-5 if s == 0 else 2e-3) and dm < (1e-5 if s == 0 else 2e-2)
 # replicas stay bit-identical to each other
 ref = m_dp._flat.params.clone()
 dist.broadcast(ref, src=0)

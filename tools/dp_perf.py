@@ -14,6 +14,16 @@ model = VAE(S, H, L).to(dev); opt = Adam(model.parameters(), lr=1e-4)
 step = rdist.DataParallelTrainStep(model, opt, 1e-4, global_batch=B * world, graph=os.environ.get("DP_GRAPH", "1") == "1")
 x = torch.rand(B, S, device=dev) * 2 - 1
 for _ in range(10): step(x)
+# raw all-reduce cost of the bucket sizes on an otherwise idle GPU (torch's NCCL communicator)
+for n in (2048 * 1024, 2048 * 256, 512 * 2048):
+    t = torch.zeros(n, device=dev)
+    for _ in range(3): dist.all_reduce(t)
+    torch.cuda.synchronize(); dist.barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(20): dist.all_reduce(t)
+    a1.record(); torch.cuda.synchronize()
+    if rank == 0: print(f'  all_reduce {4*n/1e6:.1f} MB: {a0.elapsed_time(a1)/20*1e3:.1f} us')
 torch.cuda.synchronize(); dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n = 100

@@ -29,7 +29,7 @@ if PIPE:   # frames gathered from a device-resident corpus; the next batch is pr
     x = None
 else:
     x = torch.rand(B, S, device=dev) * 2 - 1
-for _ in range(5):
+for _ in range(12):
     step(x)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

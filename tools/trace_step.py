@@ -9,13 +9,28 @@ from rawaudiovae_kelsey_b200.optim import Adam
 from rawaudiovae_kelsey_b200 import ops
 
 B, S, H, L = 8192, 1024, 2048, 256
-dev = torch.device("cuda", 0)
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+if WORLD > 1:   # torchrun: trace the data-parallel step (rank 0 prints)
+    from rawaudiovae_kelsey_b200 import dist as rdist
+    RANK, WORLD, local = rdist.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+else:
+    dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = VAE(S, H, L).to(dev)
 opt = Adam(model.parameters(), lr=1e-4)
-step = FusedTrainStep(model, opt, 1e-4)
+if WORLD > 1:
+    step = rdist.DataParallelTrainStep(model, opt, 1e-4, global_batch=B * WORLD)
+else:
+    step = FusedTrainStep(model, opt, 1e-4)
+if RANK != 0:
+    import builtins
+    builtins.print = lambda *a, **k: None
 if os.environ.get('STEP_PIPE', '0') == '1':
     from rawvae.model import FrameBatch
+    torch.manual_seed(1 + RANK)
     audio = torch.rand(32 * 30 * 44100, device=dev) * 2 - 1
     nfr = (audio.numel() - S) // 128 + 1
     idx = torch.randint(0, nfr, (64, B), device=dev)
@@ -33,13 +48,15 @@ for _ in range(5):
     step(x)
 torch.cuda.synchronize()
 NAMES = ["F1", "F2", "F3", "F4", "B4d", "B4w", "B3d", "B3w", "B2d", "B2w", "B1w"]
+if os.environ.get("RVAE_DUAL_PAIRS", "64") != "0":   # backward stages 0..2 are fused dgrad + wgrad launches
+    NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
 NSTEP = 3
 W, HDR = ops.TRACE_WORDS_PER_CTA, ops.TRACE_HEADER
 nsm = ops.num_sms()
 nl = len(NAMES) * NSTEP
 buf = torch.zeros(nl * W * nsm, dtype=torch.int64, device=dev)
-AUXN = 16 * NSTEP
-aux = torch.zeros(AUXN, 4, dtype=torch.int64, device=dev)
+AUXN = 24 * NSTEP
+aux = torch.zeros(AUXN, 8, dtype=torch.int64, device=dev)
 aux[:, 0] = 2 ** 62
 ops.set_aux_trace(aux, AUXN)
 ops.set_trace(buf, nl)
@@ -53,12 +70,15 @@ ops.set_trace(None)
 ops.set_aux_trace(None)
 print(f"{NSTEP} traced steps: {1e3 * e0.elapsed_time(e1) / NSTEP:.1f} us/step")
 t = buf.cpu().numpy().reshape(nl, nsm, W)
-AUXK = {1: "gather", 2: "randn", 3: "latent", 4: "adam"}
+AUXK = {1: "gather", 2: "randn", 3: "latent", 4: "adam", 5: "allreduce"}
 rows = []   # (start, text)
 a = aux.cpu().numpy()
 for j in range(AUXN):
     if a[j, 1] > 0:
-        rows.append((float(a[j, 0]), float(a[j, 1]), f"{AUXK.get(int(a[j, 2]), '?'):6s} blocks {int(a[j, 3]):4d}"))
+        extra = ""
+        if int(a[j, 2]) == 5:
+            extra = "  [slowest CTA: barrier1 %.1f  reduce+push %.1f  barrier2 %.1f us]" % tuple(a[j, 4:7] / 1e3)
+        rows.append((float(a[j, 0]), float(a[j, 1]), f"{AUXK.get(int(a[j, 2]), '?'):6s} blocks {int(a[j, 3]):4d}{extra}"))
 t0 = None
 prev_end = None
 gemm_rows = []
@@ -77,7 +97,7 @@ for i in range(nl):
             print(f"   ---- step period {(first - t0) / 1e3:.1f} us")
         t0 = first
     gap = "" if prev_end is None else f" gap {((first - prev_end) / 1e3):6.1f}"
-    print(f"{NAMES[i % len(NAMES)]:4s} ctas {int(live.sum()):3d}  enter {((first - t0) / 1e3):7.1f}..{((last_in - t0) / 1e3):7.1f}  "
+    print(f"{NAMES[i % len(NAMES)]:8s} ctas {int(live.sum()):3d}  enter {((first - t0) / 1e3):7.1f}..{((last_in - t0) / 1e3):7.1f}  "
           f"exit {((first_out - t0) / 1e3):7.1f}..{((last - t0) / 1e3):7.1f}  span {((last - first) / 1e3):6.1f}  pdl-wait {pdl:5.1f}{gap}")
     prev_end = last
     gemm_rows.append((first, last, NAMES[i % len(NAMES)]))
@@ -86,3 +106,8 @@ print("---- merged timeline (us since the first GEMM of the first traced step)")
 allr = [(f, l, f"GEMM {n}") for f, l, n in gemm_rows] + rows
 for f, l, name in sorted(allr):
     print(f"  {(f - base) / 1e3:8.1f} -> {(l - base) / 1e3:8.1f}  ({(l - f) / 1e3:6.1f})  {name}")
+
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
