@@ -296,8 +296,17 @@ def run_ours(args):
         passes = 3 if args.precision == "fp32" else 1
         achieved = flops / (gemm_ms * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
+        traffic, traffic_src = None, None
+        ncu_json = ROOT / "profiles" / "r1_gemms_ncu.json"     # dram__bytes_read + write of the 11 GEMMs, one ncu capture
+        if ncu_json.exists() and args.precision == "bf16":
+            try:
+                traffic = json.loads(ncu_json.read_text())["dram_bytes_per_step"]
+                traffic_src = "profiles/r1_gemms_ncu.json (ncu --set full, sum over the 11 GEMM launches of a step)"
+            except Exception:
+                traffic = None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "rvae::gemm_kernel<*> (11 launches/step)",
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel": "rvae::gemm_kernel<*> (11 GEMMs/step; the training step fuses 6 of them into 3 launches)",
                     "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
                     "algorithmic_flops_per_step": flops, "gemm_ms_per_step": gemm_ms,
                     "tensor_passes": passes}
