@@ -501,6 +501,7 @@ struct rvae_plan {
   cudaEvent_t ev_hp_fork, ev_hp_join;
   // data parallelism: gradient all-reduces run on their own stream, bucket by bucket as backward completes them
   cudaStream_t comm_stream;
+  cudaStream_t comm_stream2;  // the step's last exchange: must not queue behind the previous one
   cudaEvent_t ev_comm_fork, ev_comm_done[5];
   // loss finalisation deferred into the latent backward kernel (rvae_plan_finish_loss_deferred)
   LossFinalize fin;
@@ -749,6 +750,7 @@ int ensure_side_stream(rvae_plan* p) {
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_fork, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_join, cudaEventDisableTiming));
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->comm_stream, cudaStreamNonBlocking, greatest));
+  RVAE_CUDA(cudaStreamCreateWithPriority(&p->comm_stream2, cudaStreamNonBlocking, greatest));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_comm_fork, cudaEventDisableTiming));
   for (int i = 0; i < 5; ++i) RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_comm_done[i], cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -880,7 +882,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
   p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
   p->hp = nullptr; p->ev_hp_fork = nullptr; p->ev_hp_join = nullptr;
-  p->comm_stream = nullptr; p->ev_comm_fork = nullptr;
+  p->comm_stream = nullptr; p->comm_stream2 = nullptr; p->ev_comm_fork = nullptr;
   for (int i = 0; i < 5; ++i) p->ev_comm_done[i] = nullptr;
   p->adam_stream = nullptr; p->ev_eps = nullptr; p->ev_adam_fork = nullptr; p->ev_adam_join = nullptr;
   p->eps_pending = false; p->fin_pending = false;
@@ -910,6 +912,8 @@ void rvae_plan_destroy(rvae_plan* plan) {
     cudaStreamSynchronize(plan->adam_stream);
     cudaStreamSynchronize(plan->hp);
     cudaStreamSynchronize(plan->comm_stream);
+    cudaStreamSynchronize(plan->comm_stream2);
+    cudaStreamDestroy(plan->comm_stream2);
     cudaEventDestroy(plan->ev_comm_fork);
     for (int i = 0; i < 5; ++i) cudaEventDestroy(plan->ev_comm_done[i]);
     cudaStreamDestroy(plan->comm_stream);
@@ -1277,7 +1281,7 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
   RVAE_REQUIRE(!dp || use_p2p || cx->comm != nullptr, RVAE_ERR_STATE, "plan_train_step: no communicator for these gradients");
   // all-reduce of the gradient buckets in `mask` as ONE operation (a flag hop between two GPUs costs ~5 us, so
   // small buckets are merged): our kernel takes them as segments, NCCL gets one call per bucket
-  auto allreduce_buckets = [&](unsigned mask, int flag_set, int ctas) -> int {
+  auto allreduce_buckets = [&](unsigned mask, int flag_set, int ctas, cudaStream_t cs) -> int {
     P2PSegs sg;
     memset(&sg, 0, sizeof(sg));
     int ns = 0;
@@ -1306,7 +1310,7 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
       static const unsigned kExchange[3] = {0x1u, 0x2u, 0x14u};
       RVAE_CUDA(cudaEventRecord(plan->ev_comm_fork, st));
       RVAE_CUDA(cudaStreamWaitEvent(cs, plan->ev_comm_fork, 0));
-      RVAE_CHECK(allreduce_buckets(kExchange[s], s, cx->p2p_ctas));
+      RVAE_CHECK(allreduce_buckets(kExchange[s], s, cx->p2p_ctas, cs));
       RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[s], cs));
       RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_comm_done[s], 0));
       RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
@@ -1319,12 +1323,16 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
   RVAE_CUDA(cudaEventRecord(plan->ev_adam_join, bg));
   RVAE_CHECK(rvae_plan_backward(plan, 3, st));
   if (dp) {
+    // The last exchange is exposed and has the machine to itself: more CTAs, more NVLink bytes in flight. With our
+    // own kernel it runs on a second communication stream, so it starts when stage 3 ends even if the previous
+    // exchange is still waiting for a slower rank (different flag sets; the earlier kernel is already resident).
+    cudaStream_t cs3 = use_p2p ? plan->comm_stream2 : cs;
     RVAE_CUDA(cudaEventRecord(plan->ev_comm_fork, st));
-    RVAE_CUDA(cudaStreamWaitEvent(cs, plan->ev_comm_fork, 0));
-    // the last exchange is exposed and has the machine to itself: more CTAs, more NVLink bytes in flight
-    RVAE_CHECK(allreduce_buckets(0x8u, 3, cx->p2p_ctas_last));
-    RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[3], cs));
-    RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_comm_done[3], 0));   // (the bias bucket precedes it on the same stream)
+    RVAE_CUDA(cudaStreamWaitEvent(cs3, plan->ev_comm_fork, 0));
+    RVAE_CHECK(allreduce_buckets(0x8u, 3, cx->p2p_ctas_last, cs3));
+    RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[3], cs3));
+    RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_comm_done[3], 0));
+    RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_comm_done[2], 0));   // the bias bucket travelled with exchange 2
   }
   RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_adam_join, 0));  // every earlier Adam launch has read the step counter
   RVAE_CHECK(adam_buckets(plan, 0x18, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, true, st));
