@@ -448,6 +448,8 @@ struct GemmSet {
   bool ready[G_COUNT];
   PreparedDual dual[3];   // backward stage s: dgrad + weight gradient in one launch
   int dual_state[3];      // 0 = not tried, 1 = ready, -1 = unsupported for these shapes (separate launches)
+  PreparedDual fwd[2];    // forward: fc1 + encoder head, fc3 + fc4/loss, chained by tile-level dependencies
+  int fwd_state[2];
 };
 
 }  // namespace
@@ -466,7 +468,9 @@ struct rvae_plan {
   Planes x_alt;
   float* eps_alt;
   int cur;                 // which input set is current (GEMM tensor maps are prepared per set)
-  int* sched_dev;          // schedules of the fused backward-stage launches: [2 input sets][3 stages][pairs][kSchedMax]
+  int* sched_dev;          // schedules of the fused launches: [2 input sets][5 launches][128 pairs][kSchedMax]
+  unsigned int* dep_flags; // row-block counters of the chained forward launches: [2 launches][256]
+  bool fuse_forward;       // env RVAE_FUSE_FORWARD (default on)
   int dual_pairs;          // CTA pairs a fused launch uses (0 = fused launches off)
   unsigned int* ticket;    // last-block ticket of the step's final Adam launch (advances the step counter)
   bool ticket_zeroed;
@@ -548,7 +552,8 @@ size_t carve(rvae_plan* p, uint8_t* base) {
   p->eps = reinterpret_cast<float*>(take(B * L * 4));
   p->eps_alt = reinterpret_cast<float*>(take(B * L * 4));
   p->ticket = reinterpret_cast<unsigned int*>(take(256));
-  p->sched_dev = reinterpret_cast<int*>(take(sizeof(int) * 2 * 3 * 128 * kSchedMax));
+  p->sched_dev = reinterpret_cast<int*>(take(sizeof(int) * 2 * 5 * 128 * kSchedMax));
+  p->dep_flags = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 2 * 256));
   p->dz = reinterpret_cast<float*>(take(B * L * 4));
   p->xhat = reinterpret_cast<float*>(take(B * S * 4));
   p->loss_acc = reinterpret_cast<double*>(take(2 * sizeof(double)));
@@ -830,13 +835,21 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && !p->timing) {
     // under data parallelism the fused launches leave the same spare SMs as the single GEMMs do: NCCL's kernels
     // run there
-    const int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
+    int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
+    if (stage == 1 && pairs > 64) pairs = 64;   // the small stage gains nothing from 10 more pairs; the background stream does
+    {  // experiments: RVAE_DUAL_PAIRS_S<stage> overrides the pair count of one stage
+      const char* names[3] = {"RVAE_DUAL_PAIRS_S0", "RVAE_DUAL_PAIRS_S1", "RVAE_DUAL_PAIRS_S2"};
+      if (const char* e = getenv(names[stage])) {
+        const int v = atoi(e);
+        if (v >= 1 && 2 * v <= p->ctx->c.num_sms_total) pairs = v;
+      }
+    }
     GemmSet* gs;
     RVAE_CHECK(get_set(p, &gs));
     if (gs->dual_state[stage] == 0) {
       RVAE_CHECK(prepare(p, *gs, kDgrad[stage]));
       RVAE_CHECK(prepare(p, *gs, kWgrad[stage]));
-      int* sched = p->sched_dev + ((size_t)p->cur * 3 + stage) * 128 * kSchedMax;
+      int* sched = p->sched_dev + ((size_t)p->cur * 5 + stage) * 128 * kSchedMax;
       const int rc = gemm_prepare_dual(&p->ctx->c, gs->g[kDgrad[stage]], gs->g[kWgrad[stage]], pairs, sched,
                                        &gs->dual[stage]);
       gs->dual_state[stage] = rc == RVAE_OK ? 1 : -1;
@@ -887,6 +900,8 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->adam_stream = nullptr; p->ev_eps = nullptr; p->ev_adam_fork = nullptr; p->ev_adam_join = nullptr;
   p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
+  p->fuse_forward = true;
+  if (const char* e = getenv("RVAE_FUSE_FORWARD")) p->fuse_forward = atoi(e) != 0;
   p->dual_pairs = ctx->c.num_sms / 2;
   if (const char* e = getenv("RVAE_DUAL_PAIRS")) {
     const int v = atoi(e);
@@ -1078,6 +1093,52 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));
 
+  // Training step: fc1 + encoder head and fc3 + fc4/loss as two chained launches (a consumer tile of row block m
+  // starts as soon as the producer tiles of row block m are stored) instead of four kernels with their fill, drain
+  // and half-empty last waves.
+  const bool chain = fused_loss && p->fuse_forward && p->dual_pairs > 0 && !p->timing && !p->out_mu && !p->out_lv &&
+                     !p->out_xhat && p->bufs.grads != nullptr;
+  if (chain) {
+    bool ok = true;
+    static const int kProd[2] = {G_F1, G_F3}, kCons[2] = {G_F2, G_F4_OUT};
+    for (int k = 0; k < 2 && ok; ++k) {
+      if (gs->fwd_state[k] == 0) {
+        RVAE_CHECK(prepare(p, *gs, kProd[k]));
+        RVAE_CHECK(prepare(p, *gs, kCons[k]));
+        int* sched = p->sched_dev + ((size_t)p->cur * 5 + 3 + k) * 128 * kSchedMax;
+        const bool fits = gs->g[kProd[k]].params.m_blocks <= 256;
+        const int rc = fits ? gemm_prepare_dual(&p->ctx->c, gs->g[kProd[k]], gs->g[kCons[k]], p->dual_pairs, sched,
+                                                &gs->fwd[k], p->dep_flags + 256 * k)
+                            : RVAE_ERR_UNSUPPORTED;
+        gs->fwd_state[k] = rc == RVAE_OK ? 1 : -1;
+        if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+      }
+      ok = gs->fwd_state[k] == 1;
+    }
+    if (ok) {
+      RVAE_REQUIRE(p->bufs.grads, RVAE_ERR_STATE, "plan_forward(fused_loss): no grads buffer bound");
+      p->kl_c0 = (float)((double)kl_beta / BL);
+      RVAE_CHECK(ensure_bias_zeroed(p, st));   // F4's epilogue accumulates db4, the backward epilogues db3, db2, db1
+      p->grads_zeroed[4] = false;
+      RVAE_CUDA(cudaMemsetAsync(p->dep_flags, 0, sizeof(unsigned int) * 2 * 256, st));
+      if (p->eps_pending) {
+        RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_eps, 0));
+        p->eps_pending = false;
+      }
+      RVAE_CHECK(gemm_run_dual(&p->ctx->c, gs->fwd[0], st));
+      PreparedDual d = gs->fwd[1];
+      d.params.p1.epi.c0 = (float)(2.0 / BS);
+      d.params.p1.epi.out_f32 = nullptr;   // want_xhat is served by the unfused path only
+      if (!want_xhat) return gemm_run_dual(&p->ctx->c, d, st);
+      // (want_xhat with the chained launch: fall through to the separate kernels for fc3 / fc4)
+      RVAE_CHECK(run(p, G_F3, st));
+      RVAE_CHECK(prepare(p, *gs, G_F4_OUT));
+      EpiArgs a = gs->g[G_F4_OUT].params.epi;
+      a.c0 = (float)(2.0 / BS);
+      a.out_f32 = p->xhat;
+      return run(p, G_F4_OUT, st, &a);
+    }
+  }
   RVAE_CHECK(run(p, G_F1, st));
   if (p->eps_pending) {
     RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_eps, 0));

@@ -132,8 +132,10 @@ struct PreparedDual {
   int smem_bytes;
 };
 // sched_dev: device buffer of at least pairs * kSchedMax ints (written here with a synchronous copy).
+// dep_flags != nullptr: problem 1 consumes problem 0's output row block by row block (device array of m_blocks
+// counters, zeroed by the caller before every launch); the schedule then orders producer units first.
 int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm& g1, int pairs, int* sched_dev,
-                      PreparedDual* out);
+                      PreparedDual* out, unsigned int* dep_flags = nullptr);
 int gemm_run_dual(Ctx* ctx, const PreparedDual& g, cudaStream_t stream);
 
 int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out);

@@ -91,6 +91,12 @@ struct alignas(64) GemmParams {
   int b_half_stride;  // K-major B: row offset of the second half-tile load
   int debug;          // experiments only (env RVAE_DEBUG, CG == 1): 1 = no MMA issue, 2 = no TMA loads
   unsigned long long* trace;  // experiments only (rvae_debug_set_trace): per-CTA, per-tile role timestamps
+  // Tile-level dependencies between the two problems of a fused launch (a layer and the layer that consumes its
+  // output): after the stores of a tile of row block m have completed, each epilogue team adds 1 to dep_signal[m];
+  // a unit of row block m loads its A operand only once dep_wait[m] has reached dep_target.
+  unsigned int* dep_signal;
+  const unsigned int* dep_wait;
+  unsigned int dep_target;
   EpiArgs epi;
 };
 
@@ -398,6 +404,21 @@ __device__ __forceinline__ void produce_unit(const GemmParams& p, int u, ProdSta
   const TileCoord t = decode_unit<CG>(p, u, sh.cta_rank);
   uint32_t stage = ps.stage, phase = ps.phase;
   bool slot_free = ps.slot_free;
+  if (p.dep_wait != nullptr) {
+    // the rows of this unit's A operand are produced by tiles of the other problem of this launch: wait until all
+    // of them have been stored (schedules list every producer unit before any consumer unit, so this cannot deadlock)
+    const unsigned int* flag = p.dep_wait + t.m_blk;
+    const long long t0 = clock64();
+    while (ptx::ld_acquire_gpu(flag) < p.dep_target) {
+      __nanosleep(64);
+      if (clock64() - t0 > 2000000000ll) {
+        printf("rvae: tile dependency timeout block %d row block %d (%u of %u)\n", (int)blockIdx.x, t.m_blk,
+               ptx::ld_acquire_gpu(flag), p.dep_target);
+        __trap();
+      }
+    }
+    ptx::fence_proxy_async_all();  // generic-proxy acquire -> async-proxy (TMA) reads of that data
+  }
   for (int pass = 0; pass < p.num_passes; ++pass) {
     const CUtensorMap* tmA = &p.tmA[pass];
     const CUtensorMap* tmB = &p.tmB[pass];
@@ -847,6 +868,12 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiSta
     if (CG == 1 || sh.leader) ptx::mbar_arrive(&sh.tmem_empty_bar[as]);
     else ptx::mbar_arrive_remote(&sh.tmem_empty_bar[as], 0);
   }
+  if (p.dep_signal != nullptr && tm.issuer) {
+    // publish this team's part of the tile to the consumer problem: its bulk stores are complete (not merely read)
+    ptx::tma_store_wait<0>();
+    __threadfence();
+    atomicAdd(p.dep_signal + tc.m_blk, 1u);
+  }
   if (team_tid == 0) trace_ev(p.trace, titer, 7 + 2 * team);
   if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
 }
@@ -979,16 +1006,17 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
                  sh.bias_strips + es.team * Cfg::kBiasFloats, sh.csum_strips + es.team * 128, 0u, 0u, 0u, es.team,
                  es.team_tid == 0};
     es.as = 0; es.aphase = 0; es.loss_local = 0.f;
-    float loss0 = 0.f;
+    float loss0 = 0.f, loss1 = 0.f;   // MSE / KL partial sums of problem 0 / problem 1 (HEAD and OUT kinds)
     int titer = 0, u;
     while (it.next(u)) {
       if (!kDual || u < split) {
         epilogue_unit<K0, BLOCK_N, CG>(p0, u, es, sh, titer);
         loss0 += es.loss_local;
-        es.loss_local = 0.f;
       } else if constexpr (kDual) {
         epilogue_unit<K1, BLOCK_N, CG>(p1, u - split, es, sh, titer);
+        loss1 += es.loss_local;
       }
+      es.loss_local = 0.f;
       ++titer;
     }
     ptx::pdl_launch_dependents();  // next kernel of the stream: its prologue overlaps our drain and teardown
@@ -996,6 +1024,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
     if constexpr (K0::EPI == EPI_HEAD || K0::EPI == EPI_OUT) {
       const float s = warp_sum(loss0);
       if (lane == 0 && p0.epi.loss_acc) atomicAdd(p0.epi.loss_acc, static_cast<double>(s));
+    }
+    if constexpr (kDual) {
+      if constexpr (K1::EPI == EPI_HEAD || K1::EPI == EPI_OUT) {
+        const float s = warp_sum(loss1);
+        if (lane == 0 && p1.epi.loss_acc) atomicAdd(p1.epi.loss_acc, static_cast<double>(s));
+      }
     }
   }
 

@@ -315,6 +315,11 @@ static const DualVariant kDualVariants[] = {
     // split-K latent dgrad |  weight gradient     (backward stage 1)
     {MAJOR_K, MAJOR_MN, EPI_REDUCE, MAJOR_MN, MAJOR_MN, EPI_REDUCE,
      gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_MN, EPI_REDUCE>, Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>>},
+    // a layer and its consumer, chained by tile-level dependencies: fc1 -> encoder head, fc3 -> fc4 + loss
+    {MAJOR_K, MAJOR_K, EPI_LINEAR, MAJOR_K, MAJOR_K, EPI_HEAD,
+     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_K, EPI_LINEAR>, Kind<MAJOR_K, MAJOR_K, EPI_HEAD>>},
+    {MAJOR_K, MAJOR_K, EPI_LINEAR, MAJOR_K, MAJOR_K, EPI_OUT,
+     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_K, EPI_LINEAR>, Kind<MAJOR_K, MAJOR_K, EPI_OUT>>},
 };
 static const int kNumDualVariants = sizeof(kDualVariants) / sizeof(kDualVariants[0]);
 
@@ -344,7 +349,7 @@ static double unit_cost(const PreparedGemm& g) {
 }
 
 int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm& g1, int pairs, int* sched_dev,
-                      PreparedDual* out) {
+                      PreparedDual* out, unsigned int* dep_flags) {
   RVAE_REQUIRE(g0.block_n == 256 && g1.block_n == 256 && g0.cg == 2 && g1.cg == 2, RVAE_ERR_UNSUPPORTED,
                "dual gemm: both problems must use 256-wide pair tiles");
   RVAE_REQUIRE(sched_dev != nullptr && pairs >= 1 && 2 * pairs <= ctx->num_sms_total, RVAE_ERR_INVALID,
@@ -367,9 +372,24 @@ int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm
   std::vector<U> units;
   units.reserve(units0 + units1);
   const double c0 = unit_cost(g0), c1 = unit_cost(g1);
-  for (int i = 0; i < units0; ++i) units.push_back({i, c0});
-  for (int i = 0; i < units1; ++i) units.push_back({units0 + i, c1});
-  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  if (dep_flags == nullptr) {
+    for (int i = 0; i < units0; ++i) units.push_back({i, c0});
+    for (int i = 0; i < units1; ++i) units.push_back({units0 + i, c1});
+  } else {
+    // chained: row-block-major order (unit = n_blk * m_blocks + m_blk), so that row blocks complete one after the
+    // other and their consumer tiles become runnable early instead of all at the very end; tiles that run at the
+    // same time then also share their A rows and B columns in L2
+    const int mb0 = g0.params.m_blocks, nb0 = g0.params.n_blocks;
+    for (int m = 0; m < mb0; ++m)
+      for (int n = 0; n < nb0; ++n) units.push_back({n * mb0 + m, c0});
+    const int mb1 = g1.params.m_blocks, nb1 = g1.params.n_blocks;
+    for (int m = 0; m < mb1; ++m)
+      for (int n = 0; n < nb1; ++n) units.push_back({units0 + n * mb1 + m, c1});
+  }
+  // chained problems (dep_flags): every pair runs all its producer units before any consumer unit, which is what
+  // makes the in-kernel dependency waits deadlock-free; independent problems: plain descending cost
+  if (dep_flags == nullptr)
+    std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
   std::vector<double> load(pairs, 0.0);
   std::vector<int> count(pairs, 0);
   std::vector<int> sched((size_t)pairs * kSchedMax, -1);
@@ -388,6 +408,13 @@ int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm
   d.params.p1 = g1.params;
   d.params.sched = sched_dev;
   d.params.units0 = units0;
+  if (dep_flags != nullptr) {
+    RVAE_REQUIRE(g0.params.k_splits == 1 && g0.params.m_blocks == g1.params.m_blocks && g0.params.M == g1.params.M,
+                 RVAE_ERR_UNSUPPORTED, "dual gemm: chained problems must share the row blocking");
+    d.params.p0.dep_signal = dep_flags;
+    d.params.p1.dep_wait = dep_flags;
+    d.params.p1.dep_target = (unsigned)(g0.params.n_blocks * 2 * kEpiTeams);   // tiles x CTAs of a pair x teams
+  }
   d.variant = variant;
   d.grid = 2 * pairs;
   d.smem_bytes = GemmCfg<256, 2>::kSmemBytes;

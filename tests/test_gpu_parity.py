@@ -455,6 +455,43 @@ def test_prefetched_steps_equal_plain_steps(dev, use_graph):
     assert rel(res["pipelined"][1], res["plain"][1]) < 1e-3      # reduction-order noise through Adam, see above
 
 
+def test_widened_vae_inference_with_overlap_add(dev):
+    """BASELINE.json configs[4]: widened VAE (segment_length 4096, n_units 4096, latent 256) inference -
+    frames of a wav at hop 512 -> encode -> latent -> decode -> overlap-add resynthesis - against the fp64 oracle
+    (bf16 tolerance), with a ragged frame count (not a multiple of the 128-row tile)."""
+    from rawvae.model import VAE
+    from rawaudiovae_kelsey_b200 import ops
+    from oracle import rawvae_oracle as O
+    S, H, L, hop = 4096, 4096, 256, 512
+    gen = torch.Generator().manual_seed(11)
+    n = (600 - 1) * hop + S - 37                               # 600 frames after the reference's zero padding
+    audio = (torch.rand(n, generator=gen) * 2 - 1)
+    frames_ref = torch.from_numpy(O.audio_dataset_frames(audio.numpy(), S, hop))
+    N = frames_ref.shape[0]
+    assert N == O.audio_dataset_len(n, S, hop) == 600
+    torch.manual_seed(0)
+    model = VAE(S, H, L).to(dev).eval()
+    p64 = {k: v.detach().cpu().double() for k, v in model.state_dict().items()}
+    frames, _, _ = ops.frame_gather(audio.to(dev), N, hop, S)
+    assert torch.equal(frames.cpu(), frames_ref)               # framing is bit-exact
+    mu, lv = model.encode(frames)
+    eps = torch.randn(N, L, generator=gen)
+    z = model.reparameterize(mu, lv, eps=eps.to(dev))
+    xh = model.decode(z)
+    act = O.forward(p64, frames_ref.double(), eps.double())
+    assert rel(mu, act["mu"]) < BF16_TOL and rel(lv, act["logvar"]) < BF16_TOL
+    assert rel(z, act["z"]) < BF16_TOL
+    assert rel(xh, act["x_hat"]) < BF16_TOL
+    # resynthesis: overlap-add of the decoded frames vs the oracle's OLA of the oracle's frames; and the identity
+    # ola(frames(x)) == zero-padded x that pins the operation (SURVEY.md 8c)
+    ola = ops.overlap_add(xh, hop)
+    ola_ref = torch.from_numpy(O.resynth_overlap_add(act["x_hat"].float().numpy(), hop))
+    assert ola.shape == ola_ref.shape and rel(ola, ola_ref) < BF16_TOL
+    ident = ops.overlap_add(frames, hop).cpu()
+    padded = torch.from_numpy(O.pad_to_multiple(audio.numpy(), hop))
+    assert torch.allclose(ident[: padded.numel()], padded, atol=1e-6)
+
+
 def test_cpu_tensors_fail_loudly(dev):
     from rawvae.model import VAE, loss_function
     from rawaudiovae_kelsey_b200._lib import RvaeError
