@@ -446,10 +446,10 @@ enum AuxSlot { T_LOAD = G_COUNT, T_EPS, T_FINALIZE, T_COLSUM, T_ADAM, T_TANHBWD,
 struct GemmSet {
   PreparedGemm g[G_COUNT];
   bool ready[G_COUNT];
-  PreparedDual dual[3];   // backward stage s: dgrad + weight gradient in one launch
+  PreparedChain dual[3];  // backward stage s: dgrad + weight gradient in one launch
   int dual_state[3];      // 0 = not tried, 1 = ready, -1 = unsupported for these shapes (separate launches)
-  PreparedDual fwd[2];    // forward: fc1 + encoder head, fc3 + fc4/loss, chained by tile-level dependencies
-  int fwd_state[2];
+  PreparedChain fwd;      // forward: fc1 -> encoder head -> fc3 -> fc4/loss chained by tile-level dependencies
+  int fwd_state;
 };
 
 }  // namespace
@@ -469,8 +469,8 @@ struct rvae_plan {
   float* eps_alt;
   int cur;                 // which input set is current (GEMM tensor maps are prepared per set)
   int* sched_dev;          // schedules of the fused launches: [2 input sets][5 launches][128 pairs][kSchedMax]
-  unsigned int* dep_flags; // row-block counters of the chained forward launches: [2 launches][256]
-  bool fuse_forward;       // env RVAE_FUSE_FORWARD (default on)
+  unsigned int* dep_flags; // row-block counters of the chained forward launch: [3 layer transitions][256]
+  bool fuse_forward;       // env RVAE_FUSE_FORWARD=1: forward pass as one chained launch (default off)
   int dual_pairs;          // CTA pairs a fused launch uses (0 = fused launches off)
   unsigned int* ticket;    // last-block ticket of the step's final Adam launch (advances the step counter)
   bool ticket_zeroed;
@@ -553,7 +553,7 @@ size_t carve(rvae_plan* p, uint8_t* base) {
   p->eps_alt = reinterpret_cast<float*>(take(B * L * 4));
   p->ticket = reinterpret_cast<unsigned int*>(take(256));
   p->sched_dev = reinterpret_cast<int*>(take(sizeof(int) * 2 * 5 * 128 * kSchedMax));
-  p->dep_flags = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 2 * 256));
+  p->dep_flags = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 3 * 256));
   p->dz = reinterpret_cast<float*>(take(B * L * 4));
   p->xhat = reinterpret_cast<float*>(take(B * S * 4));
   p->loss_acc = reinterpret_cast<double*>(take(2 * sizeof(double)));
@@ -850,13 +850,13 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
       RVAE_CHECK(prepare(p, *gs, kDgrad[stage]));
       RVAE_CHECK(prepare(p, *gs, kWgrad[stage]));
       int* sched = p->sched_dev + ((size_t)p->cur * 5 + stage) * 128 * kSchedMax;
-      const int rc = gemm_prepare_dual(&p->ctx->c, gs->g[kDgrad[stage]], gs->g[kWgrad[stage]], pairs, sched,
-                                       &gs->dual[stage]);
+      const PreparedGemm* both[2] = {&gs->g[kDgrad[stage]], &gs->g[kWgrad[stage]]};
+      const int rc = gemm_prepare_chain(&p->ctx->c, both, 2, pairs, sched, &gs->dual[stage]);
       gs->dual_state[stage] = rc == RVAE_OK ? 1 : -1;
       if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
     }
     if (gs->dual_state[stage] == 1) {
-      RVAE_CHECK(gemm_run_dual(&p->ctx->c, gs->dual[stage], st));
+      RVAE_CHECK(gemm_run_chain(&p->ctx->c, gs->dual[stage], st));
       fused = true;
     }
   }
@@ -900,7 +900,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->adam_stream = nullptr; p->ev_eps = nullptr; p->ev_adam_fork = nullptr; p->ev_adam_join = nullptr;
   p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
-  p->fuse_forward = true;
+  p->fuse_forward = false;  // measured: no faster than the four separate launches (profiles/README.md); opt-in
   if (const char* e = getenv("RVAE_FUSE_FORWARD")) p->fuse_forward = atoi(e) != 0;
   p->dual_pairs = ctx->c.num_sms / 2;
   if (const char* e = getenv("RVAE_DUAL_PAIRS")) {
@@ -1093,50 +1093,42 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));
 
-  // Training step: fc1 + encoder head and fc3 + fc4/loss as two chained launches (a consumer tile of row block m
-  // starts as soon as the producer tiles of row block m are stored) instead of four kernels with their fill, drain
-  // and half-empty last waves.
-  const bool chain = fused_loss && p->fuse_forward && p->dual_pairs > 0 && !p->timing && !p->out_mu && !p->out_lv &&
-                     !p->out_xhat && p->bufs.grads != nullptr;
+  // Training step: the whole forward pass (fc1 -> encoder head -> fc3 -> fc4 + loss) as ONE persistent launch whose
+  // tiles are chained by row-block dependencies (a tile of the next layer starts as soon as the tiles of its row
+  // block are stored) - instead of four kernels with their fill, drain and half-empty last waves.
+  const bool chain = fused_loss && !want_xhat && p->fuse_forward && p->dual_pairs > 0 && !p->timing && !p->out_mu &&
+                     !p->out_lv && !p->out_xhat && p->bufs.grads != nullptr;
   if (chain) {
-    bool ok = true;
-    static const int kProd[2] = {G_F1, G_F3}, kCons[2] = {G_F2, G_F4_OUT};
-    for (int k = 0; k < 2 && ok; ++k) {
-      if (gs->fwd_state[k] == 0) {
-        RVAE_CHECK(prepare(p, *gs, kProd[k]));
-        RVAE_CHECK(prepare(p, *gs, kCons[k]));
-        int* sched = p->sched_dev + ((size_t)p->cur * 5 + 3 + k) * 128 * kSchedMax;
-        const bool fits = gs->g[kProd[k]].params.m_blocks <= 256;
-        const int rc = fits ? gemm_prepare_dual(&p->ctx->c, gs->g[kProd[k]], gs->g[kCons[k]], p->dual_pairs, sched,
-                                                &gs->fwd[k], p->dep_flags + 256 * k)
-                            : RVAE_ERR_UNSUPPORTED;
-        gs->fwd_state[k] = rc == RVAE_OK ? 1 : -1;
-        if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+    if (gs->fwd_state == 0) {
+      static const int kLayers[4] = {G_F1, G_F2, G_F3, G_F4_OUT};
+      const PreparedGemm* layers[4];
+      for (int k = 0; k < 4; ++k) {
+        RVAE_CHECK(prepare(p, *gs, kLayers[k]));
+        layers[k] = &gs->g[kLayers[k]];
       }
-      ok = gs->fwd_state[k] == 1;
+      int* sched = p->sched_dev + ((size_t)p->cur * 5 + 3) * 128 * kSchedMax;
+      int fpairs = p->dual_pairs;
+      if (const char* e = getenv("RVAE_DUAL_PAIRS_F")) {
+        const int v = atoi(e);
+        if (v >= 1 && 2 * v <= p->ctx->c.num_sms_total) fpairs = v;
+      }
+      const int rc = gemm_prepare_chain(&p->ctx->c, layers, 4, fpairs, sched, &gs->fwd, p->dep_flags);
+      gs->fwd_state = rc == RVAE_OK ? 1 : -1;
+      if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
     }
-    if (ok) {
-      RVAE_REQUIRE(p->bufs.grads, RVAE_ERR_STATE, "plan_forward(fused_loss): no grads buffer bound");
+    if (gs->fwd_state == 1) {
       p->kl_c0 = (float)((double)kl_beta / BL);
       RVAE_CHECK(ensure_bias_zeroed(p, st));   // F4's epilogue accumulates db4, the backward epilogues db3, db2, db1
       p->grads_zeroed[4] = false;
-      RVAE_CUDA(cudaMemsetAsync(p->dep_flags, 0, sizeof(unsigned int) * 2 * 256, st));
+      RVAE_CUDA(cudaMemsetAsync(p->dep_flags, 0, sizeof(unsigned int) * 3 * 256, st));
       if (p->eps_pending) {
         RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_eps, 0));
         p->eps_pending = false;
       }
-      RVAE_CHECK(gemm_run_dual(&p->ctx->c, gs->fwd[0], st));
-      PreparedDual d = gs->fwd[1];
-      d.params.p1.epi.c0 = (float)(2.0 / BS);
-      d.params.p1.epi.out_f32 = nullptr;   // want_xhat is served by the unfused path only
-      if (!want_xhat) return gemm_run_dual(&p->ctx->c, d, st);
-      // (want_xhat with the chained launch: fall through to the separate kernels for fc3 / fc4)
-      RVAE_CHECK(run(p, G_F3, st));
-      RVAE_CHECK(prepare(p, *gs, G_F4_OUT));
-      EpiArgs a = gs->g[G_F4_OUT].params.epi;
-      a.c0 = (float)(2.0 / BS);
-      a.out_f32 = p->xhat;
-      return run(p, G_F4_OUT, st, &a);
+      PreparedChain d = gs->fwd;
+      d.params.p[3].epi.c0 = (float)(2.0 / BS);
+      d.params.p[3].epi.out_f32 = nullptr;
+      return gemm_run_chain(&p->ctx->c, d, st);
     }
   }
   RVAE_CHECK(run(p, G_F1, st));
@@ -1312,7 +1304,8 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
   cudaStream_t st = plan->hp, bg = plan->adam_stream;
   RVAE_CUDA(cudaEventRecord(plan->ev_hp_fork, S_(stream)));
   RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_hp_fork, 0));
-  if (p->pf.registered) {
+  auto enqueue_prefetch = [&]() -> int {
+    if (!p->pf.registered) return RVAE_OK;
     // next step's inputs: frames gathered into the alternate x planes, noise drawn into the alternate eps buffer
     const rvae_plan::Prefetch& f = p->pf;
     RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_hp_fork, 0));
@@ -1323,8 +1316,15 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
                             f.add_step ? b.step : nullptr, bg));
     p->pf.ready_batch = f.count;
     p->pf.registered = false;
-  }
+    return RVAE_OK;
+  };
+  static const bool pf_late = getenv("RVAE_PF_LATE") ? atoi(getenv("RVAE_PF_LATE")) != 0 : false;
+  if (!pf_late) RVAE_CHECK(enqueue_prefetch());
   RVAE_CHECK(rvae_plan_forward(plan, kl_beta, 1, 0, st));
+  if (pf_late) {   // experiment: the GEMMs of the forward pass are in the hardware queues first
+    RVAE_CUDA(cudaEventRecord(plan->ev_hp_fork, st));
+    RVAE_CHECK(enqueue_prefetch());
+  }
   RVAE_CHECK(rvae_plan_finish_loss_deferred(plan, kl_beta, loss_out, ring_size));  // runs inside stage 1
   plan->fin.inc_step = 0;
   // Adam per bucket as soon as the bucket's gradient is complete; the dgrad GEMM that reads the bucket's bf16

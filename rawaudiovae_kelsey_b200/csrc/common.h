@@ -123,20 +123,24 @@ struct PreparedGemm {
 
 int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& args, bool force);
 
-// Two prepared GEMMs fused into one persistent launch (gemm_dual_kernel_2cta): units are assigned to CTA pairs by a
-// host-built longest-processing-time-first schedule stored in device memory.
-struct PreparedDual {
-  DualParams params;
-  int variant;  // index into the dual kernel table
+// Up to four prepared GEMMs fused into one persistent launch (gemm_chain_kernel_2cta): units are assigned to CTA pairs
+// by a host-built schedule stored in device memory.
+struct PreparedChain {
+  ChainParams params;
+  int count;    // problems
+  int variant;  // index into the chain kernel table
   int grid;
   int smem_bytes;
 };
-// sched_dev: device buffer of at least pairs * kSchedMax ints (written here with a synchronous copy).
-// dep_flags != nullptr: problem 1 consumes problem 0's output row block by row block (device array of m_blocks
-// counters, zeroed by the caller before every launch); the schedule then orders producer units first.
-int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm& g1, int pairs, int* sched_dev,
-                      PreparedDual* out, unsigned int* dep_flags = nullptr);
-int gemm_run_dual(Ctx* ctx, const PreparedDual& g, cudaStream_t stream);
+// g[0..count): the problems. sched_dev: device buffer of at least pairs * kSchedMax ints (written here with a
+// synchronous copy). dep_flags == nullptr: independent problems, longest-processing-time-first schedule.
+// dep_flags != nullptr: problem i + 1 consumes problem i's output row block by row block; dep_flags points to
+// (count - 1) x 256 device counters the caller zeroes before every launch, and the schedule lists the problems
+// layer by layer (every pair runs a subsequence of one global order in which producers precede consumers, which
+// makes the in-kernel dependency waits deadlock-free).
+int gemm_prepare_chain(const Ctx* ctx, const PreparedGemm* const* g, int count, int pairs, int* sched_dev,
+                       PreparedChain* out, unsigned int* dep_flags = nullptr);
+int gemm_run_chain(Ctx* ctx, const PreparedChain& g, cudaStream_t stream);
 
 int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out);
 int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream);

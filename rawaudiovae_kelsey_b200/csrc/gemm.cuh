@@ -331,10 +331,11 @@ struct Kind {
 
 constexpr int kSchedMax = 16;  // units per CTA group in a host-built schedule (entries < 0 terminate the list)
 
-struct alignas(64) DualParams {
-  GemmParams p0, p1;
-  const int* sched;  // [groups][kSchedMax] unit indices in the combined space [0, units0) + [units0, units0 + units1)
-  int units0;
+constexpr int kMaxChain = 4;    // problems per fused launch
+struct alignas(64) ChainParams {
+  GemmParams p[kMaxChain];
+  const int* sched;           // [groups][kSchedMax] unit indices in the combined unit space
+  int base[kMaxChain + 1];    // problem i owns units [base[i], base[i + 1]); unused problems are empty ranges
 };
 
 // Units of one CTA group: strided over a single problem's unit space, or read from the schedule table.
@@ -878,19 +879,40 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiSta
   if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
 }
 
-struct NoKind {};
-template <class K1>
-struct is_dual { static constexpr bool value = true; };
+struct NoKind {
+  static constexpr int A = 0, B = 0, EPI = -1;
+};
+template <class K>
+struct is_kind { static constexpr bool value = true; };
 template <>
-struct is_dual<NoKind> { static constexpr bool value = false; };
+struct is_kind<NoKind> { static constexpr bool value = false; };
 
-// p1 / sched / units0 are only read when K1 is a real Kind.
-template <int BLOCK_N, int CG, class K0, class K1>
-__device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams& p1, const int* sched, int units0) {
+// The problems of a launch as the device code sees them.
+struct ProblemSet {
+  const GemmParams* p[kMaxChain];
+  int base[kMaxChain + 1];
+  const int* sched;   // nullptr: one problem, units strided over the CTA groups
+};
+
+// call FN<Ki, BLOCK_N, CG>(problem i, unit within problem i, ...) for the problem that owns unit u
+#define RVAE_DISPATCH(FN, STATE)                                                                                  \
+  do {                                                                                                            \
+    if (u < ps.base[1]) {                                                                                         \
+      FN<K0, BLOCK_N, CG>(*ps.p[0], u, STATE, sh, titer);                                                         \
+    } else if (u < ps.base[2]) {                                                                                  \
+      if constexpr (is_kind<K1>::value) FN<K1, BLOCK_N, CG>(*ps.p[1], u - ps.base[1], STATE, sh, titer);          \
+    } else if (u < ps.base[3]) {                                                                                  \
+      if constexpr (is_kind<K2>::value) FN<K2, BLOCK_N, CG>(*ps.p[2], u - ps.base[2], STATE, sh, titer);          \
+    } else {                                                                                                      \
+      if constexpr (is_kind<K3>::value) FN<K3, BLOCK_N, CG>(*ps.p[3], u - ps.base[3], STATE, sh, titer);          \
+    }                                                                                                             \
+  } while (0)
+
+template <int BLOCK_N, int CG, class K0, class K1, class K2, class K3>
+__device__ __forceinline__ void gemm_body(const ProblemSet& ps) {
   using Cfg = GemmCfg<BLOCK_N, CG>;
   constexpr int kStages = Cfg::kStages;
-  constexpr bool kDual = is_dual<K1>::value;
-  const GemmParams& p = p0;  // trace / debug switches come from the first problem
+  const GemmParams& p = *ps.p[0];  // trace / debug switches come from the first problem
 
   extern __shared__ __align__(1024) uint8_t smem[];
   Shared sh;
@@ -922,24 +944,19 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
     trace_hdr(p.trace, 1, clock64());
   }
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p0.num_passes; ++i) {
-      ptx::prefetch_tensormap(&p0.tmA[i]);
-      ptx::prefetch_tensormap(&p0.tmB[i]);
-    }
-    ptx::prefetch_tensormap(&p0.tmOutHi);
-    ptx::prefetch_tensormap(&p0.tmOutLo);
-    ptx::prefetch_tensormap(&p0.tmOutF32);
-    ptx::prefetch_tensormap(&p0.tmOutF32b);
-    ptx::prefetch_tensormap(&p0.tmSide);
-    if constexpr (kDual) {
-      for (int i = 0; i < p1.num_passes; ++i) {
-        ptx::prefetch_tensormap(&p1.tmA[i]);
-        ptx::prefetch_tensormap(&p1.tmB[i]);
+#pragma unroll
+    for (int q = 0; q < kMaxChain; ++q) {
+      if (ps.base[q + 1] == ps.base[q]) continue;
+      const GemmParams& pq = *ps.p[q];
+      for (int i = 0; i < pq.num_passes; ++i) {
+        ptx::prefetch_tensormap(&pq.tmA[i]);
+        ptx::prefetch_tensormap(&pq.tmB[i]);
       }
-      ptx::prefetch_tensormap(&p1.tmOutHi);
-      ptx::prefetch_tensormap(&p1.tmOutLo);
-      ptx::prefetch_tensormap(&p1.tmOutF32);
-      ptx::prefetch_tensormap(&p1.tmSide);
+      ptx::prefetch_tensormap(&pq.tmOutHi);
+      ptx::prefetch_tensormap(&pq.tmOutLo);
+      ptx::prefetch_tensormap(&pq.tmOutF32);
+      ptx::prefetch_tensormap(&pq.tmOutF32b);
+      ptx::prefetch_tensormap(&pq.tmSide);
     }
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&sh.full_bar[i], 1);    // leader's barrier: its producer arrives once with the pair's byte count
@@ -966,18 +983,15 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
   ptx::pdl_wait();
   if (threadIdx.x == 0) trace_hdr(p.trace, 3, clock64());
 
-  const int total0 = p0.m_blocks * p0.n_blocks * p0.k_splits;
-  const int split = kDual ? units0 : total0;  // units below `split` belong to problem 0
-  UnitIter it(kDual ? sched : nullptr, group_id, num_groups, total0);
+  UnitIter it(ps.sched, group_id, num_groups, ps.base[1]);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
-      ProdState ps{0u, 0u, ptx::mbar_try_wait(&sh.empty_bar[0], 1)};
+      ProdState st{0u, 0u, ptx::mbar_try_wait(&sh.empty_bar[0], 1)};
       int titer = 0, u;
       while (it.next(u)) {
-        if (!kDual || u < split) produce_unit<K0, BLOCK_N, CG>(p0, u, ps, sh, titer);
-        else if constexpr (kDual) produce_unit<K1, BLOCK_N, CG>(p1, u - split, ps, sh, titer);
+        RVAE_DISPATCH(produce_unit, st);
         ++titer;
       }
       trace_hdr(p.trace, 4, clock64());
@@ -985,11 +999,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
   } else if (warp == 1) {
     // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
     if (lane == 0 && sh.leader) {
-      MmaState ms{0u, 0u, 0u, 0u, false};
+      MmaState st{0u, 0u, 0u, 0u, false};
       int titer = 0, u;
       while (it.next(u)) {
-        if (!kDual || u < split) mma_unit<K0, BLOCK_N, CG>(p0, u, ms, sh, titer);
-        else if constexpr (kDual) mma_unit<K1, BLOCK_N, CG>(p1, u - split, ms, sh, titer);
+        RVAE_DISPATCH(mma_unit, st);
         ++titer;
       }
     }
@@ -1006,31 +1019,29 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
                  sh.bias_strips + es.team * Cfg::kBiasFloats, sh.csum_strips + es.team * 128, 0u, 0u, 0u, es.team,
                  es.team_tid == 0};
     es.as = 0; es.aphase = 0; es.loss_local = 0.f;
-    float loss0 = 0.f, loss1 = 0.f;   // MSE / KL partial sums of problem 0 / problem 1 (HEAD and OUT kinds)
+    float loss[kMaxChain] = {0.f, 0.f, 0.f, 0.f};   // MSE / KL partial sums per problem (HEAD and OUT kinds)
     int titer = 0, u;
     while (it.next(u)) {
-      if (!kDual || u < split) {
-        epilogue_unit<K0, BLOCK_N, CG>(p0, u, es, sh, titer);
-        loss0 += es.loss_local;
-      } else if constexpr (kDual) {
-        epilogue_unit<K1, BLOCK_N, CG>(p1, u - split, es, sh, titer);
-        loss1 += es.loss_local;
-      }
+      RVAE_DISPATCH(epilogue_unit, es);
+      const int q = (u >= ps.base[1]) + (u >= ps.base[2]) + (u >= ps.base[3]);
+#pragma unroll
+      for (int i = 0; i < kMaxChain; ++i)
+        if (i == q) loss[i] += es.loss_local;
       es.loss_local = 0.f;
       ++titer;
     }
     ptx::pdl_launch_dependents();  // next kernel of the stream: its prologue overlaps our drain and teardown
     if (es.tm.issuer) ptx::tma_store_wait<0>();  // all bulk stores issued by this thread have completed
-    if constexpr (K0::EPI == EPI_HEAD || K0::EPI == EPI_OUT) {
-      const float s = warp_sum(loss0);
-      if (lane == 0 && p0.epi.loss_acc) atomicAdd(p0.epi.loss_acc, static_cast<double>(s));
-    }
-    if constexpr (kDual) {
-      if constexpr (K1::EPI == EPI_HEAD || K1::EPI == EPI_OUT) {
-        const float s = warp_sum(loss1);
-        if (lane == 0 && p1.epi.loss_acc) atomicAdd(p1.epi.loss_acc, static_cast<double>(s));
+    auto flush_loss = [&](int i, int epi) {
+      if (epi == EPI_HEAD || epi == EPI_OUT) {
+        const float s = warp_sum(loss[i]);
+        if (lane == 0 && ps.p[i]->epi.loss_acc) atomicAdd(ps.p[i]->epi.loss_acc, static_cast<double>(s));
       }
-    }
+    };
+    flush_loss(0, K0::EPI);
+    if constexpr (is_kind<K1>::value) flush_loss(1, K1::EPI);
+    if constexpr (is_kind<K2>::value) flush_loss(2, K2::EPI);
+    if constexpr (is_kind<K3>::value) flush_loss(3, K3::EPI);
   }
 
   ptx::tc_fence_before();
@@ -1046,23 +1057,40 @@ __device__ __forceinline__ void gemm_body(const GemmParams& p0, const GemmParams
   }
 }
 
+__device__ __forceinline__ ProblemSet single_problem(const GemmParams& p) {
+  ProblemSet ps;
+  const int total = p.m_blocks * p.n_blocks * p.k_splits;
+  ps.p[0] = ps.p[1] = ps.p[2] = ps.p[3] = &p;
+  ps.base[0] = 0;
+  ps.base[1] = ps.base[2] = ps.base[3] = ps.base[4] = total;
+  ps.sched = nullptr;
+  return ps;
+}
+
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  gemm_body<BLOCK_N, 1, Kind<A_MAJOR, B_MAJOR, EPI>, NoKind>(p, p, nullptr, 0);
+  gemm_body<BLOCK_N, 1, Kind<A_MAJOR, B_MAJOR, EPI>, NoKind, NoKind, NoKind>(single_problem(p));
 }
 
 template <int BLOCK_N, int A_MAJOR, int B_MAJOR, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_kernel_2cta(const __grid_constant__ GemmParams p) {
-  gemm_body<BLOCK_N, 2, Kind<A_MAJOR, B_MAJOR, EPI>, NoKind>(p, p, nullptr, 0);
+  gemm_body<BLOCK_N, 2, Kind<A_MAJOR, B_MAJOR, EPI>, NoKind, NoKind, NoKind>(single_problem(p));
 }
 
-// Two independent GEMMs in one persistent launch (CTA pairs, 256-wide tiles); units are assigned by the host-built
-// schedule dp.sched.
-template <int BLOCK_N, class K0, class K1>
+// Up to four GEMMs in one persistent launch (CTA pairs, 256-wide tiles): independent ones (the dgrad and the weight
+// gradient of a backward stage) or a chain of layers whose tiles depend on each other row block by row block (the
+// forward pass). Units are assigned to the pairs by the host-built schedule cp.sched.
+template <int BLOCK_N, class K0, class K1, class K2, class K3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_dual_kernel_2cta(const __grid_constant__ DualParams dp) {
-  gemm_body<BLOCK_N, 2, K0, K1>(dp.p0, dp.p1, dp.sched, dp.units0);
+gemm_chain_kernel_2cta(const __grid_constant__ ChainParams cp) {
+  ProblemSet ps;
+#pragma unroll
+  for (int i = 0; i < kMaxChain; ++i) ps.p[i] = &cp.p[i];
+#pragma unroll
+  for (int i = 0; i <= kMaxChain; ++i) ps.base[i] = cp.base[i];
+  ps.sched = cp.sched;
+  gemm_body<BLOCK_N, 2, K0, K1, K2, K3>(ps);
 }
 
 }  // namespace rvae

@@ -301,35 +301,44 @@ int gemm_run(Ctx* ctx, const PreparedGemm& g, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused pairs of GEMMs
+// fused launches of several GEMMs
 // ------------------------------------------------------------------------------------------------
-typedef void (*DualKernel)(const DualParams);
-struct DualVariant {
-  int a0, b0, e0, a1, b1, e1;
-  DualKernel fn;
+typedef void (*ChainKernel)(const ChainParams);
+struct KindId {
+  int a, b, e;
 };
-static const DualVariant kDualVariants[] = {
-    // dgrad + ReLU mask  |  weight gradient      (backward stages 0 and 2)
-    {MAJOR_K, MAJOR_MN, EPI_DRELU, MAJOR_MN, MAJOR_MN, EPI_REDUCE,
-     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_MN, EPI_DRELU>, Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>>},
-    // split-K latent dgrad |  weight gradient     (backward stage 1)
-    {MAJOR_K, MAJOR_MN, EPI_REDUCE, MAJOR_MN, MAJOR_MN, EPI_REDUCE,
-     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_MN, EPI_REDUCE>, Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>>},
-    // a layer and its consumer, chained by tile-level dependencies: fc1 -> encoder head, fc3 -> fc4 + loss
-    {MAJOR_K, MAJOR_K, EPI_LINEAR, MAJOR_K, MAJOR_K, EPI_HEAD,
-     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_K, EPI_LINEAR>, Kind<MAJOR_K, MAJOR_K, EPI_HEAD>>},
-    {MAJOR_K, MAJOR_K, EPI_LINEAR, MAJOR_K, MAJOR_K, EPI_OUT,
-     gemm_dual_kernel_2cta<256, Kind<MAJOR_K, MAJOR_K, EPI_LINEAR>, Kind<MAJOR_K, MAJOR_K, EPI_OUT>>},
+struct ChainVariant {
+  int count;
+  KindId k[kMaxChain];
+  ChainKernel fn;
 };
-static const int kNumDualVariants = sizeof(kDualVariants) / sizeof(kDualVariants[0]);
+using KDrelu = Kind<MAJOR_K, MAJOR_MN, EPI_DRELU>;
+using KWgrad = Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>;
+using KDz = Kind<MAJOR_K, MAJOR_MN, EPI_REDUCE>;
+using KLinear = Kind<MAJOR_K, MAJOR_K, EPI_LINEAR>;
+using KHead = Kind<MAJOR_K, MAJOR_K, EPI_HEAD>;
+using KOut = Kind<MAJOR_K, MAJOR_K, EPI_OUT>;
+#define RVAE_KID(K) {K::A, K::B, K::EPI}
+static const ChainVariant kChainVariants[] = {
+    // dgrad + ReLU mask | weight gradient            (backward stages 0 and 2)
+    {2, {RVAE_KID(KDrelu), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDrelu, KWgrad, NoKind, NoKind>},
+    // split-K latent dgrad | weight gradient         (backward stage 1)
+    {2, {RVAE_KID(KDz), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDz, KWgrad, NoKind, NoKind>},
+    // layers chained by tile-level dependencies: fc1 -> head, fc3 -> fc4 + loss, and the whole forward pass
+    {2, {RVAE_KID(KLinear), RVAE_KID(KHead)}, gemm_chain_kernel_2cta<256, KLinear, KHead, NoKind, NoKind>},
+    {2, {RVAE_KID(KLinear), RVAE_KID(KOut)}, gemm_chain_kernel_2cta<256, KLinear, KOut, NoKind, NoKind>},
+    {4, {RVAE_KID(KLinear), RVAE_KID(KHead), RVAE_KID(KLinear), RVAE_KID(KOut)},
+     gemm_chain_kernel_2cta<256, KLinear, KHead, KLinear, KOut>},
+};
+static const int kNumChainVariants = sizeof(kChainVariants) / sizeof(kChainVariants[0]);
 
-static int configure_dual_variants() {
+static int configure_chain_variants() {
   static int rc = -1;
   static std::once_flag once;
   std::call_once(once, [] {
     rc = RVAE_OK;
-    for (int i = 0; i < kNumDualVariants; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kDualVariants[i].fn),
+    for (int i = 0; i < kNumChainVariants; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kChainVariants[i].fn),
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, 2>::kSmemBytes);
       if (e != cudaSuccess) {
         rc = cuda_error(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
@@ -348,91 +357,98 @@ static double unit_cost(const PreparedGemm& g) {
   return (mma > epi ? mma : epi) + 2.0;
 }
 
-int gemm_prepare_dual(const Ctx* ctx, const PreparedGemm& g0, const PreparedGemm& g1, int pairs, int* sched_dev,
-                      PreparedDual* out, unsigned int* dep_flags) {
-  RVAE_REQUIRE(g0.block_n == 256 && g1.block_n == 256 && g0.cg == 2 && g1.cg == 2, RVAE_ERR_UNSUPPORTED,
-               "dual gemm: both problems must use 256-wide pair tiles");
+int gemm_prepare_chain(const Ctx* ctx, const PreparedGemm* const* g, int count, int pairs, int* sched_dev,
+                       PreparedChain* out, unsigned int* dep_flags) {
+  RVAE_REQUIRE(count >= 2 && count <= kMaxChain, RVAE_ERR_INVALID, "chain gemm: %d problems", count);
+  for (int i = 0; i < count; ++i)
+    RVAE_REQUIRE(g[i]->block_n == 256 && g[i]->cg == 2, RVAE_ERR_UNSUPPORTED,
+                 "chain gemm: every problem must use 256-wide pair tiles");
   RVAE_REQUIRE(sched_dev != nullptr && pairs >= 1 && 2 * pairs <= ctx->num_sms_total, RVAE_ERR_INVALID,
-               "dual gemm: bad schedule buffer / pair count %d", pairs);
-  RVAE_CHECK(configure_dual_variants());
+               "chain gemm: bad schedule buffer / pair count %d", pairs);
+  RVAE_CHECK(configure_chain_variants());
   int variant = -1;
-  for (int i = 0; i < kNumDualVariants; ++i) {
-    const DualVariant& v = kDualVariants[i];
-    if (v.a0 == g0.a_major && v.b0 == g0.b_major && v.e0 == g0.epi && v.a1 == g1.a_major && v.b1 == g1.b_major &&
-        v.e1 == g1.epi)
-      variant = i;
+  for (int v = 0; v < kNumChainVariants && variant < 0; ++v) {
+    const ChainVariant& cv = kChainVariants[v];
+    if (cv.count != count) continue;
+    bool match = true;
+    for (int i = 0; i < count; ++i)
+      match = match && cv.k[i].a == g[i]->a_major && cv.k[i].b == g[i]->b_major && cv.k[i].e == g[i]->epi;
+    if (match) variant = v;
   }
-  RVAE_REQUIRE(variant >= 0, RVAE_ERR_UNSUPPORTED, "dual gemm: no fused kernel for this pair of problems");
-  const int units0 = g0.params.m_blocks * g0.params.n_blocks * g0.params.k_splits;
-  const int units1 = g1.params.m_blocks * g1.params.n_blocks * g1.params.k_splits;
-  RVAE_REQUIRE(units0 + units1 <= pairs * kSchedMax, RVAE_ERR_UNSUPPORTED, "dual gemm: %d units exceed the schedule",
-               units0 + units1);
-  // longest-processing-time-first: units in descending cost, each to the least loaded pair
+  RVAE_REQUIRE(variant >= 0, RVAE_ERR_UNSUPPORTED, "chain gemm: no fused kernel for this combination of problems");
+  int nunits[kMaxChain], base[kMaxChain + 1];
+  base[0] = 0;
+  for (int i = 0; i < kMaxChain; ++i) {
+    nunits[i] = i < count ? g[i]->params.m_blocks * g[i]->params.n_blocks * g[i]->params.k_splits : 0;
+    base[i + 1] = base[i] + nunits[i];
+  }
+  RVAE_REQUIRE(base[kMaxChain] <= pairs * kSchedMax, RVAE_ERR_UNSUPPORTED, "chain gemm: %d units exceed the schedule",
+               base[kMaxChain]);
   struct U { int id; double cost; };
   std::vector<U> units;
-  units.reserve(units0 + units1);
-  const double c0 = unit_cost(g0), c1 = unit_cost(g1);
+  units.reserve(base[kMaxChain]);
   if (dep_flags == nullptr) {
-    for (int i = 0; i < units0; ++i) units.push_back({i, c0});
-    for (int i = 0; i < units1; ++i) units.push_back({units0 + i, c1});
-  } else {
-    // chained: row-block-major order (unit = n_blk * m_blocks + m_blk), so that row blocks complete one after the
-    // other and their consumer tiles become runnable early instead of all at the very end; tiles that run at the
-    // same time then also share their A rows and B columns in L2
-    const int mb0 = g0.params.m_blocks, nb0 = g0.params.n_blocks;
-    for (int m = 0; m < mb0; ++m)
-      for (int n = 0; n < nb0; ++n) units.push_back({n * mb0 + m, c0});
-    const int mb1 = g1.params.m_blocks, nb1 = g1.params.n_blocks;
-    for (int m = 0; m < mb1; ++m)
-      for (int n = 0; n < nb1; ++n) units.push_back({units0 + n * mb1 + m, c1});
-  }
-  // chained problems (dep_flags): every pair runs all its producer units before any consumer unit, which is what
-  // makes the in-kernel dependency waits deadlock-free; independent problems: plain descending cost
-  if (dep_flags == nullptr)
+    // independent problems: longest-processing-time-first
+    for (int i = 0; i < count; ++i)
+      for (int u = 0; u < nunits[i]; ++u) units.push_back({base[i] + u, unit_cost(*g[i])});
     std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  } else {
+    // chained: layer by layer, row-block-major within a layer (unit = n_blk * m_blocks + m_blk), so that row blocks
+    // complete one after the other and tiles that run at the same time share their A rows and B columns in L2
+    for (int i = 0; i < count; ++i) {
+      const int mb = g[i]->params.m_blocks, nb = g[i]->params.n_blocks;
+      RVAE_REQUIRE(g[i]->params.k_splits == 1 && mb == g[0]->params.m_blocks && g[i]->params.M == g[0]->params.M &&
+                       mb <= 256,
+                   RVAE_ERR_UNSUPPORTED, "chain gemm: chained problems must share the row blocking");
+      for (int m = 0; m < mb; ++m)
+        for (int n = 0; n < nb; ++n) units.push_back({base[i] + n * mb + m, unit_cost(*g[i])});
+    }
+  }
+  // each unit, in that order, to the least loaded pair: every pair runs a subsequence of the global order
   std::vector<double> load(pairs, 0.0);
-  std::vector<int> count(pairs, 0);
+  std::vector<int> cnt(pairs, 0);
   std::vector<int> sched((size_t)pairs * kSchedMax, -1);
   for (const U& u : units) {
     int best = -1;
     for (int pidx = 0; pidx < pairs; ++pidx)
-      if (count[pidx] < kSchedMax && (best < 0 || load[pidx] < load[best] - 1e-9)) best = pidx;
-    RVAE_REQUIRE(best >= 0, RVAE_ERR_UNSUPPORTED, "dual gemm: schedule overflow");
-    sched[(size_t)best * kSchedMax + count[best]++] = u.id;
+      if (cnt[pidx] < kSchedMax && (best < 0 || load[pidx] < load[best] - 1e-9)) best = pidx;
+    RVAE_REQUIRE(best >= 0, RVAE_ERR_UNSUPPORTED, "chain gemm: schedule overflow");
+    sched[(size_t)best * kSchedMax + cnt[best]++] = u.id;
     load[best] += u.cost;
   }
   RVAE_CUDA(cudaMemcpy(sched_dev, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice));
-  PreparedDual& d = *out;
+  PreparedChain& d = *out;
   memset(&d, 0, sizeof(d));
-  d.params.p0 = g0.params;
-  d.params.p1 = g1.params;
+  for (int i = 0; i < kMaxChain; ++i) d.params.p[i] = g[i < count ? i : 0]->params;
+  for (int i = 0; i <= kMaxChain; ++i) d.params.base[i] = base[i];
   d.params.sched = sched_dev;
-  d.params.units0 = units0;
   if (dep_flags != nullptr) {
-    RVAE_REQUIRE(g0.params.k_splits == 1 && g0.params.m_blocks == g1.params.m_blocks && g0.params.M == g1.params.M,
-                 RVAE_ERR_UNSUPPORTED, "dual gemm: chained problems must share the row blocking");
-    d.params.p0.dep_signal = dep_flags;
-    d.params.p1.dep_wait = dep_flags;
-    d.params.p1.dep_target = (unsigned)(g0.params.n_blocks * 2 * kEpiTeams);   // tiles x CTAs of a pair x teams
+    for (int i = 0; i + 1 < count; ++i) {
+      unsigned int* flags = dep_flags + 256 * i;
+      d.params.p[i].dep_signal = flags;
+      d.params.p[i + 1].dep_wait = flags;
+      d.params.p[i + 1].dep_target = (unsigned)(g[i]->params.n_blocks * 2 * kEpiTeams);  // tiles x CTAs x teams
+    }
   }
+  d.count = count;
   d.variant = variant;
   d.grid = 2 * pairs;
   d.smem_bytes = GemmCfg<256, 2>::kSmemBytes;
   return RVAE_OK;
 }
 
-int gemm_run_dual(Ctx* ctx, const PreparedDual& g, cudaStream_t stream) {
+int gemm_run_chain(Ctx* ctx, const PreparedChain& g, cudaStream_t stream) {
   if (ctx->trace != nullptr) {
-    DualParams p = g.params;
+    ChainParams p = g.params;
     const uint64_t slab = ctx->trace_launches > 1 ? ctx->trace_seq % (uint64_t)ctx->trace_launches : 0;
-    p.p0.trace = ctx->trace + slab * (uint64_t)ctx->num_sms_total * kTraceCtaWords;
+    for (int i = 0; i < kMaxChain; ++i) p.p[i].trace = ctx->trace + slab * (uint64_t)ctx->num_sms_total * kTraceCtaWords;
     ctx->trace_seq++;
-    RVAE_CUDA(launch_kernel(ctx, kDualVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
+    RVAE_CUDA(launch_kernel(ctx, kChainVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
                             stream, p));
     ctx->launches++;
     return RVAE_OK;
   }
-  RVAE_CUDA(launch_kernel(ctx, kDualVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
+  RVAE_CUDA(launch_kernel(ctx, kChainVariants[g.variant].fn, dim3(g.grid), dim3(kGemmThreads), (size_t)g.smem_bytes,
                           stream, g.params));
   ctx->launches++;
   return RVAE_OK;

@@ -121,6 +121,20 @@ def _precision(config) -> str:
     return config['VAE'].get('precision', fallback='bf16')
 
 
+def _with_next(iterable):
+    """(item, next item or None) pairs: the device-side analogue of a prefetching DataLoader - the step functions
+    gather the next batch on their background stream while the current step's GEMMs run."""
+    it = iter(iterable)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, nxt
+        cur = nxt
+    yield cur, None
+
+
 def _flush_losses(writer, pending, print_fmt=None):
     """Read back a block of per-batch losses (device scalars) with one sync and log them under the reference's tag."""
     if not pending:
@@ -211,10 +225,10 @@ def run_epoch_trainer(argv=None):
         model.train()
         train_loss = 0.0
         pending = []
-        for b, data in enumerate(loader):
+        for b, (data, nxt) in enumerate(_with_next(loader)):
             if world > 1:  # the last batch of an epoch may be short: normalise by the true global batch size
                 step.global_batch = min(batch_size, len(training_dataset) - b * batch_size)
-            loss = step(data)
+            loss = step(data, next_data=nxt)   # the next batch is gathered in the background of this step
             pending.append((batch_id, loss))
             writer.add_scalar('Learning Rate', optimizer.param_groups[0]['lr'], batch_id)
             batch_id += 1
@@ -356,8 +370,8 @@ def run_stream_trainer(argv=None):
         batch_id = 0
         pending = []
         fmt = '====> Batch: {} - Loss: {:.9f}'
-        for data in islice(stream, total_num_batches):
-            loss = step(data)
+        for data, nxt in _with_next(islice(stream, total_num_batches)):
+            loss = step(data, next_data=nxt)   # the next batch is gathered in the background of this step
             pending.append((batch_id, loss))
             writer.add_scalar('Learning Rate', optimizer.param_groups[0]['lr'], batch_id)
             at_checkpoint = batch_id % checkpoint_interval == 0 and batch_id != 0

@@ -492,6 +492,118 @@ def test_widened_vae_inference_with_overlap_add(dev):
     assert torch.allclose(ident[: padded.numel()], padded, atol=1e-6)
 
 
+def test_chained_forward_launch_equals_separate_kernels(dev, monkeypatch):
+    """RVAE_FUSE_FORWARD=1 runs fc1 -> head -> fc3 -> fc4/loss as ONE persistent launch whose tiles wait for the
+    row blocks they consume (tile-level dependency counters). Same arithmetic, same operands: losses and weights
+    match the four separate launches up to the reduction-order noise of the loss / bias-gradient atomics."""
+    from rawvae.model import VAE, FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L, B, n = 512, 768, 128, 1300, 6          # 11 row blocks (ragged), several column blocks per layer
+    gen = torch.Generator().manual_seed(21)
+    x = (torch.rand(n, B, S, generator=gen) * 2 - 1).to(dev)
+    eps = torch.randn(n, B, L, generator=gen).to(dev)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RVAE_FUSE_FORWARD", mode)     # read when the plan is created
+        torch.manual_seed(0)
+        model = VAE(S, H, L).to(dev)
+        opt = Adam(model.parameters(), lr=1e-3)
+        step = FusedTrainStep(model, opt, 1e-3, ring=8)
+        losses = [float(step(x[i], eps=eps[i])) for i in range(n)]
+        res[mode] = (torch.tensor(losses), model._flat.params.clone())
+    assert torch.allclose(res["1"][0], res["0"][0], rtol=1e-4, atol=0)
+    assert rel(res["1"][1], res["0"][1]) < 1e-3
+
+
+def _write_wav_folder(root, n_files, seconds, sr, seed):
+    from scipy.io import wavfile
+    from oracle.rawvae_oracle import synth_wav
+    rng = np.random.default_rng(seed)
+    root.mkdir(parents=True, exist_ok=True)
+    for i in range(n_files):
+        x = synth_wav(rng, int(seconds * sr), sr)
+        wavfile.write(root / f"clip{i}.wav", sr, np.round(x * 32767).astype(np.int16))
+
+
+def _trainer_ini(path, datapath, *, batch, extra_training):
+    path.write_text(f"""[audio]
+sampling_rate = 44100
+hop_length = 128
+segment_length = 1024
+
+[dataset]
+datapath = {datapath}
+test_dataset = test_audio
+generate_test = True
+check_audio = True
+check_dataset = True
+workspace =
+run_number = 0
+total_frames =
+
+[VAE]
+latent_dim = 64
+n_units = 256
+kl_beta = 0.0001
+device = cuda:0
+
+[training]
+learning_rate = 0.0001
+batch_size = {batch}
+loss_reduction = mean
+{extra_training}
+
+[notes]
+additional_notes =
+
+[extra]
+normalize_examples = False
+example_length = 10
+plot_model = False
+description = unit-test
+start =
+end =
+time_elapsed =
+""")
+
+
+@pytest.mark.parametrize("which", ["epoch", "stream"])
+def test_drop_in_trainers_produce_reference_artefacts(dev, tmp_path, which):
+    """train.py / train_iterable.py drop-ins (train.py:94-307, train_iterable.py:95-329) on a tiny synthetic wav
+    folder: same workspace tree, and a checkpoint whose state_dict has the reference's keys / shapes (so it loads
+    into the reference VAE, tutorial.ipynb:292-297) plus a torch.optim.Adam-format optimizer state."""
+    from rawaudiovae_kelsey_b200 import trainer
+    data = tmp_path / "data"
+    _write_wav_folder(data / "audio", 3, 1.5, 44100, 1)
+    _write_wav_folder(data / "test_audio", 1, 0.5, 44100, 2)
+    ini = tmp_path / "cfg.ini"
+    if which == "epoch":
+        _trainer_ini(ini, data, batch=512, extra_training="epochs = 3\nsave_best_model_after = 1\ncheckpoint_interval = 2")
+        rc = trainer.run_epoch_trainer(["--config", str(ini)])
+    else:
+        _trainer_ini(ini, data, batch=256,
+                     extra_training="epochs = 1\ntotal_num_frames = 2560\ncheckpoint_interval = 4\nlog_interval = 2")
+        rc = trainer.run_stream_trainer(["--config", str(ini)])
+    assert rc in (0, None)
+    runs = sorted((data / "unit-test").glob("run-*"))
+    assert len(runs) == 1
+    run = runs[0]
+    assert (run / "config.ini").exists() and (run / "model" / "last_model.pt").exists()
+    ckpts = sorted((run / "model" / "checkpoints").glob("ckpt_*"))
+    assert ckpts, "no checkpoint written"
+    state = torch.load(ckpts[-1], map_location="cpu", weights_only=False)
+    sd = state["state_dict"]
+    shapes = {"fc1.weight": (256, 1024), "fc1.bias": (256,), "fc21.weight": (64, 256), "fc21.bias": (64,),
+              "fc22.weight": (64, 256), "fc22.bias": (64,), "fc3.weight": (256, 64), "fc3.bias": (256,),
+              "fc4.weight": (1024, 256), "fc4.bias": (1024,)}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == shapes
+    assert all(v.dtype == torch.float32 and torch.isfinite(v).all() for v in sd.values())
+    opt = state["optimizer"]
+    assert len(opt["state"]) == 10 and sorted(opt["state"][0]) == ["exp_avg", "exp_avg_sq", "step"]
+    assert float(opt["state"][0]["step"]) > 0
+    assert (run / "audio_logs" / "test_original.wav").exists()
+
+
 def test_cpu_tensors_fail_loudly(dev):
     from rawvae.model import VAE, loss_function
     from rawaudiovae_kelsey_b200._lib import RvaeError

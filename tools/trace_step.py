@@ -51,7 +51,7 @@ NAMES = ["F1", "F2", "F3", "F4", "B4d", "B4w", "B3d", "B3w", "B2d", "B2w", "B1w"
 if os.environ.get("RVAE_DUAL_PAIRS", "64") != "0":   # backward stages 0..2 are fused dgrad + wgrad launches
     NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
     if os.environ.get("RVAE_FUSE_FORWARD", "1") != "0":   # fc1 + head and fc3 + fc4 are chained launches
-        NAMES = ["F1+F2", "F3+F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
+        NAMES = ["F1>F2>F3>F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
 NSTEP = 3
 W, HDR = ops.TRACE_WORDS_PER_CTA, ops.TRACE_HEADER
 nsm = ops.num_sms()
@@ -99,7 +99,7 @@ for i in range(nl):
             print(f"   ---- step period {(first - t0) / 1e3:.1f} us")
         t0 = first
     gap = "" if prev_end is None else f" gap {((first - prev_end) / 1e3):6.1f}"
-    print(f"{NAMES[i % len(NAMES)]:8s} ctas {int(live.sum()):3d}  enter {((first - t0) / 1e3):7.1f}..{((last_in - t0) / 1e3):7.1f}  "
+    print(f"{NAMES[i % len(NAMES)]:11s} ctas {int(live.sum()):3d}  enter {((first - t0) / 1e3):7.1f}..{((last_in - t0) / 1e3):7.1f}  "
           f"exit {((first_out - t0) / 1e3):7.1f}..{((last - t0) / 1e3):7.1f}  span {((last - first) / 1e3):6.1f}  pdl-wait {pdl:5.1f}{gap}")
     prev_end = last
     gemm_rows.append((first, last, NAMES[i % len(NAMES)]))
@@ -113,3 +113,26 @@ if WORLD > 1:
     import torch.distributed as dist
     dist.barrier()
     dist.destroy_process_group()
+
+# per-tile role summary of one launch of the last traced step (TRACE_LAUNCH = index within the step, default 0)
+li = int(os.environ.get("TRACE_LAUNCH", "0"))
+NE, NT = ops.TRACE_EVENTS, ops.TRACE_TILES
+i = (NSTEP - 1) * len(NAMES) + li
+hdr = t[i, :, :HDR].astype(np.float64)
+ev = t[i, :, HDR:].reshape(nsm, NT, NE).astype(np.float64)
+live = hdr[:, 1] > 0
+ghz = float(np.median((hdr[live, 5] - hdr[live, 1]) / np.maximum(hdr[live, 6] - hdr[live, 0], 1)))
+us = lambda c: c / ghz / 1e3
+print(f"---- roles of launch {li} ({NAMES[li]}), {int(live.sum())} CTAs, clock {ghz:.2f} GHz; times in us since the CTA passed its PDL wait")
+for it in range(NT):
+    e = ev[live, it, :]
+    ran = e[:, 6] > 0
+    if not ran.any():
+        break
+    e = e[ran]; base = hdr[live, 3][ran]
+    mm = e[:, 3] > 0
+    med = lambda a: float(np.median(a)) if len(a) else float("nan")
+    mx = lambda a: float(np.max(a)) if len(a) else float("nan")
+    print(f"   tile {it:2d} ({int(ran.sum()):3d} CTAs): prod start {us(med(e[:,0]-base)):6.1f} | mma acc-wait {us(med(e[mm,3]-e[mm,2])):5.2f} "
+          f"data-wait med {us(med(e[mm,4]-e[mm,3])):5.2f} max {us(mx(e[mm,4]-e[mm,3])):5.2f} issue {us(med(e[mm,5]-e[mm,4])):5.2f} commit at {us(med(e[mm,5]-base[mm])):6.1f} (max {us(mx(e[mm,5]-base[mm])):6.1f}) | "
+          f"epi {us(med(e[:,6]-base)):6.1f}->{us(med(e[:,7]-base)):6.1f}")
