@@ -1377,9 +1377,14 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
       RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
       continue;
     }
-    RVAE_CUDA(cudaEventRecord(plan->ev_adam_fork, st));
-    RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_adam_fork, 0));
-    RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
+    // single process: only W4 (the first bucket to complete, with the most GEMM time left to hide under) is updated
+    // in the background; W3 and W2 would queue behind it and end up as two more exposed launches after stage 3, so
+    // they join W1 and the biases in the final launch (W1|W2|W3 are contiguous in the flat buffer)
+    if (s == 0) {
+      RVAE_CUDA(cudaEventRecord(plan->ev_adam_fork, st));
+      RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_adam_fork, 0));
+      RVAE_CHECK(adam_buckets(plan, kBucketMask[0], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
+    }
   }
   RVAE_CUDA(cudaEventRecord(plan->ev_adam_join, bg));
   RVAE_CHECK(rvae_plan_backward(plan, 3, st));
@@ -1396,7 +1401,7 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
     RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_comm_done[2], 0));   // the bias bucket travelled with exchange 2
   }
   RVAE_CUDA(cudaStreamWaitEvent(st, plan->ev_adam_join, 0));  // every earlier Adam launch has read the step counter
-  RVAE_CHECK(adam_buckets(plan, 0x18, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, true, st));
+  RVAE_CHECK(adam_buckets(plan, dp ? 0x18u : 0x1eu, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, true, st));
   RVAE_CUDA(cudaEventRecord(plan->ev_hp_join, st));
   RVAE_CUDA(cudaStreamWaitEvent(S_(stream), plan->ev_hp_join, 0));
   return RVAE_OK;

@@ -232,3 +232,12 @@ def test_data_parallel_sum_allreduce_equals_single_process_gradient(B):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) < 1e-12
+
+
+def test_trainer_lookahead_pairs():
+    """trainer._with_next: (batch, next batch) pairs in order, None after the last - what lets a training step
+    prefetch the next batch in the background (device-side analogue of the DataLoader's prefetch)."""
+    from rawaudiovae_kelsey_b200.trainer import _with_next
+    assert list(_with_next([])) == []
+    assert list(_with_next([1])) == [(1, None)]
+    assert list(_with_next(iter("abc"))) == [("a", "b"), ("b", "c"), ("c", None)]

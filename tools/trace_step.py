@@ -50,7 +50,7 @@ torch.cuda.synchronize()
 NAMES = ["F1", "F2", "F3", "F4", "B4d", "B4w", "B3d", "B3w", "B2d", "B2w", "B1w"]
 if os.environ.get("RVAE_DUAL_PAIRS", "64") != "0":   # backward stages 0..2 are fused dgrad + wgrad launches
     NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
-    if os.environ.get("RVAE_FUSE_FORWARD", "1") != "0":   # fc1 + head and fc3 + fc4 are chained launches
+    if os.environ.get("RVAE_FUSE_FORWARD", "0") != "0":   # fc1 + head and fc3 + fc4 are chained launches
         NAMES = ["F1>F2>F3>F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
 NSTEP = 3
 W, HDR = ops.TRACE_WORDS_PER_CTA, ops.TRACE_HEADER
