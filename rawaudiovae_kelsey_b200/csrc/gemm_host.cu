@@ -208,8 +208,11 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   int splits = 1;
   if (d.epi == EPI_REDUCE) {
     const int tiles = p.m_blocks * p.n_blocks;
+    static const int env_splits = getenv("RVAE_WGRAD_SPLITS") ? atoi(getenv("RVAE_WGRAD_SPLITS")) : 0;
     if (d.k_splits > 0) {
       splits = d.k_splits;
+    } else if (env_splits > 0 && d.A.major == MAJOR_MN) {   // experiments: finer weight-gradient units
+      splits = env_splits;
     } else {
       // smallest split (<= 8, >= 8 k-blocks each) whose last wave is >= 90% full; else the best seen
       double best = 0.0;

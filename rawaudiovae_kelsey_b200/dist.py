@@ -99,13 +99,32 @@ def adopt_symmetric_grads(model, group=None) -> bool:
             return False               # one symmetric gradient buffer per device: other models use NCCL
         grads = _SYM_READY[key][0]
     else:
+        # Every step below is agreed on by ALL ranks before anyone relies on it: if a single rank cannot allocate,
+        # export or map the buffers (no CUDA IPC in this container, no peer access), the whole group stays on NCCL.
         lib = _lib.load()
         ptr, handle = C.c_void_p(), (C.c_char * 64)()
+        ok = True
         with torch.cuda.device(flat.device):
-            _lib.check(lib.rvae_dp_sym_alloc(ops.ctx(flat.device), flat.total * 4, C.byref(ptr), handle))
+            try:
+                _lib.check(lib.rvae_dp_sym_alloc(ops.ctx(flat.device), flat.total * 4, C.byref(ptr), handle))
+            except _lib.RvaeError as e:
+                ok = False
+                print(f"[rank {rank}] symmetric gradient buffer unavailable ({e}); using NCCL", flush=True)
             box = [None] * world
-            dist.all_gather_object(box, bytes(handle), group=group)
-            _lib.check(lib.rvae_dp_sym_open(ops.ctx(flat.device), b"".join(box), rank, world))
+            dist.all_gather_object(box, (ok, bytes(handle)), group=group)
+            if not all(o for o, _ in box):
+                _SYM_READY[key] = (None, -1)
+                return False
+            try:
+                _lib.check(lib.rvae_dp_sym_open(ops.ctx(flat.device), b"".join(h for _, h in box), rank, world))
+            except _lib.RvaeError as e:
+                ok = False
+                print(f"[rank {rank}] cannot map the peers' gradient buffers ({e}); using NCCL", flush=True)
+            box = [None] * world
+            dist.all_gather_object(box, ok, group=group)
+            if not all(box):
+                _SYM_READY[key] = (None, -1)
+                return False
         grads = torch.as_tensor(_DevBuffer(ptr.value, flat.total), device=flat.device)
         _SYM_READY[key] = (grads, flat.total)
     if flat.grads.data_ptr() != grads.data_ptr():
