@@ -489,10 +489,10 @@ struct rvae_plan {
   float kl_c0;           // kl_beta / (B L) of the last fused-loss forward (KL gradient scale of the latent backward)
   bool dz_zeroed;        // the split-K latent dgrad accumulator holds zeros (left so by the latent backward kernel)
   bool grads_zeroed[5];  // gradient bucket s (0..3 weights, 4 biases) already holds zeros (left so by the fused Adam)
-  // the weight-gradient GEMM of a backward stage runs on a side stream, concurrently with the stage's dgrad GEMM
-  cudaStream_t side;
-  cudaEvent_t ev_fork, ev_join;
-  bool two_streams;
+  // internal streams (created on first use): see rvae_plan_train_step
+  bool streams_ready;
+  cudaEvent_t ev_fork;
+  bool two_streams;      // env RVAE_TWO_STREAMS=0: everything on the caller's stream (debugging / attribution)
   bool have_eps;
   // eps is generated on the side stream, concurrently with the batch load and fc1; F2 waits for ev_eps
   cudaEvent_t ev_eps;
@@ -746,10 +746,9 @@ int ensure_bias_zeroed(rvae_plan* p, cudaStream_t st) {
 }
 
 int ensure_side_stream(rvae_plan* p) {
-  if (p->side) return RVAE_OK;
+  if (p->streams_ready) return RVAE_OK;
   int least = 0, greatest = 0;
   RVAE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-  RVAE_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, greatest));
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->hp, cudaStreamNonBlocking, greatest));
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->adam_stream, cudaStreamNonBlocking, least));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_fork, cudaEventDisableTiming));
@@ -759,10 +758,10 @@ int ensure_side_stream(rvae_plan* p) {
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_comm_fork, cudaEventDisableTiming));
   for (int i = 0; i < 5; ++i) RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_comm_done[i], cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_eps, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_adam_fork, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_adam_join, cudaEventDisableTiming));
+  p->streams_ready = true;
   return RVAE_OK;
 }
 
@@ -893,7 +892,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->cur = 0; p->ticket_zeroed = false; p->ticket = nullptr;
   memset(&p->pf, 0, sizeof(p->pf));
   for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
-  p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
+  p->streams_ready = false; p->ev_fork = nullptr;
   p->hp = nullptr; p->ev_hp_fork = nullptr; p->ev_hp_join = nullptr;
   p->comm_stream = nullptr; p->comm_stream2 = nullptr; p->ev_comm_fork = nullptr;
   for (int i = 0; i < 5; ++i) p->ev_comm_done[i] = nullptr;
@@ -922,8 +921,7 @@ void rvae_plan_destroy(rvae_plan* plan) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
   }
-  if (plan->side) {
-    cudaStreamSynchronize(plan->side);
+  if (plan->streams_ready) {
     cudaStreamSynchronize(plan->adam_stream);
     cudaStreamSynchronize(plan->hp);
     cudaStreamSynchronize(plan->comm_stream);
@@ -936,11 +934,9 @@ void rvae_plan_destroy(rvae_plan* plan) {
     cudaEventDestroy(plan->ev_hp_join);
     cudaStreamDestroy(plan->hp);
     cudaEventDestroy(plan->ev_fork);
-    cudaEventDestroy(plan->ev_join);
     cudaEventDestroy(plan->ev_eps);
     cudaEventDestroy(plan->ev_adam_fork);
     cudaEventDestroy(plan->ev_adam_join);
-    cudaStreamDestroy(plan->side);
     cudaStreamDestroy(plan->adam_stream);
   }
   delete plan;
