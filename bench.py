@@ -233,6 +233,8 @@ def run_ours(args):
     host_loss = torch.zeros(total_steps, dtype=torch.float32).pin_memory()
     dbuf = [torch.empty(chunk, dtype=torch.float32, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)     # loss read-back: off the compute stream, so it never delays a step
+    step_done = [torch.cuda.Event() for _ in range(4)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     main = torch.cuda.current_stream()
@@ -257,7 +259,11 @@ def run_ours(args):
             nxt = pending[i + 1] = issue_copy(i + 1)     # its frames are gathered in the background of step i
         loss = step_fn(cur, next_data=nxt)
         freed[(i + 1) % 2 if nxt is not None else i % 2].record(main)           # that buffer has been gathered
-        host_loss[i].copy_(loss, non_blocking=True)                             # D2H read of the step's result
+        ev = step_done[i % 4]
+        ev.record(main)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev)
+            host_loss[i].copy_(loss, non_blocking=True)                         # D2H read of the step's result
         return loss
 
     for b in range(2):
@@ -268,6 +274,7 @@ def run_ours(args):
     e0.record()
     for i in range(args.warmup, total_steps):
         e2e_step(i)
+    main.wait_stream(d2h_stream)          # the timed region ends when the last loss has reached the host buffer
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
