@@ -45,9 +45,20 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def synth_wav(rng: np.random.Generator, n_samples: int, sr: int = SR) -> np.ndarray:
+    """0.5*sin(2*pi*f*t + phi) + 0.05*N(0,1), f log-uniform in [55, 7040] Hz, clipped, as the float32
+    value of 16-bit PCM (int16 / 32768). Same formula as the tests' generator; restated here so that the GPU arm
+    of the bench imports nothing from oracle/."""
+    f = math.exp(rng.uniform(math.log(55.0), math.log(7040.0)))
+    phi = rng.uniform(0, 2 * math.pi)
+    t = np.arange(n_samples) / sr
+    x = 0.5 * np.sin(2 * math.pi * f * t + phi) + 0.05 * rng.standard_normal(n_samples)
+    pcm = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
+    return (pcm.astype(np.float32) / 32768.0).astype(np.float32)
+
+
 def synth_corpus(n_files: int, seconds: float, seed: int = 1234) -> np.ndarray:
     """SURVEY.md 8(d) synthetic wav folder, concatenated as train.py:118-126 does: float32 = int16 PCM / 32768."""
-    from oracle.rawvae_oracle import synth_wav  # data generator only (shared with the tests); not a compute path
     rng = np.random.default_rng(seed)
     return np.concatenate([synth_wav(rng, int(seconds * SR), SR) for _ in range(n_files)])
 

@@ -241,3 +241,19 @@ def test_trainer_lookahead_pairs():
     assert list(_with_next([])) == []
     assert list(_with_next([1])) == [(1, None)]
     assert list(_with_next(iter("abc"))) == [("a", "b"), ("b", "c"), ("c", None)]
+
+
+def test_bench_data_generator_matches_the_tests_generator():
+    """bench.py restates the SURVEY.md 8(d) wav generator so that its GPU arm imports nothing from oracle/; the two
+    stay bit-identical. And no module of the product package imports the oracle."""
+    import importlib
+    import re
+    from pathlib import Path
+    from oracle.rawvae_oracle import synth_wav
+    bench = importlib.import_module("bench")
+    a = bench.synth_wav(np.random.default_rng(7), 5000)
+    b = synth_wav(np.random.default_rng(7), 5000)
+    assert a.dtype == np.float32 and np.array_equal(a, b)
+    root = Path(bench.__file__).resolve().parent
+    for f in list((root / "rawaudiovae_kelsey_b200").glob("*.py")) + list((root / "rawvae").glob("*.py")):
+        assert not re.search(r"^\s*(from|import)\s+oracle", f.read_text(), re.M), f
