@@ -443,11 +443,18 @@ enum GemmId { G_F1, G_F2, G_F3, G_F4_OUT, G_F4_LIN, G_B4W, G_B4D, G_B3W, G_B3D, 
 // timing slots of the non-GEMM kernels follow the GEMM slots
 enum AuxSlot { T_LOAD = G_COUNT, T_EPS, T_FINALIZE, T_COLSUM, T_ADAM, T_TANHBWD, T_LATENT, T_COUNT };
 
+// internal slot past the public ones: the latent dgrad with the reparameterisation / KL backward fused into its
+// epilogue (timed and reported as G_B3D)
+constexpr int G_B3D_LAT = G_COUNT;
+constexpr int kGemmSlots = G_COUNT + 1;
+
 struct GemmSet {
-  PreparedGemm g[G_COUNT];
-  bool ready[G_COUNT];
+  PreparedGemm g[kGemmSlots];
+  bool ready[kGemmSlots];
   PreparedChain dual[3];  // backward stage s: dgrad + weight gradient in one launch
   int dual_state[3];      // 0 = not tried, 1 = ready, -1 = unsupported for these shapes (separate launches)
+  PreparedChain dual_lat; // stage 1 with the fused latent epilogue (G_B3D_LAT + G_B3W)
+  int dual_lat_state;
   PreparedChain fwd;      // forward: fc1 -> encoder head -> fc3 -> fc4/loss chained by tile-level dependencies
   int fwd_state;
 };
@@ -469,8 +476,11 @@ struct rvae_plan {
   float* eps_alt;
   int cur;                 // which input set is current (GEMM tensor maps are prepared per set)
   int* sched_dev;          // schedules of the fused launches: [2 input sets][5 launches][128 pairs][kSchedMax]
+  int sched_batch;         // the batch size those schedules were built for (0 = none yet): the buffer holds ONE set of
+                           // schedules, so other batch sizes of this plan (a ragged last batch) run separate launches
   unsigned int* dep_flags; // row-block counters of the chained forward launch: [3 layer transitions][256]
   bool fuse_forward;       // env RVAE_FUSE_FORWARD=1: forward pass as one chained launch (default off)
+  bool fuse_latent;        // env RVAE_FUSE_LATENT: backward of reparameterize + KL inside the latent dgrad's epilogue
   int dual_pairs;          // CTA pairs a fused launch uses (0 = fused launches off)
   unsigned int* ticket;    // last-block ticket of the step's final Adam launch (advances the step counter)
   bool ticket_zeroed;
@@ -639,6 +649,15 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.A = opnd(p->da3, MAJOR_K, H); d.B = wopnd(p, ly.w3, MAJOR_MN, L);
       d.args.out_f32 = p->dz; d.args.ldo = L; d.args.accumulate = 1;
       break;
+    case G_B3D_LAT:
+      // d_ml = [dz + c mu | dz eps sigma / 2 + c (sigma^2 - 1) / 2] and db2 straight from the accumulator (bf16 mode):
+      // no split-K, no dz round trip, no separate latent backward kernel
+      d.epi = EPI_DLATENT; d.M = B; d.N = L; d.K = H;
+      d.A = opnd(p->da3, MAJOR_K, H); d.B = wopnd(p, ly.w3, MAJOR_MN, L);
+      d.args.in0 = p->eps; d.args.in1 = p->lv; d.args.in2 = p->mu;
+      d.args.out_hi = p->dml.hi; d.args.ldo = 2 * L; d.args.L = L;
+      d.args.colsum = grads + ly.b2;                     // [db21; db22] = column sums of d_ml
+      break;
     case G_B2W:
       d.epi = EPI_REDUCE; d.M = 2 * L; d.N = H; d.K = B;
       d.A = opnd(p->dml, MAJOR_MN, 2 * L); d.B = opnd(p->h1, MAJOR_MN, H);
@@ -722,9 +741,10 @@ int run(rvae_plan* p, int id, cudaStream_t st, const EpiArgs* override_args = nu
   RVAE_CUDA(cudaEventRecord(p->ev_pool[slot].first, st));
   RVAE_CHECK(run_untimed(p, gs, id, st, override_args));
   RVAE_CUDA(cudaEventRecord(p->ev_pool[slot].second, st));
-  p->ev_used.emplace_back(id, (int)slot);
+  const int tid = id == G_B3D_LAT ? G_B3D : id;
+  p->ev_used.emplace_back(tid, (int)slot);
   const GemmParams& gp = gs->g[id].params;
-  p->t_flops[id] = 2.0 * gp.M * gp.N * gp.K;
+  p->t_flops[tid] = 2.0 * gp.M * gp.N * gp.K;
   return RVAE_OK;
 }
 
@@ -816,6 +836,54 @@ struct LatentExt {
   const float* lv;
 };
 
+// Fused launches read their tile schedule from the plan's one schedule buffer: usable by the batch size that owns it.
+bool sched_usable(const rvae_plan* p) { return p->sched_batch == 0 || p->sched_batch == p->batch; }
+
+// Stage 1 runs the reparameterisation / KL backward inside the latent dgrad's epilogue (bf16 mode, fused loss)
+bool latent_fused(const rvae_plan* p) {
+  return p->fuse_latent && p->precision == RVAE_PRECISION_BF16 && p->batch > kBlockM;
+}
+
+// Stage 1 with G_B3D_LAT: [d_ml, db2 = latent dgrad + fused epilogue | dW3] as one fused launch (or two GEMMs when
+// fused launches are off / timed). The weight-gradient bucket has been cleared by the caller.
+int backward_stage_latent_fused(rvae_plan* p, cudaStream_t st) {
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  if (p->fin_pending) {
+    // no latent backward kernel to carry the deferred loss finalisation (rvae_plan_train_step moves it to the
+    // background stream before it gets here)
+    RVAE_CHECK(launch_loss_finalize_prepared(&p->ctx->c, p->fin, st));
+    p->fin_pending = false;
+  }
+  if (p->dual_pairs > 0 && !p->timing && sched_usable(p)) {
+    int pairs = p->dual_pairs > 64 ? 64 : p->dual_pairs;
+    if (const char* e = getenv("RVAE_DUAL_PAIRS_S1")) {
+      const int v = atoi(e);
+      if (v >= 1 && 2 * v <= p->ctx->c.num_sms_total) pairs = v;
+    }
+    if (gs->dual_lat_state == 0) {
+      RVAE_CHECK(prepare(p, *gs, G_B3D_LAT));
+      RVAE_CHECK(prepare(p, *gs, G_B3W));
+      int* sched = p->sched_dev + ((size_t)p->cur * 5 + 4) * 128 * kSchedMax;
+      const PreparedGemm* both[2] = {&gs->g[G_B3D_LAT], &gs->g[G_B3W]};
+      const int rc = gemm_prepare_chain(&p->ctx->c, both, 2, pairs, sched, &gs->dual_lat);
+      gs->dual_lat_state = rc == RVAE_OK ? 1 : -1;
+      if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+      if (rc == RVAE_OK) p->sched_batch = p->batch;
+    }
+    if (gs->dual_lat_state == 1) {
+      PreparedChain d = gs->dual_lat;
+      d.params.p[0].epi.c0 = p->kl_c0;
+      return gemm_run_chain(&p->ctx->c, d, st);
+    }
+  }
+  RVAE_CHECK(prepare(p, *gs, G_B3D_LAT));
+  EpiArgs a = gs->g[G_B3D_LAT].params.epi;
+  a.c0 = p->kl_c0;
+  RVAE_CHECK(run(p, G_B3D_LAT, st, &a));
+  return run(p, G_B3W, st);
+}
+
 int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t st) {
   const int S = p->S, H = p->H, L = p->L;
   const rvae_layout& ly = p->lay;
@@ -827,11 +895,13 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   const size_t wcount[4] = {(size_t)S * H, (size_t)H * L, (size_t)2 * L * H, (size_t)H * S};
   if (!p->grads_zeroed[stage]) RVAE_CUDA(cudaMemsetAsync(wptr[stage], 0, sizeof(float) * wcount[stage], st));
   p->grads_zeroed[stage] = false;
+  // stage 1, bf16 mode, fused loss: the reparameterisation / KL backward runs inside the latent dgrad's epilogue
+  if (stage == 1 && ext == nullptr && latent_fused(p)) return backward_stage_latent_fused(p, st);
   if (stage == 1 && !p->dz_zeroed)
     RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
   // dgrad and weight gradient of the stage as ONE persistent launch over a mixed, load-balanced tile list
   bool fused = false;
-  if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && !p->timing) {
+  if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && !p->timing && sched_usable(p)) {
     // under data parallelism the fused launches leave the same spare SMs as the single GEMMs do: NCCL's kernels
     // run there
     int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
@@ -853,6 +923,7 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
       const int rc = gemm_prepare_chain(&p->ctx->c, both, 2, pairs, sched, &gs->dual[stage]);
       gs->dual_state[stage] = rc == RVAE_OK ? 1 : -1;
       if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+      if (rc == RVAE_OK) p->sched_batch = p->batch;
     }
     if (gs->dual_state[stage] == 1) {
       RVAE_CHECK(gemm_run_chain(&p->ctx->c, gs->dual[stage], st));
@@ -890,6 +961,8 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->timing = false;
   p->kl_c0 = 0.f; p->dz_zeroed = false; p->dp_enabled = false;
   p->cur = 0; p->ticket_zeroed = false; p->ticket = nullptr;
+  p->fuse_latent = false;
+  p->sched_batch = 0;
   memset(&p->pf, 0, sizeof(p->pf));
   for (int i = 0; i < 5; ++i) p->grads_zeroed[i] = false;
   p->streams_ready = false; p->ev_fork = nullptr;
@@ -900,6 +973,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
   p->fuse_forward = false;  // measured: no faster than the four separate launches (profiles/README.md); opt-in
+  if (const char* e = getenv("RVAE_FUSE_LATENT")) p->fuse_latent = atoi(e) != 0;
   if (const char* e = getenv("RVAE_FUSE_FORWARD")) p->fuse_forward = atoi(e) != 0;
   p->dual_pairs = ctx->c.num_sms / 2;
   if (const char* e = getenv("RVAE_DUAL_PAIRS")) {
@@ -983,6 +1057,7 @@ int rvae_plan_bind(rvae_plan* plan, const rvae_plan_buffers* b) {
   if (plan->precision == RVAE_PRECISION_BF16) plan->bufs.shadow_lo = nullptr;
   carve(plan, reinterpret_cast<uint8_t*>(b->workspace));
   plan->sets.clear();
+  plan->sched_batch = 0;
   for (int i = 0; i < 5; ++i) plan->grads_zeroed[i] = false;
   plan->dz_zeroed = false;
   plan->cur = 0; plan->ticket_zeroed = false;
@@ -1068,7 +1143,12 @@ int rvae_plan_enable_dp(rvae_plan* plan, int on) {
   RVAE_REQUIRE(plan, RVAE_ERR_INVALID, "null rvae_plan");
   RVAE_REQUIRE(!on || plan->ctx->comm != nullptr || plan->ctx->p2p_ready, RVAE_ERR_STATE,
                "plan_enable_dp: call rvae_dp_init / rvae_dp_sym_open first");
-  if (plan->dp_enabled != (on != 0)) plan->sets.clear();   // fused-launch schedules depend on the SM budget
+  if (plan->dp_enabled != (on != 0) && !plan->sets.empty()) {
+    // fused-launch schedules depend on the SM budget: rebuild them - once nothing in flight reads the old ones
+    RVAE_CUDA(cudaDeviceSynchronize());
+    plan->sets.clear();
+    plan->sched_batch = 0;
+  }
   plan->dp_enabled = on != 0;
   return RVAE_OK;
 }
@@ -1092,7 +1172,7 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
   // Training step: the whole forward pass (fc1 -> encoder head -> fc3 -> fc4 + loss) as ONE persistent launch whose
   // tiles are chained by row-block dependencies (a tile of the next layer starts as soon as the tiles of its row
   // block are stored) - instead of four kernels with their fill, drain and half-empty last waves.
-  const bool chain = fused_loss && !want_xhat && p->fuse_forward && p->dual_pairs > 0 && !p->timing && !p->out_mu &&
+  const bool chain = fused_loss && !want_xhat && p->fuse_forward && p->dual_pairs > 0 && !p->timing && sched_usable(p) && !p->out_mu &&
                      !p->out_lv && !p->out_xhat && p->bufs.grads != nullptr;
   if (chain) {
     if (gs->fwd_state == 0) {
@@ -1111,6 +1191,7 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
       const int rc = gemm_prepare_chain(&p->ctx->c, layers, 4, fpairs, sched, &gs->fwd, p->dep_flags);
       gs->fwd_state = rc == RVAE_OK ? 1 : -1;
       if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+      if (rc == RVAE_OK) p->sched_batch = p->batch;
     }
     if (gs->fwd_state == 1) {
       p->kl_c0 = (float)((double)kl_beta / BL);
@@ -1359,6 +1440,14 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
     return RVAE_OK;
   };
   static const unsigned kBucketMask[3] = {0x1, 0x2, 0x4};
+  // with the latent backward fused into a GEMM epilogue no elementwise kernel of the critical chain is left to carry
+  // the deferred loss finalisation: it rides on the background stream once the forward pass is known complete
+  auto finalize_on_bg = [&]() -> int {
+    if (!(plan->fin_pending && latent_fused(plan))) return RVAE_OK;
+    RVAE_CHECK(launch_loss_finalize_prepared(&cx->c, plan->fin, bg));
+    plan->fin_pending = false;
+    return RVAE_OK;
+  };
   for (int s = 0; s < 3; ++s) {
     RVAE_CHECK(rvae_plan_backward(plan, s, st));
     if (dp) {
@@ -1370,6 +1459,7 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
       RVAE_CHECK(allreduce_buckets(kExchange[s], s, cx->p2p_ctas, cs));
       RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[s], cs));
       RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_comm_done[s], 0));
+      if (s == 0) RVAE_CHECK(finalize_on_bg());
       RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
       continue;
     }
@@ -1379,6 +1469,7 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
     if (s == 0) {
       RVAE_CUDA(cudaEventRecord(plan->ev_adam_fork, st));
       RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_adam_fork, 0));
+      RVAE_CHECK(finalize_on_bg());
       RVAE_CHECK(adam_buckets(plan, kBucketMask[0], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
     }
   }

@@ -208,6 +208,7 @@ struct LossFinalize {
 };
 LossFinalize make_loss_finalize(double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
                                 float* step);
+int launch_loss_finalize_prepared(Ctx* ctx, const LossFinalize& f, cudaStream_t stream);
 int launch_latent_bwd(Ctx* ctx, float* dz, const float* eps, const float* lv, const float* mu, const float* g_mu_ext,
                       const float* g_lv_ext, float kl_grad_scale, int64_t M, int L, __nv_bfloat16* dml_hi,
                       __nv_bfloat16* dml_lo, float* bias_grad, int clear_dz, const LossFinalize* fin,

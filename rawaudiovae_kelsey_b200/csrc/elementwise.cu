@@ -147,14 +147,58 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
 // K-D2 overlap-add resynthesis (gather form, no atomics): out[t] = sum_i frames[i, t - i*hop] / count(t)
 // over the frames i that cover sample t. With hop == S this is the reference's frames.view(-1).
 // ------------------------------------------------------------------------------------------------
+template <bool VEC>
 __global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_frames, int S, int hop,
                                    float* __restrict__ out, int64_t n_out) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_out; t += (int64_t)gridDim.x * blockDim.x) {
+  // VEC: S, hop and both base addresses are multiples of 4 elements, so the 4 samples of an aligned group are
+  // covered by the same frames at offsets that stay 16-byte aligned; the per-sample sum order (ascending frame
+  // index) is the scalar path's, hence bit-identical results. The scalar path also finishes a ragged tail.
+  constexpr int W = VEC ? 4 : 1;
+  const int64_t n_groups = VEC ? (n_out >> 2) : n_out;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_groups; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = w * W;
     int64_t i_hi = t / hop;
     if (i_hi > n_frames - 1) i_hi = n_frames - 1;
     int64_t i_lo = (t - S + hop) / hop;  // ceil((t - S + 1) / hop) for t - S + 1 > 0
+    if (t - S + 1 <= 0) i_lo = 0;
+    float acc[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[j] = 0.f;
+    int cnt = 0;
+    for (int64_t i = i_lo; i <= i_hi; ++i) {
+      const int64_t off = t - i * hop;
+      if (off >= 0 && off < S) {
+        if constexpr (VEC) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(frames + i * S + off));
+          acc[0] += f.x; acc[1] += f.y; acc[2] += f.z; acc[3] += f.w;
+        } else {
+          acc[0] += __ldg(frames + i * S + off);
+        }
+        ++cnt;
+      }
+    }
+    const float c = static_cast<float>(cnt);
+    if constexpr (VEC) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cnt > 0) o = make_float4(acc[0] / c, acc[1] / c, acc[2] / c, acc[3] / c);
+      *reinterpret_cast<float4*>(out + t) = o;
+    } else {
+      out[t] = cnt > 0 ? acc[0] / c : 0.f;
+    }
+  }
+}
+
+// samples [t0, n_out) of the scalar rule (the < 4-sample tail the vector path leaves)
+__global__ void overlap_add_tail_kernel(const float* __restrict__ frames, int64_t n_frames, int S, int hop,
+                                        float* __restrict__ out, int64_t t0, int64_t n_out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  for (int64_t t = t0 + threadIdx.x; t < n_out; t += blockDim.x) {
+    int64_t i_hi = t / hop;
+    if (i_hi > n_frames - 1) i_hi = n_frames - 1;
+    int64_t i_lo = (t - S + hop) / hop;
     if (t - S + 1 <= 0) i_lo = 0;
     float acc = 0.f;
     int cnt = 0;
@@ -175,7 +219,20 @@ int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, i
   RVAE_REQUIRE(S > 0 && hop > 0 && hop <= S, RVAE_ERR_UNSUPPORTED, "overlap_add: need 0 < hop <= S");
   if (n_out <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel, dim3(grid_for(ctx, n_out, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, n_out));
+  const bool vec = S % 4 == 0 && hop % 4 == 0 && ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  int64_t done = 0;
+  if (vec && n_out >= 4) {
+    done = n_out & ~(int64_t)3;
+    RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel<true>, dim3(grid_for(ctx, done >> 2, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, done));
+  }
+  if (done < n_out) {
+    if (done == 0) {
+      RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel<false>, dim3(grid_for(ctx, n_out, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, n_out));
+    } else {
+      // ragged tail (< 4 samples) of the vector path
+      RVAE_CUDA(launch_kernel(ctx, overlap_add_tail_kernel, dim3(1), dim3(32), (size_t)0, stream, frames, n_frames, S, hop, out, done, n_out));
+    }
+  }
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -395,10 +452,12 @@ __device__ __forceinline__ void loss_finalize_body(double* acc, double inv_rec, 
 }
 
 __global__ void loss_finalize_kernel(double* __restrict__ acc, double inv_rec, double kl_scale,
-                                     float* __restrict__ loss_out, int ring_size, float* __restrict__ step) {
+                                     float* __restrict__ loss_out, int ring_size, float* __restrict__ step,
+                                     int inc_step) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  if (threadIdx.x == 0 && blockIdx.x == 0) loss_finalize_body(acc, inv_rec, kl_scale, loss_out, ring_size, step, 1);
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    loss_finalize_body(acc, inv_rec, kl_scale, loss_out, ring_size, step, inc_step);
 }
 
 LossFinalize make_loss_finalize(double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
@@ -417,9 +476,13 @@ LossFinalize make_loss_finalize(double* acc, int64_t B, int S, int L, float beta
 int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
                          float* step, cudaStream_t stream) {
   RVAE_REQUIRE(acc, RVAE_ERR_INVALID, "loss_finalize: null accumulator");
-  const LossFinalize f = make_loss_finalize(acc, B, S, L, beta, loss_out, ring_size, step);
-  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, acc, f.inv_rec, f.kl_scale,
-                          loss_out, ring_size, step));
+  return launch_loss_finalize_prepared(ctx, make_loss_finalize(acc, B, S, L, beta, loss_out, ring_size, step), stream);
+}
+
+int launch_loss_finalize_prepared(Ctx* ctx, const LossFinalize& f, cudaStream_t stream) {
+  RVAE_REQUIRE(f.acc, RVAE_ERR_INVALID, "loss_finalize: null accumulator");
+  RVAE_CUDA(launch_kernel(ctx, loss_finalize_kernel, dim3(1), dim3(32), (size_t)0, stream, f.acc, f.inv_rec, f.kl_scale,
+                          f.loss_out, f.ring_size, f.step, f.inc_step));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }

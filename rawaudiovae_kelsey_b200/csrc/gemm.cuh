@@ -43,7 +43,7 @@ constexpr int kSlotBytes = 128 * 128;  // one epilogue slot: 128 rows x 128 byte
 constexpr int kSlotsPerTeam = 3;
 
 enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
-enum : int { EPI_LINEAR = 0, EPI_HEAD = 1, EPI_OUT = 2, EPI_DRELU = 3, EPI_REDUCE = 5 };
+enum : int { EPI_LINEAR = 0, EPI_HEAD = 1, EPI_OUT = 2, EPI_DRELU = 3, EPI_REDUCE = 5, EPI_DLATENT = 6 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_TANH_APPROX = 3 };
 
 // Epilogue arguments. Slot meaning per epilogue kind:
@@ -66,6 +66,7 @@ struct EpiArgs {
   float* out_f32_b;
   const void* in0;
   const void* in1;
+  const void* in2;  // DLATENT: mu
   double* loss_acc;
   float* colsum;  // OUT / DRELU: colsum[c] += sum over rows of the emitted values (bias gradients)
   int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and of the bf16 inputs in0/in1
@@ -254,6 +255,26 @@ __device__ __forceinline__ void warp_colsum64(float* v, int lane) {
       }
     }
   }
+}
+
+// The same for a [32 rows x 16 columns] tile (15 + 1 shuffles): afterwards lane l holds the sum of column l >> 1
+// in v[0] (both lanes of a pair hold it). Destroys v.
+__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int half = 8 >> step;
+    const int mask = 16 >> step;
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < half) {
+        const float send = upper ? v[j] : v[j + half];
+        const float keep = upper ? v[j + half] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // Accurate tanh is only used by the fp32-emulation path; kept out of line so the hot epilogues stay small enough for
@@ -664,6 +685,109 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiSta
               ptx::tma_store_commit();
             }
           }
+        }
+      } else if constexpr (EPI == EPI_DLATENT) {
+        // ---- latent dgrad with the backward of reparameterize + the KL gradient fused (rawvae/model.py:24-26,45):
+        //        dz = acc;  sigma = exp(lv / 2)
+        //        d_mu = dz + c0 * mu                          -> out_hi[:, n]      (bf16, leading dimension ldo = 2L)
+        //        d_lv = dz * eps * sigma / 2 + c0 (sigma^2 - 1) / 2 -> out_hi[:, L + n]
+        //        colsum[n] += sum_rows d_mu, colsum[L + n] += sum_rows d_lv      (db21, db22)
+        //      Team t owns the 64-column groups t, t + 2 of the tile and walks them in 8-column pieces, one output row
+        //      per thread: mu, logvar, eps (fp32) come straight from global memory (one 32-byte sector per array, row
+        //      and piece; the next piece's loads are issued before this piece is computed), results go straight back
+        //      as 16-byte stores. The volume is small (16 + 4 bytes per latent element) and a CTA pair runs ONE such
+        //      tile per launch, so the code is kept short and rolled: a first pass through a long unrolled epilogue
+        //      costs more in instruction-cache misses than the whole tile's arithmetic (measured).
+        constexpr int kSubs = BLOCK_N / 64;
+        constexpr int kUnitsPerTeam = (kSubs + kEpiTeams - 1) / kEpiTeams;
+        constexpr int kPieces = kUnitsPerTeam * 8;
+        const int L = e.L;
+        const float* src[3] = {reinterpret_cast<const float*>(e.in2), reinterpret_cast<const float*>(e.in1),
+                               reinterpret_cast<const float*>(e.in0)};  // mu, logvar, eps
+        const size_t row_off = static_cast<size_t>(m) * L;
+        auto piece_col = [&](int pc) { return n_blk * BLOCK_N + (team + (pc >> 3) * kEpiTeams) * 64 + (pc & 7) * 8; };
+        float4 nx[6];  // the next piece's mu[0:8], logvar[0:8], eps[0:8]
+        auto load_piece = [&](int pc) {
+          const int col = pc < kPieces ? piece_col(pc) : p.N;
+          if (row_ok && col < p.N) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const float4* g4 = reinterpret_cast<const float4*>(src[a] + row_off + col);
+              nx[2 * a] = __ldg(g4);
+              nx[2 * a + 1] = __ldg(g4 + 1);
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) nx[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        if (row_ok && !(p.debug & 4)) {
+          // written by the forward pass and long evicted: have the L2 fetch this row's inputs while the MMAs run
+#pragma unroll
+          for (int j = 0; j < kUnitsPerTeam; ++j) {
+            const int n0 = n_blk * BLOCK_N + (team + j * kEpiTeams) * 64;
+            if (team + j * kEpiTeams < kSubs && n0 < p.N) {
+#pragma unroll
+              for (int a = 0; a < 3; ++a) ptx::prefetch_l2_bulk(src[a] + row_off + n0, 256u);
+            }
+          }
+        }
+        ptx::mbar_wait(&tmem_full_bar[as], aphase);
+        ptx::tc_fence_after();
+        if (team_tid == 0) trace_ev(p.trace, titer, 6 + 2 * team);
+        load_piece(0);
+        float* cs_mu = tm.csum_s;        // both column-sum strips are zero between units
+        float* cs_lv = tm.csum_s + 64;
+        __nv_bfloat16* out_row = e.out_hi + static_cast<size_t>(m) * e.ldo;
+#pragma unroll 1
+        for (int pc = 0; pc < kPieces; ++pc) {
+          const int col = piece_col(pc);
+          if (col >= p.N) break;          // (uniform over the team; columns grow with pc)
+          uint32_t r[8];
+          ptx::tmem_ld_32x8(t_acc + (col - n_blk * BLOCK_N), r);
+          float in[24];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            in[4 * a] = nx[a].x; in[4 * a + 1] = nx[a].y; in[4 * a + 2] = nx[a].z; in[4 * a + 3] = nx[a].w;
+          }
+          load_piece(pc + 1);
+          ptx::tmem_ld_wait();
+          float o[16];                    // d_mu[0:8], d_lv[0:8]
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float d = __uint_as_float(r[q]);
+            const float sig = expf(0.5f * in[8 + q]);
+            const float gl = 0.5f * e.c0 * (sig * sig - 1.f);
+            o[q] = row_ok ? d + e.c0 * in[q] : 0.f;
+            o[8 + q] = row_ok ? fmaf(d, 0.5f * in[16 + q] * sig, gl) : 0.f;
+          }
+          if (row_ok) {
+            *reinterpret_cast<uint4*>(out_row + col) =
+                make_uint4(ptx::pack_bf16x2(o[0], o[1]), ptx::pack_bf16x2(o[2], o[3]), ptx::pack_bf16x2(o[4], o[5]),
+                           ptx::pack_bf16x2(o[6], o[7]));
+            *reinterpret_cast<uint4*>(out_row + L + col) =
+                make_uint4(ptx::pack_bf16x2(o[8], o[9]), ptx::pack_bf16x2(o[10], o[11]),
+                           ptx::pack_bf16x2(o[12], o[13]), ptx::pack_bf16x2(o[14], o[15]));
+          }
+          if (e.colsum) {
+            warp_colsum16(o, lane);       // lane l: sum over the warp's 32 rows of value (l >> 1)
+            if ((lane & 1) == 0) {
+              const int idx = lane >> 1;
+              atomicAdd((idx < 8 ? cs_mu : cs_lv - 8) + (pc & 7) * 8 + idx, o[0]);
+            }
+            if ((pc & 7) == 7) {          // the group's 64 + 64 column sums are complete: flush and clear the strips
+              const int n0 = col - 56;
+              tm.sync();
+              if (team_tid < 64) {
+                atomicAdd(e.colsum + n0 + team_tid, cs_mu[team_tid]);
+                atomicAdd(e.colsum + L + n0 + team_tid, cs_lv[team_tid]);
+                cs_mu[team_tid] = 0.f;
+                cs_lv[team_tid] = 0.f;
+              }
+              tm.sync();
+            }
+          }
+          if (tr && (pc & 7) == 7) trace_ev(p.trace, titer, 14 + (pc >> 3));   // 14 / 15: group stored
         }
       } else if constexpr (EPI == EPI_REDUCE) {
         ptx::mbar_wait(&tmem_full_bar[as], aphase);

@@ -120,6 +120,9 @@ static const Variant kVariants[] = {
     RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_DRELU),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_DRELU),
     RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_REDUCE),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_REDUCE),
     RVAE_VARIANT(256, MAJOR_MN, MAJOR_MN, EPI_REDUCE), RVAE_VARIANT(128, MAJOR_MN, MAJOR_MN, EPI_REDUCE),
+    // latent dgrad with the reparameterisation / KL backward fused: pair tiles only
+    {256, MAJOR_K, MAJOR_MN, EPI_DLATENT, 2, gemm_kernel_2cta<256, MAJOR_K, MAJOR_MN, EPI_DLATENT>,
+     GemmCfg<256, 2>::kSmemBytes},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -195,7 +198,11 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   } else {
     // reduce-add GEMMs (weight gradients, latent dgrad): 256-wide tiles, split-K fills the machine; others: by
     // wave count
-    choose_tile(ctx, d.M, d.N, d.epi != EPI_REDUCE || d.N % 256 != 0, true, &block_n, &cg);
+    choose_tile(ctx, d.M, d.N, d.epi != EPI_DLATENT && (d.epi != EPI_REDUCE || d.N % 256 != 0), true, &block_n, &cg);
+    if (d.epi == EPI_DLATENT)
+      RVAE_REQUIRE(d.args.in0 && d.args.in1 && d.args.in2 && d.args.out_hi && !d.args.out_lo && !d.A.lo && !d.B.lo &&
+                       d.args.L == d.N && d.args.ldo == 2 * d.N,
+                   RVAE_ERR_UNSUPPORTED, "latent dgrad gemm: bf16 mode with eps, logvar, mu and d_ml [M, 2L] only");
     p.n_blocks = ceil_div(d.N, block_n);
     p.b_tile_stride = block_n;
     p.b_half_stride = block_n / 2;
@@ -264,6 +271,9 @@ int gemm_prepare(const Ctx* ctx, const GemmDesc& d, PreparedGemm* out) {
   if (d.epi == EPI_HEAD) {            // z [M, L] bf16; mu, logvar, eps [M, L] fp32
     g.out_cols_bf16 = d.head_L; g.out_ld_bf16 = d.head_L;
     g.out_cols_f32 = d.head_L; g.out_ld_f32 = d.head_L;
+  } else if (d.epi == EPI_DLATENT) {  // d_ml = [d_mu | d_logvar], [M, 2L] bf16
+    g.out_cols_bf16 = 2 * d.N; g.out_ld_bf16 = d.args.ldo;
+    g.out_cols_f32 = d.N; g.out_ld_f32 = d.N;
   } else {
     g.out_cols_bf16 = d.N; g.out_ld_bf16 = d.args.ldo;
     g.out_cols_f32 = d.N; g.out_ld_f32 = d.args.ldo;
@@ -318,6 +328,7 @@ struct ChainVariant {
 using KDrelu = Kind<MAJOR_K, MAJOR_MN, EPI_DRELU>;
 using KWgrad = Kind<MAJOR_MN, MAJOR_MN, EPI_REDUCE>;
 using KDz = Kind<MAJOR_K, MAJOR_MN, EPI_REDUCE>;
+using KDlat = Kind<MAJOR_K, MAJOR_MN, EPI_DLATENT>;
 using KLinear = Kind<MAJOR_K, MAJOR_K, EPI_LINEAR>;
 using KHead = Kind<MAJOR_K, MAJOR_K, EPI_HEAD>;
 using KOut = Kind<MAJOR_K, MAJOR_K, EPI_OUT>;
@@ -327,6 +338,8 @@ static const ChainVariant kChainVariants[] = {
     {2, {RVAE_KID(KDrelu), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDrelu, KWgrad, NoKind, NoKind>},
     // split-K latent dgrad | weight gradient         (backward stage 1)
     {2, {RVAE_KID(KDz), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDz, KWgrad, NoKind, NoKind>},
+    // latent dgrad with fused reparameterisation / KL backward | weight gradient   (backward stage 1, bf16 mode)
+    {2, {RVAE_KID(KDlat), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDlat, KWgrad, NoKind, NoKind>},
     // layers chained by tile-level dependencies: fc1 -> head, fc3 -> fc4 + loss, and the whole forward pass
     {2, {RVAE_KID(KLinear), RVAE_KID(KHead)}, gemm_chain_kernel_2cta<256, KLinear, KHead, NoKind, NoKind>},
     {2, {RVAE_KID(KLinear), RVAE_KID(KOut)}, gemm_chain_kernel_2cta<256, KLinear, KOut, NoKind, NoKind>},
@@ -357,6 +370,8 @@ static int configure_chain_variants() {
 static double unit_cost(const PreparedGemm& g) {
   const double mma = (double)g.params.kb_per_split * g.params.num_passes;
   const double epi = (g.epi == EPI_DRELU || g.epi == EPI_OUT) ? 11.0 : 8.0;
+  // the fused latent epilogue is long and such a unit is the only one of its pair: nothing overlaps it
+  if (g.epi == EPI_DLATENT) return mma + 22.0 + 2.0;
   return (mma > epi ? mma : epi) + 2.0;
 }
 

@@ -346,6 +346,29 @@ def test_full_size_framing_roundtrip_and_checksum(dev):
     assert torch.equal(ops.overlap_add(tf, S), tf.view(-1))
 
 
+def test_overlap_add_vector_scalar_and_ragged_paths(dev):
+    """The float4 path (S, hop multiples of 4), its < 4-sample ragged tail, the scalar path (odd hop) and a
+    truncated / over-long output length all follow the oracle's rule; vector and scalar paths agree bit for bit."""
+    from rawaudiovae_kelsey_b200 import ops
+    from oracle import rawvae_oracle as O
+    gen = torch.Generator().manual_seed(11)
+    for n_frames, S, hop in [(37, 64, 16), (37, 64, 12), (19, 60, 15), (5, 64, 64), (1, 32, 8), (23, 128, 6)]:
+        fr = torch.randn(n_frames, S, generator=gen)
+        ref = torch.from_numpy(O.resynth_overlap_add(fr.numpy(), hop)).float()
+        full = (n_frames - 1) * hop + S
+        for n_out in (full, full - 1, full - 3, full + 5, 3):
+            got = ops.overlap_add(fr.to(dev), hop, n_out).cpu()
+            want = torch.zeros(n_out)
+            k = min(n_out, full)
+            want[:k] = ref[:k]
+            assert got.shape == want.shape and torch.allclose(got, want, atol=1e-6), (n_frames, S, hop, n_out)
+        # a misaligned view forces the scalar path: same bits as the vector path
+        if S % 4 == 0 and hop % 4 == 0:
+            buf = torch.empty(n_frames * S + 1, device=dev)
+            buf[1:] = fr.view(-1).to(dev)
+            assert torch.equal(ops.overlap_add(buf[1:].view(n_frames, S), hop), ops.overlap_add(fr.to(dev), hop))
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_gradient_additivity_and_api_agreement(dev):
     """BASELINE config (default.ini dims, 8192 frames): size-independent properties instead of an 8192-row oracle run.
@@ -513,6 +536,65 @@ def test_chained_forward_launch_equals_separate_kernels(dev, monkeypatch):
         res[mode] = (torch.tensor(losses), model._flat.params.clone())
     assert torch.allclose(res["1"][0], res["0"][0], rtol=1e-4, atol=0)
     assert rel(res["1"][1], res["0"][1]) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(512, 768, 128, 1300), (1024, 2048, 256, 768)])
+def test_fused_latent_epilogue_matches_latent_kernel(dev, monkeypatch, shape):
+    """RVAE_FUSE_LATENT=1 computes d_ml = [dz + c mu | dz eps sigma / 2 + c (sigma^2 - 1) / 2] and db2 in the epilogue
+    of the latent dgrad GEMM (no split-K dz round trip, no latent backward kernel). Same formulas on the same
+    operands as the kernel path: losses, weights and Adam moments agree up to accumulation-order noise. Ragged rows
+    (B % 256 != 0) and a latent width below the tile width are covered by the first shape."""
+    from rawvae.model import VAE, FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L, B = shape
+    n = 4
+    gen = torch.Generator().manual_seed(23)
+    x = (torch.rand(n, B, S, generator=gen) * 2 - 1).to(dev)
+    eps = torch.randn(n, B, L, generator=gen).to(dev)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RVAE_FUSE_LATENT", mode)      # read when the plan is created
+        torch.manual_seed(0)
+        model = VAE(S, H, L).to(dev)
+        opt = Adam(model.parameters(), lr=1e-3)
+        step = FusedTrainStep(model, opt, 1e-2, ring=8)   # a KL weight large enough for its gradient to matter
+        losses = [float(step(x[0], eps=eps[0]))]
+        # after the first step exp_avg = (1 - beta1) * gradient: compared per tensor, so that the 2L bias gradients
+        # the epilogue sums itself are not drowned by the weight matrices
+        flat = model._flat
+        m1 = {name: flat.view(flat.exp_avg, name).clone() for name in flat.offsets}
+        losses += [float(step(x[i], eps=eps[i])) for i in range(1, n)]
+        res[mode] = (torch.tensor(losses), flat.params.clone(), m1)
+    assert torch.allclose(res["1"][0], res["0"][0], rtol=1e-4, atol=0)
+    for name, m in res["1"][2].items():
+        assert rel(m, res["0"][2][name]) < 2e-3, name
+    # (Adam turns the accumulation-order noise of near-zero gradients into +-lr steps: a looser bound than above)
+    assert rel(res["1"][1], res["0"][1]) < 3e-3
+
+
+def test_alternating_batch_sizes_share_one_plan(dev, monkeypatch):
+    """A plan serves every batch size up to its capacity (a ragged last batch of an epoch), but holds ONE set of
+    fused-launch tile schedules: other batch sizes must fall back to separate launches instead of running the
+    owner's schedule. Reference: the same steps with fused launches disabled."""
+    from rawvae.model import VAE, FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L = 512, 768, 128
+    sizes = [1536, 700, 1536, 1024, 1536]
+    gen = torch.Generator().manual_seed(29)
+    xs = [(torch.rand(b, S, generator=gen) * 2 - 1).to(dev) for b in sizes]
+    es = [torch.randn(b, L, generator=gen).to(dev) for b in sizes]
+    res = {}
+    for pairs in ("default", "0"):
+        if pairs == "0":
+            monkeypatch.setenv("RVAE_DUAL_PAIRS", "0")    # no fused launches at all
+        torch.manual_seed(0)
+        model = VAE(S, H, L).to(dev)
+        opt = Adam(model.parameters(), lr=1e-3)
+        step = FusedTrainStep(model, opt, 1e-3, ring=8)
+        losses = [float(step(x, eps=e)) for x, e in zip(xs, es)]
+        res[pairs] = (torch.tensor(losses), model._flat.params.clone())
+    assert torch.allclose(res["default"][0], res["0"][0], rtol=1e-4, atol=0)
+    assert rel(res["default"][1], res["0"][1]) < 1e-3
 
 
 def _write_wav_folder(root, n_files, seconds, sr, seed):

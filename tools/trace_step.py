@@ -124,15 +124,27 @@ live = hdr[:, 1] > 0
 ghz = float(np.median((hdr[live, 5] - hdr[live, 1]) / np.maximum(hdr[live, 6] - hdr[live, 0], 1)))
 us = lambda c: c / ghz / 1e3
 print(f"---- roles of launch {li} ({NAMES[li]}), {int(live.sum())} CTAs, clock {ghz:.2f} GHz; times in us since the CTA passed its PDL wait")
-for it in range(NT):
-    e = ev[live, it, :]
+# TRACE_SPLIT=n: summarise CTAs [0, n) and [n, ..) separately (fused launches: the two problems' CTA pairs)
+split = int(os.environ.get("TRACE_SPLIT", "0"))
+groups = [("", live)]
+if split > 0:
+    lo = live.copy(); lo[split:] = False
+    hi = live.copy(); hi[:split] = False
+    groups = [(f"ctas < {split}", lo), (f"ctas >= {split}", hi)]
+for gname, gl in groups:
+  if gname:
+    print(f" -- {gname}: exit {us(np.median(hdr[gl, 5] - hdr[gl, 3])):6.1f} us after the PDL wait (max {us(np.max(hdr[gl, 5] - hdr[gl, 3])):6.1f})")
+  for it in range(NT):
+    e = ev[gl, it, :]
     ran = e[:, 6] > 0
     if not ran.any():
         break
-    e = e[ran]; base = hdr[live, 3][ran]
+    e = e[ran]; base = hdr[gl, 3][ran]
     mm = e[:, 3] > 0
     med = lambda a: float(np.median(a)) if len(a) else float("nan")
     mx = lambda a: float(np.max(a)) if len(a) else float("nan")
     print(f"   tile {it:2d} ({int(ran.sum()):3d} CTAs): prod start {us(med(e[:,0]-base)):6.1f} | mma acc-wait {us(med(e[mm,3]-e[mm,2])):5.2f} "
           f"data-wait med {us(med(e[mm,4]-e[mm,3])):5.2f} max {us(mx(e[mm,4]-e[mm,3])):5.2f} issue {us(med(e[mm,5]-e[mm,4])):5.2f} commit at {us(med(e[mm,5]-base[mm])):6.1f} (max {us(mx(e[mm,5]-base[mm])):6.1f}) | "
-          f"epi {us(med(e[:,6]-base)):6.1f}->{us(med(e[:,7]-base)):6.1f}")
+          f"epi {us(med(e[:,6]-base)):6.1f}->{us(med(e[:,7]-base)):6.1f}"
+          + ("  ev10..15 after acc-ready: " + " ".join(f"{us(med(e[e[:,k]>0,k]-e[e[:,k]>0,6])):5.1f}" for k in range(10, 16))
+             if os.environ.get("TRACE_EPI_DETAIL") else ""))
