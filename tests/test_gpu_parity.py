@@ -567,9 +567,9 @@ def test_fused_latent_epilogue_matches_latent_kernel(dev, monkeypatch, shape):
         res[mode] = (torch.tensor(losses), flat.params.clone(), m1)
     assert torch.allclose(res["1"][0], res["0"][0], rtol=1e-4, atol=0)
     for name, m in res["1"][2].items():
-        assert rel(m, res["0"][2][name]) < 2e-3, name
-    # (Adam turns the accumulation-order noise of near-zero gradients into +-lr steps: a looser bound than above)
-    assert rel(res["1"][1], res["0"][1]) < 3e-3
+        assert rel(m, res["0"][2][name]) < 5e-3, name    # (a dropped row / column block would show as O(0.1 .. 1))
+    # (Adam turns the accumulation-order noise of near-zero gradients into +-lr steps: measured 1.4e-3)
+    assert rel(res["1"][1], res["0"][1]) < 5e-3
 
 
 def test_alternating_batch_sizes_share_one_plan(dev, monkeypatch):
@@ -594,7 +594,7 @@ def test_alternating_batch_sizes_share_one_plan(dev, monkeypatch):
         losses = [float(step(x, eps=e)) for x, e in zip(xs, es)]
         res[pairs] = (torch.tensor(losses), model._flat.params.clone())
     assert torch.allclose(res["default"][0], res["0"][0], rtol=1e-4, atol=0)
-    assert rel(res["default"][1], res["0"][1]) < 1e-3
+    assert rel(res["default"][1], res["0"][1]) < 2e-3   # (a stale schedule drops tiles: O(1) after the third step)
 
 
 def _write_wav_folder(root, n_files, seconds, sr, seed):
