@@ -162,6 +162,60 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
+class NvmlSampler:
+    """SM clock / clocks-event reasons DURING the timed region, polled through NVML every few milliseconds by a
+    thread (nvidia-smi -lms cannot sample faster than ~100 ms, longer than a 20-step block). Falls back to the
+    nvidia-smi sampler when NVML is unavailable."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"))
+
+    def __init__(self, dev: torch.device, period_s: float = 0.005):
+        self.period, self.samples, self.bits, self.h, self.nv = period_s, [], 0, None, None
+        self.fallback = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(dev)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+            self.fallback = ClockSampler(dev.index or 0)
+
+    def _loop(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons_fn(self.h))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.h is None:
+            return self.fallback.start()
+        self._stop = threading.Event()
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        if self.h is None:
+            return self.fallback.stop()
+        self._stop.set()
+        self.t.join(timeout=1.0)
+        sm = self.samples
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": [n for b, n in self.REASONS if self.bits & b],
+                "samples": len(sm), "source": "nvml, polled during the timed blocks"}
+
+
 def run_ours(args):
     from rawaudiovae_kelsey_b200 import dist as rdist
     from rawaudiovae_kelsey_b200 import ops
@@ -185,7 +239,7 @@ def run_ours(args):
     # model + optimizer (random init of the default.ini architecture)
     torch.manual_seed(0)
     model = VAE(S, H, L, precision=args.precision).to(dev)
-    model.eps_seed = 1 + rank
+    model.eps_seed = 1
     opt = Adam(model.parameters(), lr=LR)
     if world > 1:
         step_fn = rdist.DataParallelTrainStep(model, opt, KL_BETA, global_batch=BATCH * world, graph=args.graph)
@@ -196,44 +250,84 @@ def run_ours(args):
     corpus = synth_corpus(args.files, args.seconds)
     audio = torch.from_numpy(corpus).to(dev)
     n_frames = (len(corpus) + HOP - 1) // HOP - S // HOP + 1
-    total_steps = args.warmup + args.steps
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    frame_idx = torch.randint(0, n_frames, (total_steps, BATCH), generator=g, device=dev, dtype=torch.int64)
-    total_steps_e2e = total_steps
 
-    # batch i as a FrameBatch; step i also hands the step function batch i + 1, which it gathers (and draws the noise
-    # for) on its background stream while the GEMMs of step i run - the device-side analogue of a DataLoader that
-    # prefetches the next batch
-    batches = [FrameBatch(audio, BATCH, HOP, S, frame_idx=frame_idx[i]) for i in range(total_steps)]
+    # Steady state before anything is timed. A CUDA-graph step function captures one graph per input signature after
+    # one eager call of that signature, and the pipelined signature contains the parity of the plan's double-buffered
+    # input set: eager, eager, capture, capture, then replays. The untimed pre-steps therefore run for at least
+    # --warmup steps AND until NEED consecutive steps were plain replays; the timed blocks assert that no capture and
+    # no eager step happened inside them.
+    NEED = 4
+    pre_steps = max(args.warmup, 2 * step_fn.graph_warmup + 2 + NEED) if args.graph else args.warmup
+    est_ms = 0.35 if args.precision == "bf16" else 1.0
+    n_blocks = args.blocks if args.blocks > 0 else int(min(200, max(7, math.ceil(300.0 / (args.steps * est_ms)))))
+
+    # batch i = a fresh random 8192-frame gather; a pool of index sets is cycled (the pool's footprint is far larger
+    # than L2). Step i also hands the step function batch i + 1, which it gathers (and draws the noise for) on its
+    # background stream while the GEMMs of step i run - the device-side analogue of a prefetching DataLoader.
+    pool = min(256, pre_steps + n_blocks * args.steps + 1)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    frame_idx = torch.randint(0, n_frames, (pool, BATCH), generator=g, device=dev, dtype=torch.int64)
+    batches = [FrameBatch(audio, BATCH, HOP, S, frame_idx=frame_idx[i]) for i in range(pool)]
 
     def device_step(i):
-        nxt = batches[i + 1] if (args.prefetch and i + 1 < total_steps) else None
-        return step_fn(batches[i], next_data=nxt)
+        nxt = batches[(i + 1) % pool] if args.prefetch else None
+        return step_fn(batches[i % pool], next_data=nxt)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def settle(step_once, i):
+        """untimed pre-steps; returns the next step index"""
+        for _ in range(pre_steps):
+            step_once(i)
+            i += 1
+        if args.graph and step_fn.steady < NEED:
+            raise RuntimeError(f"graph replay not steady after {pre_steps} pre-steps: {step_fn.stats}")
+        return i
+
+    def timed_blocks(step_once, i, end_of_block=None):
+        """n_blocks blocks of EXACTLY --steps steps, each bracketed by barrier + synchronize; block times are the
+        max over ranks. Returns (block ms list, next step index, last loss, stats delta)."""
+        s0 = dict(step_fn.stats)
+        times, loss = [], None
+        for _ in range(n_blocks):
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                loss = step_once(i)
+                i += 1
+            if end_of_block is not None:
+                end_of_block()
+            e1.record()
+            barrier()
+            times.append(e0.elapsed_time(e1))
+        t = torch.tensor(times, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        delta = {k: step_fn.stats[k] - s0[k] for k in s0}
+        return [float(v) for v in t.cpu()], i, loss, delta
 
     # ---- value: inputs resident in HBM, whole step = framing + fwd + loss + bwd (+ allreduce) + Adam
-    for i in range(args.warmup):
-        device_step(i)
+    i = settle(device_step, 0)
     barrier()
-    clocks = ClockSampler(local_rank)
+    if world > 1:   # data parallelism kept the replicas bit-identical through the pre-steps (checked once, untimed)
+        ref_params = model._flat.params.clone()
+        dist.broadcast(ref_params, src=0)
+        same = torch.tensor([int(torch.equal(ref_params, model._flat.params))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert int(same) == 1, "data-parallel replicas diverged"
+        del ref_params
+    clocks = NvmlSampler(dev)
     if rank == 0:
         clocks.start()
     l0 = ops.launch_count(dev) + step_fn.replayed_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.warmup, total_steps):
-        loss = device_step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    block_ms, i, loss, delta = timed_blocks(device_step, i)
     launches = ops.launch_count(dev) + step_fn.replayed_launches - l0   # eager launches + kernels inside graph replays
     clk = clocks.stop() if rank == 0 else None
     last_loss = float(loss)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
+    ms = float(np.median(block_ms))
     value = BATCH * world * args.steps / (ms * 1e-3)
+    if args.graph:
+        assert delta["captures"] == 0 and delta["eager"] == 0, f"capture / eager step inside the timed region: {delta}"
 
     # ---- e2e: HOST buffers. Every step the host supplies the next chunk of the wav stream from pinned memory
     # (train_iterable.py's streaming pattern: 8192 consecutive frames at hop 128 = 1 049 472 samples), the GPU
@@ -241,7 +335,8 @@ def run_ours(args):
     chunk = (BATCH - 1) * HOP + S
     n_chunks = max(1, (len(corpus) - chunk) // (BATCH * HOP))
     host_audio = torch.from_numpy(corpus).pin_memory()
-    host_loss = torch.zeros(total_steps, dtype=torch.float32).pin_memory()
+    n_e2e = pre_steps + n_blocks * args.steps
+    host_loss = torch.zeros(n_e2e, dtype=torch.float32).pin_memory()
     dbuf = [torch.empty(chunk, dtype=torch.float32, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)     # loss read-back: off the compute stream, so it never delays a step
@@ -263,37 +358,31 @@ def run_ours(args):
 
     pending = {}
 
-    def e2e_step(i):
-        cur = pending.pop(i, None) or issue_copy(i)
+    def e2e_step(j):
+        cur = pending.pop(j, None) or issue_copy(j)
         nxt = None
-        if args.prefetch and i + 1 < total_steps_e2e:
-            nxt = pending[i + 1] = issue_copy(i + 1)     # its frames are gathered in the background of step i
+        if args.prefetch:
+            nxt = pending[j + 1] = issue_copy(j + 1)     # its frames are gathered in the background of step j
         loss = step_fn(cur, next_data=nxt)
-        freed[(i + 1) % 2 if nxt is not None else i % 2].record(main)           # that buffer has been gathered
-        ev = step_done[i % 4]
+        freed[(j + 1) % 2 if nxt is not None else j % 2].record(main)           # that buffer has been gathered
+        ev = step_done[j % 4]
         ev.record(main)
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(ev)
-            host_loss[i].copy_(loss, non_blocking=True)                         # D2H read of the step's result
+            host_loss[j % n_e2e].copy_(loss, non_blocking=True)                 # D2H read of the step's result
         return loss
 
     for b in range(2):
         freed[b].record(main)
-    for i in range(args.warmup):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(args.warmup, total_steps):
-        e2e_step(i)
-    main.wait_stream(d2h_stream)          # the timed region ends when the last loss has reached the host buffer
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t)
+    j = settle(e2e_step, 0)
+    # a block ends when its last loss has reached the host buffer
+    e2e_block_ms, j, _, e2e_delta = timed_blocks(e2e_step, j, end_of_block=lambda: main.wait_stream(d2h_stream))
+    e2e_ms = float(np.median(e2e_block_ms))
     e2e_value = BATCH * world * args.steps / (e2e_ms * 1e-3)
+    torch.cuda.synchronize()
     assert np.isfinite(host_loss.numpy()).all()
+    if args.graph:
+        assert e2e_delta["captures"] == 0 and e2e_delta["eager"] == 0, f"capture / eager step in the e2e region: {e2e_delta}"
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMMs), timed live with CUDA events on the launch stream
     roofline, breakdown = None, None
@@ -302,8 +391,8 @@ def run_ours(args):
         plan.enable_timing(True)
         nroof = min(args.steps, 20)
         local_step = FusedTrainStep(model, opt, KL_BETA)   # no collectives: only rank 0 runs this attribution pass
-        for i in range(nroof):
-            local_step(FrameBatch(audio, BATCH, HOP, S, frame_idx=frame_idx[args.warmup + i]))
+        for k in range(nroof):
+            local_step(batches[k % pool])
         torch.cuda.synchronize()
         tm_all = plan.read_timing()
         plan.enable_timing(False)
@@ -313,19 +402,23 @@ def run_ours(args):
         flops = sum(v[1] * v[2] for v in tm.values()) / nroof
         passes = 3 if args.precision == "fp32" else 1
         achieved = flops / (gemm_ms * 1e-3) / 1e12
-        peak = peaks["bf16_sustained"]
+        # the attribution pass times each GEMM launch ALONE (events serialise the stream, ~10 ms in total): that is
+        # a burst measurement, so the denominator is the measured burst peak
+        peak = peaks["bf16_burst"]
         traffic, traffic_src = None, None
-        ncu_json = ROOT / "profiles" / "r1_gemms_ncu.json"     # dram__bytes_read + write of the 11 GEMMs, one ncu capture
-        if ncu_json.exists() and args.precision == "bf16":
-            try:
-                traffic = json.loads(ncu_json.read_text())["dram_bytes_per_step"]
-                traffic_src = "profiles/r1_gemms_ncu.json (ncu --set full, sum over the 11 GEMM launches of a step)"
-            except Exception:
-                traffic = None
+        for name in ("r2_gemms_ncu.json", "r1_gemms_ncu.json"):   # dram__bytes_read + write of the 11 GEMMs, one ncu capture
+            ncu_json = ROOT / "profiles" / name
+            if ncu_json.exists() and args.precision == "bf16":
+                try:
+                    traffic = json.loads(ncu_json.read_text())["dram_bytes_per_step"]
+                    traffic_src = f"profiles/{name} (ncu --set full, sum over the 11 GEMM launches of a step)"
+                    break
+                except Exception:
+                    traffic = None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src,
                     "kernel": "rvae::gemm_kernel<*> (11 GEMMs/step; the training step fuses 6 of them into 3 launches)",
-                    "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
+                    "peak_kind": f"bf16_tflops burst ({peaks['source']}): each launch timed alone",
                     "algorithmic_flops_per_step": flops, "gemm_ms_per_step": gemm_ms,
                     "tensor_passes": passes}
         breakdown = {k: {"us": 1e3 * v[0] / max(v[1], 1), "tflops": (v[2] / (v[0] / max(v[1], 1) * 1e-3) / 1e12)
@@ -345,7 +438,7 @@ def run_ours(args):
 
     if rank == 0:
         ms_per_step = ms / args.steps
-        frac_of_peak = value * FLOP_PER_FRAME / world / 1e12 / peaks["bf16_sustained"]
+        whole_tflops = value * FLOP_PER_FRAME / world / 1e12
         out = {
             "metric": "train frames/sec (fwd+bwd+Adam)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -356,7 +449,13 @@ def run_ours(args):
                        "l2": "per-step working set ~330 MB (activations + weights + moments) exceeds the 126 MB L2; "
                              "a different random 8192-frame gather from a %.0f MB corpus every step" % (corpus.nbytes / 1e6),
                        "corpus": f"{args.files} files x {args.seconds:.0f} s, 0.5*sin+0.05*noise, rng 1234"},
-            "frac_of_bf16_peak_whole_step": frac_of_peak,
+            "timing": {"blocks": n_blocks, "steps_per_block": args.steps, "statistic": "median block, max over ranks",
+                       "pre_steps_untimed": pre_steps, "block_ms": [round(v, 4) for v in block_ms],
+                       "captures_in_timed_region": delta["captures"], "eager_steps_in_timed_region": delta["eager"],
+                       "graph_replays_in_timed_region": delta["replays"],
+                       "e2e_block_ms": [round(v, 4) for v in e2e_block_ms],
+                       "e2e_captures_in_timed_region": e2e_delta["captures"],
+                       "e2e_eager_steps_in_timed_region": e2e_delta["eager"]},
             "final_loss": last_loss,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": chunk * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps,
@@ -364,6 +463,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roofline,
+            "roofline_whole_step": {"bound": "tensor", "achieved": whole_tflops, "peak": peaks["bf16_sustained"],
+                                    "unit": "TFLOP/s", "frac": whole_tflops / peaks["bf16_sustained"],
+                                    "frac_of_burst": whole_tflops / peaks["bf16_burst"],
+                                    "peak_kind": f"bf16_tflops_sustained ({peaks['source']}): whole step incl. framing, "
+                                                 "loss, Adam" + (", all-reduce" if world > 1 else "")},
             "gemm_breakdown": breakdown,
             "cpu_baseline": cpu_baseline,
         }
@@ -384,6 +488,8 @@ def main():
     ap.add_argument("--files", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocks", type=int, default=0,
+                    help="timed blocks of --steps steps each (median reported); 0 = enough for >= 0.3 s of load, >= 7")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every step eagerly (no CUDA graph)")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="every step gathers its own batch (no background prefetch of the next one)")

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RVAE_ABI_VERSION 2
+#define RVAE_ABI_VERSION 3
 
 typedef struct rvae_ctx rvae_ctx;   /* per-device context (SM count, launch counter) */
 typedef struct rvae_plan rvae_plan; /* a bound training / inference step for fixed shapes and buffers */
@@ -43,6 +43,9 @@ typedef struct rvae_plan rvae_plan; /* a bound training / inference step for fix
 #define RVAE_PRECISION_FP32 1 /* split-bf16 (hi+lo) operands, 3 tensor-core passes, ~2^-16 relative */
 
 int rvae_abi_version(void);
+/* 1 when the library was built with -DRVAE_EXPERIMENTS=1 (measured-and-rejected paths: chained forward launch,
+ * fused latent epilogue, GEMM debug modes); 0 for the default build, which contains none of them. */
+int rvae_build_experiments(void);
 const char* rvae_last_error(void);
 
 int rvae_ctx_create(int device, rvae_ctx** out);
@@ -75,6 +78,11 @@ int rvae_dp_sym_alloc(rvae_ctx* ctx, size_t data_bytes, void** data_ptr, void* i
  * otherwise. What rvae_plan_train_step issues per gradient bucket. */
 int rvae_dp_allreduce(rvae_ctx* ctx, float* ptr, int64_t count, int bucket, void* stream);
 int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world);
+/* Health of the peer-memory all-reduce. Its barriers wait for a slower peer for RVAE_P2P_TIMEOUT_S seconds (default
+ * 600) and never trap; the first wait that gives up records bit 31 | peer << 8 | flag set << 4 | phase here, and every
+ * later wait falls through at once, so the process stays alive and the host can report the failure. 0 = healthy.
+ * Synchronous 4-byte read: call it where the host synchronises anyway (loss read-back, checkpoints). */
+int rvae_dp_status(rvae_ctx* ctx, unsigned int* status);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Framing and resynthesis (rawvae/dataset.py)
@@ -99,8 +107,19 @@ int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S
  * Elementwise pieces of the model / loss / optimizer
  * ------------------------------------------------------------------------------------------------------- */
 
-/* eps ~ N(0,1), Philox4x32-10 + Box-Muller keyed by (seed, offset). Replaces torch.randn_like (model.py:25). */
-int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* eps ~ N(0,1), Philox4x32-10 + Box-Muller keyed by (seed, offset). Replaces torch.randn_like (model.py:25).
+ * out[i] is element (elem_base + i) of the logical noise tensor of that (seed, offset): a rank that owns rows
+ * [r0, r1) of a global [B, L] batch passes elem_base = r0 * L (a multiple of 4) and draws exactly the values a
+ * single process would have drawn for those rows. */
+int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, int64_t elem_base, void* stream);
+
+/* Latent interpolation of the inference pattern (tutorial.ipynb:496-510, 905-932): per row r,
+ *   mu = (1 - alpha[r]) mu_a + alpha[r] mu_b, logvar likewise, z = mu + eps * exp(logvar / 2)   (eps NULL = 0).
+ * alpha: `rows` floats, or doubles when alpha_is_f64 (the notebook's interp1d output); the lerp is then carried out
+ * in double. Outputs (each may be NULL, not all): z, mu_out, logvar_out, fp32 [rows, L]. */
+int rvae_lerp_reparameterize(rvae_ctx* ctx, const float* mu_a, const float* logvar_a, const float* mu_b,
+                             const float* logvar_b, const void* alpha, int alpha_is_f64, const float* eps,
+                             int64_t rows, int L, float* z, float* mu_out, float* logvar_out, void* stream);
 
 /* fp32 -> bf16 planes (hi, optional lo). Used for weight shadows and fp32 inputs. */
 int rvae_split_bf16(rvae_ctx* ctx, const float* src, int64_t n, void* hi, void* lo, void* stream);
@@ -232,6 +251,10 @@ int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* strea
  * CUDA graph draws fresh noise on every replay. */
 int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream);
 int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_step, void* stream);
+/* Data parallelism: this rank's shard starts at row `first_global_row` of the global batch. The noise of
+ * rvae_plan_gen_eps / rvae_plan_prefetch_frames is then drawn from Philox counters first_global_row * L onwards, so
+ * with the SAME seed on every rank the shards' noise is disjoint and equal to the single-process draw. */
+int rvae_plan_set_noise_rows(rvae_plan* plan, int64_t first_global_row);
 
 /* Redirect the fp32 results of the next forward calls into caller tensors ([batch,L], [batch,L], [batch,S]);
  * NULL = keep them in the workspace. Used by the autograd wrapper so returned tensors outlive the step. */
@@ -339,6 +362,12 @@ int rvae_debug_set_aux_trace(rvae_ctx* ctx, void* buf, int launches);
 
 /* Inference: decode latents z (fp32 [batch, L]) -> xhat fp32 [batch, S] (model.py:28-30). */
 int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out, void* stream);
+/* Inference, interpolation pattern (tutorial.ipynb:496-510, 905-932) as one chained enqueue: lerp of two latent
+ * distributions with one alpha per frame -> reparameterize -> decode. z is written straight into fc3's bf16 operand
+ * (no fp32 z round trip); arguments as rvae_lerp_reparameterize, xhat_out fp32 [batch, S]. */
+int rvae_plan_decode_lerp(rvae_plan* plan, const float* mu_a, const float* logvar_a, const float* mu_b,
+                          const float* logvar_b, const void* alpha, int alpha_is_f64, const float* eps, int batch,
+                          float* xhat_out, void* stream);
 /* Inference: encode the loaded batch -> mu, logvar (model.py:19-21); results via rvae_plan_mu/logvar. */
 int rvae_plan_encode(rvae_plan* plan, void* stream);
 

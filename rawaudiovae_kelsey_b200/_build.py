@@ -26,6 +26,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
+if os.environ.get("RVAE_EXPERIMENTS", "0") not in ("", "0"):
+    NVCC_FLAGS.append("-DRVAE_EXPERIMENTS=1")   # measured-and-rejected paths (csrc/gemm.cuh); part of the fingerprint
 
 
 def _nvcc() -> str:
@@ -49,11 +51,26 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link librvae_b200.so. Returns the library path."""
+    """Compile every CUDA source for sm_100a and link librvae_b200.so. Returns the library path.
+    Safe under torchrun: an inter-process file lock serialises concurrent first-use builds (the ranks that lose the
+    race find an up-to-date library when they get the lock) and the library is linked to a temporary name and moved
+    into place atomically, so nobody can dlopen a half-written file."""
     if not force and not needs_build():
         return LIB_PATH
-    nvcc = _nvcc()
+    import fcntl
     BUILD_DIR.mkdir(exist_ok=True)
+    with open(BUILD_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
+    nvcc = _nvcc()
 
     def compile_one(src: str) -> Path:
         obj = BUILD_DIR / (Path(src).stem + ".o")
@@ -68,10 +85,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static", "-ldl"]
+    tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB_PATH)
     (BUILD_DIR / "fingerprint").write_text(_fingerprint())
     return LIB_PATH
 

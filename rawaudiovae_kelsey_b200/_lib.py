@@ -13,6 +13,7 @@ from . import _build
 
 _LIB = None
 _LOCK = threading.Lock()
+ABI_VERSION = 3
 
 c_void_p, c_int, c_int64, c_uint64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 
@@ -34,6 +35,7 @@ class PlanBuffers(C.Structure):
 P = c_void_p
 SIGNATURES = {
     "rvae_abi_version": (c_int, []),
+    "rvae_build_experiments": (c_int, []),
     "rvae_last_error": (C.c_char_p, []),
     "rvae_ctx_create": (c_int, [c_int, C.POINTER(P)]),
     "rvae_ctx_destroy": (None, [P]),
@@ -47,7 +49,11 @@ SIGNATURES = {
     "rvae_dp_allreduce": (c_int, [P, P, c_int64, c_int, P]),
     "rvae_frame_gather": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, P, P]),
     "rvae_overlap_add": (c_int, [P, P, c_int64, c_int, c_int, P, c_int64, P]),
-    "rvae_randn": (c_int, [P, P, c_int64, c_uint64, c_uint64, P]),
+    "rvae_randn": (c_int, [P, P, c_int64, c_uint64, c_uint64, c_int64, P]),
+    "rvae_lerp_reparameterize": (c_int, [P, P, P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P]),
+    "rvae_dp_status": (c_int, [P, C.POINTER(C.c_uint)]),
+    "rvae_plan_set_noise_rows": (c_int, [P, c_int64]),
+    "rvae_plan_decode_lerp": (c_int, [P, P, P, P, P, P, c_int, P, c_int, P, P]),
     "rvae_split_bf16": (c_int, [P, P, c_int64, P, P, P]),
     "rvae_reparameterize": (c_int, [P, P, P, P, c_int64, P, P]),
     "rvae_loss_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_float, P, P, P]),
@@ -108,6 +114,15 @@ def library_path() -> Path:
     return _build.LIB_PATH
 
 
+def _stale() -> bool:
+    """The library exists but was built from other sources (fingerprint mismatch) and can be rebuilt here. Where the
+    sources or nvcc are unavailable (a deployed copy), the existing library is used as it is."""
+    try:
+        return _build.needs_build() and bool(_build._nvcc())
+    except Exception:
+        return False
+
+
 def load(build_if_missing: bool = True):
     """Load librvae_b200.so (building it in-tree with nvcc if it is absent). Raises if that is impossible."""
     global _LIB
@@ -117,9 +132,11 @@ def load(build_if_missing: bool = True):
         if _LIB is not None:
             return _LIB
         path = library_path()
-        if not path.exists():
+        stale = path.exists() and _stale()
+        if not path.exists() or stale:
             if not build_if_missing:
-                raise RvaeError(f"{path} is missing: the CUDA extension has not been built (no CPU fallback exists)")
+                raise RvaeError(f"{path} is {'stale' if stale else 'missing'}: the CUDA extension has not been built "
+                                "(no CPU fallback exists)")
             _build.build()
         lib = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
@@ -127,8 +144,8 @@ def load(build_if_missing: bool = True):
             fn.restype = res
             fn.argtypes = args
         got = lib.rvae_abi_version()
-        if got != 2:
-            raise RvaeError(f"librvae_b200 ABI version {got}, expected 2")
+        if got != ABI_VERSION:
+            raise RvaeError(f"librvae_b200 ABI version {got}, expected {ABI_VERSION}")
         _LIB = lib
     return _LIB
 

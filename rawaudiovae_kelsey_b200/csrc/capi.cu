@@ -53,6 +53,7 @@ static inline __nv_bfloat16* BF(void* p) { return reinterpret_cast<__nv_bfloat16
 extern "C" {
 
 int rvae_abi_version(void) { return RVAE_ABI_VERSION; }
+int rvae_build_experiments(void) { return RVAE_EXPERIMENTS; }
 const char* rvae_last_error(void) { return rvae::last_error(); }
 
 int rvae_ctx_create(int device, rvae_ctx** out) {
@@ -211,10 +212,18 @@ int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world) {
     ctx->p2p.data[p] = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + kP2PFlagBytes);
   }
   // local: epochs and tickets behind the flag table
-  static_assert(kP2PMaxBuckets * kP2PMaxCtas * kP2PMaxWorld * kP2PFlagStride * 4 + 2 * kP2PMaxBuckets * 4 <= kP2PFlagBytes,
+  static_assert(kP2PMaxBuckets * kP2PMaxCtas * kP2PMaxWorld * kP2PFlagStride * 4 + 2 * kP2PMaxBuckets * 4 + 4 <= kP2PFlagBytes,
                 "flag area");
   ctx->p2p.epoch = reinterpret_cast<uint32_t*>(ctx->sym_base) + kP2PMaxBuckets * kP2PMaxCtas * kP2PMaxWorld * kP2PFlagStride;
   ctx->p2p.ticket = ctx->p2p.epoch + kP2PMaxBuckets;
+  ctx->p2p.status = ctx->p2p.ticket + kP2PMaxBuckets;
+  {  // how long a barrier waits for a peer before it records a failure (never a trap): minutes, in SM clocks
+    double seconds = 600.0;
+    if (const char* e = getenv("RVAE_P2P_TIMEOUT_S")) seconds = atof(e) > 0 ? atof(e) : seconds;
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->c.device) != cudaSuccess || khz <= 0) khz = 1965000;
+    ctx->p2p.timeout_cycles = static_cast<long long>(seconds * 1e3 * khz);
+  }
   ctx->p2p.rank = rank;
   ctx->p2p.world = world;
   ctx->p2p.mode = 1;
@@ -222,6 +231,14 @@ int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world) {
   ctx->dp_rank = rank;
   ctx->dp_world = world;
   ctx->p2p_ready = true;
+  return RVAE_OK;
+}
+int rvae_dp_status(rvae_ctx* ctx, unsigned int* status) {
+  RVAE_REQUIRE(ctx && status, RVAE_ERR_INVALID, "dp_status: null argument");
+  *status = 0;
+  if (!ctx->p2p_ready) return RVAE_OK;
+  // (synchronous 4-byte read on the legacy stream: call it where the host synchronises anyway - a loss read-back)
+  RVAE_CUDA(cudaMemcpy(status, ctx->p2p.status, sizeof(unsigned int), cudaMemcpyDeviceToHost));
   return RVAE_OK;
 }
 int rvae_ctx_num_sms(const rvae_ctx* ctx) { return ctx ? ctx->c.num_sms : 0; }
@@ -261,9 +278,17 @@ int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S
   CTX_OR_FAIL(ctx);
   return launch_overlap_add(&ctx->c, frames, n_frames, S, hop, out, n_out, S_(stream));
 }
-int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, int64_t elem_base,
+               void* stream) {
   CTX_OR_FAIL(ctx);
-  return launch_randn(&ctx->c, out, n, seed, offset, nullptr, S_(stream));
+  return launch_randn(&ctx->c, out, n, seed, offset, nullptr, elem_base, S_(stream));
+}
+int rvae_lerp_reparameterize(rvae_ctx* ctx, const float* mu_a, const float* logvar_a, const float* mu_b,
+                             const float* logvar_b, const void* alpha, int alpha_is_f64, const float* eps,
+                             int64_t rows, int L, float* z, float* mu_out, float* logvar_out, void* stream) {
+  CTX_OR_FAIL(ctx);
+  return launch_lerp_reparam(&ctx->c, mu_a, logvar_a, mu_b, logvar_b, alpha, alpha_is_f64, eps, rows, L, z, nullptr,
+                             nullptr, mu_out, logvar_out, S_(stream));
 }
 int rvae_split_bf16(rvae_ctx* ctx, const float* src, int64_t n, void* hi, void* lo, void* stream) {
   CTX_OR_FAIL(ctx);
@@ -489,12 +514,15 @@ struct rvae_plan {
     int ready_batch;       // > 0: the alternate set holds this many frames (+ their noise), enqueued by a train step
     const void* audio; int audio_is_i16; int64_t n_samples; const int64_t* frame_idx; int64_t first_frame;
     int count, hop; uint64_t seed, offset; int add_step;
+    int64_t noise_row0;    // plan->noise_row0 at registration time (the shard of the NEXT global batch)
   } pf;
   double* loss_acc;
   // redirected outputs
   float *out_mu, *out_lv, *out_xhat;
   int batch;        // current batch
   int64_t global_batch;  // loss normalisation under data parallelism (0 = local batch)
+  int64_t noise_row0;    // first row of this rank's shard in the global batch: Philox counters start at row0 * L, so
+                         // the ranks draw disjoint pieces of the single-process noise tensor (0 = single process)
   bool dp_enabled;       // rvae_plan_enable_dp: this plan's train steps all-reduce their gradients
   float kl_c0;           // kl_beta / (B L) of the last fused-loss forward (KL gradient scale of the latent backward)
   bool dz_zeroed;        // the split-K latent dgrad accumulator holds zeros (left so by the latent backward kernel)
@@ -957,7 +985,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   rvae_plan* p = new (std::nothrow) rvae_plan();
   RVAE_REQUIRE(p, RVAE_ERR_INVALID, "plan_create: out of host memory");
   p->ctx = ctx; p->S = S; p->H = H; p->L = L; p->max_batch = max_batch; p->precision = precision;
-  p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0;
+  p->lay = lay; p->bound = false; p->batch = 0; p->have_eps = false; p->global_batch = 0; p->noise_row0 = 0;
   p->timing = false;
   p->kl_c0 = 0.f; p->dz_zeroed = false; p->dp_enabled = false;
   p->cur = 0; p->ticket_zeroed = false; p->ticket = nullptr;
@@ -973,8 +1001,10 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
   p->fuse_forward = false;  // measured: no faster than the four separate launches (profiles/README.md); opt-in
+#if RVAE_EXPERIMENTS
   if (const char* e = getenv("RVAE_FUSE_LATENT")) p->fuse_latent = atoi(e) != 0;
   if (const char* e = getenv("RVAE_FUSE_FORWARD")) p->fuse_forward = atoi(e) != 0;
+#endif
   p->dual_pairs = ctx->c.num_sms / 2;
   if (const char* e = getenv("RVAE_DUAL_PAIRS")) {
     const int v = atoi(e);
@@ -1123,14 +1153,14 @@ int rvae_plan_gen_eps(rvae_plan* plan, uint64_t seed, uint64_t offset, int add_s
     RVAE_CUDA(cudaEventRecord(plan->ev_fork, st));
     RVAE_CUDA(cudaStreamWaitEvent(plan->adam_stream, plan->ev_fork, 0));
     RVAE_CHECK(launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset,
-                            add_step ? plan->bufs.step : nullptr, plan->adam_stream));
+                            add_step ? plan->bufs.step : nullptr, plan->noise_row0 * plan->L, plan->adam_stream));
     RVAE_CUDA(cudaEventRecord(plan->ev_eps, plan->adam_stream));
     plan->eps_pending = true;
     return RVAE_OK;
   }
   TimedScope ts(plan, T_EPS, st);
   return launch_randn(&plan->ctx->c, plan->eps, (int64_t)plan->batch * plan->L, seed, offset,
-                      add_step ? plan->bufs.step : nullptr, st);
+                      add_step ? plan->bufs.step : nullptr, plan->noise_row0 * plan->L, st);
 }
 
 int rvae_plan_set_outputs(rvae_plan* plan, float* mu, float* logvar, float* xhat) {
@@ -1150,6 +1180,12 @@ int rvae_plan_enable_dp(rvae_plan* plan, int on) {
     plan->sched_batch = 0;
   }
   plan->dp_enabled = on != 0;
+  return RVAE_OK;
+}
+
+int rvae_plan_set_noise_rows(rvae_plan* plan, int64_t first_global_row) {
+  RVAE_REQUIRE(plan && first_global_row >= 0, RVAE_ERR_INVALID, "plan_set_noise_rows: bad argument");
+  plan->noise_row0 = first_global_row;
   return RVAE_OK;
 }
 
@@ -1299,6 +1335,7 @@ int rvae_plan_prefetch_frames(rvae_plan* plan, const void* audio, int audio_is_i
   rvae_plan::Prefetch& f = plan->pf;
   f.audio = audio; f.audio_is_i16 = audio_is_i16; f.n_samples = n_samples; f.frame_idx = frame_idx;
   f.first_frame = first_frame; f.count = count; f.hop = hop; f.seed = seed; f.offset = offset; f.add_step = add_step;
+  f.noise_row0 = plan->noise_row0;
   f.registered = true;
   return RVAE_OK;
 }
@@ -1390,7 +1427,7 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
                                    f.hop, p->S, p->x_alt.hi, p->x_alt.lo, nullptr, bg));
     // the consumer sees a step counter advanced by one
     RVAE_CHECK(launch_randn(&p->ctx->c, p->eps_alt, (int64_t)f.count * p->L, f.seed, f.offset + (f.add_step ? 1 : 0),
-                            f.add_step ? b.step : nullptr, bg));
+                            f.add_step ? b.step : nullptr, f.noise_row0 * p->L, bg));
     p->pf.ready_batch = f.count;
     p->pf.registered = false;
     return RVAE_OK;
@@ -1536,6 +1573,29 @@ int rvae_plan_decode(rvae_plan* plan, const float* z, int batch, float* xhat_out
   p->batch = batch;
   p->have_eps = false;
   RVAE_CHECK(launch_split_bf16(&p->ctx->c, z, (int64_t)batch * p->L, p->z.hi, p->z.lo, st));
+  RVAE_CHECK(run(p, G_F3, st));
+  GemmSet* gs;
+  RVAE_CHECK(get_set(p, &gs));
+  RVAE_CHECK(prepare(p, *gs, G_F4_LIN));
+  EpiArgs a = gs->g[G_F4_LIN].params.epi;
+  a.out_f32 = xhat_out;
+  return run(p, G_F4_LIN, st, &a);
+}
+
+int rvae_plan_decode_lerp(rvae_plan* plan, const float* mu_a, const float* logvar_a, const float* mu_b,
+                          const float* logvar_b, const void* alpha, int alpha_is_f64, const float* eps, int batch,
+                          float* xhat_out, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(mu_a && logvar_a && mu_b && logvar_b && alpha && xhat_out, RVAE_ERR_INVALID, "plan_decode_lerp: null buffer");
+  RVAE_REQUIRE(batch > 0 && batch <= plan->max_batch, RVAE_ERR_INVALID, "plan_decode_lerp: batch %d not in 1..%d", batch,
+               plan->max_batch);
+  rvae_plan* p = plan;
+  cudaStream_t st = S_(stream);
+  p->batch = batch;
+  p->have_eps = false;
+  // interpolated latents -> z written straight into fc3's bf16 operand planes (no fp32 z, no split pass)
+  RVAE_CHECK(launch_lerp_reparam(&p->ctx->c, mu_a, logvar_a, mu_b, logvar_b, alpha, alpha_is_f64, eps, batch, p->L, nullptr,
+                                 p->z.hi, p->z.lo, nullptr, nullptr, st));
   RVAE_CHECK(run(p, G_F3, st));
   GemmSet* gs;
   RVAE_CHECK(get_set(p, &gs));

@@ -153,7 +153,7 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
 int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
                        cudaStream_t stream);
 int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, const float* offset_src,
-                 cudaStream_t stream);
+                 int64_t elem_base, cudaStream_t stream);
 int launch_split_bf16(Ctx* ctx, const float* src, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,
                       cudaStream_t stream);
 int launch_colsum(Ctx* ctx, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t M, int N, int ld, float* out,
@@ -167,6 +167,9 @@ int launch_tanh_bwd(Ctx* ctx, const float* g_xhat, const float* xhat, int64_t n,
                     __nv_bfloat16* da_lo, cudaStream_t stream);
 int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps, int64_t n, float* z,
                    cudaStream_t stream);
+int launch_lerp_reparam(Ctx* ctx, const float* mu_a, const float* lv_a, const float* mu_b, const float* lv_b,
+                        const void* alpha, int alpha_is_f64, const float* eps, int64_t rows, int L, float* z_f32,
+                        __nv_bfloat16* z_hi, __nv_bfloat16* z_lo, float* mu_out, float* lv_out, cudaStream_t stream);
 int launch_loss_finalize(Ctx* ctx, double* acc, int64_t B, int S, int L, float beta, float* loss_out, int ring_size,
                          float* step, cudaStream_t stream);
 int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
@@ -189,6 +192,8 @@ struct P2PArgs {
   uint32_t* flags[kP2PMaxWorld];   // flag area of rank p
   uint32_t* epoch;                 // local: [kP2PMaxBuckets]
   unsigned int* ticket;            // local: [kP2PMaxBuckets]
+  uint32_t* status;                // local: 0 = healthy; else the first barrier timeout (bit 31 | peer << 8 | bucket << 4 | phase)
+  long long timeout_cycles;        // SM clocks a barrier waits for a peer before it gives up (minutes, RVAE_P2P_TIMEOUT_S)
   int rank, world;
   int mode;                        // barrier flavour (experiments: RVAE_P2P_MODE)
 };

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the hot path: framing / overlap-add, Philox normal noise, bf16 plane splitting,
 // bias-gradient column sums, the fused reparameterisation + reconstruction/KL loss kernels, and fused Adam.
 // All are coalesced, 128-bit vectorised, grid-strided with grids sized in multiples of the SM count.
+#include <cstdlib>
+
 #include "common.h"
 
 namespace rvae {
@@ -61,64 +63,83 @@ __global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_sa
   aux_begin(tr, 1);
   const int vec_per_frame = S >> 3;
   const int64_t total = n_frames * vec_per_frame;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t f = i / vec_per_frame;
-    const int c = static_cast<int>(i - f * vec_per_frame) << 3;
-    const int64_t fi = frame_idx ? frame_idx[f] : first_frame + f;
-    const int64_t s0 = fi * hop + c;
-    float v[8];
-    if (s0 + 8 <= n_samples && s0 >= 0) {
+  // U groups of 8 samples per thread and trip: the U frame indices are fetched first, then all 2 U 16-byte loads are
+  // issued before the first convert / store, so each thread keeps U x 32 bytes of dependent-address loads in flight
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    int64_t fr[U], s0[U];
+    int col[U];
+    bool fast[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      fr[u] = i < total ? i / vec_per_frame : -1;
+      col[u] = fr[u] >= 0 ? static_cast<int>(i - fr[u] * vec_per_frame) << 3 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t fi = fr[u] < 0 ? 0 : (frame_idx ? __ldg(frame_idx + fr[u]) : first_frame + fr[u]);
+      s0[u] = fi * hop + col[u];
+      // 16-byte aligned source address (the buffer base may itself be an unaligned view of a longer stream)
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(audio) + static_cast<uintptr_t>(s0[u]) * (I16 ? 2 : 4);
+      fast[u] = fr[u] >= 0 && s0[u] >= 0 && s0[u] + 8 <= n_samples && (addr & 15) == 0;
+    }
+    float v[U][8];
+    uint4 raw[U][2];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!fast[u]) continue;
       if constexpr (I16) {
-        const int16_t* a = reinterpret_cast<const int16_t*>(audio) + s0;
-        if ((s0 & 7) == 0) {
-          const uint4 t = __ldg(reinterpret_cast<const uint4*>(a));
-          const int16_t* h = reinterpret_cast<const int16_t*>(&t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = h[j] * (1.0f / 32768.0f);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __ldg(a + j) * (1.0f / 32768.0f);
-        }
+        raw[u][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const int16_t*>(audio) + s0[u]));
       } else {
-        const float* a = reinterpret_cast<const float*>(audio) + s0;
-        if ((s0 & 3) == 0) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(a));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(a) + 1);
-          v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
-          v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+        const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(audio) + s0[u]);
+        raw[u][0] = __ldg(a);
+        raw[u][1] = __ldg(a + 1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (fr[u] < 0) continue;
+      if (fast[u]) {
+        if constexpr (I16) {
+          const int16_t* h = reinterpret_cast<const int16_t*>(&raw[u][0]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = h[j] * (1.0f / 32768.0f);
         } else {
+          const float* f = reinterpret_cast<const float*>(&raw[u][0]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __ldg(a + j);
+          for (int j = 0; j < 8; ++j) v[u][j] = f[j];
+        }
+      } else {   // unaligned start, or the zero-padded tail beyond n_samples
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t sidx = s0[u] + j;
+          float x = 0.f;
+          if (sidx >= 0 && sidx < n_samples) {
+            if constexpr (I16) x = __ldg(reinterpret_cast<const int16_t*>(audio) + sidx) * (1.0f / 32768.0f);
+            else x = __ldg(reinterpret_cast<const float*>(audio) + sidx);
+          }
+          v[u][j] = x;
         }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int64_t s = s0 + j;
-        float x = 0.f;
-        if (s >= 0 && s < n_samples) {
-          if constexpr (I16) x = reinterpret_cast<const int16_t*>(audio)[s] * (1.0f / 32768.0f);
-          else x = reinterpret_cast<const float*>(audio)[s];
-        }
-        v[j] = x;
+      const int64_t o = fr[u] * S + col[u];
+      if (out_hi) {
+        *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(pack2(v[u][0], v[u][1]), pack2(v[u][2], v[u][3]),
+                                                           pack2(v[u][4], v[u][5]), pack2(v[u][6], v[u][7]));
       }
-    }
-    const int64_t o = f * S + c;
-    if (out_hi) {
-      *reinterpret_cast<uint4*>(out_hi + o) =
-          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-    }
-    if (out_lo) {
-      float r[8];
+      if (out_lo) {
+        float r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-      *reinterpret_cast<uint4*>(out_lo + o) =
-          make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
-    }
-    if (out_f32) {
-      float4* d = reinterpret_cast<float4*>(out_f32 + o);
-      d[0] = make_float4(v[0], v[1], v[2], v[3]);
-      d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        for (int j = 0; j < 8; ++j) r[j] = v[u][j] - __bfloat162float(__float2bfloat16_rn(v[u][j]));
+        *reinterpret_cast<uint4*>(out_lo + o) =
+            make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+      }
+      if (out_f32) {
+        float4* d = reinterpret_cast<float4*>(out_f32 + o);
+        d[0] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+        d[1] = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+      }
     }
   }
   aux_end(tr);
@@ -131,7 +152,7 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
   RVAE_REQUIRE(S > 0 && S % 8 == 0 && hop > 0, RVAE_ERR_UNSUPPORTED, "frame_gather: S=%d must be a multiple of 8", S);
   if (n_frames <= 0) return RVAE_OK;
   const int threads = 256;
-  const int grid = grid_for(ctx, n_frames * (S / 8), threads, 16);
+  const int grid = grid_for(ctx, (n_frames * (S / 8) + 3) / 4, threads, 8);
   const AuxTrace tr = next_aux(ctx, 1);
   if (audio_is_i16)
     RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<true>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop, S,
@@ -255,7 +276,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 }
 
 __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
-                             const float* __restrict__ offset_src, AuxTrace tr) {
+                             const float* __restrict__ offset_src, int64_t vec_base, AuxTrace tr) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   aux_begin(tr, 2);
@@ -263,7 +284,10 @@ __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, 
   if (offset_src) offset += static_cast<uint64_t>(__ldg(offset_src));
   const int64_t nvec = (n + 3) >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(offset),
+    // vec_base: this buffer is elements [4 * vec_base, ...) of a larger logical tensor (a rank's rows of the global
+    // batch under data parallelism): the ranks draw disjoint pieces of ONE stream, the single-process draw
+    const int64_t ci = i + vec_base;
+    uint32_t c[4] = {static_cast<uint32_t>(ci), static_cast<uint32_t>(ci >> 32), static_cast<uint32_t>(offset),
                      static_cast<uint32_t>(offset >> 32)};
     philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     float z[4];
@@ -288,11 +312,12 @@ __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, 
 }
 
 int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, const float* offset_src,
-                 cudaStream_t stream) {
+                 int64_t elem_base, cudaStream_t stream) {
   RVAE_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, RVAE_ERR_INVALID, "randn: bad output buffer");
+  RVAE_REQUIRE(elem_base >= 0 && (elem_base & 3) == 0, RVAE_ERR_INVALID, "randn: elem_base must be a multiple of 4");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset, offset_src, next_aux(ctx, 2)));
+  RVAE_CUDA(launch_kernel(ctx, randn_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, out, n, seed, offset, offset_src, elem_base >> 2, next_aux(ctx, 2)));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -582,16 +607,92 @@ __global__ void reparam_kernel(const float* __restrict__ mu, const float* __rest
                                const float* __restrict__ eps, int64_t n, float* __restrict__ z) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+  const int64_t nv = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const float4 m = __ldcs(reinterpret_cast<const float4*>(mu) + i);
+    const float4 l = __ldcs(reinterpret_cast<const float4*>(lv) + i);
+    const float4 e = __ldcs(reinterpret_cast<const float4*>(eps) + i);
+    reinterpret_cast<float4*>(z)[i] = make_float4(fmaf(e.x, expf(0.5f * l.x), m.x), fmaf(e.y, expf(0.5f * l.y), m.y),
+                                                  fmaf(e.z, expf(0.5f * l.z), m.z), fmaf(e.w, expf(0.5f * l.w), m.w));
+  }
+  for (int64_t i = (nv << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
     z[i] = fmaf(eps[i], expf(0.5f * lv[i]), mu[i]);
 }
 
 int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps, int64_t n, float* z,
                    cudaStream_t stream) {
   RVAE_REQUIRE(mu && lv && eps && z, RVAE_ERR_INVALID, "reparam: null buffer");
+  RVAE_REQUIRE(((reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(lv) | reinterpret_cast<uintptr_t>(eps) |
+                 reinterpret_cast<uintptr_t>(z)) & 15) == 0, RVAE_ERR_INVALID, "reparam: buffers must be 16-byte aligned");
   if (n <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, reparam_kernel, dim3(grid_for(ctx, n, threads, 8)), dim3(threads), (size_t)0, stream, mu, lv, eps, n, z));
+  RVAE_CUDA(launch_kernel(ctx, reparam_kernel, dim3(grid_for(ctx, (n + 3) / 4, threads, 8)), dim3(threads), (size_t)0, stream, mu, lv, eps, n, z));
+  RVAE_LAUNCH_CHECK(ctx);
+  return RVAE_OK;
+}
+
+// Latent interpolation of the tutorial's inference pattern (tutorial.ipynb:496-510 global alpha, :905-932 per-frame
+// alpha from interp1d, float64): mu = (1-a) mu_a + a mu_b, logvar likewise, z = mu + eps * exp(logvar / 2), with one
+// alpha per FRAME (row). Emits z as fp32 and / or as the bf16 planes fc3's GEMM reads, so the interpolated latents
+// never make an fp32 round trip through HBM before decode. The lerp itself is done in double when alpha is double
+// (the notebook's dtype), then rounded to fp32 once.
+template <typename AT>
+__global__ void lerp_reparam_kernel(const float* __restrict__ mu_a, const float* __restrict__ lv_a,
+                                    const float* __restrict__ mu_b, const float* __restrict__ lv_b,
+                                    const AT* __restrict__ alpha, const float* __restrict__ eps, int64_t rows, int L,
+                                    float* __restrict__ z_f32, __nv_bfloat16* __restrict__ z_hi,
+                                    __nv_bfloat16* __restrict__ z_lo, float* __restrict__ mu_out,
+                                    float* __restrict__ lv_out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int q = L >> 2;
+  const int64_t nv = rows * q;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / q;
+    const AT al = alpha[r];
+    const float4 ma = __ldcs(reinterpret_cast<const float4*>(mu_a) + i), mb = __ldcs(reinterpret_cast<const float4*>(mu_b) + i);
+    const float4 la = __ldcs(reinterpret_cast<const float4*>(lv_a) + i), lb = __ldcs(reinterpret_cast<const float4*>(lv_b) + i);
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (eps) e = __ldcs(reinterpret_cast<const float4*>(eps) + i);
+    const float* pma = reinterpret_cast<const float*>(&ma); const float* pmb = reinterpret_cast<const float*>(&mb);
+    const float* pla = reinterpret_cast<const float*>(&la); const float* plb = reinterpret_cast<const float*>(&lb);
+    const float* pe = reinterpret_cast<const float*>(&e);
+    float m[4], l[4], z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m[j] = static_cast<float>((AT(1) - al) * AT(pma[j]) + al * AT(pmb[j]));
+      l[j] = static_cast<float>((AT(1) - al) * AT(pla[j]) + al * AT(plb[j]));
+      z[j] = fmaf(pe[j], expf(0.5f * l[j]), m[j]);
+    }
+    if (mu_out) reinterpret_cast<float4*>(mu_out)[i] = make_float4(m[0], m[1], m[2], m[3]);
+    if (lv_out) reinterpret_cast<float4*>(lv_out)[i] = make_float4(l[0], l[1], l[2], l[3]);
+    if (z_f32) reinterpret_cast<float4*>(z_f32)[i] = make_float4(z[0], z[1], z[2], z[3]);
+    if (z_hi) reinterpret_cast<uint2*>(z_hi)[i] = make_uint2(pack2(z[0], z[1]), pack2(z[2], z[3]));
+    if (z_lo) {
+      float rr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rr[j] = z[j] - __bfloat162float(__float2bfloat16_rn(z[j]));
+      reinterpret_cast<uint2*>(z_lo)[i] = make_uint2(pack2(rr[0], rr[1]), pack2(rr[2], rr[3]));
+    }
+  }
+}
+
+int launch_lerp_reparam(Ctx* ctx, const float* mu_a, const float* lv_a, const float* mu_b, const float* lv_b,
+                        const void* alpha, int alpha_is_f64, const float* eps, int64_t rows, int L, float* z_f32,
+                        __nv_bfloat16* z_hi, __nv_bfloat16* z_lo, float* mu_out, float* lv_out, cudaStream_t stream) {
+  RVAE_REQUIRE(mu_a && lv_a && mu_b && lv_b && alpha, RVAE_ERR_INVALID, "lerp_reparam: null buffer");
+  RVAE_REQUIRE(z_f32 || z_hi || mu_out, RVAE_ERR_INVALID, "lerp_reparam: no output buffer");
+  RVAE_REQUIRE(L > 0 && L % 4 == 0, RVAE_ERR_UNSUPPORTED, "lerp_reparam: latent_dim=%d must be a multiple of 4", L);
+  if (rows <= 0) return RVAE_OK;
+  const int threads = 256;
+  const dim3 grid(grid_for(ctx, rows * (L / 4), threads, 8));
+  if (alpha_is_f64)
+    RVAE_CUDA(launch_kernel(ctx, lerp_reparam_kernel<double>, grid, dim3(threads), (size_t)0, stream, mu_a, lv_a, mu_b, lv_b,
+                            reinterpret_cast<const double*>(alpha), eps, rows, L, z_f32, z_hi, z_lo, mu_out, lv_out));
+  else
+    RVAE_CUDA(launch_kernel(ctx, lerp_reparam_kernel<float>, grid, dim3(threads), (size_t)0, stream, mu_a, lv_a, mu_b, lv_b,
+                            reinterpret_cast<const float*>(alpha), eps, rows, L, z_f32, z_hi, z_lo, mu_out, lv_out));
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }
@@ -604,6 +705,7 @@ int launch_reparam(Ctx* ctx, const float* mu, const float* lv, const float* eps,
 // ------------------------------------------------------------------------------------------------
 // A launch covers elements [0, n) and, optionally, a second segment [off_b, off_b + n_b) of the same buffers (both
 // multiples of 4 then): the per-bucket launches of a training step (W3|W4, W2, W1 + bias block).
+template <int U>
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, int64_t off_b, int64_t n_b, float lr, float beta1,
                             float beta2, float eps, float weight_decay, float grad_scale, float* step,
@@ -629,38 +731,56 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   const int64_t nvec = n >> 2;
   const int64_t nvec_all = nvec + (n_b >> 2);
   const int64_t shift_b = (off_b >> 2) - nvec;
-  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nvec_all; w += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = w < nvec ? w : w + shift_b;
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = reinterpret_cast<const float4*>(g)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    float* pa = reinterpret_cast<float*>(&pp);
-    const float* ga = reinterpret_cast<const float*>(&gg);
-    float* ma = reinterpret_cast<float*>(&mm);
-    float* va = reinterpret_cast<float*>(&vv);
+  // U (= 2) float4 groups per thread and trip, all 4 U loads issued before the first use: loads and the previous trip's
+  // stores overlap in time, so the kernel streams instead of alternating between a read phase and a write phase.
+  // p, m, v are touched once per step: streaming (evict-first) loads and stores keep them from displacing the
+  // activations and bf16 shadow weights the GEMMs want in L2. The cleared gradient and the shadow use the default
+  // policy: the next step's split-K reduce-adds and operand loads hit them in L2.
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w0 < nvec_all; w0 += U * stride) {
+    int64_t idx[U];
+    float4 pp[U], gg[U], mm[U], vv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float gr = ga[j] * grad_scale;
-      if (weight_decay != 0.f) gr = fmaf(weight_decay, pa[j], gr);
-      ma[j] = ma[j] + (1.f - beta1) * (gr - ma[j]);
-      va[j] = beta2 * va[j] + (1.f - beta2) * gr * gr;
-      const float denom = sqrtf(va[j]) / sqrt_bc2 + eps;
-      pa[j] = pa[j] - step_size * (ma[j] / denom);
+    for (int u = 0; u < U; ++u) {
+      const int64_t w = w0 + u * stride;
+      idx[u] = w < nvec_all ? (w < nvec ? w : w + shift_b) : -1;
+      if (idx[u] >= 0) {
+        pp[u] = __ldcs(reinterpret_cast<const float4*>(p) + idx[u]);
+        gg[u] = __ldcs(reinterpret_cast<const float4*>(g) + idx[u]);
+        mm[u] = __ldcs(reinterpret_cast<const float4*>(m) + idx[u]);
+        vv[u] = __ldcs(reinterpret_cast<const float4*>(v) + idx[u]);
+      }
     }
-    reinterpret_cast<float4*>(p)[i] = pp;
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    // zero_grads: the next step's split-K weight gradients reduce-add into this buffer (saves 4 memsets / step).
-    // Stored last: a store issued while the load of the same line is still in flight serialises the LSU.
-    if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sh_hi) {
-      reinterpret_cast<uint2*>(sh_hi)[i] = make_uint2(pack2(pa[0], pa[1]), pack2(pa[2], pa[3]));
-      if (sh_lo) {
-        float r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = pa[j] - __bfloat162float(__float2bfloat16_rn(pa[j]));
-        reinterpret_cast<uint2*>(sh_lo)[i] = make_uint2(pack2(r[0], r[1]), pack2(r[2], r[3]));
+    for (int u = 0; u < U; ++u) {
+      if (idx[u] < 0) continue;
+      const int64_t i = idx[u];
+      float* pa = reinterpret_cast<float*>(&pp[u]);
+      const float* ga = reinterpret_cast<const float*>(&gg[u]);
+      float* ma = reinterpret_cast<float*>(&mm[u]);
+      float* va = reinterpret_cast<float*>(&vv[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float gr = ga[j] * grad_scale;
+        if (weight_decay != 0.f) gr = fmaf(weight_decay, pa[j], gr);
+        ma[j] = ma[j] + (1.f - beta1) * (gr - ma[j]);
+        va[j] = beta2 * va[j] + (1.f - beta2) * gr * gr;
+        const float denom = sqrtf(va[j]) / sqrt_bc2 + eps;
+        pa[j] = pa[j] - step_size * (ma[j] / denom);
+      }
+      __stcs(reinterpret_cast<float4*>(p) + i, pp[u]);
+      __stcs(reinterpret_cast<float4*>(m) + i, mm[u]);
+      __stcs(reinterpret_cast<float4*>(v) + i, vv[u]);
+      // zero_grads: the next step's split-K weight gradients reduce-add into this buffer (saves 4 memsets / step)
+      if (zero_grads) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sh_hi) {
+        reinterpret_cast<uint2*>(sh_hi)[i] = make_uint2(pack2(pa[0], pa[1]), pack2(pa[2], pa[3]));
+        if (sh_lo) {
+          float r[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[j] = pa[j] - __bfloat162float(__float2bfloat16_rn(pa[j]));
+          reinterpret_cast<uint2*>(sh_lo)[i] = make_uint2(pack2(r[0], r[1]), pack2(r[2], r[3]));
+        }
       }
     }
   }
@@ -717,7 +837,14 @@ int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, in
                RVAE_ERR_INVALID, "adam: shadow planes must be 8-byte aligned");
   if (n + n_b <= 0) return RVAE_OK;
   const int threads = 256;
-  RVAE_CUDA(launch_kernel(ctx, adam_kernel, dim3(grid_for(ctx, (n + n_b + 3) / 4, threads, 8)), dim3(threads), (size_t)0,
+  // one wave of 4 blocks per SM (a multiple of the SM count); each thread walks ~10 float4 groups at the default
+  // sizes. RVAE_ADAM_UNROLL / RVAE_ADAM_BPS: tuning knobs (tools/ncu_hbm_kernels.py sweeps them).
+  static const int unroll = getenv("RVAE_ADAM_UNROLL") ? atoi(getenv("RVAE_ADAM_UNROLL")) : 2;
+  static const int bps = getenv("RVAE_ADAM_BPS") ? atoi(getenv("RVAE_ADAM_BPS")) : 4;
+  const int64_t groups = (n + n_b + 3) / 4;
+  const dim3 grid(grid_for(ctx, (groups + unroll - 1) / unroll, threads, bps > 0 ? bps : 4));
+  auto kern = unroll == 1 ? adam_kernel<1> : (unroll == 4 ? adam_kernel<4> : adam_kernel<2>);
+  RVAE_CUDA(launch_kernel(ctx, kern, grid, dim3(threads), (size_t)0,
                           stream, p, g, m, v, n, off_b, n_b, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
                           step_bias, ticket, shadow_hi, shadow_lo, zero_grads, next_aux(ctx, 4)));
   RVAE_LAUNCH_CHECK(ctx);
@@ -751,47 +878,67 @@ __global__ void latent_bwd_kernel(float* __restrict__ dz, const float* __restric
   const int cx = threadIdx.x % q;          // column group of this thread
   const int ry = threadIdx.x / q;
   float smu[4] = {0.f, 0.f, 0.f, 0.f}, slv[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t r = (int64_t)blockIdx.x * rpp + ry; r < M; r += (int64_t)gridDim.x * rpp) {
-    const size_t i = (size_t)r * q + cx;
-    const float4 d4 = reinterpret_cast<const float4*>(dz)[i];
-    const float4 e4 = __ldg(reinterpret_cast<const float4*>(eps) + i);
-    const float4 l4 = __ldg(reinterpret_cast<const float4*>(lv) + i);
-    float4 a4, b4 = make_float4(0.f, 0.f, 0.f, 0.f);  // additive terms of d_mu, d_lv
-    if (g_lv_ext != nullptr) {
-      a4 = __ldg(reinterpret_cast<const float4*>(g_mu_ext) + i);
-      b4 = __ldg(reinterpret_cast<const float4*>(g_lv_ext) + i);
-    } else {
-      a4 = __ldg(reinterpret_cast<const float4*>(mu) + i);
-    }
-    const float* d = reinterpret_cast<const float*>(&d4);
-    const float* e = reinterpret_cast<const float*>(&e4);
-    const float* l = reinterpret_cast<const float*>(&l4);
-    const float* a = reinterpret_cast<const float*>(&a4);
-    const float* b = reinterpret_cast<const float*>(&b4);
-    float dmu[4], dlv[4];
+  // U rows per thread and trip, all loads (4 or 5 float4 per row) issued before the first use
+  constexpr int U = 2;
+  const bool ext = g_lv_ext != nullptr;
+  const int64_t rstride = (int64_t)gridDim.x * rpp;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpp + ry; r0 < M; r0 += U * rstride) {
+    float4 d4[U], e4[U], l4[U], a4[U], b4[U];
+    size_t idx[U];
+    bool ok[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float sig = expf(0.5f * l[j]);
-      const float gm = (g_lv_ext != nullptr) ? a[j] : c * a[j];
-      const float gl = (g_lv_ext != nullptr) ? b[j] : 0.5f * c * (sig * sig - 1.f);
-      dmu[j] = d[j] + gm;
-      dlv[j] = fmaf(d[j], 0.5f * e[j] * sig, gl);
-      smu[j] += dmu[j];
-      slv[j] += dlv[j];
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * rstride;
+      ok[u] = r < M;
+      idx[u] = (size_t)(ok[u] ? r : 0) * q + cx;
+      if (ok[u]) {
+        d4[u] = __ldcs(reinterpret_cast<const float4*>(dz) + idx[u]);
+        e4[u] = __ldcs(reinterpret_cast<const float4*>(eps) + idx[u]);
+        l4[u] = __ldcs(reinterpret_cast<const float4*>(lv) + idx[u]);
+        b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);  // additive term of d_lv
+        if (ext) {
+          a4[u] = __ldcs(reinterpret_cast<const float4*>(g_mu_ext) + idx[u]);
+          b4[u] = __ldcs(reinterpret_cast<const float4*>(g_lv_ext) + idx[u]);
+        } else {
+          a4[u] = __ldcs(reinterpret_cast<const float4*>(mu) + idx[u]);
+        }
+      }
     }
-    if (clear_dz) reinterpret_cast<float4*>(dz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t o = (size_t)r * (2 * L) + 4 * cx;
-    *reinterpret_cast<uint2*>(dml_hi + o) = make_uint2(pack2(dmu[0], dmu[1]), pack2(dmu[2], dmu[3]));
-    *reinterpret_cast<uint2*>(dml_hi + o + L) = make_uint2(pack2(dlv[0], dlv[1]), pack2(dlv[2], dlv[3]));
-    if (dml_lo) {
-      float rm[4], rl[4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const int64_t r = r0 + u * rstride;
+      const size_t i = idx[u];
+      const float* d = reinterpret_cast<const float*>(&d4[u]);
+      const float* e = reinterpret_cast<const float*>(&e4[u]);
+      const float* l = reinterpret_cast<const float*>(&l4[u]);
+      const float* a = reinterpret_cast<const float*>(&a4[u]);
+      const float* b = reinterpret_cast<const float*>(&b4[u]);
+      float dmu[4], dlv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        rm[j] = dmu[j] - __bfloat162float(__float2bfloat16_rn(dmu[j]));
-        rl[j] = dlv[j] - __bfloat162float(__float2bfloat16_rn(dlv[j]));
+        const float sig = expf(0.5f * l[j]);
+        const float gm = ext ? a[j] : c * a[j];
+        const float gl = ext ? b[j] : 0.5f * c * (sig * sig - 1.f);
+        dmu[j] = d[j] + gm;
+        dlv[j] = fmaf(d[j], 0.5f * e[j] * sig, gl);
+        smu[j] += dmu[j];
+        slv[j] += dlv[j];
       }
-      *reinterpret_cast<uint2*>(dml_lo + o) = make_uint2(pack2(rm[0], rm[1]), pack2(rm[2], rm[3]));
-      *reinterpret_cast<uint2*>(dml_lo + o + L) = make_uint2(pack2(rl[0], rl[1]), pack2(rl[2], rl[3]));
+      if (clear_dz) reinterpret_cast<float4*>(dz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const size_t o = (size_t)r * (2 * L) + 4 * cx;
+      *reinterpret_cast<uint2*>(dml_hi + o) = make_uint2(pack2(dmu[0], dmu[1]), pack2(dmu[2], dmu[3]));
+      *reinterpret_cast<uint2*>(dml_hi + o + L) = make_uint2(pack2(dlv[0], dlv[1]), pack2(dlv[2], dlv[3]));
+      if (dml_lo) {
+        float rm[4], rl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rm[j] = dmu[j] - __bfloat162float(__float2bfloat16_rn(dmu[j]));
+          rl[j] = dlv[j] - __bfloat162float(__float2bfloat16_rn(dlv[j]));
+        }
+        *reinterpret_cast<uint2*>(dml_lo + o) = make_uint2(pack2(rm[0], rm[1]), pack2(rm[2], rm[3]));
+        *reinterpret_cast<uint2*>(dml_lo + o + L) = make_uint2(pack2(rl[0], rl[1]), pack2(rl[2], rl[3]));
+      }
     }
   }
   if (bias_grad != nullptr) {
@@ -905,11 +1052,21 @@ __global__ void __launch_bounds__(512, 1) allreduce_p2p_kernel(P2PArgs a, P2PSeg
         __threadfence_system();
         *reinterpret_cast<volatile uint32_t*>(theirs) = want;
       }
+      // A peer may legitimately be seconds behind (rank 0 writing a checkpoint, a slow filesystem, a graph being
+      // instantiated): wait for minutes, not seconds, and never trap - a trapped context poisons the process and
+      // leaves the peers spinning. On timeout the FIRST failure is recorded in a status word the host polls
+      // (rvae_dp_status), and every later wait of this context falls through at once.
       const long long t0 = clock64();
-      while ((a.mode == 0 ? ld_acquire_sys(mine) : *reinterpret_cast<const volatile uint32_t*>(mine)) < want) {
-        if (clock64() - t0 > 4000000000ll) {
-          printf("rvae: all-reduce barrier timeout rank %d cta %d bucket %d phase %u peer %d\n", me, c, bucket, phase, p);
-          __trap();
+      bool dead = *reinterpret_cast<volatile uint32_t*>(a.status) != 0u;
+      unsigned spins = 0;
+      while (!dead && (a.mode == 0 ? ld_acquire_sys(mine) : *reinterpret_cast<const volatile uint32_t*>(mine)) < want) {
+        if ((++spins & 1023u) == 0u) {
+          if (clock64() - t0 > a.timeout_cycles) {
+            atomicCAS(a.status, 0u, 0x80000000u | (static_cast<uint32_t>(p) << 8) | (static_cast<uint32_t>(bucket) << 4) | phase);
+            dead = true;
+          } else if (*reinterpret_cast<volatile uint32_t*>(a.status) != 0u) {
+            dead = true;
+          }
         }
         if (a.mode >= 5) __nanosleep(40);
       }

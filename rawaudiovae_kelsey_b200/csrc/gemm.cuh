@@ -31,6 +31,14 @@
 
 #include "ptx.cuh"
 
+// Paths that were measured and did NOT win (profiles/README.md) are compiled only with -DRVAE_EXPERIMENTS=1
+// (RVAE_EXPERIMENTS=1 python -m rawaudiovae_kelsey_b200._build): the forward pass as one launch chained by tile-level
+// dependencies, the latent backward fused into the latent dgrad's epilogue (EPI_DLATENT), and the producer-only /
+// MMA-only debug modes. The default build carries none of their instructions in the hot loops.
+#ifndef RVAE_EXPERIMENTS
+#define RVAE_EXPERIMENTS 0
+#endif
+
 namespace rvae {
 
 constexpr int kBlockM = 128;
@@ -426,6 +434,7 @@ __device__ __forceinline__ void produce_unit(const GemmParams& p, int u, ProdSta
   const TileCoord t = decode_unit<CG>(p, u, sh.cta_rank);
   uint32_t stage = ps.stage, phase = ps.phase;
   bool slot_free = ps.slot_free;
+#if RVAE_EXPERIMENTS
   if (p.dep_wait != nullptr) {
     // the rows of this unit's A operand are produced by tiles of the other problem of this launch: wait until all
     // of them have been stored (schedules list every producer unit before any consumer unit, so this cannot deadlock)
@@ -441,6 +450,7 @@ __device__ __forceinline__ void produce_unit(const GemmParams& p, int u, ProdSta
     }
     ptx::fence_proxy_async_all();  // generic-proxy acquire -> async-proxy (TMA) reads of that data
   }
+#endif
   for (int pass = 0; pass < p.num_passes; ++pass) {
     const CUtensorMap* tmA = &p.tmA[pass];
     const CUtensorMap* tmB = &p.tmB[pass];
@@ -452,11 +462,13 @@ __device__ __forceinline__ void produce_unit(const GemmParams& p, int u, ProdSta
         slot_free = ptx::mbar_try_wait(&sh.empty_bar[ns], np ^ 1);
       }
       uint64_t* fb = &sh.full_bar[stage];
+#if RVAE_EXPERIMENTS
       if (CG == 1 && (p.debug & 2)) {  // experiment: measure the MMA side alone (operands are stale smem)
         ptx::mbar_arrive(fb);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
         continue;
       }
+#endif
       if constexpr (CG == 1) {
         ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
       } else {
@@ -530,11 +542,13 @@ __device__ __forceinline__ void mma_unit(const GemmParams& p, int u, MmaState& m
     }
     ptx::tc_fence_after();
     if (it == 0) trace_ev(p.trace, titer, 4);
+#if RVAE_EXPERIMENTS
     if (CG == 1 && (p.debug & 1)) {  // experiment: measure the TMA side alone
       ptx::mbar_arrive(&sh.empty_bar[stage]);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
       continue;
     }
+#endif
     const uint32_t a_addr = ptx::smem_u32(sh.smem + stage * Cfg::kStageBytes);
     const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
@@ -548,8 +562,11 @@ __device__ __forceinline__ void mma_unit(const GemmParams& p, int u, MmaState& m
     ptx::umma_commit<CG>(&sh.empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
     if (++stage == kStages) { stage = 0; phase ^= 1; }
   }
+#if RVAE_EXPERIMENTS
   if (CG == 1 && (p.debug & 1)) ptx::mbar_arrive(&sh.tmem_full_bar[ms.as]);
-  else ptx::umma_commit<CG>(&sh.tmem_full_bar[ms.as]);  // accumulator complete -> epilogue (of both CTAs)
+  else
+#endif
+  ptx::umma_commit<CG>(&sh.tmem_full_bar[ms.as]);  // accumulator complete -> epilogue (of both CTAs)
   trace_ev(p.trace, titer, 5);
   if (++ms.as == Cfg::kAccStages) { ms.as = 0; ms.aphase ^= 1; }
   ms.stage = stage; ms.phase = phase; ms.data_ready = data_ready;
@@ -993,12 +1010,14 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiSta
     if (CG == 1 || sh.leader) ptx::mbar_arrive(&sh.tmem_empty_bar[as]);
     else ptx::mbar_arrive_remote(&sh.tmem_empty_bar[as], 0);
   }
+#if RVAE_EXPERIMENTS
   if (p.dep_signal != nullptr && tm.issuer) {
     // publish this team's part of the tile to the consumer problem: its bulk stores are complete (not merely read)
     ptx::tma_store_wait<0>();
     __threadfence();
     atomicAdd(p.dep_signal + tc.m_blk, 1u);
   }
+#endif
   if (team_tid == 0) trace_ev(p.trace, titer, 7 + 2 * team);
   if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
 }

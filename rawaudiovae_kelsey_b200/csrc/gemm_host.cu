@@ -120,9 +120,11 @@ static const Variant kVariants[] = {
     RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_DRELU),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_DRELU),
     RVAE_VARIANT(256, MAJOR_K, MAJOR_MN, EPI_REDUCE),  RVAE_VARIANT(128, MAJOR_K, MAJOR_MN, EPI_REDUCE),
     RVAE_VARIANT(256, MAJOR_MN, MAJOR_MN, EPI_REDUCE), RVAE_VARIANT(128, MAJOR_MN, MAJOR_MN, EPI_REDUCE),
+#if RVAE_EXPERIMENTS
     // latent dgrad with the reparameterisation / KL backward fused: pair tiles only
     {256, MAJOR_K, MAJOR_MN, EPI_DLATENT, 2, gemm_kernel_2cta<256, MAJOR_K, MAJOR_MN, EPI_DLATENT>,
      GemmCfg<256, 2>::kSmemBytes},
+#endif
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -338,6 +340,7 @@ static const ChainVariant kChainVariants[] = {
     {2, {RVAE_KID(KDrelu), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDrelu, KWgrad, NoKind, NoKind>},
     // split-K latent dgrad | weight gradient         (backward stage 1)
     {2, {RVAE_KID(KDz), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDz, KWgrad, NoKind, NoKind>},
+#if RVAE_EXPERIMENTS
     // latent dgrad with fused reparameterisation / KL backward | weight gradient   (backward stage 1, bf16 mode)
     {2, {RVAE_KID(KDlat), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDlat, KWgrad, NoKind, NoKind>},
     // layers chained by tile-level dependencies: fc1 -> head, fc3 -> fc4 + loss, and the whole forward pass
@@ -345,6 +348,7 @@ static const ChainVariant kChainVariants[] = {
     {2, {RVAE_KID(KLinear), RVAE_KID(KOut)}, gemm_chain_kernel_2cta<256, KLinear, KOut, NoKind, NoKind>},
     {4, {RVAE_KID(KLinear), RVAE_KID(KHead), RVAE_KID(KLinear), RVAE_KID(KOut)},
      gemm_chain_kernel_2cta<256, KLinear, KHead, KLinear, KOut>},
+#endif
 };
 static const int kNumChainVariants = sizeof(kChainVariants) / sizeof(kChainVariants[0]);
 
@@ -440,6 +444,8 @@ int gemm_prepare_chain(const Ctx* ctx, const PreparedGemm* const* g, int count, 
   for (int i = 0; i < kMaxChain; ++i) d.params.p[i] = g[i < count ? i : 0]->params;
   for (int i = 0; i <= kMaxChain; ++i) d.params.base[i] = base[i];
   d.params.sched = sched_dev;
+  RVAE_REQUIRE(dep_flags == nullptr || RVAE_EXPERIMENTS, RVAE_ERR_UNSUPPORTED,
+               "chain gemm: dependent problems need a build with RVAE_EXPERIMENTS=1");
   if (dep_flags != nullptr) {
     for (int i = 0; i + 1 < count; ++i) {
       unsigned int* flags = dep_flags + 256 * i;

@@ -150,16 +150,19 @@ class TestDataset(torch.utils.data.Dataset):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU fast path
-def sampler_permutation(n: int) -> torch.Tensor:
-    """The permutation torch's RandomSampler would draw (DataLoader(shuffle=True) without a generator):
-    the iterator first draws its _base_seed, then RandomSampler draws
-    seed = int(torch.empty((), dtype=torch.int64).random_().item()) from the global RNG and returns
-    torch.randperm(n, generator=Generator().manual_seed(seed)). Same global seed => same batches as the
-    reference's DataLoader (train.py:134)."""
+def sampler_seed() -> int:
+    """The seed torch's RandomSampler would draw (DataLoader(shuffle=True) without a generator): the iterator first
+    draws its _base_seed, then RandomSampler draws seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    from the global RNG."""
     torch.empty((), dtype=torch.int64).random_()  # the DataLoader iterator's _base_seed draw comes first
-    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return int(torch.empty((), dtype=torch.int64).random_().item())
+
+
+def sampler_permutation(n: int, seed: Optional[int] = None) -> torch.Tensor:
+    """torch.randperm(n, generator=Generator().manual_seed(seed)) with seed = sampler_seed(): same global seed => same
+    batches as the reference's DataLoader (train.py:134)."""
     gen = torch.Generator()
-    gen.manual_seed(seed)
+    gen.manual_seed(sampler_seed() if seed is None else seed)
     return torch.randperm(n, generator=gen)
 
 
@@ -197,17 +200,26 @@ class GpuFrameLoader:
     def __iter__(self) -> Iterator[FrameBatch]:
         n, bs = self.n_frames, self.batch_size
         if self.shuffle:
-            perm = sampler_permutation(n).to(self.device, non_blocking=True)
+            # every rank draws a seed (its global RNG advances like the reference's DataLoader would); under data
+            # parallelism rank 0's seed wins (8 bytes travel, not the n indices): the shards below are slices of ONE
+            # permutation - the single-process one - never overlapping, never missing a frame
+            seed = sampler_seed()
+            if self.world > 1:
+                from . import dist as rdist
+                seed = rdist.agree(seed)
+            perm = sampler_permutation(n, seed).to(self.device, non_blocking=True)
         for b in range(len(self)):
             lo, hi = b * bs, min((b + 1) * bs, n)
-            s_lo, s_hi = shard_bounds(hi - lo, self.rank, self.world)
+            gb = hi - lo
+            if gb < self.world:
+                continue   # fewer frames than ranks: dropped on EVERY rank, so no rank skips a collective step alone
+            s_lo, s_hi = shard_bounds(gb, self.rank, self.world)
             lo, hi = lo + s_lo, lo + s_hi
-            if hi <= lo:
-                continue
+            rows = dict(global_row0=s_lo, global_batch=gb) if self.world > 1 else {}
             if self.shuffle:
-                yield FrameBatch(self.audio, hi - lo, self.hop, self.segment_length, frame_idx=perm[lo:hi])
+                yield FrameBatch(self.audio, hi - lo, self.hop, self.segment_length, frame_idx=perm[lo:hi], **rows)
             else:
-                yield FrameBatch(self.audio, hi - lo, self.hop, self.segment_length, first_frame=lo)
+                yield FrameBatch(self.audio, hi - lo, self.hop, self.segment_length, first_frame=lo, **rows)
 
 
 class GpuFrameStream:
@@ -239,6 +251,9 @@ class GpuFrameStream:
         files = self.ds.shuffled_data_list if self.ds.shuffle else self.ds.audio_file_list
         if not files:
             raise RuntimeError("no wav files in {}".format(self.ds.audio_folder))
+        if self.world > 1:   # ONE file order for the group (rank 0's): the ranks shard the same frame stream
+            from . import dist as rdist
+            files = [Path(f) for f in rdist.agree([str(f) for f in files])]
         S, hop, bs = 1024, self.ds.hop_size, self.batch_size
         pending: List[FrameBatch] = []
         have = 0
@@ -263,6 +278,7 @@ class GpuFrameStream:
         for r in runs:
             a, b = max(lo, pos), min(hi, pos + r.n_frames)
             if b > a:
-                out.append(FrameBatch(r.audio, b - a, r.hop, r.segment_length, first_frame=r.first_frame + (a - pos)))
+                out.append(FrameBatch(r.audio, b - a, r.hop, r.segment_length, first_frame=r.first_frame + (a - pos),
+                                      global_row0=lo, global_batch=self.batch_size))
             pos += r.n_frames
         return out

@@ -136,6 +136,36 @@ def adopt_symmetric_grads(model, group=None) -> bool:
     return True
 
 
+def check_health(device: Optional[torch.device] = None) -> None:
+    """Raise if the peer-memory all-reduce recorded a barrier timeout (a rank that stopped taking part). Reads 4
+    bytes synchronously: call it where the host synchronises anyway (loss read-back, checkpoints)."""
+    from . import _lib, ops
+    import ctypes as C
+    st = C.c_uint(0)
+    _lib.check(_lib.load().rvae_dp_status(ops.ctx(device), C.byref(st)))
+    if st.value:
+        v = st.value
+        raise RuntimeError(f"data-parallel all-reduce timed out waiting for rank {(v >> 8) & 0xff} "
+                           f"(flag set {(v >> 4) & 0xf}, phase {v & 0xf}); gradients since then are invalid")
+
+
+def sync_ranks(group=None) -> None:
+    """Host-level barrier (no-op in a single process). The trainers call it after every rank-0-only block
+    (checkpoints, histograms, test-audio reconstruction) so that no rank runs ahead into an all-reduce the others
+    only join once rank 0 is back."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group)
+
+
+def agree(value, group=None, src: int = 0):
+    """Every rank gets rank `src`'s value of a picklable object (sampler seeds, file orders)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return value
+    box = [value]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]
+
+
 def init_native_comm(device: torch.device, group=None) -> None:
     """Create librvae_b200's own NCCL communicator for `device`: rank 0 draws the 128-byte NCCL id, torch.distributed
     carries it to the other ranks (plumbing only), every rank calls rvae_dp_init. Idempotent."""
@@ -176,16 +206,51 @@ class DataParallelTrainStep(_StepBase):
         super().__init__(model, optimizer, kl_beta, ring, graph)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.global_batch = global_batch
         self.reduce_loss = reduce_loss
         self._synced = False
 
-    def _enqueue(self, plan):
-        gb = self.global_batch if self.global_batch is not None else plan.batch * self.world
-        plan.set_global_batch(gb if self.world > 1 else 0)
-        if self.world > 1 and not getattr(plan, "_dp_on", False):
+    # Which rows of the global batch a shard holds. The sharding loaders (dataset.GpuFrameLoader / GpuFrameStream)
+    # stamp it on the FrameBatch; otherwise equal contiguous shards of `global_batch` are assumed.
+    def _rows(self, data):
+        from .dataset import shard_bounds
+        fb = data[0] if isinstance(data, (list, tuple)) and data else data
+        n = sum(r.n_frames for r in data) if isinstance(data, (list, tuple)) else \
+            (data.n_frames if hasattr(data, "n_frames") else data.numel() // self.model.segment_length)
+        gb = getattr(fb, "global_batch", None)
+        if gb is None:
+            gb = self.global_batch if self.global_batch is not None else n * self.world
+        row0 = getattr(fb, "global_row0", None)
+        if row0 is None:
+            row0 = shard_bounds(gb, self.rank, self.world)[0]
+        return int(row0), int(gb)
+
+    def _configure(self, plan, data):
+        if self.world <= 1:
+            plan.set_global_batch(0)
+            return
+        row0, gb = self._rows(data)
+        plan.set_global_batch(gb)      # loss normalisation: the SUM over ranks is the gradient of the global batch
+        plan.set_noise_rows(row0)      # Philox counters: the same seed on every rank draws disjoint rows of one tensor
+        if not getattr(plan, "_dp_on", False):
             plan.enable_dp(True)
             plan._dp_on = True
+
+    def _key_extra(self, data):
+        return self._rows(data) if self.world > 1 else ()
+
+    def _prefetch(self, plan, data, next_data, frame_idx, first_frame):
+        if self.world > 1:             # the prefetched noise belongs to the NEXT batch's shard rows
+            plan.set_noise_rows(self._rows(next_data)[0])
+        super()._prefetch(plan, data, next_data, frame_idx, first_frame)
+        if self.world > 1 and data is not None:
+            plan.set_noise_rows(self._rows(data)[0])
+
+    def _seed(self):
+        return self._shared_seed if getattr(self, "_shared_seed", None) is not None else super()._seed()
+
+    def _enqueue(self, plan):
         g = self.optimizer.param_groups[0]
         b1, b2 = g["betas"]
         plan.train_step(self.kl_beta, g["lr"], b1, b2, g["eps"], g.get("weight_decay", 0.0), loss_out=self.ring,
@@ -199,8 +264,13 @@ class DataParallelTrainStep(_StepBase):
             flat = self._prepare()
             broadcast_parameters(flat.params, self.group)
             flat.sync_shadow()
+            # ONE noise stream for the whole group: rank 0's seed everywhere, decorrelated by global row (see _rows)
+            box = [super()._seed()]
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            self._shared_seed = int(box[0])
             self._synced = True
         slot = self._run(data, eps, next_data)
+        self._calls = getattr(self, "_calls", 0) + 1
         if self.reduce_loss and self.world > 1:
             dist.all_reduce(slot, op=dist.ReduceOp.SUM, group=self.group)
             slot.div_(self.world)

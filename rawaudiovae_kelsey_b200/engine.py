@@ -17,6 +17,23 @@ from ._lib import check
 
 PRECISIONS = {"bf16": ops.PRECISION_BF16, "fp32": ops.PRECISION_FP32}
 
+# nn.Parameter -> (FlatState, parameter name). Kept OUTSIDE the parameters: torch pickles a Parameter's custom
+# attributes, so hanging the FlatState on them would drag gradients, both Adam moments and the bf16 shadows into
+# torch.save(model) (best_model.pt / last_model.pt) and make the file unloadable where only the reference's
+# rawvae.model exists. Identity-keyed and weak: entries vanish with their parameters.
+from torch.utils.weak import WeakTensorKeyDictionary  # noqa: E402
+
+_FLAT_OF = WeakTensorKeyDictionary()
+
+
+def register_flat(param: torch.Tensor, flat: "FlatState", name: str) -> None:
+    _FLAT_OF[param] = (flat, name)
+
+
+def flat_of(param: torch.Tensor):
+    """(FlatState, name) of a parameter that is a view of a flat buffer, else None."""
+    return _FLAT_OF.get(param)
+
 # parameter name -> (layout field, row offset factor) ; fc21/fc22 share the stacked W2 / b2 blocks
 PARAM_SLOTS = ("fc1.weight", "fc1.bias", "fc21.weight", "fc21.bias", "fc22.weight", "fc22.bias",
                "fc3.weight", "fc3.bias", "fc4.weight", "fc4.bias")
@@ -183,6 +200,11 @@ class Plan:
     def enable_dp(self, on: bool = True) -> None:
         check(self.lib.rvae_plan_enable_dp(self.handle, int(on)))
 
+    def set_noise_rows(self, first_global_row: int) -> None:
+        """Data parallelism: this rank's shard starts at row `first_global_row` of the global batch (Philox counters
+        of gen_eps / prefetch_frames start there, so equal seeds give the single-process noise on every rank)."""
+        check(self.lib.rvae_plan_set_noise_rows(self.handle, int(first_global_row)))
+
     def set_global_batch(self, global_batch: int) -> None:
         check(self.lib.rvae_plan_set_global_batch(self.handle, int(global_batch)))
 
@@ -231,6 +253,16 @@ class Plan:
         self.batch = z.shape[0]
         self.token += 1
 
+    def decode_lerp(self, mu_a, lv_a, mu_b, lv_b, alpha, eps, xhat_out) -> None:
+        """lerp(alpha per frame) -> reparameterize -> decode as one chained enqueue (tutorial.ipynb:496-510, 905-932)."""
+        n = mu_a.shape[0]
+        check(self.lib.rvae_plan_decode_lerp(self.handle, mu_a.data_ptr(), lv_a.data_ptr(), mu_b.data_ptr(),
+                                             lv_b.data_ptr(), alpha.data_ptr(), int(alpha.dtype == torch.float64),
+                                             eps.data_ptr() if eps is not None else None, n, xhat_out.data_ptr(),
+                                             self._stream()))
+        self.batch = n
+        self.token += 1
+
     GEMM_SLOTS = ("F1", "F2", "F3", "F4_out", "F4_lin", "B4w", "B4d", "B3w", "B3d", "B2w", "B2d", "B1w")
     AUX_SLOTS = ("load", "eps", "finalize", "colsum", "adam", "tanh_bwd", "latent_bwd")
 
@@ -261,6 +293,15 @@ class Plan:
             n = self.batch * cols.value
             return self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.batch, cols.value)
         return view(hi.value), view(lo.value)
+
+    def latent(self, name: str) -> torch.Tensor:
+        """fp32 view [batch, L] of the current batch's `eps` (the noise the step used - Philox or injected), `mu` or
+        `logvar` in the workspace. Introspection for tests: aliases the workspace, overwritten by the next step."""
+        fn = {"eps": self.lib.rvae_plan_eps, "mu": self.lib.rvae_plan_mu, "logvar": self.lib.rvae_plan_logvar}[name]
+        ptr = int(fn(self.handle))
+        off = ptr - self.workspace.data_ptr()
+        n = self.batch * self.flat.L
+        return self.workspace[off:off + 4 * n].view(torch.float32).view(self.batch, self.flat.L)
 
     def bucket(self, s: int) -> torch.Tensor:
         """Gradient bucket s as a view of flat.grads (0..3 = W4, W3, W2, W1 in backward order; 4 = biases)."""

@@ -31,9 +31,13 @@ class FrameBatch:
     the bf16 operand buffer of fc1 and never materialised as an fp32 [B, S] tensor."""
 
     def __init__(self, audio: torch.Tensor, n_frames: int, hop: int, segment_length: int,
-                 frame_idx: Optional[torch.Tensor] = None, first_frame: int = 0):
+                 frame_idx: Optional[torch.Tensor] = None, first_frame: int = 0,
+                 global_row0: Optional[int] = None, global_batch: Optional[int] = None):
         self.audio, self.n_frames, self.hop, self.segment_length = audio, int(n_frames), int(hop), int(segment_length)
         self.frame_idx, self.first_frame = frame_idx, int(first_frame)
+        # data parallelism: this batch is rows [global_row0, global_row0 + n_frames) of a global batch of
+        # `global_batch` frames (set by the sharding loaders; None = not sharded / equal shards assumed)
+        self.global_row0, self.global_batch = global_row0, global_batch
 
     @property
     def shape(self):
@@ -137,7 +141,7 @@ class VAE(nn.Module):
                     v.copy_(p.data)
                     p.data = v
                     p.grad = None
-                    p._rvae_flat = (flat, n)
+                    engine.register_flat(p, flat, n)
             self._flat, self._plans = flat, {}
             flat.shadow_version = -1
         version = sum(p._version for _, p in named)
@@ -236,9 +240,39 @@ class VAE(nn.Module):
         plan.decode(z, out)
         return out
 
+    def reference_forward(self, x, eps: Optional[torch.Tensor] = None):
+        """The forward pass as plain torch ops on the SAME parameters (rawvae/model.py:19-35, op for op): what a
+        tracer can follow. The sm_100a kernels are reached through ctypes and are invisible to torch.jit.trace /
+        torch.onnx.export, so `forward` routes here while it is being traced or exported
+        (export-onnx.ipynb:361-362: torch.onnx.export(raw_model, torch.randn(1024), "rawaudiovae.onnx")) - an export
+        path, not a compute fallback: ordinary calls never take it. Works on any device, any float dtype."""
+        x = x.view(-1, self.segment_length)
+        h1 = torch.relu(self.fc1(x))
+        mu, logvar = self.fc21(h1), self.fc22(h1)
+        std = torch.exp(0.5 * logvar)
+        if eps is None:
+            eps = torch.randn_like(std)
+        z = mu + eps * std
+        h3 = torch.relu(self.fc3(z))
+        return torch.tanh(self.fc4(h3)), mu, logvar
+
+    @staticmethod
+    def _being_traced() -> bool:
+        if torch.jit.is_tracing() or torch.jit.is_scripting():
+            return True
+        try:
+            if torch.onnx.is_in_onnx_export():
+                return True
+        except Exception:
+            pass
+        is_exporting = getattr(getattr(torch, "compiler", None), "is_exporting", None)
+        return bool(is_exporting and is_exporting())
+
     def forward(self, x, eps: Optional[torch.Tensor] = None):
         """(x_hat, mu, logvar); differentiable w.r.t. the parameters (loss.backward() works as in the reference).
         `eps` optionally injects the reparameterisation noise (parity tests); the reference draws it internally."""
+        if self._being_traced():
+            return self.reference_forward(x, eps)
         self._ensure_flat()
         params = [p for _, p in self._named()]
         return _VAEForward.apply(self, x, eps, *params)
@@ -319,16 +353,22 @@ class _StepBase:
     read from device memory: frame indices from a static index buffer, the Philox offset and the loss-ring slot
     from the optimizer's step counter."""
 
-    def __init__(self, model, optimizer, kl_beta, ring, graph, graph_warmup=3):
+    def __init__(self, model, optimizer, kl_beta, ring, graph, graph_warmup=1):
         self.model, self.optimizer, self.kl_beta = model, optimizer, float(kl_beta)
         self.ring_size = int(ring)
         self.ring = None
         self.i = None            # host mirror of the device step counter (slot = i % ring_size)
         self.graph = bool(graph)
-        self.graph_warmup = graph_warmup
+        # eager calls per input signature before its graph is captured: ONE is needed (the first call of a signature
+        # builds tensor maps and tile schedules with synchronous copies, which a capture must not contain)
+        self.graph_warmup = max(1, int(graph_warmup))
         self._graphs = {}        # key -> dict(graph, static buffers, plan)
         self.replayed_launches = 0   # kernels launched by graph replays (the library's launch counter only sees eager ones)
         self._seen = {}          # key -> eager calls so far
+        # what each call did, so that a caller timing steady state can prove no capture / eager step fell into its
+        # timed region: totals, and the number of CONSECUTIVE replayed steps up to now
+        self.stats = {"eager": 0, "captures": 0, "replays": 0}
+        self.steady = 0
 
     # -- helpers
     def _prepare(self):
@@ -352,8 +392,7 @@ class _StepBase:
         elif model.eps_source == "torch":
             plan.set_eps(torch.randn((plan.batch, model.latent_dim), device=model._flat.device))
         else:
-            seed = model.eps_seed if model.eps_seed is not None else torch.initial_seed()
-            plan.gen_eps(int(seed) & 0xFFFFFFFFFFFFFFFF, 0, add_step=True)   # offset = device step counter
+            plan.gen_eps(self._seed(), 0, add_step=True)   # offset = device step counter
 
     def _graph_key(self, data):
         """Input signature for graph reuse, or None when the input cannot be served by a replay."""
@@ -406,52 +445,79 @@ class _StepBase:
         if not prefetch:
             # ---- plain path: load inside the step (captured graph: from static index / input buffers)
             key = self._graph_key(data) if graphable else None
+            if key is not None:
+                key = key + self._key_extra(data)
             if key is not None and key in self._graphs:
                 st = self._graphs[key]
                 self._load_static(key, data, st)
                 st["graph"].replay()
                 self.replayed_launches += st["launches"]
                 st["plan"].token += 1
+                self._count("replays")
             elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
                 self._capture(key, data)
+                self._count("captures")
             else:
                 if key is not None:
                     self._seen[key] = self._seen.get(key, 0) + 1
                 plan = model._load(data)
+                self._configure(plan, data)
                 self._eps(plan, eps)
                 self._enqueue(plan)
+                self._count("eager")
         else:
             # ---- pipelined path: the current batch is already in the plan (or loaded eagerly now), the next one is
             #      prefetched by this step
             if plan is None:
                 plan = model._load(data)
+                self._configure(plan, data)
                 self._eps(plan, eps)
+            else:
+                self._configure(plan, data)
             do_pf = self._can_prefetch(next_data, eps) and next_data.n_frames <= plan.max_batch
             key = None
             if graphable and do_pf and isinstance(data, FrameBatch):
                 key = ("pf", plan.handle.value, next_data.audio.data_ptr(), plan.batch, next_data.n_frames,
-                       next_data.hop, self._plan_cur(plan))
+                       next_data.hop, self._plan_cur(plan)) + self._key_extra(data) + self._key_extra(next_data)
             if key is not None and key in self._graphs:
                 st = self._graphs[key]
                 self._fill_idx(st, next_data)
                 st["graph"].replay()
                 self.replayed_launches += st["launches"]
                 self._mark_prefetched(plan, next_data)
+                self._count("replays")
             elif key is not None and self._seen.get(key, 0) >= self.graph_warmup:
                 self._capture_pipelined(key, plan, next_data)
+                self._count("captures")
             else:
+                self._count("eager")
                 if key is not None:
                     self._seen[key] = self._seen.get(key, 0) + 1
                 if do_pf:
-                    plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop,
-                                         frame_idx=next_data.frame_idx, first_frame=next_data.first_frame,
-                                         seed=self._seed(), offset=0, add_step=True)
+                    self._prefetch(plan, data, next_data, next_data.frame_idx, next_data.first_frame)
                 self._enqueue(plan)
                 if do_pf:
                     self._pf = (plan, next_data)
         slot = self._slot()
         self.i += 1
         return slot
+
+    # -- hooks of the data-parallel subclass
+    def _configure(self, plan, data):
+        """Per-step plan settings that depend on the batch (global batch size, first global row of the shard)."""
+
+    def _key_extra(self, data):
+        """What _configure bakes into a captured graph, as part of the graph key."""
+        return ()
+
+    def _prefetch(self, plan, data, next_data, frame_idx, first_frame):
+        """Register next_data (frames + noise) as the batch the coming train step gathers in the background."""
+        plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop, frame_idx=frame_idx,
+                             first_frame=first_frame, seed=self._seed(), offset=0, add_step=True)
+
+    def _count(self, what):
+        self.stats[what] += 1
+        self.steady = self.steady + 1 if what == "replays" else 0
 
     def _plan_cur(self, plan):
         """Parity of the plan's current input set (captured graphs bake in its addresses): tracked on the host."""
@@ -478,8 +544,7 @@ class _StepBase:
         g = torch.cuda.CUDAGraph()
         l0 = ops.launch_count(dev)
         with torch.cuda.graph(g):
-            plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop, frame_idx=st["idx"],
-                                 seed=self._seed(), offset=0, add_step=True)
+            self._prefetch(plan, None, next_data, st["idx"], 0)
             self._enqueue(plan)
         st["graph"], st["plan"], st["launches"] = g, plan, ops.launch_count(dev) - l0
         self._graphs[key] = st
@@ -504,6 +569,7 @@ class _StepBase:
         l0 = ops.launch_count(dev)
         with torch.cuda.graph(g):
             plan = model._load(static_in)
+            self._configure(plan, data)
             self._eps(plan, None)
             self._enqueue(plan)
         st["graph"], st["plan"], st["launches"] = g, plan, ops.launch_count(dev) - l0

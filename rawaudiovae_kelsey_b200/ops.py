@@ -128,11 +128,30 @@ def overlap_add(frames: torch.Tensor, hop: int, n_out: Optional[int] = None) -> 
 
 
 # --------------------------------------------------------------------------------------------- elementwise
-def randn(shape, seed: int, offset: int = 0, device=None) -> torch.Tensor:
+def randn(shape, seed: int, offset: int = 0, device=None, elem_base: int = 0) -> torch.Tensor:
+    """eps ~ N(0,1) from Philox (seed, offset); `elem_base` (a multiple of 4) makes the result elements
+    [elem_base, elem_base + n) of the logical noise tensor - a rank's rows of a global batch."""
     lib = _lib.load()
     out = torch.empty(shape, dtype=torch.float32, device=device or "cuda")
-    check(lib.rvae_randn(ctx(out.device), _ptr(out), out.numel(), seed, offset, _stream()))
+    check(lib.rvae_randn(ctx(out.device), _ptr(out), out.numel(), seed, offset, elem_base, _stream()))
     return out
+
+
+def lerp_reparameterize(mu_a, logvar_a, mu_b, logvar_b, alpha, eps=None, *, want_z=True, want_dist=False):
+    """Per-frame latent interpolation + reparameterisation (tutorial.ipynb:496-510, 905-932).
+    alpha: [rows] float32 or float64 CUDA tensor. Returns (z or None, mu or None, logvar or None), fp32 [rows, L]."""
+    lib = _lib.load()
+    rows, L = mu_a.shape
+    if alpha.dtype not in (torch.float32, torch.float64) or alpha.numel() != rows:
+        raise _lib.RvaeError("alpha must be a float32 / float64 tensor with one entry per frame")
+    dev = mu_a.device
+    f = lambda on: torch.empty((rows, L), dtype=torch.float32, device=dev) if on else None
+    z, mu, lv = f(want_z), f(want_dist), f(want_dist)
+    check(lib.rvae_lerp_reparameterize(ctx(dev), _ptr(mu_a, torch.float32, "mu_a"), _ptr(logvar_a, torch.float32, "logvar_a"),
+                                       _ptr(mu_b, torch.float32, "mu_b"), _ptr(logvar_b, torch.float32, "logvar_b"),
+                                       _ptr(alpha, None, "alpha"), int(alpha.dtype == torch.float64),
+                                       _ptr(eps, torch.float32, "eps"), rows, L, _ptr(z), _ptr(mu), _ptr(lv), _stream()))
+    return z, mu, lv
 
 
 def split_bf16(src: torch.Tensor, want_lo: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

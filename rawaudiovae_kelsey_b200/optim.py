@@ -34,7 +34,7 @@ class Adam(torch.optim.Optimizer):
         self._flat = flat
         for group in self.param_groups:
             for p in group["params"]:
-                tag = getattr(p, "_rvae_flat", None)
+                tag = engine.flat_of(p)
                 if tag is None or tag[0] is not flat:
                     continue
                 name = tag[1]
@@ -45,7 +45,7 @@ class Adam(torch.optim.Optimizer):
         flat = None
         for group in self.param_groups:
             for p in group["params"]:
-                tag = getattr(p, "_rvae_flat", None)
+                tag = engine.flat_of(p)
                 if tag is None:
                     return None
                 f, name = tag
@@ -76,7 +76,7 @@ class Adam(torch.optim.Optimizer):
                 return loss
             g0 = flat.grads.data_ptr()
             for p in params:
-                _, name = p._rvae_flat
+                _, name = engine.flat_of(p)
                 off, _ = flat.offsets[name]
                 view = flat.view(flat.grads, name)
                 if p.grad is None:
@@ -102,7 +102,7 @@ class Adam(torch.optim.Optimizer):
                 ops.adam_step(p.data.view(-1), p.grad.contiguous().view(-1), st["exp_avg"].view(-1),
                               st["exp_avg_sq"].view(-1), st["step"], group["lr"], b1, b2, group["eps"],
                               group["weight_decay"])
-                tag = getattr(p, "_rvae_flat", None)
+                tag = engine.flat_of(p)
                 if tag is not None:
                     tag[0].shadow_version = -1  # shadows are stale; refreshed at the next forward
         return loss
@@ -115,7 +115,7 @@ class Adam(torch.optim.Optimizer):
         step = None
         for group in self.param_groups:
             for p in group["params"]:
-                tag = getattr(p, "_rvae_flat", None)
+                tag = engine.flat_of(p)
                 st = self.state.get(p)
                 if tag is None or not st:
                     continue

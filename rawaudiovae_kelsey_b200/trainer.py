@@ -135,11 +135,13 @@ def _with_next(iterable):
     yield cur, None
 
 
-def _flush_losses(writer, pending, print_fmt=None):
+def _flush_losses(writer, pending, print_fmt=None, world=1):
     """Read back a block of per-batch losses (device scalars) with one sync and log them under the reference's tag."""
     if not pending:
         return 0.0
     vals = torch.stack([l for _, l in pending]).cpu().tolist()
+    if world > 1:
+        rdist.check_health(pending[0][1].device)   # a rank that dropped out of the gradient exchange: fail loudly
     for (step_id, _), v in zip(pending, vals):
         writer.add_scalar('Loss/Batch', v, step_id)
         if print_fmt:
@@ -233,8 +235,8 @@ def run_epoch_trainer(argv=None):
             writer.add_scalar('Learning Rate', optimizer.param_groups[0]['lr'], batch_id)
             batch_id += 1
             if len(pending) >= log_interval:
-                train_loss += _flush_losses(writer, pending)
-        train_loss += _flush_losses(writer, pending)
+                train_loss += _flush_losses(writer, pending, world=world)
+        train_loss += _flush_losses(writer, pending, world=world)
         print('====> Epoch: {} - Total loss: {} - Average loss: {:.9f}'.format(
             epoch, train_loss, train_loss / len(training_dataset)))
         writer.add_scalar('Loss/train_total', train_loss, epoch)
@@ -261,6 +263,9 @@ def run_epoch_trainer(argv=None):
                 best_loss = train_loss
             elif train_loss > train_loss_prev:
                 print("Average loss did not improve.")
+        # rank 0 alone wrote histograms / checkpoints / test audio above: nobody runs ahead into the next epoch's
+        # gradient exchanges until it is back (the exchange waits for minutes, but there is no reason to queue up)
+        rdist.sync_ranks()
         final_loss = train_loss
 
     if rank == 0:
@@ -376,7 +381,7 @@ def run_stream_trainer(argv=None):
             writer.add_scalar('Learning Rate', optimizer.param_groups[0]['lr'], batch_id)
             at_checkpoint = batch_id % checkpoint_interval == 0 and batch_id != 0
             if len(pending) >= log_interval or at_checkpoint:
-                train_loss += _flush_losses(writer, pending, fmt if rank == 0 else None)
+                train_loss += _flush_losses(writer, pending, fmt if rank == 0 else None, world=world)
             if rank == 0 and histogram_interval > 0 and batch_id % histogram_interval == 0:
                 for name, param in model.named_parameters():
                     writer.add_histogram(name, param, batch_id)
@@ -398,8 +403,10 @@ def run_stream_trainer(argv=None):
                     best_loss = train_loss
                 elif train_loss > train_loss_prev:
                     print("Loss did not improve.")
+            if at_checkpoint or (histogram_interval > 0 and batch_id % histogram_interval == 0):
+                rdist.sync_ranks()   # rank 0 alone did I/O above (same condition on every rank): wait for it
             batch_id += 1
-        train_loss += _flush_losses(writer, pending, fmt if rank == 0 else None)
+        train_loss += _flush_losses(writer, pending, fmt if rank == 0 else None, world=world)
         final_loss = train_loss
 
         if rank == 0:

@@ -515,7 +515,14 @@ def test_widened_vae_inference_with_overlap_add(dev):
     assert torch.allclose(ident[: padded.numel()], padded, atol=1e-6)
 
 
+def _needs_experiments():
+    from rawaudiovae_kelsey_b200 import _lib
+    if not _lib.load().rvae_build_experiments():
+        pytest.skip("measured-and-rejected path: only in builds with RVAE_EXPERIMENTS=1")
+
+
 def test_chained_forward_launch_equals_separate_kernels(dev, monkeypatch):
+    _needs_experiments()
     """RVAE_FUSE_FORWARD=1 runs fc1 -> head -> fc3 -> fc4/loss as ONE persistent launch whose tiles wait for the
     row blocks they consume (tile-level dependency counters). Same arithmetic, same operands: losses and weights
     match the four separate launches up to the reduction-order noise of the loss / bias-gradient atomics."""
@@ -540,6 +547,7 @@ def test_chained_forward_launch_equals_separate_kernels(dev, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(512, 768, 128, 1300), (1024, 2048, 256, 768)])
 def test_fused_latent_epilogue_matches_latent_kernel(dev, monkeypatch, shape):
+    _needs_experiments()
     """RVAE_FUSE_LATENT=1 computes d_ml = [dz + c mu | dz eps sigma / 2 + c (sigma^2 - 1) / 2] and db2 in the epilogue
     of the latent dgrad GEMM (no split-K dz round trip, no latent backward kernel). Same formulas on the same
     operands as the kernel path: losses, weights and Adam moments agree up to accumulation-order noise. Ragged rows

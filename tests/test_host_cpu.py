@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rvae_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.rvae_abi_version() == 2
+    assert lib.rvae_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_param_layout_matches_reference_parameter_count():
@@ -86,6 +86,34 @@ def test_vae_surface_matches_reference():
     for k, p in m.named_parameters():
         assert torch.equal(p.detach(), ref[k]), k       # same default init stream as the reference
     assert VAE.__module__ == "rawvae.model"
+
+
+def test_reference_forward_traces_and_matches_the_oracle():
+    """SURVEY.md 8f N4 (export-onnx.ipynb:361-362): the ctypes kernels are invisible to a tracer, so forward() routes to
+    reference_forward - plain torch ops on the same parameters - while traced / exported. Its values equal the
+    oracle's, and torch.jit.trace(model, torch.randn(1024)) (the notebook's 1-D example input; the TorchScript ONNX
+    exporter traces the same way) yields a graph with the reference's outputs. No onnx runtime exists in this image."""
+    from rawvae.model import VAE
+    from oracle import rawvae_oracle as O
+    torch.manual_seed(0)
+    m = VAE(1024, 256, 64)
+    p = {k: v.detach().double() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 1024, generator=gen) * 2 - 1
+    eps = torch.randn(5, 64, generator=gen)
+    xh, mu, lv = m.reference_forward(x, eps)
+    act = O.forward(p, x.double(), eps.double())
+    for got, want in ((xh, act["x_hat"]), (mu, act["mu"]), (lv, act["logvar"])):
+        assert float((got.double() - want).norm() / want.norm()) < 1e-6
+    one = torch.randn(1024, generator=gen)
+    traced = torch.jit.trace(m, (one, torch.zeros(1, 64)), check_trace=False)     # forward() itself, on CPU
+    t_xh, t_mu, t_lv = traced(one, torch.zeros(1, 64))
+    r_xh, r_mu, r_lv = m.reference_forward(one, torch.zeros(1, 64))
+    assert t_xh.shape == (1, 1024) and torch.allclose(t_xh, r_xh) and torch.allclose(t_mu, r_mu)
+    ops = {n.kind() for n in traced.graph.nodes()} | {n.kind() for n in traced.inlined_graph.nodes()}
+    assert any("tanh" in k for k in ops) and any("linear" in k or "addmm" in k for k in ops), ops
+    with pytest.raises(Exception):
+        m(one)        # an ordinary (untraced) call on CPU still fails loudly: no CPU fallback
 
 
 def test_vae_pickles_like_a_plain_module(tmp_path):

@@ -32,6 +32,7 @@ def rel(a, b):
 def make():
     torch.manual_seed(0)
     m = VAE(S, H, L).to(dev)
+    m.eps_seed = 123
     return m, Adam(m.parameters(), lr=1e-3)
 
 
@@ -53,6 +54,26 @@ for s in range(3):
     # step 0 is a pure reassociation difference; later steps inherit Adam's sign-like amplification of that noise
     # (step 0: fp32 reassociation only - split-K reduce-adds, bias-gradient atomics, the all-reduce's summation order)
     ok &= dl < 1e-5 and dw < (5e-5 if s == 0 else 2e-3) and dm < (1e-5 if s == 0 else 2e-2)
+# In-library noise: with ONE seed for the group and Philox counters offset by the shard's first global row, the
+# ranks draw exactly the rows a single process draws for the concatenated batch (never the same noise twice).
+philox_ok = True
+for s in range(3, 5):
+    l_dp = step_dp(x[lo:hi].contiguous())
+    l_1 = step_1(x)
+    torch.cuda.synchronize()
+    e_dp = m_dp._plan_for(hi - lo).latent("eps")
+    e_1 = m_1._plan_for(B).latent("eps")
+    philox_ok &= bool(torch.equal(e_dp, e_1[lo:hi]))
+    dl = abs(float(l_dp) - float(l_1)) / float(l_1)
+    dw = rel(m_dp._flat.params, m_1._flat.params)
+    if rank == 0:
+        print(f"step {s} (philox): loss rel {dl:.2e}; weights rel {dw:.2e}; eps shard == single-process rows: {philox_ok}")
+    ok &= dl < 1e-4 and dw < 4e-3
+pf = torch.tensor([int(philox_ok)], device=dev)
+dist.all_reduce(pf, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("philox shards match the single-process draw:", bool(int(pf)))
+ok &= bool(int(pf))
 # replicas stay bit-identical to each other
 ref = m_dp._flat.params.clone()
 dist.broadcast(ref, src=0)

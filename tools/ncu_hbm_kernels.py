@@ -56,12 +56,15 @@ CASES = [
 ]
 
 under_ncu = "--ncu" in sys.argv
+only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""
 out = {}
 for name, fn, nbytes in CASES:
+    if only and only not in name:
+        continue
     fn()
     torch.cuda.synchronize()
     times = []
-    for _ in range(1 if under_ncu else 5):
+    for _ in range(1 if under_ncu else 9):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -73,7 +76,7 @@ for name, fn, nbytes in CASES:
     out[name] = {"us_events_incl_launch": round(us, 2), "algorithmic_bytes": nbytes,
                  "GB_per_s_events": round(nbytes / us / 1e3, 1)}
     print(f"{name:80s} {us:8.1f} us  {nbytes / 1e6:8.1f} MB  {nbytes / us / 1e3:8.1f} GB/s", flush=True)
-if not under_ncu:
+if not under_ncu and not only:
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/hbm_kernels_events.json", "w"), indent=1)
 print("done")
