@@ -436,6 +436,11 @@ def run_ours(args):
                         "sample": f"{len(times)} full {BATCH}-frame training steps of the oracle port "
                                   f"(torch CPU fp32, {threads} threads, {sum(times):.1f} s)"}
 
+    # ---- the other BASELINE.json configs (N = 1 only): extra keys of the same line
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = extra_legs(dev, audio, n_frames, peaks)
+
     if rank == 0:
         ms_per_step = ms / args.steps
         whole_tflops = value * FLOP_PER_FRAME / world / 1e12
@@ -471,11 +476,156 @@ def run_ours(args):
             "gemm_breakdown": breakdown,
             "cpu_baseline": cpu_baseline,
         }
+        if extras:
+            out.update(extras)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# ----------------------------------------------------------------------------------------------------- other configs
+def _median_blocks(step_once, n_blocks, steps, i0=0):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out, i = [], i0
+    for _ in range(n_blocks):
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step_once(i)
+            i += 1
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return float(np.median(out)), out, i
+
+
+def leg_fp32_mode(dev, audio, n_frames, peaks):
+    """default.ini VAE, B = 8192, fp32 mode: every GEMM as 3 tensor-core passes over split-bf16 operands into one fp32
+    TMEM accumulator (~2^-16 relative; the north star's "fp32-mode within 1e-4")."""
+    from rawaudiovae_kelsey_b200.model import FrameBatch, FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    from rawvae.model import VAE
+    torch.manual_seed(0)
+    model = VAE(S, H, L, precision="fp32").to(dev)
+    model.eps_seed = 1
+    step_fn = FusedTrainStep(model, Adam(model.parameters(), lr=LR), KL_BETA, graph=True)
+    g = torch.Generator(device=dev).manual_seed(7)
+    pool = 32
+    idx = torch.randint(0, n_frames, (pool, BATCH), generator=g, device=dev, dtype=torch.int64)
+    fbs = [FrameBatch(audio, BATCH, HOP, S, frame_idx=idx[k]) for k in range(pool)]
+    once = lambda i: step_fn(fbs[i % pool], next_data=fbs[(i + 1) % pool])
+    for i in range(10):
+        once(i)
+    assert step_fn.steady >= 4, step_fn.stats
+    s0 = dict(step_fn.stats)
+    ms, blocks, _ = _median_blocks(once, 5, 20, 10)
+    assert step_fn.stats["captures"] == s0["captures"] and step_fn.stats["eager"] == s0["eager"]
+    fps = BATCH * 20 / (ms * 1e-3)
+    alg = fps * FLOP_PER_FRAME / 1e12
+    return {"workload": "default.ini VAE fp32 mode (3-pass split-bf16), batch 8192, whole training step",
+            "value": fps, "unit": "frames/s", "ms_per_step": ms / 20, "block_ms": [round(v, 3) for v in blocks],
+            "roofline": {"bound": "tensor", "achieved": 3 * alg, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": 3 * alg / peaks["bf16_sustained"], "algorithmic_tflops": alg, "tensor_passes": 3,
+                         "peak_kind": f"bf16_tflops_sustained ({peaks['source']}), executed tensor flops = 3 x algorithmic"}}
+
+
+def leg_stream_4096(dev, peaks):
+    """kelsey_iterable.ini pattern (BASELINE.json configs[3]): batch 4096, frames of long wav streams framed on the GPU.
+    END TO END from wav files on disk: a worker thread decodes PCM16 files into pinned memory, they are copied into a
+    device ring smaller than the corpus (so every cycle re-uploads: the streaming case), batches straddle files."""
+    import tempfile
+    import scipy.io.wavfile as wavfile
+    from rawaudiovae_kelsey_b200.dataset import IterableAudioDataset
+    from rawaudiovae_kelsey_b200.model import FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    from rawaudiovae_kelsey_b200.trainer import _with_next
+    from rawvae.model import VAE
+    B4, n_files, secs = 4096, 8, 30.0
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(4321)
+        for k in range(n_files):
+            x = synth_wav(rng, int(secs * SR), SR)
+            wavfile.write(os.path.join(tmp, f"stream{k}.wav"), SR, np.round(x * 32768.0).clip(-32768, 32767).astype(np.int16))
+        ds = IterableAudioDataset(tmp, SR, HOP, torch.float32, dev, shuffle=True)
+        file_bytes = int(secs * SR) * 2
+        stream = ds.gpu_stream(B4, dev, pcm16=True, cache_bytes=int(3.5 * file_bytes))
+        torch.manual_seed(0)
+        model = VAE(S, H, L).to(dev)
+        model.eps_seed = 1
+        step_fn = FusedTrainStep(model, Adam(model.parameters(), lr=LR), KL_BETA, graph=True)
+        pairs = _with_next(iter(stream))
+        once = lambda i: _stream_step(step_fn, pairs)
+        for i in range(12):
+            once(i)
+        s0 = dict(step_fn.stats)
+        up0 = dict(stream.stats)
+        ms, blocks, _ = _median_blocks(once, 7, 40, 12)
+        d = {k: step_fn.stats[k] - s0[k] for k in s0}
+        fps = B4 * 40 / (ms * 1e-3)
+        uploaded = stream.stats["bytes_uploaded"] - up0["bytes_uploaded"]
+        return {"workload": "kelsey_iterable.ini pattern: default.ini VAE bf16 training, batch 4096, frames streamed "
+                            f"from {n_files} PCM16 wav files x {secs:.0f} s through a {stream.capacity * 2 / 1e6:.1f} MB "
+                            "ingest ring (smaller than the corpus), end to end from disk",
+                "value": fps, "unit": "frames/s", "ms_per_step": ms / 40, "block_ms": [round(v, 3) for v in blocks],
+                "h2d_bytes_per_step": uploaded / (7 * 40), "graph_stats_in_timed_region": d,
+                "ingest": dict(stream.stats),
+                "frac_of_bf16_sustained_peak": fps * FLOP_PER_FRAME / 1e12 / peaks["bf16_sustained"]}
+
+
+def _stream_step(step_fn, pairs):
+    cur, nxt = next(pairs)
+    return step_fn(cur, next_data=nxt)
+
+
+def leg_widened_inference(dev, peaks):
+    """BASELINE.json configs[4]: widened VAE (segment_length 4096, n_units 4096, latent 256) inference over 1 M frames
+    at hop 512, batches of 16 384: PCM16 wav in HBM -> frames -> encode -> reparameterize -> decode -> overlap-add
+    across batch boundaries (inference.reconstruct_audio)."""
+    from rawaudiovae_kelsey_b200 import inference as inf
+    from rawvae.model import VAE
+    Sw, Hw, Lw, hop, Bw, N = 4096, 4096, 256, 512, 16384, 1 << 20
+    flop_per_frame = 73400320                    # SURVEY.md 8(a) a13
+    torch.manual_seed(0)
+    model = VAE(Sw, Hw, Lw).to(dev).eval()
+    model.eps_seed = 3
+    n_samples = (N - 1) * hop + Sw
+    wav = torch.randint(-20000, 20000, (n_samples,), dtype=torch.int16, device=dev)
+    inf.reconstruct_audio(model, wav[:(4 * Bw - 1) * hop + Sw], hop=hop, batch_size=Bw)       # warm-up: plans, tensor maps
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = inf.reconstruct_audio(model, wav, hop=hop, batch_size=Bw)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    assert out.numel() == n_samples and bool(torch.isfinite(out[::4097]).all())
+    ms = float(np.median(times))
+    fps = N / (ms * 1e-3)
+    tf = fps * flop_per_frame / 1e12
+    return {"workload": "widened VAE (S=4096,H=4096,L=256) bf16 inference, 1 Mi frames at hop 512, batch 16384: "
+                        "frames -> encode -> reparameterize -> decode -> overlap-add",
+            "value": fps, "unit": "frames/s", "ms_total": ms, "runs_ms": [round(v, 2) for v in times],
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["bf16_sustained"], "frac_of_burst": tf / peaks["bf16_burst"],
+                         "peak_kind": f"bf16_tflops_sustained ({peaks['source']}): ~{ms:.0f} ms of back-to-back GEMMs"}}
+
+
+def extra_legs(dev, audio, n_frames, peaks):
+    out = {}
+    for name, fn in (("fp32_mode", lambda: leg_fp32_mode(dev, audio, n_frames, peaks)),
+                     ("stream_4096", lambda: leg_stream_4096(dev, peaks)),
+                     ("widened_inference", lambda: leg_widened_inference(dev, peaks))):
+        try:
+            out[name] = fn()
+        except Exception as e:   # a failing side leg must never take the headline line down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -488,6 +638,8 @@ def main():
     ap.add_argument("--files", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the side legs (fp32 mode, kelsey_iterable.ini streaming, widened-VAE inference)")
     ap.add_argument("--blocks", type=int, default=0,
                     help="timed blocks of --steps steps each (median reported); 0 = enough for >= 0.3 s of load, >= 7")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every step eagerly (no CUDA graph)")

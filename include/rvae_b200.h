@@ -98,10 +98,11 @@ int rvae_frame_gather(rvae_ctx* ctx, const void* audio, int audio_is_i16, int64_
                       const int64_t* frame_idx, int64_t first_frame, int64_t n_frames, int hop, int S,
                       void* out_hi, void* out_lo, float* out_f32, void* stream);
 
-/* Overlap-add resynthesis: out[t] = mean over the frames covering t of frames[i, t - i*hop], t in [0, n_out).
+/* Overlap-add resynthesis: out[t - t_begin] = mean over the frames covering t of frames[i, t - i*hop], for
+ * t in [t_begin, t_begin + n_out) (t_begin > 0: one window of a long signal that is resynthesised batch by batch).
  * With hop == S this is frames.view(-1) (train_iterable.py:246, tutorial.ipynb:543). frames is fp32 [n_frames, S]. */
 int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out,
-                     int64_t n_out, void* stream);
+                     int64_t t_begin, int64_t n_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Elementwise pieces of the model / loss / optimizer

@@ -48,7 +48,7 @@ SIGNATURES = {
     "rvae_dp_sym_open": (c_int, [P, P, c_int, c_int]),
     "rvae_dp_allreduce": (c_int, [P, P, c_int64, c_int, P]),
     "rvae_frame_gather": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, P, P]),
-    "rvae_overlap_add": (c_int, [P, P, c_int64, c_int, c_int, P, c_int64, P]),
+    "rvae_overlap_add": (c_int, [P, P, c_int64, c_int, c_int, P, c_int64, c_int64, P]),
     "rvae_randn": (c_int, [P, P, c_int64, c_uint64, c_uint64, c_int64, P]),
     "rvae_lerp_reparameterize": (c_int, [P, P, P, P, P, P, c_int, P, c_int64, c_int, P, P, P, P]),
     "rvae_dp_status": (c_int, [P, C.POINTER(C.c_uint)]),

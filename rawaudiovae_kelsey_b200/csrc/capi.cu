@@ -273,10 +273,10 @@ int rvae_frame_gather(rvae_ctx* ctx, const void* audio, int audio_is_i16, int64_
   return launch_frame_gather(&ctx->c, audio, audio_is_i16, n_samples, frame_idx, first_frame, n_frames, hop, S,
                              BF(out_hi), BF(out_lo), out_f32, S_(stream));
 }
-int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
-                     void* stream) {
+int rvae_overlap_add(rvae_ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t t_begin,
+                     int64_t n_out, void* stream) {
   CTX_OR_FAIL(ctx);
-  return launch_overlap_add(&ctx->c, frames, n_frames, S, hop, out, n_out, S_(stream));
+  return launch_overlap_add(&ctx->c, frames, n_frames, S, hop, out, t_begin, n_out, S_(stream));
 }
 int rvae_randn(rvae_ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, int64_t elem_base,
                void* stream) {

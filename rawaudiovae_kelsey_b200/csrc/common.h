@@ -150,8 +150,8 @@ int gemm_launch(Ctx* ctx, const GemmDesc& d, cudaStream_t stream);  // prepare +
 int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n_samples, const int64_t* frame_idx,
                         int64_t first_frame, int64_t n_frames, int hop, int S, __nv_bfloat16* out_hi,
                         __nv_bfloat16* out_lo, float* out_f32, cudaStream_t stream);
-int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
-                       cudaStream_t stream);
+int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t t_begin,
+                       int64_t n_out, cudaStream_t stream);
 int launch_randn(Ctx* ctx, float* out, int64_t n, uint64_t seed, uint64_t offset, const float* offset_src,
                  int64_t elem_base, cudaStream_t stream);
 int launch_split_bf16(Ctx* ctx, const float* src, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo,

@@ -170,7 +170,7 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
 // ------------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_frames, int S, int hop,
-                                   float* __restrict__ out, int64_t n_out) {
+                                   float* __restrict__ out, int64_t t_begin, int64_t n_out) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   // VEC: S, hop and both base addresses are multiples of 4 elements, so the 4 samples of an aligned group are
@@ -178,8 +178,9 @@ __global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_f
   // index) is the scalar path's, hence bit-identical results. The scalar path also finishes a ragged tail.
   constexpr int W = VEC ? 4 : 1;
   const int64_t n_groups = VEC ? (n_out >> 2) : n_out;
+  out -= t_begin;   // out[t - t_begin] = OLA(t) for t in [t_begin, t_begin + n_out)
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_groups; w += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = w * W;
+    const int64_t t = t_begin + w * W;
     int64_t i_hi = t / hop;
     if (i_hi > n_frames - 1) i_hi = n_frames - 1;
     int64_t i_lo = (t - S + hop) / hop;  // ceil((t - S + 1) / hop) for t - S + 1 > 0
@@ -213,10 +214,11 @@ __global__ void overlap_add_kernel(const float* __restrict__ frames, int64_t n_f
 
 // samples [t0, n_out) of the scalar rule (the < 4-sample tail the vector path leaves)
 __global__ void overlap_add_tail_kernel(const float* __restrict__ frames, int64_t n_frames, int S, int hop,
-                                        float* __restrict__ out, int64_t t0, int64_t n_out) {
+                                        float* __restrict__ out, int64_t t_begin, int64_t t0, int64_t t_end) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  for (int64_t t = t0 + threadIdx.x; t < n_out; t += blockDim.x) {
+  out -= t_begin;
+  for (int64_t t = t0 + threadIdx.x; t < t_end; t += blockDim.x) {
     int64_t i_hi = t / hop;
     if (i_hi > n_frames - 1) i_hi = n_frames - 1;
     int64_t i_lo = (t - S + hop) / hop;
@@ -234,24 +236,25 @@ __global__ void overlap_add_tail_kernel(const float* __restrict__ frames, int64_
   }
 }
 
-int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t n_out,
-                       cudaStream_t stream) {
+int launch_overlap_add(Ctx* ctx, const float* frames, int64_t n_frames, int S, int hop, float* out, int64_t t_begin,
+                       int64_t n_out, cudaStream_t stream) {
   RVAE_REQUIRE(frames && out, RVAE_ERR_INVALID, "overlap_add: null buffer");
-  RVAE_REQUIRE(S > 0 && hop > 0 && hop <= S, RVAE_ERR_UNSUPPORTED, "overlap_add: need 0 < hop <= S");
+  RVAE_REQUIRE(S > 0 && hop > 0 && hop <= S && t_begin >= 0, RVAE_ERR_UNSUPPORTED, "overlap_add: need 0 < hop <= S, t_begin >= 0");
   if (n_out <= 0) return RVAE_OK;
   const int threads = 256;
-  const bool vec = S % 4 == 0 && hop % 4 == 0 && ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const bool vec = S % 4 == 0 && hop % 4 == 0 && t_begin % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   int64_t done = 0;
   if (vec && n_out >= 4) {
     done = n_out & ~(int64_t)3;
-    RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel<true>, dim3(grid_for(ctx, done >> 2, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, done));
+    RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel<true>, dim3(grid_for(ctx, done >> 2, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, t_begin, done));
   }
   if (done < n_out) {
     if (done == 0) {
-      RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel<false>, dim3(grid_for(ctx, n_out, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, n_out));
+      RVAE_CUDA(launch_kernel(ctx, overlap_add_kernel<false>, dim3(grid_for(ctx, n_out, threads, 16)), dim3(threads), (size_t)0, stream, frames, n_frames, S, hop, out, t_begin, n_out));
     } else {
       // ragged tail (< 4 samples) of the vector path
-      RVAE_CUDA(launch_kernel(ctx, overlap_add_tail_kernel, dim3(1), dim3(32), (size_t)0, stream, frames, n_frames, S, hop, out, done, n_out));
+      RVAE_CUDA(launch_kernel(ctx, overlap_add_tail_kernel, dim3(1), dim3(32), (size_t)0, stream, frames, n_frames, S, hop, out, t_begin, t_begin + done, t_begin + n_out));
     }
   }
   RVAE_LAUNCH_CHECK(ctx);

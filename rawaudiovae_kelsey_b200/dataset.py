@@ -223,31 +223,55 @@ class GpuFrameLoader:
 
 
 class GpuFrameStream:
-    """IterableAudioDataset's endless stream, batched on the GPU: each file is decoded once, padded to a multiple
-    of hop and uploaded (as PCM16 or float32); a batch is a list of (file buffer, first frame, count) runs that the
-    framing kernel gathers into one [B, 1024] operand. Batches straddle file boundaries exactly as the reference's
-    DataLoader(batch_size=B, shuffle=False) over the iterable dataset does (train_iterable.py:143-151)."""
+    """IterableAudioDataset's endless stream, batched on the GPU through a bounded ingest ring.
+
+    Host side: a worker thread decodes the next files (wav -> mono channel 0 -> resample if needed -> zero-pad to a
+    multiple of hop, rawvae/dataset.py:47-63) into PINNED buffers while the GPU trains; each file is then copied
+    (PCM16 on the wire when `pcm16`, else float32) on a copy stream into a device RING of `cache_bytes` - the only HBM
+    the corpus ever occupies, so corpora larger than HBM (or than the ring) stream through, and a file that is
+    still resident when the stream cycles back to it is not uploaded again. Device side: a batch is ONE FrameBatch
+    over the ring - `first_frame` when its frames are one run of one file, else an int64 index list built on the
+    device - so batches straddle file boundaries exactly as the reference's DataLoader(batch_size=B, shuffle=False)
+    over the iterable dataset does (train_iterable.py:143-151), the framing kernel converts int16 -> bf16 while it
+    gathers, and every batch has the same input signature (one CUDA graph serves the whole stream).
+
+    A ring region is overwritten only after the steps that read it have run: every batch records which files it
+    touches, an event is recorded on the consumer's stream each time the consumer comes back for another batch, and
+    the copy stream waits for the event that covers the last reader of the region it is about to reuse."""
+
+    LAG = 3   # a batch handed out at yield j has been enqueued by the consumer once yield j + LAG is requested
 
     def __init__(self, dataset: IterableAudioDataset, batch_size: int, device, pcm16: bool = False,
-                 rank: int = 0, world: int = 1, cache_files: bool = True):
+                 rank: int = 0, world: int = 1, cache_bytes: int = 2 << 30, lookahead: int = 2):
         self.ds, self.batch_size, self.device = dataset, int(batch_size), torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("GpuFrameStream needs a CUDA device (no CPU fallback)")
-        self.pcm16, self.rank, self.world = pcm16, rank, world
-        self.cache = {} if cache_files else None
+        self.pcm16, self.rank, self.world = bool(pcm16), rank, world
+        self.dtype = torch.int16 if self.pcm16 else torch.float32
+        self.esize = 2 if self.pcm16 else 4
+        self.capacity = max(int(cache_bytes) // self.esize // 1024 * 1024, 1024)   # samples
+        self.lookahead = max(1, int(lookahead))
+        self.ring: Optional[torch.Tensor] = None
+        self.stats = {"files_uploaded": 0, "bytes_uploaded": 0, "resident_hits": 0, "ring_wraps": 0}
 
-    def _file_buffer(self, path) -> torch.Tensor:
-        if self.cache is not None and path in self.cache:
-            return self.cache[path]
-        audio = self.ds.load_file(path)
+    # ---- host side
+    def _decode(self, path) -> torch.Tensor:
+        """Pinned host tensor of the file's padded samples in the wire format."""
+        audio = self.ds.load_file(path)                       # float32, zero-padded to a multiple of hop
         if self.pcm16:
             audio = torch.round(audio * 32768.0).clamp_(-32768, 32767).to(torch.int16)
-        buf = audio.to(self.device)
-        if self.cache is not None:
-            self.cache[path] = buf
-        return buf
+        return audio.contiguous().pin_memory()
 
-    def __iter__(self) -> Iterator[List[FrameBatch]]:
+    # ---- device side
+    def _ensure_ring(self, need: int) -> None:
+        if need > self.capacity:
+            raise RuntimeError(f"a file of {need} samples does not fit the ingest ring ({self.capacity} samples); "
+                               f"raise cache_bytes to at least {need * self.esize}")
+        if self.ring is None:
+            self.ring = torch.zeros(self.capacity, dtype=self.dtype, device=self.device)
+
+    def __iter__(self) -> Iterator[FrameBatch]:
+        from concurrent.futures import ThreadPoolExecutor
         files = self.ds.shuffled_data_list if self.ds.shuffle else self.ds.audio_file_list
         if not files:
             raise RuntimeError("no wav files in {}".format(self.ds.audio_folder))
@@ -255,30 +279,135 @@ class GpuFrameStream:
             from . import dist as rdist
             files = [Path(f) for f in rdist.agree([str(f) for f in files])]
         S, hop, bs = 1024, self.ds.hop_size, self.batch_size
-        pending: List[FrameBatch] = []
-        have = 0
-        for path in cycle(files):
-            buf = self._file_buffer(path)
-            n_frames = (buf.numel() - S) // hop + 1 if buf.numel() >= S else 0
-            start = 0
-            while start < n_frames:
-                take = min(n_frames - start, bs - have)
-                pending.append(FrameBatch(buf, take, hop, S, first_frame=start))
-                have += take
-                start += take
-                if have == bs:
-                    yield self._shard(pending)
-                    pending, have = [], 0
+        dev = self.device
+        copy_stream = torch.cuda.Stream(device=dev)
+        pool = ThreadPoolExecutor(max_workers=1)
+        order = cycle(files)
+        queue = []          # [(path, decode future or None)] - the next files of the stream, decoded ahead
+        regions = {}        # region id -> {off, n, path, last_yield, ready}: live pieces of the ring
+        resident = {}       # path -> region id of its newest upload
+        events = {}         # k -> event recorded on the consumer's stream when it came back after batch k
+        state = {"write": 0, "next_id": 0, "yields": 0}
 
-    def _shard(self, runs: List[FrameBatch]) -> List[FrameBatch]:
-        if self.world == 1:
-            return runs
-        lo, hi = shard_bounds(self.batch_size, self.rank, self.world)
+        def top_up():
+            while len(queue) < self.lookahead + 1:
+                path = next(order)
+                queue.append((path, None if path in resident else pool.submit(self._decode, path)))
+
+        def reclaim(off, n, strict):
+            """Make ring[off : off + n) writable: retire the regions it overlaps once their last readers have run.
+            Returns False (and changes nothing) when a region cannot be retired yet; raises instead when `strict`."""
+            hit = [rid for rid, r in regions.items() if r["off"] < off + n and off < r["off"] + r["n"]]
+            wait = []
+            for rid in hit:
+                r = regions[rid]
+                need = r["last_yield"] + self.LAG
+                covering = [k for k in events if k >= need]
+                if any(t is r for t in touched) or (r["last_yield"] > 0 and not covering):
+                    if strict:
+                        raise RuntimeError(
+                            "GpuFrameStream: the ingest ring is too small - a region would be overwritten while a batch "
+                            "that reads it may still be pending; raise cache_bytes (now {} bytes)".format(
+                                self.capacity * self.esize))
+                    return False
+                if r["last_yield"] > 0:
+                    wait.append(events[min(covering)])
+            for rid in hit:
+                r = regions.pop(rid)
+                if resident.get(r["path"]) == rid:
+                    del resident[r["path"]]
+            for ev in wait:
+                copy_stream.wait_event(ev)
+            return True
+
+        def place(path, host, strict=True):
+            n = host.numel()
+            self._ensure_ring(n)
+            off = 0 if state["write"] + n > self.capacity else state["write"]
+            if not reclaim(off, n, strict):
+                return None
+            if off == 0 and state["write"] != 0:
+                self.stats["ring_wraps"] += 1
+            with torch.cuda.stream(copy_stream):
+                self.ring[off:off + n].copy_(host, non_blocking=True)    # pinned host -> ring, off the step's stream
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            rid = state["next_id"]
+            state["next_id"] += 1
+            regions[rid] = {"off": off, "n": n, "path": path, "last_yield": 0, "ready": ready}
+            resident[path] = rid
+            state["write"] = off + n
+            self.stats["files_uploaded"] += 1
+            self.stats["bytes_uploaded"] += n * self.esize
+            return regions[rid]
+
+        def upload_ahead():
+            """The next file's host->device copy is issued as soon as its decode is done and its ring space is free,
+            while the batches of the current file are still being consumed."""
+            if queue and queue[0][1] is not None and queue[0][1].done() and queue[0][0] not in resident:
+                path, fut = queue[0]
+                r = place(path, fut.result(), strict=False)
+                if r is not None:
+                    queue[0] = (path, None)
+                    ahead[path] = r["ready"]
+
+        runs, have, touched, waits, ahead = [], 0, [], [], {}
+        try:
+            while True:
+                top_up()
+                path, fut = queue.pop(0)
+                rid = resident.get(path)
+                if rid is not None:
+                    r = regions[rid]                 # uploaded ahead, or still in the ring from an earlier pass
+                    if path in ahead:
+                        waits.append(ahead.pop(path))
+                    else:
+                        self.stats["resident_hits"] += 1
+                else:
+                    r = place(path, fut.result() if fut is not None else self._decode(path))
+                    waits.append(r["ready"])
+                n_frames = (r["n"] - S) // hop + 1 if r["n"] >= S else 0
+                f0 = r["off"] // hop                  # files are padded to a multiple of hop: offsets stay hop-aligned
+                start = 0
+                while start < n_frames:
+                    take = min(n_frames - start, bs - have)
+                    runs.append((f0 + start, take))
+                    touched.append(r)
+                    have += take
+                    start += take
+                    if have == bs:
+                        main = torch.cuda.current_stream(dev)
+                        for ev in waits:              # the uploads this batch reads
+                            main.wait_event(ev)
+                        waits = []
+                        state["yields"] += 1
+                        for t in touched:
+                            t["last_yield"] = state["yields"]
+                        batch = self._batch(runs, hop, S)
+                        runs, have, touched = [], 0, []
+                        upload_ahead()
+                        yield batch
+                        # The consumer is back for more. With a one-batch lookahead (trainer._with_next) the gather of
+                        # batch k has been enqueued by the time it returns after batch k + 1; LAG = 3 leaves margin.
+                        ev = torch.cuda.Event()
+                        ev.record(torch.cuda.current_stream(dev))
+                        events[state["yields"]] = ev
+                        events.pop(state["yields"] - 256, None)
+        finally:
+            pool.shutdown(wait=False, cancel_futures=True)
+
+    def _batch(self, runs, hop: int, S: int) -> FrameBatch:
+        """One FrameBatch over the ring for the global batch `runs` = [(first ring frame, count)], sharded by rank."""
+        bs = self.batch_size
+        lo, hi = shard_bounds(bs, self.rank, self.world) if self.world > 1 else (0, bs)
+        rows = dict(global_row0=lo, global_batch=bs) if self.world > 1 else {}
         out, pos = [], 0
-        for r in runs:
-            a, b = max(lo, pos), min(hi, pos + r.n_frames)
+        for f0, cnt in runs:                          # this rank's rows [lo, hi) of the global batch
+            a, b = max(lo, pos), min(hi, pos + cnt)
             if b > a:
-                out.append(FrameBatch(r.audio, b - a, r.hop, r.segment_length, first_frame=r.first_frame + (a - pos),
-                                      global_row0=lo, global_batch=self.batch_size))
-            pos += r.n_frames
-        return out
+                out.append((f0 + (a - pos), b - a))
+            pos += cnt
+        if len(out) == 1:
+            return FrameBatch(self.ring, out[0][1], hop, S, first_frame=out[0][0], **rows)
+        idx = torch.cat([torch.arange(f, f + c, dtype=torch.int64, device=self.device) for f, c in out])
+        return FrameBatch(self.ring, hi - lo, hop, S, frame_idx=idx, **rows)

@@ -182,12 +182,63 @@ def resynthesize(frames: torch.Tensor, mode: str = "concat", hop: Optional[int] 
 
 @torch.no_grad()
 def reconstruct_audio(model: VAE, wav, *, hop: Optional[int] = None, mode: Optional[str] = None,
-                      batch_size: int = 16384, sample: bool = True) -> torch.Tensor:
-    """wav -> frames -> model(frames)[0] -> audio: the test-audio reconstruction of the trainers
-    (train_iterable.py:228-246) and the notebook's resynthesis, in one call. hop None = TestDataset framing + concat;
-    with a hop the default resynthesis is overlap-add."""
-    mu, lv = encode_audio(model, wav, hop=hop, batch_size=batch_size)
-    frames = interpolate(model, mu, lv, mu, lv, 0.0, sample=sample, batch_size=batch_size)
-    if hop is None:
-        return resynthesize(frames, "concat")
-    return resynthesize(frames, mode or "ola", hop=hop)
+                      batch_size: int = 16384, sample: bool = True, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wav -> frames -> encode -> reparameterize -> decode -> audio, streamed batch by batch (BASELINE.json configs[4]:
+    the widened-VAE inference pattern; also the trainers' test-audio reconstruction, train_iterable.py:228-246).
+
+    hop None: TestDataset framing (non-overlapping frames) + concatenation, as the reference resynthesises.
+    hop given: AudioDataset framing at stride hop; mode 'ola' (default) overlap-adds across batch boundaries - the
+    last S/hop - 1 decoded frames of a batch are carried into the next one, each output sample is finalised once -
+    so memory stays O(batch) however long the audio is; mode 'concat' reproduces the notebook's frames.view(-1).
+    The wav stays in HBM as it came (int16 or float32); frames are never materialised in fp32; decoded frames live
+    in one [S/hop - 1 + batch, S] buffer. Noise: `eps` [n_frames, L] if given, else Philox per frame (sample=True)
+    or none (sample=False: the mean path)."""
+    dev = _device_of(model)
+    S, L = model.segment_length, model.latent_dim
+    step = S if hop is None else int(hop)
+    if S % step != 0:
+        raise ValueError("segment_length {} is not a multiple of hop_size {}".format(S, step))
+    n = int(wav.shape[0])
+    audio = _audio_to_device(wav, dev, step)
+    N = frame_count(n, S, hop)
+    ola = hop is not None and (mode or "ola") == "ola"
+    if hop is not None and (mode or "ola") not in ("ola", "concat"):
+        raise ValueError("mode must be 'concat' or 'ola'")
+    r = S // step if ola else 1                         # frames covering one sample
+    n_out = (N - 1) * step + S if ola else N * S
+    out = torch.empty(n_out, dtype=torch.float32, device=dev)
+    B = min(batch_size, N)
+    buf = torch.empty((r - 1 + B, S), dtype=torch.float32, device=dev)   # [carry of the previous batch | this batch]
+    mu = torch.empty((B, L), dtype=torch.float32, device=dev)
+    lv = torch.empty_like(mu)
+    zero = torch.zeros(B, dtype=torch.float32, device=dev)
+    seed, off = model._eps_args() if (eps is None and sample and model.eps_source != "torch") else (0, 0)
+    for lo in range(0, N, B):
+        hi = min(N, lo + B)
+        b = hi - lo
+        plan = model._load(FrameBatch(audio, b, step, S, first_frame=lo))
+        plan.set_outputs(mu[:b], lv[:b], None)
+        plan.encode()
+        plan.set_outputs(None, None, None)
+        if eps is not None:
+            e = eps[lo:hi].to(device=dev, dtype=torch.float32).contiguous()
+        elif not sample:
+            e = None
+        elif model.eps_source == "torch":
+            e = torch.randn((b, L), device=dev)
+        else:
+            e = ops.randn((b, L), seed, off, device=dev, elem_base=lo * L)    # one noise tensor over all frames
+        frames = buf[r - 1:r - 1 + b]
+        plan.decode_lerp(mu[:b], lv[:b], mu[:b], lv[:b], zero[:b], e, frames)  # alpha = 0: z goes straight to fc3
+        if not ola:
+            out[lo * S:hi * S].copy_(frames.reshape(-1))
+            continue
+        # finalise samples [lo * hop, hi * hop) (+ the tail after the last frame): every frame covering them is in buf
+        valid = min(r - 1, lo)                       # carried frames that exist (fewer than r - 1 near the start)
+        src = buf[r - 1 - valid:r - 1 + b]
+        t0 = valid * step                            # local sample index of global sample lo * hop
+        cnt = (b * step) if hi < N else (b - 1) * step + S
+        ops.overlap_add(src, step, cnt, t_begin=t0, out=out[lo * step:lo * step + cnt])
+        if hi < N and r > 1:
+            buf[:r - 1].copy_(buf[b:b + r - 1].clone())     # carry the last r - 1 frames (b >= r - 1 for full batches)
+    return out

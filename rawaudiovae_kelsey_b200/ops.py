@@ -116,14 +116,20 @@ def frame_gather(audio: torch.Tensor, n_frames: int, hop: int, S: int, *, frame_
     return f32, hi, lo
 
 
-def overlap_add(frames: torch.Tensor, hop: int, n_out: Optional[int] = None) -> torch.Tensor:
+def overlap_add(frames: torch.Tensor, hop: int, n_out: Optional[int] = None, *, t_begin: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[t - t_begin] = overlap-add of `frames` (fp32 [n, S], cut at stride hop) at sample t, for n_out samples from
+    t_begin on (default: the whole signal). `out`: write into this 1-D fp32 tensor instead of allocating."""
     lib = _lib.load()
     n_frames, S = frames.shape
     if n_out is None:
-        n_out = (n_frames - 1) * hop + S if n_frames > 0 else 0
-    out = torch.empty((n_out,), dtype=torch.float32, device=frames.device)
+        n_out = out.numel() if out is not None else max((n_frames - 1) * hop + S - t_begin, 0) if n_frames > 0 else 0
+    if out is None:
+        out = torch.empty((n_out,), dtype=torch.float32, device=frames.device)
+    elif out.numel() < n_out:
+        raise _lib.RvaeError("overlap_add: output tensor too small")
     check(lib.rvae_overlap_add(ctx(frames.device), _ptr(frames, torch.float32, "frames"), n_frames, S, hop,
-                               _ptr(out), n_out, _stream()))
+                               _ptr(out, torch.float32, "out"), t_begin, n_out, _stream()))
     return out
 
 

@@ -214,6 +214,19 @@ def test_inference_api_interpolation_pattern_vs_oracle(dev):
     fr = torch.from_numpy(O.audio_dataset_frames(wav_a, S_, HOP)).to(dev)
     ola = inf.resynthesize(fr, mode="ola", hop=HOP)
     assert torch.allclose(ola.cpu(), torch.from_numpy(O.pad_to_multiple(wav_a, HOP)), atol=1e-6)
+    # streamed reconstruction (encode -> reparameterize -> decode -> overlap-add, batch by batch with a carry of the last
+    # S/hop - 1 decoded frames) == everything at once; ragged last batch, batch smaller than the carry included
+    mu_h, lv_h = inf.encode_audio(model, wav_a, hop=HOP)
+    Nh = mu_h.shape[0]
+    eps_h = torch.randn(Nh, L_, generator=torch.Generator().manual_seed(3)).to(dev)
+    whole = inf.resynthesize(inf.decode_latents(model, inf.lerp_latents(mu_h, lv_h, mu_h, lv_h, 0.0, eps=eps_h)),
+                             mode="ola", hop=HOP)
+    for bs in (Nh, 500, 37, 5):
+        streamed = inf.reconstruct_audio(model, wav_a, hop=HOP, batch_size=bs, eps=eps_h)
+        assert streamed.shape == whole.shape and float((streamed - whole).abs().max()) < 2e-5, bs
+    rec = inf.reconstruct_audio(model, wav_a, batch_size=64, sample=False)          # TestDataset framing + concat
+    mean_path = inf.decode_latents(model, mu_a)
+    assert rec.shape == (N * S_,) and float((rec - mean_path.reshape(-1)).abs().max()) < 2e-5
     # bf16 mode within its tolerance too
     model.set_precision("bf16")
     assert rel(inf.interpolate(model, mu_a, lv_a, mu_b, lv_b, al, eps=eps.to(dev)), x_ref) < BF16_TOL

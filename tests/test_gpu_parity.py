@@ -305,20 +305,67 @@ def test_gpu_stream_matches_reference_stream(dev, golden_dir, tmp_path):
     it = IterableAudioDataset(tmp_path, 44100, 128, torch.float32, dev, shuffle=False)
     it.audio_file_list = [tmp_path / n for n in order]             # glob order is filesystem dependent
     got = []
-    for runs in it.gpu_stream(batch_size=50):
-        for r in runs:
-            got.append(r.materialize())
+    for fb in it.gpu_stream(batch_size=50):
+        got.append(fb.materialize())
         if sum(len(g) for g in got) >= 150:
             break
     got = torch.cat(got)[:150].cpu().numpy()
     np.testing.assert_array_equal(got, ds["stream_frames"])
-    # PCM16-resident variant decodes to the same floats
+    # PCM16 on the wire / in the ring decodes to the same floats
     got16 = []
-    for runs in it.gpu_stream(batch_size=50, pcm16=True):
-        got16 += [r.materialize() for r in runs]
+    stream16 = it.gpu_stream(batch_size=50, pcm16=True)
+    for fb in stream16:
+        got16.append(fb.materialize())
         if sum(len(g) for g in got16) >= 150:
             break
     np.testing.assert_array_equal(torch.cat(got16)[:150].cpu().numpy(), ds["stream_frames"])
+    assert stream16.ring.dtype == torch.int16
+
+
+def _write_mixed_corpus(root):
+    """14 short wavs: 44.1 kHz mono, 48 kHz and 22.05 kHz (resampled on ingest), one stereo (channel 0 is kept)."""
+    import scipy.io.wavfile as wavfile
+    from oracle.rawvae_oracle import synth_wav
+    rng = np.random.default_rng(11)
+    names = []
+    for i in range(14):
+        rate = (44100, 48000, 44100, 22050, 44100, 44100, 44100)[i % 7]
+        secs = 0.3 + 0.2 * rng.random()
+        x = np.round(synth_wav(rng, int(rate * secs), rate) * 32767).astype(np.int16)
+        if i == 4:
+            x = np.stack([x, x[::-1]], axis=1)
+        wavfile.write(str(root / f"f{i:02d}.wav"), rate, x)
+        names.append(root / f"f{i:02d}.wav")
+    return names
+
+
+def test_gpu_stream_ring_smaller_than_corpus_and_resampled_file(dev, tmp_path):
+    """a corpus LARGER than the ingest ring streams through it (regions are overwritten only after
+    their readers ran, files still resident are not uploaded again), a 48 kHz file is resampled to the training rate
+    exactly as the reference does (rawvae/dataset.py:50-51: torchaudio.functional.resample), a stereo file keeps
+    channel 0 - and every frame equals the CPU IterableAudioDataset stream's frame, bit for bit, over several cycles."""
+    import scipy.io.wavfile as wavfile
+    from itertools import islice
+    from rawvae.dataset import IterableAudioDataset
+    from oracle.rawvae_oracle import synth_wav
+    names = _write_mixed_corpus(tmp_path)
+    sr = 44100
+    ds = IterableAudioDataset(tmp_path, sr, 128, torch.float32, "cpu", shuffle=False)
+    ds.audio_file_list = names
+    B, n_batches = 32, 200                                 # ~3 cycles over the files
+    want = torch.stack(list(islice(iter(ds), B * n_batches))).numpy()
+    total = sum(ds.load_file(f).numel() for f in names)
+    stream = ds.gpu_stream(batch_size=B, device=dev)
+    stream.capacity = int(0.4 * total) // 1024 * 1024      # the ring holds less than half of the corpus
+    got = torch.cat([fb.materialize() for fb in islice(iter(stream), n_batches)]).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert stream.stats["ring_wraps"] >= 3 and stream.stats["files_uploaded"] > len(names)
+    assert stream.ring.numel() * 4 < total * 4
+    # a ring that holds everything uploads each file once and then serves it from HBM
+    big = ds.gpu_stream(batch_size=B, device=dev)
+    got2 = torch.cat([fb.materialize() for fb in islice(iter(big), n_batches)]).cpu().numpy()
+    np.testing.assert_array_equal(got2, want)
+    assert big.stats["files_uploaded"] == len(names) and big.stats["resident_hits"] > len(names)
 
 
 def test_full_size_framing_roundtrip_and_checksum(dev):

@@ -262,6 +262,73 @@ def test_data_parallel_sum_allreduce_equals_single_process_gradient(B):
     assert ret.get(timeout=5) < 1e-12
 
 
+def test_ingest_ring_logic_with_mocked_cuda(tmp_path, monkeypatch):
+    """GpuFrameStream's host logic (file placement in a ring smaller than the corpus, region reuse, batches that
+    straddle files, resampled / stereo files, rank sharding) without a GPU: CUDA streams and events are mocked, the
+    ring lives in host memory and frames are gathered with numpy from the (first_frame | frame_idx) descriptors. Every
+    frame equals the CPU IterableAudioDataset stream's; with the one-batch lookahead of the trainers, too."""
+    from itertools import islice
+    from test_gpu_parity import _write_mixed_corpus
+    from rawaudiovae_kelsey_b200 import dataset as D
+    from rawaudiovae_kelsey_b200.trainer import _with_next
+
+    class Ev:
+        def record(self, *_): pass
+    class St:
+        def wait_event(self, *_): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    monkeypatch.setattr(torch.cuda, "Stream", lambda **k: St())
+    monkeypatch.setattr(torch.cuda, "Event", lambda **k: Ev())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: St())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: s)
+
+    class HostRingStream(D.GpuFrameStream):
+        def __init__(self, ds, bs, **kw):
+            self.ds, self.batch_size, self.device = ds, bs, torch.device("cpu")
+            self.pcm16, self.rank, self.world = False, kw.get("rank", 0), kw.get("world", 1)
+            self.dtype, self.esize, self.capacity, self.lookahead = torch.float32, 4, kw["capacity"], 2
+            self.ring, self.stats = None, {"files_uploaded": 0, "bytes_uploaded": 0, "resident_hits": 0, "ring_wraps": 0}
+        def _decode(self, path):
+            return self.ds.load_file(path).contiguous()
+
+    def gather(fb):
+        idx = fb.frame_idx.numpy() if fb.frame_idx is not None else fb.first_frame + np.arange(fb.n_frames)
+        a = fb.audio.numpy()
+        return np.stack([a[i * fb.hop: i * fb.hop + fb.segment_length].copy() for i in idx])
+
+    names = _write_mixed_corpus(tmp_path)
+    ds = D.IterableAudioDataset(tmp_path, 44100, 128, torch.float32, "cpu", shuffle=False)
+    ds.audio_file_list = names
+    B, n_batches = 32, 200
+    want = torch.stack(list(islice(iter(ds), B * n_batches))).numpy()
+    total = sum(ds.load_file(f).numel() for f in names)
+    cap = int(0.4 * total) // 1024 * 1024
+    st = HostRingStream(ds, B, capacity=cap)
+    got = np.concatenate([gather(fb) for fb in islice(iter(st), n_batches)])     # gather BEFORE asking for the next batch
+    np.testing.assert_array_equal(got, want)
+    assert st.stats["ring_wraps"] >= 3 and st.stats["files_uploaded"] > len(names) and st.ring.numel() == cap
+    # trainer-style lookahead: batch k is gathered only after batch k + 1 has been requested
+    st = HostRingStream(ds, B, capacity=cap)
+    got = np.concatenate([gather(cur) for cur, nxt in _with_next(islice(iter(st), n_batches))])
+    np.testing.assert_array_equal(got, want)
+    # everything resident: one upload per file, later cycles are hits
+    st = HostRingStream(ds, B, capacity=2 * total)
+    got = np.concatenate([gather(fb) for fb in islice(iter(st), n_batches)])
+    np.testing.assert_array_equal(got, want)
+    assert st.stats["files_uploaded"] == len(names) and st.stats["resident_hits"] > len(names)
+    # data parallel: the ranks' shards tile every global batch
+    ranks = [iter(HostRingStream(ds, B, capacity=cap, rank=r, world=3)) for r in range(3)]
+    for k in range(60):
+        shards = [next(it) for it in ranks]
+        rows = np.concatenate([gather(fb) for fb in shards])
+        np.testing.assert_array_equal(rows, want[k * B:(k + 1) * B])
+        assert [fb.global_row0 for fb in shards] == [0, 11, 22] and shards[0].global_batch == B
+    # a ring that cannot hold a file next to its predecessor says so instead of corrupting a pending batch
+    with pytest.raises(RuntimeError, match="too small|does not fit"):
+        list(islice(iter(HostRingStream(ds, B, capacity=24 * 1024)), n_batches))
+
+
 def test_trainer_lookahead_pairs():
     """trainer._with_next: (batch, next batch) pairs in order, None after the last - what lets a training step
     prefetch the next batch in the background (device-side analogue of the DataLoader's prefetch)."""
