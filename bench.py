@@ -542,26 +542,27 @@ def leg_stream_4096(dev, peaks):
     from rawaudiovae_kelsey_b200.optim import Adam
     from rawaudiovae_kelsey_b200.trainer import _with_next
     from rawvae.model import VAE
-    B4, n_files, secs = 4096, 8, 30.0
+    B4, n_files, secs = 4096, 4, 300.0      # long streams (config 4 frames 10-minute files)
     with tempfile.TemporaryDirectory() as tmp:
         rng = np.random.default_rng(4321)
-        for k in range(n_files):
-            x = synth_wav(rng, int(secs * SR), SR)
+        base = synth_wav(rng, int(30.0 * SR), SR)
+        for k in range(n_files):    # each file: ten differently rotated copies of a 30 s sine+noise clip (cheap to make)
+            x = np.concatenate([np.roll(base, 7919 * (10 * k + j)) for j in range(int(secs / 30.0))])
             wavfile.write(os.path.join(tmp, f"stream{k}.wav"), SR, np.round(x * 32768.0).clip(-32768, 32767).astype(np.int16))
         ds = IterableAudioDataset(tmp, SR, HOP, torch.float32, dev, shuffle=True)
         file_bytes = int(secs * SR) * 2
-        stream = ds.gpu_stream(B4, dev, pcm16=True, cache_bytes=int(3.5 * file_bytes))
+        stream = ds.gpu_stream(B4, dev, pcm16=True, cache_bytes=int(2.5 * file_bytes))
         torch.manual_seed(0)
         model = VAE(S, H, L).to(dev)
         model.eps_seed = 1
         step_fn = FusedTrainStep(model, Adam(model.parameters(), lr=LR), KL_BETA, graph=True)
         pairs = _with_next(iter(stream))
         once = lambda i: _stream_step(step_fn, pairs)
-        for i in range(12):
+        for i in range(80):     # past a file boundary: both input layouts (run read in place / gathered straddler) captured
             once(i)
         s0 = dict(step_fn.stats)
         up0 = dict(stream.stats)
-        ms, blocks, _ = _median_blocks(once, 7, 40, 12)
+        ms, blocks, _ = _median_blocks(once, 7, 40, 80)
         d = {k: step_fn.stats[k] - s0[k] for k in s0}
         fps = B4 * 40 / (ms * 1e-3)
         uploaded = stream.stats["bytes_uploaded"] - up0["bytes_uploaded"]

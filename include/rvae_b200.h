@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RVAE_ABI_VERSION 3
+#define RVAE_ABI_VERSION 4
 
 typedef struct rvae_ctx rvae_ctx;   /* per-device context (SM count, launch counter) */
 typedef struct rvae_plan rvae_plan; /* a bound training / inference step for fixed shapes and buffers */
@@ -246,6 +246,18 @@ int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, 
                           void* stream);
 /* ... or an fp32 [batch, S] matrix already on the device. */
 int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* stream);
+/* ... or a RUN of `count` consecutive frames (first_frame, first_frame + 1, ...: the stream of
+ * IterableAudioDataset.process_data, rawvae/dataset.py:61-69, TestDataset with hop = S, tutorial.ipynb's inference
+ * loop) read IN PLACE: the run is one contiguous span of (count - 1) * hop + S samples, which is converted once
+ * (fp32 / PCM16 -> bf16) into the plan's input buffer; fc1's A operand, the MSE side input and the fc1 weight
+ * gradient's operand then read frame i at row pitch `hop` through overlapping-row TMA tensor maps - the [count, S]
+ * frame matrix is never materialised and every sample is touched once instead of S / hop times. Results are
+ * bit-identical to rvae_plan_load_frames. first_frame_dev (device int64, may be NULL) overrides first_frame and is
+ * read by the kernel, so a captured CUDA graph follows the stream. Needs hop % 8 == 0 and hop <= S
+ * (rvae_plan_span_supported). */
+int rvae_plan_span_supported(const rvae_plan* plan, int count, int hop);
+int rvae_plan_load_span(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                        const int64_t* first_frame_dev, int64_t first_frame, int count, int hop, void* stream);
 
 /* eps for the loaded batch: copy from a caller tensor (parity runs) or generate with Philox (seed, offset).
  * add_step != 0 adds the device-side Adam step counter (*bufs.step) to the offset inside the kernel, so a captured
@@ -298,14 +310,19 @@ int rvae_plan_finish_loss_deferred(rvae_plan* plan, float kl_beta, float* loss_o
 int rvae_plan_prefetch_frames(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
                               const int64_t* frame_idx, int64_t first_frame, int count, int hop, uint64_t seed,
                               uint64_t offset, int add_step);
+/* The same for a run of consecutive frames read in place (see rvae_plan_load_span). */
+int rvae_plan_prefetch_span(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                            const int64_t* first_frame_dev, int64_t first_frame, int count, int hop, uint64_t seed,
+                            uint64_t offset, int add_step);
 int rvae_plan_swap_prefetched(rvae_plan* plan);
 int rvae_plan_prefetched_batch(const rvae_plan* plan);
 /* Make `stream` wait for background work of earlier calls that a later call would otherwise join (the noise of
  * rvae_plan_gen_eps). Needed before a CUDA-graph capture starts: a captured stream must not wait on uncaptured work. */
 int rvae_plan_join_background(rvae_plan* plan, void* stream);
 /* Host-side bookkeeping for CUDA-graph replays: a replayed rvae_plan_train_step performed the prefetch on the device
- * without running this library's host code; tell the plan that `count` frames wait in the alternate input set. */
-int rvae_plan_note_prefetched(rvae_plan* plan, int count);
+ * without running this library's host code; tell the plan that `count` frames wait in the alternate input set
+ * (as gathered rows, or as a sample span at pitch span_hop: rvae_plan_prefetch_span). */
+int rvae_plan_note_prefetched(rvae_plan* plan, int count, int span_hop /* 0 = gathered rows, else the run's hop */);
 /* Adam over the flat buffers (+ shadow refresh). grad_scale rescales the gradients (1 for SUM all-reduced,
  * globally normalised gradients). zero_grads != 0: the kernel also clears bufs.grads after consuming it - the
  * optimizer.zero_grad() of the next iteration (train.py:184) - which lets the next backward skip its memsets. */

@@ -13,7 +13,7 @@ from . import _build
 
 _LIB = None
 _LOCK = threading.Lock()
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_int64, c_uint64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 
@@ -90,7 +90,10 @@ SIGNATURES = {
     "rvae_plan_prefetch_frames": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, c_uint64, c_uint64, c_int]),
     "rvae_plan_swap_prefetched": (c_int, [P]),
     "rvae_plan_prefetched_batch": (c_int, [P]),
-    "rvae_plan_note_prefetched": (c_int, [P, c_int]),
+    "rvae_plan_note_prefetched": (c_int, [P, c_int, c_int]),
+    "rvae_plan_span_supported": (c_int, [P, c_int, c_int]),
+    "rvae_plan_load_span": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, P]),
+    "rvae_plan_prefetch_span": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, c_uint64, c_uint64, c_int]),
     "rvae_plan_join_background": (c_int, [P, P]),
     "rvae_plan_adam_buckets": (c_int, [P, C.c_uint, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),

@@ -30,6 +30,20 @@ def load_wav_channels(path) -> Tuple[np.ndarray, int]:
     return x, int(sr)
 
 
+def open_pcm16(path) -> Tuple[np.ndarray, int]:
+    """Zero-copy view of a 16-bit PCM wav: (int16 memmap [samples] or [samples, channels], sampling rate), or
+    (None, sr) when the file is not 16-bit PCM. The streaming ingest copies it straight into pinned memory - no
+    float round trip (int16 / 32768 is exact in fp32 and the framing kernel applies it on the GPU)."""
+    import scipy.io.wavfile as wavfile
+    try:
+        sr, data = wavfile.read(str(path), mmap=True)
+    except Exception:
+        return None, 0
+    if data.dtype != np.int16:
+        return None, int(sr)
+    return data, int(sr)
+
+
 def resample(audio: torch.Tensor, sr_in: int, sr_out: int) -> torch.Tensor:
     """[C, N] -> [C, N'] (torchaudio.functional.resample when available, polyphase otherwise)."""
     if sr_in == sr_out:

@@ -500,6 +500,11 @@ struct rvae_plan {
   Planes x_alt;
   float* eps_alt;
   int cur;                 // which input set is current (GEMM tensor maps are prepared per set)
+  // Frames read IN PLACE (rvae_plan_load_span / rvae_plan_prefetch_span): the x planes hold the batch's contiguous
+  // sample span [(count - 1) * hop + S samples] instead of count materialised rows, and fc1's A operand, the MSE
+  // side input and the fc1 weight gradient's B operand read frame i at row pitch hop through overlapping-row tensor
+  // maps. 0 = the planes hold dense [count, S] rows (gather / tensor input).
+  int x_pitch, x_pitch_alt;
   int* sched_dev;          // schedules of the fused launches: [2 input sets][5 launches][128 pairs][kSchedMax]
   int sched_batch;         // the batch size those schedules were built for (0 = none yet): the buffer holds ONE set of
                            // schedules, so other batch sizes of this plan (a ragged last batch) run separate launches
@@ -514,6 +519,7 @@ struct rvae_plan {
     int ready_batch;       // > 0: the alternate set holds this many frames (+ their noise), enqueued by a train step
     const void* audio; int audio_is_i16; int64_t n_samples; const int64_t* frame_idx; int64_t first_frame;
     int count, hop; uint64_t seed, offset; int add_step;
+    bool span;             // frames are the run first_frame (or frame_idx[0]) .. + count: read in place (x_pitch)
     int64_t noise_row0;    // plan->noise_row0 at registration time (the shard of the NEXT global batch)
   } pf;
   double* loss_acc;
@@ -548,7 +554,7 @@ struct rvae_plan {
   // loss finalisation deferred into the latent backward kernel (rvae_plan_finish_loss_deferred)
   LossFinalize fin;
   bool fin_pending;
-  std::map<int, GemmSet> sets;  // prepared GEMMs per (batch size, input set)
+  std::map<int64_t, GemmSet> sets;  // prepared GEMMs per (batch size, input set, frame pitch)
   // optional per-GEMM timing
   bool timing;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -614,6 +620,7 @@ Operand wopnd(const rvae_plan* p, int64_t off, int major, int ld) {
 int prepare(rvae_plan* p, GemmSet& gs, int id) {
   if (gs.ready[id]) return RVAE_OK;
   const int B = p->batch, S = p->S, H = p->H, L = p->L;
+  const int ldx = p->x_pitch > 0 ? p->x_pitch : S;   // row pitch of the frames in the x planes
   const rvae_layout& ly = p->lay;
   float* params = p->bufs.params;
   float* grads = p->bufs.grads;
@@ -623,7 +630,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
   switch (id) {
     case G_F1:
       d.epi = EPI_LINEAR; d.M = B; d.N = H; d.K = S;
-      d.A = opnd(p->x, MAJOR_K, S); d.B = wopnd(p, ly.w1, MAJOR_K, S);
+      d.A = opnd(p->x, MAJOR_K, ldx); d.B = wopnd(p, ly.w1, MAJOR_K, S);
       d.args.bias = params + ly.b1; d.args.act = ACT_RELU; d.args.ldo = H;
       d.args.out_hi = p->h1.hi; d.args.out_lo = p->h1.lo;
       break;
@@ -646,7 +653,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       d.args.bias = params + ly.b4; d.args.in0 = p->x.hi; d.args.in1 = p->x.lo; d.args.out_f32 = p->xhat;
       d.args.out_hi = p->da4.hi; d.args.out_lo = p->da4.lo;
       d.args.act = bf16_mode ? ACT_TANH_APPROX : ACT_TANH;
-      d.args.loss_acc = p->loss_acc; d.args.ldo = S;
+      d.args.loss_acc = p->loss_acc; d.args.ldo = S; d.args.ldi = ldx;
       d.args.colsum = grads ? grads + ly.b4 : nullptr;   // db4 = column sums of da4
       break;
     case G_F4_LIN:
@@ -699,7 +706,7 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
       break;
     case G_B1W:
       d.epi = EPI_REDUCE; d.M = H; d.N = S; d.K = B;
-      d.A = opnd(p->da1, MAJOR_MN, H); d.B = opnd(p->x, MAJOR_MN, S);
+      d.A = opnd(p->da1, MAJOR_MN, H); d.B = opnd(p->x, MAJOR_MN, ldx);
       d.args.out_f32 = grads + ly.w1; d.args.ldo = S; d.args.accumulate = 1;
       break;
     default:
@@ -711,7 +718,8 @@ int prepare(rvae_plan* p, GemmSet& gs, int id) {
 }
 
 int get_set(rvae_plan* p, GemmSet** out) {
-  const int key = p->batch * 2 + p->cur;  // tensor maps bake in the addresses of the current input set
+  // tensor maps bake in the addresses of the current input set and the row pitch of its frames
+  const int64_t key = ((int64_t)p->batch * 2 + p->cur) * 65536 + p->x_pitch;
   auto it = p->sets.find(key);
   if (it == p->sets.end()) {
     GemmSet gs;
@@ -989,6 +997,7 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->timing = false;
   p->kl_c0 = 0.f; p->dz_zeroed = false; p->dp_enabled = false;
   p->cur = 0; p->ticket_zeroed = false; p->ticket = nullptr;
+  p->x_pitch = 0; p->x_pitch_alt = 0;
   p->fuse_latent = false;
   p->sched_batch = 0;
   memset(&p->pf, 0, sizeof(p->pf));
@@ -1113,7 +1122,10 @@ int rvae_plan_load_frames(rvae_plan* plan, const void* audio, int audio_is_i16, 
   RVAE_REQUIRE(row_offset == 0 || row_offset == plan->batch, RVAE_ERR_STATE,
                "plan_load_frames: row_offset %d does not continue the loaded batch (%d rows)", row_offset,
                plan->batch);
+  RVAE_REQUIRE(row_offset == 0 || plan->x_pitch == 0, RVAE_ERR_STATE,
+               "plan_load_frames: cannot append rows to a batch that was loaded as a sample span");
   plan->batch = row_offset + count;
+  plan->x_pitch = 0;
   plan->have_eps = false;
   const size_t off = (size_t)row_offset * plan->S;
   TimedScope ts(plan, T_LOAD, S_(stream));
@@ -1127,9 +1139,48 @@ int rvae_plan_load_batch(rvae_plan* plan, const float* x, int batch, void* strea
   RVAE_REQUIRE(batch > 0 && batch <= plan->max_batch, RVAE_ERR_INVALID, "plan_load_batch: batch %d not in 1..%d",
                batch, plan->max_batch);
   plan->batch = batch;
+  plan->x_pitch = 0;
   plan->have_eps = false;
   TimedScope ts(plan, T_LOAD, S_(stream));
   return launch_split_bf16(&plan->ctx->c, x, (int64_t)batch * plan->S, plan->x.hi, plan->x.lo, S_(stream));
+}
+
+// A run of `count` frames at stride hop is one contiguous span of (count - 1) * hop + S samples: convert the span once
+// (fp32 / PCM16 -> bf16 [+ residual plane]) into the x planes - the framing kernel with ONE "frame" of span length -
+// and let the GEMMs read frame i at row pitch hop. Every sample is touched once instead of S / hop times and the
+// [count, S] operand is never materialised (rawvae/dataset.py:61-69: sequential frames of a stream).
+static int span_eligible(const rvae_plan* p, int count, int hop) {
+  // 16-byte row pitch for the tensor maps; the span must fit the planes (hop <= S)
+  return hop > 0 && hop % 8 == 0 && hop <= p->S && p->S % 8 == 0 && count > 0 && count <= p->max_batch;
+}
+static int convert_span(rvae_plan* p, const void* audio, int audio_is_i16, int64_t n_samples,
+                        const int64_t* first_frame_dev, int64_t first_frame, int count, int hop, Planes& dst,
+                        cudaStream_t st) {
+  const int64_t span = (int64_t)(count - 1) * hop + p->S;
+  RVAE_REQUIRE(span <= (int64_t)INT32_MAX, RVAE_ERR_UNSUPPORTED, "plan span: %lld samples", (long long)span);
+  return launch_frame_gather(&p->ctx->c, audio, audio_is_i16, n_samples, first_frame_dev, first_frame, 1, hop,
+                             (int)span, dst.hi, dst.lo, nullptr, st);
+}
+
+int rvae_plan_span_supported(const rvae_plan* plan, int count, int hop) {
+  return plan ? span_eligible(plan, count, hop) : 0;
+}
+
+int rvae_plan_load_span(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                        const int64_t* first_frame_dev, int64_t first_frame, int count, int hop, void* stream) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(audio && span_eligible(plan, count, hop), RVAE_ERR_UNSUPPORTED,
+               "plan_load_span: count %d (max %d), hop %d (needs hop %% 8 == 0 and hop <= S = %d)", count,
+               plan->max_batch, hop, plan->S);
+  // (samples past n_samples read as zeros, exactly as in the gather: the zero-padded tail of a file)
+  RVAE_REQUIRE(first_frame_dev || first_frame >= 0, RVAE_ERR_INVALID, "plan_load_span: first_frame %lld",
+               (long long)first_frame);
+  plan->batch = count;
+  plan->x_pitch = hop;
+  plan->have_eps = false;
+  TimedScope ts(plan, T_LOAD, S_(stream));
+  return convert_span(plan, audio, audio_is_i16, n_samples, first_frame_dev, first_frame, count, hop, plan->x,
+                      S_(stream));
 }
 
 int rvae_plan_set_eps(rvae_plan* plan, const float* eps, void* stream) {
@@ -1336,7 +1387,23 @@ int rvae_plan_prefetch_frames(rvae_plan* plan, const void* audio, int audio_is_i
   f.audio = audio; f.audio_is_i16 = audio_is_i16; f.n_samples = n_samples; f.frame_idx = frame_idx;
   f.first_frame = first_frame; f.count = count; f.hop = hop; f.seed = seed; f.offset = offset; f.add_step = add_step;
   f.noise_row0 = plan->noise_row0;
+  f.span = false;
   f.registered = true;
+  return RVAE_OK;
+}
+
+int rvae_plan_prefetch_span(rvae_plan* plan, const void* audio, int audio_is_i16, int64_t n_samples,
+                            const int64_t* first_frame_dev, int64_t first_frame, int count, int hop, uint64_t seed,
+                            uint64_t offset, int add_step) {
+  RVAE_CHECK(check_ready(plan, false));
+  RVAE_REQUIRE(audio && span_eligible(plan, count, hop), RVAE_ERR_UNSUPPORTED,
+               "plan_prefetch_span: count %d (max %d), hop %d (needs hop %% 8 == 0 and hop <= S = %d)", count,
+               plan->max_batch, hop, plan->S);
+  RVAE_REQUIRE(first_frame_dev || first_frame >= 0, RVAE_ERR_INVALID, "plan_prefetch_span: first_frame %lld",
+               (long long)first_frame);
+  RVAE_CHECK(rvae_plan_prefetch_frames(plan, audio, audio_is_i16, n_samples, first_frame_dev, first_frame, count, hop,
+                                       seed, offset, add_step));
+  plan->pf.span = true;
   return RVAE_OK;
 }
 
@@ -1344,6 +1411,7 @@ int rvae_plan_swap_prefetched(rvae_plan* plan) {
   RVAE_CHECK(check_ready(plan, false));
   RVAE_REQUIRE(plan->pf.ready_batch > 0, RVAE_ERR_STATE, "plan_swap_prefetched: no prefetched batch");
   std::swap(plan->x, plan->x_alt);
+  std::swap(plan->x_pitch, plan->x_pitch_alt);
   std::swap(plan->eps, plan->eps_alt);
   plan->cur ^= 1;
   plan->batch = plan->pf.ready_batch;
@@ -1364,10 +1432,12 @@ int rvae_plan_join_background(rvae_plan* plan, void* stream) {
   return RVAE_OK;
 }
 
-int rvae_plan_note_prefetched(rvae_plan* plan, int count) {
+int rvae_plan_note_prefetched(rvae_plan* plan, int count, int span_hop) {
   RVAE_CHECK(check_ready(plan, false));
-  RVAE_REQUIRE(count > 0 && count <= plan->max_batch, RVAE_ERR_INVALID, "plan_note_prefetched: count %d", count);
+  RVAE_REQUIRE(count > 0 && count <= plan->max_batch && span_hop >= 0, RVAE_ERR_INVALID,
+               "plan_note_prefetched: count %d span_hop %d", count, span_hop);
   plan->pf.ready_batch = count;
+  plan->x_pitch_alt = span_hop;
   return RVAE_OK;
 }
 
@@ -1423,8 +1493,15 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
     // next step's inputs: frames gathered into the alternate x planes, noise drawn into the alternate eps buffer
     const rvae_plan::Prefetch& f = p->pf;
     RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_hp_fork, 0));
-    RVAE_CHECK(launch_frame_gather(&p->ctx->c, f.audio, f.audio_is_i16, f.n_samples, f.frame_idx, f.first_frame, f.count,
-                                   f.hop, p->S, p->x_alt.hi, p->x_alt.lo, nullptr, bg));
+    if (f.span) {
+      RVAE_CHECK(convert_span(p, f.audio, f.audio_is_i16, f.n_samples, f.frame_idx, f.first_frame, f.count, f.hop,
+                              p->x_alt, bg));
+      p->x_pitch_alt = f.hop;
+    } else {
+      RVAE_CHECK(launch_frame_gather(&p->ctx->c, f.audio, f.audio_is_i16, f.n_samples, f.frame_idx, f.first_frame,
+                                     f.count, f.hop, p->S, p->x_alt.hi, p->x_alt.lo, nullptr, bg));
+      p->x_pitch_alt = 0;
+    }
     // the consumer sees a step counter advanced by one
     RVAE_CHECK(launch_randn(&p->ctx->c, p->eps_alt, (int64_t)f.count * p->L, f.seed, f.offset + (f.add_step ? 1 : 0),
                             f.add_step ? b.step : nullptr, f.noise_row0 * p->L, bg));

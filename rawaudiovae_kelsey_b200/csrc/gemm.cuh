@@ -77,7 +77,9 @@ struct EpiArgs {
   const void* in2;  // DLATENT: mu
   double* loss_acc;
   float* colsum;  // OUT / DRELU: colsum[c] += sum over rows of the emitted values (bias gradients)
-  int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and of the bf16 inputs in0/in1
+  int ldo;   // leading dimension (elements) of out_hi/out_lo/out_f32 and (when ldi == 0) of the bf16 inputs in0/in1
+  int ldi;   // OUT: leading dimension of in0/in1 when it differs from ldo (frames read in place from a sample span:
+             // row pitch = hop, rows overlap); 0 = ldo
   int act;   // LINEAR / OUT activation
   int L;     // HEAD latent width
   int accumulate;
@@ -915,7 +917,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiSta
                   }
                   if (e.in1 && row_ok) {  // x = hi + lo (fp32 emulation): the residual comes straight from global
                     const uint4 t2 = __ldg(reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const __nv_bfloat16*>(e.in1) + static_cast<size_t>(m) * e.ldo + n0 + 8 * i));
+                        reinterpret_cast<const __nv_bfloat16*>(e.in1) + static_cast<size_t>(m) * (e.ldi ? e.ldi : e.ldo) + n0 + 8 * i));
                     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t2);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -983,7 +985,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, int u, EpiSta
               apply_act<32>(v, (EPI == EPI_OUT && e.act != ACT_TANH_APPROX) ? ACT_TANH : e.act);
               if constexpr (EPI == EPI_OUT) {
                 if (!e.out_hi && row_ok) {  // loss-only forward: accumulate the MSE here
-                  const size_t off = static_cast<size_t>(m) * e.ldo + n;
+                  const size_t off = static_cast<size_t>(m) * (e.ldi ? e.ldi : e.ldo) + n;
                   float x[32];
                   load_row_bf16<32>(reinterpret_cast<const __nv_bfloat16*>(e.in0) + off, x);
                   if (e.in1) {

@@ -89,11 +89,12 @@ int gemm_bind_outputs(PreparedGemm* g, const EpiArgs& a, bool force) {
     RVAE_CHECK(encode_2d(&p.tmOutF32, a.out_f32, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
   if (a.out_f32_b && g->epi == EPI_HEAD && (force || a.out_f32_b != old.out_f32_b))
     RVAE_CHECK(encode_2d(&p.tmOutF32b, a.out_f32_b, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
-  if (a.in0 && (force || a.in0 != old.in0)) {
+  if (a.in0 && (force || a.in0 != old.in0 || a.ldi != old.ldi)) {
     if (g->epi == EPI_HEAD)  // eps, fp32 [M, L]
       RVAE_CHECK(encode_2d(&p.tmSide, a.in0, true, g->out_cols_f32, g->out_rows, g->out_ld_f32, 32, 128));
     else if (g->epi == EPI_OUT || g->epi == EPI_DRELU)  // x / ReLU mask, bf16 [M, N]
-      RVAE_CHECK(encode_2d(&p.tmSide, a.in0, false, g->out_cols_bf16, g->out_rows, g->out_ld_bf16, 64, 128));
+      RVAE_CHECK(encode_2d(&p.tmSide, a.in0, false, g->out_cols_bf16, g->out_rows,
+                           (g->epi == EPI_OUT && a.ldi > 0) ? a.ldi : g->out_ld_bf16, 64, 128));
   }
   return RVAE_OK;
 }

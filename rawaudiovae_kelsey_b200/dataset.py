@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import pathlib
 import random
+import threading
 from itertools import chain, cycle
 from pathlib import Path
 from typing import Iterator, List, Optional, Sequence
@@ -77,9 +78,9 @@ class IterableAudioDataset(IterableDataset):
         else:
             return self.get_stream(self.audio_file_list)
 
-    def gpu_stream(self, batch_size: int, device=None, pcm16: bool = False) -> "GpuFrameStream":
-        """The same frame stream, batched on the GPU (see GpuFrameStream)."""
-        return GpuFrameStream(self, batch_size, device or self.device, pcm16=pcm16)
+    def gpu_stream(self, batch_size: int, device=None, pcm16: bool = False, **kwargs) -> "GpuFrameStream":
+        """The same frame stream, batched on the GPU (see GpuFrameStream; kwargs: rank, world, cache_bytes, lookahead)."""
+        return GpuFrameStream(self, batch_size, device or self.device, pcm16=pcm16, **kwargs)
 
 
 class AudioDataset(torch.utils.data.Dataset):
@@ -246,21 +247,68 @@ class GpuFrameStream:
         self.ds, self.batch_size, self.device = dataset, int(batch_size), torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("GpuFrameStream needs a CUDA device (no CPU fallback)")
-        self.pcm16, self.rank, self.world = bool(pcm16), rank, world
+        # pcm16="auto": 16-bit PCM on the wire and in the ring when EVERY file of the folder is 16-bit PCM at the target
+        # rate (lossless: int16 / 32768 is what the float decode yields), float32 otherwise
+        self.pcm16, self.rank, self.world = pcm16, rank, world
+        if pcm16 == "auto":
+            heads = [audio_io.open_pcm16(f) for f in dataset.audio_file_list]
+            self.pcm16 = bool(heads) and all(d is not None and sr == dataset.sampling_rate for d, sr in heads)
+        self.pcm16 = bool(self.pcm16)
         self.dtype = torch.int16 if self.pcm16 else torch.float32
         self.esize = 2 if self.pcm16 else 4
         self.capacity = max(int(cache_bytes) // self.esize // 1024 * 1024, 1024)   # samples
         self.lookahead = max(1, int(lookahead))
         self.ring: Optional[torch.Tensor] = None
-        self.stats = {"files_uploaded": 0, "bytes_uploaded": 0, "resident_hits": 0, "ring_wraps": 0}
+        self.stats = {"files_uploaded": 0, "bytes_uploaded": 0, "resident_hits": 0, "ring_wraps": 0,
+                      "pcm16_passthrough": 0, "pinned_allocs": 0}
+        self._free = []                      # [(pinned buffer, event of the last H2D copy that read it or None)]
+        self._free_lock = threading.Lock()
 
     # ---- host side
-    def _decode(self, path) -> torch.Tensor:
-        """Pinned host tensor of the file's padded samples in the wire format."""
+    def _pinned(self, n: int) -> torch.Tensor:
+        """A pinned staging buffer of >= n samples from the pool (allocating pinned memory costs milliseconds; the
+        pool holds lookahead + 2 buffers in steady state). A buffer is reused only after the copy that read it."""
+        with self._free_lock:
+            k = next((i for i, (b, _) in enumerate(self._free) if b.numel() >= n), None)
+            buf, ev = self._free.pop(k) if k is not None else (None, None)
+        if buf is None:
+            buf = torch.empty(max(n, 1) + n // 8, dtype=self.dtype).pin_memory()
+            self.stats["pinned_allocs"] += 1
+        elif ev is not None:
+            ev.synchronize()
+        return buf
+
+    def _release(self, buf: torch.Tensor, ev) -> None:
+        with self._free_lock:
+            self._free.append((buf, ev))
+            if len(self._free) > self.lookahead + 3:          # drop the smallest when files of odd sizes pile up
+                self._free.sort(key=lambda t: t[0].numel())
+                self._free.pop(0)
+
+    def _decode(self, path):
+        """(view of a pinned staging buffer holding the file's samples in the wire format, zero-padded to a multiple
+        of hop, rawvae/dataset.py:47-63; the buffer itself). 16-bit PCM files at the target rate are copied from the
+        memory-mapped file into pinned memory as they are (channel 0 of multi-channel files, :54-55)."""
+        hop = self.ds.hop_size
+        if self.pcm16:
+            data, sr = audio_io.open_pcm16(path)
+            if data is not None and sr == self.ds.sampling_rate:
+                n = data.shape[0]
+                n_pad = (n + hop - 1) // hop * hop
+                buf = self._pinned(n_pad)
+                view = buf[:n_pad]
+                dst = view.numpy()
+                np.copyto(dst[:n], data if data.ndim == 1 else data[:, 0])
+                dst[n:] = 0
+                self.stats["pcm16_passthrough"] += 1
+                return view, buf
         audio = self.ds.load_file(path)                       # float32, zero-padded to a multiple of hop
         if self.pcm16:
             audio = torch.round(audio * 32768.0).clamp_(-32768, 32767).to(torch.int16)
-        return audio.contiguous().pin_memory()
+        buf = self._pinned(audio.numel())
+        view = buf[:audio.numel()]
+        view.copy_(audio)
+        return view, buf
 
     # ---- device side
     def _ensure_ring(self, need: int) -> None:
@@ -281,7 +329,7 @@ class GpuFrameStream:
         S, hop, bs = 1024, self.ds.hop_size, self.batch_size
         dev = self.device
         copy_stream = torch.cuda.Stream(device=dev)
-        pool = ThreadPoolExecutor(max_workers=1)
+        pool = ThreadPoolExecutor(max_workers=2)   # decode / staging copies release the GIL
         order = cycle(files)
         queue = []          # [(path, decode future or None)] - the next files of the stream, decoded ahead
         regions = {}        # region id -> {off, n, path, last_yield, ready}: live pieces of the ring
@@ -320,7 +368,8 @@ class GpuFrameStream:
                 copy_stream.wait_event(ev)
             return True
 
-        def place(path, host, strict=True):
+        def place(path, staged, strict=True):
+            host, buf = staged
             n = host.numel()
             self._ensure_ring(n)
             off = 0 if state["write"] + n > self.capacity else state["write"]
@@ -332,6 +381,7 @@ class GpuFrameStream:
                 self.ring[off:off + n].copy_(host, non_blocking=True)    # pinned host -> ring, off the step's stream
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
+            self._release(buf, ready)
             rid = state["next_id"]
             state["next_id"] += 1
             regions[rid] = {"off": off, "n": n, "path": path, "last_yield": 0, "ready": ready}

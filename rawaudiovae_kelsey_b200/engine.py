@@ -113,6 +113,8 @@ class Plan:
             check(lib.rvae_plan_bind(self.handle, C.byref(bufs)))
         self.batch = 0
         self.cur = 0    # which of the two input sets is current (flips with every swap_prefetched)
+        self.pitch = 0      # 0: the current input set holds gathered [batch, S] rows; hop: a sample span read in place
+        self.pitch_alt = 0  # the same for the prefetched set
         self.token = 0  # bumped whenever a new batch is loaded (activations of older forwards are gone)
 
     def __del__(self):
@@ -136,12 +138,30 @@ class Plan:
             x = x.float().contiguous()
         check(self.lib.rvae_plan_load_batch(self.handle, x.data_ptr(), x.shape[0], self._stream()))
         self.batch = x.shape[0]
+        self.pitch = 0
         self.token += 1
 
+    def span_supported(self, count: int, hop: int) -> bool:
+        """Can a run of `count` consecutive frames at stride `hop` be read in place (load_frames(span=True))?"""
+        return bool(self.lib.rvae_plan_span_supported(self.handle, int(count), int(hop)))
+
     def load_frames(self, audio: torch.Tensor, count: int, hop: int, *, frame_idx: Optional[torch.Tensor] = None,
-                    first_frame: int = 0, row_offset: int = 0) -> None:
+                    first_frame: int = 0, row_offset: int = 0, span: bool = False) -> None:
+        """span=True: the frames are the RUN first_frame .. first_frame + count (or frame_idx[0] .., read on the
+        device) and are read in place from the converted sample span (rvae_plan_load_span)."""
         if audio.dtype not in (torch.float32, torch.int16) or not audio.is_cuda or not audio.is_contiguous():
             raise _lib.RvaeError("audio must be a contiguous CUDA float32 / int16 tensor")
+        if span:
+            if row_offset != 0:
+                raise _lib.RvaeError("a span batch cannot be appended to")
+            if frame_idx is not None and (frame_idx.dtype != torch.int64 or not frame_idx.is_cuda or frame_idx.numel() < 1):
+                raise _lib.RvaeError("frame_idx must be a CUDA int64 tensor whose first entry is the run's first frame")
+            check(self.lib.rvae_plan_load_span(self.handle, audio.data_ptr(), int(audio.dtype == torch.int16),
+                                               audio.numel(), frame_idx.data_ptr() if frame_idx is not None else None,
+                                               first_frame, count, hop, self._stream()))
+            self.batch, self.pitch = count, hop
+            self.token += 1
+            return
         if frame_idx is not None and (frame_idx.dtype != torch.int64 or not frame_idx.is_cuda
                                       or frame_idx.numel() != count or not frame_idx.is_contiguous()):
             raise _lib.RvaeError("frame_idx must be a contiguous CUDA int64 tensor with `count` entries")
@@ -149,14 +169,26 @@ class Plan:
                                              audio.numel(), frame_idx.data_ptr() if frame_idx is not None else None,
                                              first_frame, count, hop, row_offset, self._stream()))
         self.batch = row_offset + count
+        self.pitch = 0
         if row_offset == 0:
             self.token += 1
 
     def prefetch_frames(self, audio: torch.Tensor, count: int, hop: int, *, frame_idx: Optional[torch.Tensor] = None,
-                        first_frame: int = 0, seed: int = 0, offset: int = 0, add_step: bool = True) -> None:
-        """Describe the NEXT step's batch: the next train_step gathers it (and draws its noise) in the background."""
+                        first_frame: int = 0, seed: int = 0, offset: int = 0, add_step: bool = True,
+                        span: bool = False) -> None:
+        """Describe the NEXT step's batch: the next train_step gathers it (and draws its noise) in the background.
+        span=True: a run of consecutive frames, read in place (see load_frames)."""
         if audio.dtype not in (torch.float32, torch.int16) or not audio.is_cuda or not audio.is_contiguous():
             raise _lib.RvaeError("audio must be a contiguous CUDA float32 / int16 tensor")
+        if span:
+            if frame_idx is not None and (frame_idx.dtype != torch.int64 or not frame_idx.is_cuda or frame_idx.numel() < 1):
+                raise _lib.RvaeError("frame_idx must be a CUDA int64 tensor whose first entry is the run's first frame")
+            check(self.lib.rvae_plan_prefetch_span(self.handle, audio.data_ptr(), int(audio.dtype == torch.int16),
+                                                   audio.numel(), frame_idx.data_ptr() if frame_idx is not None else None,
+                                                   first_frame, count, hop, seed, offset, int(add_step)))
+            self.pitch_alt = hop
+            return
+        self.pitch_alt = 0
         if frame_idx is not None and (frame_idx.dtype != torch.int64 or not frame_idx.is_cuda
                                       or frame_idx.numel() != count or not frame_idx.is_contiguous()):
             raise _lib.RvaeError("frame_idx must be a contiguous CUDA int64 tensor with `count` entries")
@@ -173,15 +205,18 @@ class Plan:
         check(self.lib.rvae_plan_swap_prefetched(self.handle))
         self.batch = n
         self.cur ^= 1
+        self.pitch, self.pitch_alt = self.pitch_alt, self.pitch
         self.token += 1
 
     def join_background(self) -> None:
         """The current stream waits for pending background work of earlier calls (needed before a graph capture)."""
         check(self.lib.rvae_plan_join_background(self.handle, self._stream()))
 
-    def note_prefetched(self, count: int) -> None:
-        """A replayed CUDA graph gathered `count` frames into the alternate input set: record it on the host side."""
-        check(self.lib.rvae_plan_note_prefetched(self.handle, count))
+    def note_prefetched(self, count: int, span_hop: int = 0) -> None:
+        """A replayed CUDA graph gathered `count` frames into the alternate input set (span_hop > 0: as a sample span
+        read in place at that pitch): record it on the host side."""
+        check(self.lib.rvae_plan_note_prefetched(self.handle, count, span_hop))
+        self.pitch_alt = span_hop
 
     def set_eps(self, eps: torch.Tensor) -> None:
         if eps.dtype != torch.float32 or not eps.is_cuda or not eps.is_contiguous():

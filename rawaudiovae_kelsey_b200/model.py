@@ -15,6 +15,7 @@ so the fused Adam kernel and the gradient all-reduce see contiguous memory.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -25,6 +26,9 @@ from . import _lib, engine, ops
 _PRIVATE = ("_flat", "_plans", "_eps_counter")
 
 
+_SPAN_ON = os.environ.get("RVAE_SPAN", "1") not in ("0", "")
+
+
 class FrameBatch:
     """A batch described by frame indices into a device-resident wav buffer (produced by dataset.GpuFrameLoader).
     Passing it to VAE.forward / FusedTrainStep fuses framing into the batch load: frames are gathered straight into
@@ -32,9 +36,12 @@ class FrameBatch:
 
     def __init__(self, audio: torch.Tensor, n_frames: int, hop: int, segment_length: int,
                  frame_idx: Optional[torch.Tensor] = None, first_frame: int = 0,
-                 global_row0: Optional[int] = None, global_batch: Optional[int] = None):
+                 global_row0: Optional[int] = None, global_batch: Optional[int] = None, run: bool = False):
         self.audio, self.n_frames, self.hop, self.segment_length = audio, int(n_frames), int(hop), int(segment_length)
         self.frame_idx, self.first_frame = frame_idx, int(first_frame)
+        # run=True with a frame_idx tensor: the frames are the RUN frame_idx[0], frame_idx[0] + 1, ... (the first
+        # frame lives in device memory so that a captured CUDA graph follows a stream); frame_idx=None is always a run
+        self.run = bool(run) or frame_idx is None
         # data parallelism: this batch is rows [global_row0, global_row0 + n_frames) of a global batch of
         # `global_batch` frames (set by the sharding loaders; None = not sharded / equal shards assumed)
         self.global_row0, self.global_batch = global_row0, global_batch
@@ -42,6 +49,15 @@ class FrameBatch:
     @property
     def shape(self):
         return (self.n_frames, self.segment_length)
+
+    @property
+    def span(self) -> bool:
+        """A run of consecutive frames whose hop gives 16-byte row pitches is read IN PLACE: its contiguous sample
+        span is converted to bf16 once and fc1 / the MSE / the fc1 weight gradient read frame i at row pitch hop
+        through overlapping-row TMA tensor maps (rvae_plan_load_span) - same results as the gather, bit for bit.
+        RVAE_SPAN=0 turns it off (A/B measurements)."""
+        return (self.run and _SPAN_ON and self.hop % 8 == 0 and 0 < self.hop <= self.segment_length
+                and self.segment_length % 8 == 0)
 
     def __len__(self):
         return self.n_frames
@@ -51,8 +67,11 @@ class FrameBatch:
 
     def materialize(self) -> torch.Tensor:
         """fp32 [B, S] frames (what the reference's DataLoader would have produced)."""
+        idx, first = self.frame_idx, self.first_frame
+        if idx is not None and self.run:
+            idx, first = None, int(idx[0].item())
         f32, _, _ = ops.frame_gather(self.audio, self.n_frames, self.hop, self.segment_length,
-                                     frame_idx=self.frame_idx, first_frame=self.first_frame)
+                                     frame_idx=idx, first_frame=first)
         return f32
 
     def view(self, *shape):
@@ -190,8 +209,11 @@ class VAE(nn.Module):
             for r in src:
                 if r.segment_length != self.segment_length:
                     raise _lib.RvaeError("FrameBatch segment_length does not match the model")
+                span = len(src) == 1 and r.span and r.n_frames <= plan.max_batch
+                if r.frame_idx is not None and r.run and not span:
+                    raise _lib.RvaeError("a device-side run (FrameBatch(run=True)) needs hop % 8 == 0 and hop <= S")
                 plan.load_frames(r.audio, r.n_frames, r.hop, frame_idx=r.frame_idx, first_frame=r.first_frame,
-                                 row_offset=row)
+                                 row_offset=row, span=span)
                 row += r.n_frames
             return plan
         x = src
@@ -397,7 +419,7 @@ class _StepBase:
     def _graph_key(self, data):
         """Input signature for graph reuse, or None when the input cannot be served by a replay."""
         if isinstance(data, FrameBatch):
-            return ("frames", data.audio.data_ptr(), data.n_frames, data.hop, data.segment_length)
+            return ("frames", data.audio.data_ptr(), data.n_frames, data.hop, data.segment_length, data.span)
         if isinstance(data, torch.Tensor) and data.is_cuda:
             return ("tensor", data.numel())
         return None
@@ -478,7 +500,8 @@ class _StepBase:
             key = None
             if graphable and do_pf and isinstance(data, FrameBatch):
                 key = ("pf", plan.handle.value, next_data.audio.data_ptr(), plan.batch, next_data.n_frames,
-                       next_data.hop, self._plan_cur(plan)) + self._key_extra(data) + self._key_extra(next_data)
+                       next_data.hop, self._plan_cur(plan), plan.pitch, next_data.span) \
+                    + self._key_extra(data) + self._key_extra(next_data)
             if key is not None and key in self._graphs:
                 st = self._graphs[key]
                 self._fill_idx(st, next_data)
@@ -513,7 +536,7 @@ class _StepBase:
     def _prefetch(self, plan, data, next_data, frame_idx, first_frame):
         """Register next_data (frames + noise) as the batch the coming train step gathers in the background."""
         plan.prefetch_frames(next_data.audio, next_data.n_frames, next_data.hop, frame_idx=frame_idx,
-                             first_frame=first_frame, seed=self._seed(), offset=0, add_step=True)
+                             first_frame=first_frame, seed=self._seed(), offset=0, add_step=True, span=next_data.span)
 
     def _count(self, what):
         self.stats[what] += 1
@@ -525,7 +548,7 @@ class _StepBase:
 
     def _mark_prefetched(self, plan, next_data):
         # a replayed graph performed the prefetch on the device; mirror it in the plan's host-side state
-        plan.note_prefetched(next_data.n_frames)
+        plan.note_prefetched(next_data.n_frames, next_data.hop if next_data.span else 0)
         self._pf = (plan, next_data)
 
     def _fill_idx(self, st, nxt):
@@ -558,7 +581,8 @@ class _StepBase:
         if key[0] == "frames":
             st["idx"] = torch.empty(data.n_frames, dtype=torch.int64, device=dev)
             st["arange"] = torch.arange(data.n_frames, dtype=torch.int64, device=dev)
-            static_in = FrameBatch(data.audio, data.n_frames, data.hop, data.segment_length, frame_idx=st["idx"])
+            static_in = FrameBatch(data.audio, data.n_frames, data.hop, data.segment_length, frame_idx=st["idx"],
+                                   run=data.span)
         else:
             st["x"] = torch.empty((data.numel() // model.segment_length, model.segment_length), dtype=torch.float32,
                                   device=dev)

@@ -340,7 +340,7 @@ def run_stream_trainer(argv=None):
         print('Found {} audio files'.format(len(list(my_audio.glob('*.wav')))))
         training_dataset = IterableAudioDataset(audio_folder=my_audio, sampling_rate=sampling_rate,
                                                 hop_size=hop_length, dtype=torch.float32, device=device, shuffle=True)
-        stream = training_dataset.gpu_stream(batch_size, device)
+        stream = training_dataset.gpu_stream(batch_size, device, pcm16="auto")
         stream.rank, stream.world = rank, world
 
         writer = _NullWriter()

@@ -484,7 +484,8 @@ def test_cuda_graph_step_equals_eager_step(dev):
             out.append(step(fb).clone())
         losses[use_graph] = torch.stack(out).cpu()
         if use_graph:
-            assert len(step._graphs) == 1
+            # one graph per input layout: gathered index batches, and runs read in place (FrameBatch.span)
+            assert len(step._graphs) == 2 and step.stats["captures"] == 2
         final = model._flat.params.clone()
         losses[("w", use_graph)] = final
     assert torch.allclose(losses[True], losses[False], rtol=1e-4, atol=0)
@@ -812,3 +813,68 @@ def test_checkpoint_roundtrip_with_reference_format(dev, small, tmp_path):
     m3 = torch.load(tmp_path / "last_model.pt", weights_only=False)
     assert torch.equal(m3(x, eps=eps)[0], a)
     assert float(o2.state_dict()["state"][0]["step"]) == 1.0
+
+
+@pytest.mark.parametrize("pcm16", [False, True])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_frames_read_in_place_equal_gathered_frames(dev, monkeypatch, precision, pcm16):
+    """SURVEY.md 2c K-F1 / VERDICT r1 missing #6: a RUN of consecutive frames (IterableAudioDataset's stream,
+    rawvae/dataset.py:61-69) is never materialised - the run's sample span is converted to bf16 once and fc1's A
+    operand, the MSE side input and the fc1 weight gradient read frame i at row pitch hop through overlapping-row TMA
+    tensor maps. Same operands, same tiles => the outputs equal the gather path's: activations bit for bit, sums that
+    go through atomics to reassociation noise. Ragged batch (not a multiple of the 128-row tile), a run that starts
+    mid-buffer and ends in the zero-padded tail, fp32 and PCM16 sources, eager / pipelined / graph-replayed steps."""
+    from rawvae.model import VAE, FusedTrainStep, FrameBatch
+    from rawaudiovae_kelsey_b200 import model as M
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L, hop, B, first = 256, 320, 64, 64, 500, 37
+    gen = torch.Generator().manual_seed(17)
+    n_samples = (first + B - 1) * hop + S - 29               # the last frame reaches 29 samples past the buffer
+    audio = (torch.rand(n_samples, generator=gen) * 2 - 1)
+    audio = torch.round(audio * 32768).clamp_(-32768, 32767).to(torch.int16).to(dev) if pcm16 else audio.to(dev)
+    eps = torch.randn(B, L, generator=gen).to(dev)
+
+    def run(span_on):
+        monkeypatch.setattr(M, "_SPAN_ON", span_on)
+        torch.manual_seed(0)
+        model = VAE(S, H, L, precision=precision).to(dev)
+        fb = FrameBatch(audio, B, hop, S, first_frame=first)
+        assert fb.span == span_on
+        with torch.no_grad():
+            xh, mu, lv = model(fb, eps=eps)
+        plan = model._plan_for(B)
+        assert plan.pitch == (hop if span_on else 0)
+        step = FusedTrainStep(model, Adam(model.parameters(), lr=1e-3), 1e-3, keep_grads=True)
+        loss = step(fb, eps=eps).clone()
+        return xh.clone(), mu.clone(), lv.clone(), loss, model._flat.grads.clone(), model._flat.params.clone()
+
+    a, b = run(True), run(False)
+    for k in range(3):
+        assert torch.equal(a[k], b[k]), ("xhat", "mu", "logvar")[k]
+    assert torch.allclose(a[3], b[3], rtol=1e-5, atol=0)
+    assert rel(a[4], b[4]) < 1e-5 and rel(a[5], b[5]) < 1e-6
+    # the materialised frames are the reference's (zero padded tail included)
+    fr = FrameBatch(audio, B, hop, S, first_frame=first).materialize().cpu()
+    a_cpu = audio.cpu().float() / (32768.0 if pcm16 else 1.0)
+    a_pad = torch.cat([a_cpu, torch.zeros(64)])
+    assert torch.equal(fr[-1], a_pad[(first + B - 1) * hop:(first + B - 1) * hop + S]) and torch.equal(fr[0], a_pad[first * hop:first * hop + S])
+
+    if precision == "fp32" or pcm16:
+        return
+    # a stream of runs through the pipelined, graph-replayed step (first frame read from device memory on replay)
+    starts = [5, 700, 333, 41, 1200, 64, 900, 2, 512, 77]
+    long_audio = (torch.rand((1300 + B) * hop + S, generator=gen) * 2 - 1).to(dev)
+    res = {}
+    for span_on in (True, False):
+        monkeypatch.setattr(M, "_SPAN_ON", span_on)
+        torch.manual_seed(0)
+        model = VAE(S, H, L).to(dev)
+        model.eps_seed = 5
+        step = FusedTrainStep(model, Adam(model.parameters(), lr=1e-3), 1e-3, ring=16, graph=True)
+        fbs = [FrameBatch(long_audio, B, hop, S, first_frame=s) for s in starts]
+        out = [step(fbs[i], next_data=fbs[i + 1] if i + 1 < len(fbs) else None).clone() for i in range(len(fbs))]
+        if span_on:
+            assert step.stats["replays"] >= 4, step.stats
+        res[span_on] = (torch.stack(out).cpu(), model._flat.params.clone())
+    assert torch.allclose(res[True][0], res[False][0], rtol=1e-4, atol=0)
+    assert rel(res[True][1], res[False][1]) < 1e-3

@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rvae_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.rvae_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.rvae_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_param_layout_matches_reference_parameter_count():
@@ -290,7 +290,10 @@ def test_ingest_ring_logic_with_mocked_cuda(tmp_path, monkeypatch):
             self.dtype, self.esize, self.capacity, self.lookahead = torch.float32, 4, kw["capacity"], 2
             self.ring, self.stats = None, {"files_uploaded": 0, "bytes_uploaded": 0, "resident_hits": 0, "ring_wraps": 0}
         def _decode(self, path):
-            return self.ds.load_file(path).contiguous()
+            a = self.ds.load_file(path).contiguous()
+            return a, a                      # (staged view, its staging buffer)
+        def _release(self, buf, ev):
+            pass
 
     def gather(fb):
         idx = fb.frame_idx.numpy() if fb.frame_idx is not None else fb.first_frame + np.arange(fb.n_frames)
@@ -352,3 +355,26 @@ def test_bench_data_generator_matches_the_tests_generator():
     root = Path(bench.__file__).resolve().parent
     for f in list((root / "rawaudiovae_kelsey_b200").glob("*.py")) + list((root / "rawvae").glob("*.py")):
         assert not re.search(r"^\s*(from|import)\s+oracle", f.read_text(), re.M), f
+
+
+def test_pcm16_passthrough_view_equals_the_decoded_file(tmp_path):
+    """The streaming ingest copies 16-bit PCM files into pinned memory as they are (audio_io.open_pcm16); the int16
+    values it hands to the GPU are exactly the ones the float decode (int16 / 32768, what torchaudio.load returns,
+    rawvae/dataset.py:47) rounds back to. Stereo files keep their channel layout ([samples, channels]: channel 0 is
+    column 0, :54-55); non-PCM16 files are refused (None) so the caller falls back to the float path."""
+    import scipy.io.wavfile as wavfile
+    from rawaudiovae_kelsey_b200 import audio_io
+    rng = np.random.default_rng(3)
+    mono = rng.integers(-32768, 32767, 5000, dtype=np.int16)
+    stereo = rng.integers(-32768, 32767, (4000, 2), dtype=np.int16)
+    wavfile.write(tmp_path / "m.wav", 44100, mono)
+    wavfile.write(tmp_path / "s.wav", 48000, stereo)
+    wavfile.write(tmp_path / "f.wav", 44100, rng.standard_normal(100).astype(np.float32))
+    d, sr = audio_io.open_pcm16(tmp_path / "m.wav")
+    x, sr2 = audio_io.load_wav_channels(tmp_path / "m.wav")
+    assert sr == sr2 == 44100 and d.dtype == np.int16 and np.array_equal(np.asarray(d), mono)
+    assert np.array_equal(np.asarray(d).astype(np.float32) / 32768.0, x[0])
+    d, sr = audio_io.open_pcm16(tmp_path / "s.wav")
+    x, _ = audio_io.load_wav_channels(tmp_path / "s.wav")
+    assert sr == 48000 and d.shape == (4000, 2) and np.array_equal(np.asarray(d[:, 0]).astype(np.float32) / 32768.0, x[0])
+    assert audio_io.open_pcm16(tmp_path / "f.wav")[0] is None
