@@ -77,6 +77,7 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
     if (v >= 2 && v <= prop.multiProcessorCount) ctx->c.num_sms = v & ~1;
   }
   ctx->c.launches = 0;
+  ctx->c.aux_grid_cap = 0;
   memset(&ctx->nccl, 0, sizeof(ctx->nccl));
   ctx->comm = nullptr; ctx->dp_rank = 0; ctx->dp_world = 1;
   ctx->sym_base = nullptr; ctx->sym_data_bytes = 0; ctx->p2p_ready = false; ctx->p2p_ctas = 20; ctx->p2p_ctas_last = 48;
@@ -547,6 +548,14 @@ struct rvae_plan {
   // rvae_plan_train_step runs its critical chain on a highest-priority stream forked from the caller's stream
   cudaStream_t hp;
   cudaEvent_t ev_hp_fork, ev_hp_join;
+  // backward stage 1 split over two streams: latent dgrad -> {latent backward kernel || fc3 weight gradient}. The
+  // HBM-bound latent kernel and the weight-gradient GEMM (held to s1_wgrad_ctas CTAs) share the machine instead of
+  // running one after the other (nothing can co-reside with a GEMM CTA: it owns the SM's shared memory)
+  cudaStream_t hp2;
+  cudaEvent_t ev_s1_fork, ev_s1_join;
+  bool split_stage1;
+  int s1_wgrad_ctas, s1_order;
+  int adam_bg_blocks;    // grid cap of the single-process background Adam launch (0 = none)
   // data parallelism: gradient all-reduces run on their own stream, bucket by bucket as backward completes them
   cudaStream_t comm_stream;
   cudaStream_t comm_stream2;  // the step's last exchange: must not queue behind the previous one
@@ -807,6 +816,9 @@ int ensure_side_stream(rvae_plan* p) {
   RVAE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->hp, cudaStreamNonBlocking, greatest));
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->adam_stream, cudaStreamNonBlocking, least));
+  RVAE_CUDA(cudaStreamCreateWithPriority(&p->hp2, cudaStreamNonBlocking, greatest));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_s1_fork, cudaEventDisableTiming));
+  RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_s1_join, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_fork, cudaEventDisableTiming));
   RVAE_CUDA(cudaEventCreateWithFlags(&p->ev_hp_join, cudaEventDisableTiming));
   RVAE_CUDA(cudaStreamCreateWithPriority(&p->comm_stream, cudaStreamNonBlocking, greatest));
@@ -935,6 +947,40 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   if (stage == 1 && ext == nullptr && latent_fused(p)) return backward_stage_latent_fused(p, st);
   if (stage == 1 && !p->dz_zeroed)
     RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
+  if (stage == 1 && p->split_stage1 && p->two_streams && !p->timing && p->batch > kBlockM) {
+    // latent dgrad, then the latent backward kernel (HBM-bound, feeds stage 2: the critical chain) on `st` while the fc3
+    // weight gradient runs beside it on a second stream, held to a part of the machine
+    RVAE_CHECK(ensure_side_stream(p));
+    GemmSet* gs;
+    RVAE_CHECK(get_set(p, &gs));
+    RVAE_CHECK(prepare(p, *gs, G_B3D));
+    RVAE_CHECK(prepare(p, *gs, G_B3W));
+    RVAE_CHECK(gemm_run(&p->ctx->c, gs->g[G_B3D], st));
+    RVAE_CUDA(cudaEventRecord(p->ev_s1_fork, st));
+    RVAE_CUDA(cudaStreamWaitEvent(p->hp2, p->ev_s1_fork, 0));
+    // Order matters: nothing co-resides with a GEMM CTA (it owns the SM's shared memory), so whichever kernel gets its
+    // blocks resident first takes the SMs. s1_order = 0: the weight gradient follows the dgrad on `st` (its CTAs take
+    // the first SMs the dgrad frees), the latent kernel fills the rest from the second stream; 1: the other way round.
+    cudaStream_t s_w = p->s1_order == 0 ? st : p->hp2;
+    cudaStream_t s_l = p->s1_order == 0 ? p->hp2 : st;
+    auto run_wgrad = [&]() -> int {
+      PreparedGemm w = gs->g[G_B3W];
+      if (w.grid > p->s1_wgrad_ctas) w.grid = p->s1_wgrad_ctas;   // persistent: the pairs stride over the units
+      return gemm_run(&p->ctx->c, w, s_w);
+    };
+    auto run_latent = [&]() -> int {
+      return launch_latent_bwd(&p->ctx->c, p->dz, p->eps, ext ? ext->lv : p->lv, p->mu, ext ? ext->g_mu : nullptr,
+                               ext ? ext->g_lv : nullptr, p->kl_c0, p->batch, L, p->dml.hi, p->dml.lo, grads + ly.b2, 1,
+                               p->fin_pending ? &p->fin : nullptr, s_l);
+    };
+    if (p->s1_order == 0) { RVAE_CHECK(run_wgrad()); RVAE_CHECK(run_latent()); }
+    else { RVAE_CHECK(run_latent()); RVAE_CHECK(run_wgrad()); }
+    RVAE_CUDA(cudaEventRecord(p->ev_s1_join, p->hp2));
+    p->fin_pending = false;
+    p->dz_zeroed = true;
+    RVAE_CUDA(cudaStreamWaitEvent(st, p->ev_s1_join, 0));
+    return RVAE_OK;
+  }
   // dgrad and weight gradient of the stage as ONE persistent launch over a mixed, load-balanced tile list
   bool fused = false;
   if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && !p->timing && sched_usable(p)) {
@@ -1009,6 +1055,18 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->adam_stream = nullptr; p->ev_eps = nullptr; p->ev_adam_fork = nullptr; p->ev_adam_join = nullptr;
   p->eps_pending = false; p->fin_pending = false;
   p->two_streams = true;
+  p->hp2 = nullptr; p->ev_s1_fork = nullptr; p->ev_s1_join = nullptr;
+  p->split_stage1 = true;
+  p->s1_wgrad_ctas = 96;   // measured (profiles/README.md): 96 CTAs, weight gradient first
+  p->s1_order = 0;
+  p->adam_bg_blocks = 0;
+  if (const char* e = getenv("RVAE_ADAM_BG_BLOCKS")) p->adam_bg_blocks = atoi(e) > 0 ? atoi(e) : 0;
+  if (const char* e = getenv("RVAE_S1_ORDER")) p->s1_order = atoi(e) != 0;
+  if (const char* e = getenv("RVAE_SPLIT_STAGE1")) p->split_stage1 = atoi(e) != 0;
+  if (const char* e = getenv("RVAE_S1_WGRAD_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= ctx->c.num_sms_total) p->s1_wgrad_ctas = v & ~1;
+  }
   p->fuse_forward = false;  // measured: no faster than the four separate launches (profiles/README.md); opt-in
 #if RVAE_EXPERIMENTS
   if (const char* e = getenv("RVAE_FUSE_LATENT")) p->fuse_latent = atoi(e) != 0;
@@ -1046,6 +1104,10 @@ void rvae_plan_destroy(rvae_plan* plan) {
     cudaEventDestroy(plan->ev_hp_fork);
     cudaEventDestroy(plan->ev_hp_join);
     cudaStreamDestroy(plan->hp);
+    cudaStreamSynchronize(plan->hp2);
+    cudaStreamDestroy(plan->hp2);
+    cudaEventDestroy(plan->ev_s1_fork);
+    cudaEventDestroy(plan->ev_s1_join);
     cudaEventDestroy(plan->ev_fork);
     cudaEventDestroy(plan->ev_eps);
     cudaEventDestroy(plan->ev_adam_fork);
@@ -1584,7 +1646,12 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, 
       RVAE_CUDA(cudaEventRecord(plan->ev_adam_fork, st));
       RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_adam_fork, 0));
       RVAE_CHECK(finalize_on_bg());
-      RVAE_CHECK(adam_buckets(plan, kBucketMask[0], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
+      // (single process) held to adam_bg_blocks blocks: it then lives on the SMs the 128-CTA GEMM grids leave free
+      // instead of taking every SM a finishing GEMM releases before the latent kernel of stage 1 gets there
+      cx->c.aux_grid_cap = plan->adam_bg_blocks;
+      const int rc_bg = adam_buckets(plan, kBucketMask[0], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg);
+      cx->c.aux_grid_cap = 0;
+      RVAE_CHECK(rc_bg);
     }
   }
   RVAE_CUDA(cudaEventRecord(plan->ev_adam_join, bg));

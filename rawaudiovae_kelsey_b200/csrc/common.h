@@ -56,6 +56,9 @@ struct Ctx {
   int aux_cap;
   uint64_t aux_seq;
   uint64_t launches;  // number of kernels launched through this context (bench.py reports it)
+  int aux_grid_cap;   // > 0: upper bound for the grid of the next Adam launch (background launches of a training step
+                      // are held to the SMs the GEMM grids leave free, so they do not squat on SMs a waiting
+                      // high-priority kernel wants: resident blocks are never preempted)
 };
 
 // Launch with programmatic stream serialization: the kernel may start (and run its prologue) while the previous

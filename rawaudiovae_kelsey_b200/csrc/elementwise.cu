@@ -845,7 +845,8 @@ int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, in
   static const int unroll = getenv("RVAE_ADAM_UNROLL") ? atoi(getenv("RVAE_ADAM_UNROLL")) : 2;
   static const int bps = getenv("RVAE_ADAM_BPS") ? atoi(getenv("RVAE_ADAM_BPS")) : 4;
   const int64_t groups = (n + n_b + 3) / 4;
-  const dim3 grid(grid_for(ctx, (groups + unroll - 1) / unroll, threads, bps > 0 ? bps : 4));
+  dim3 grid(grid_for(ctx, (groups + unroll - 1) / unroll, threads, bps > 0 ? bps : 4));
+  if (ctx->aux_grid_cap > 0 && (int)grid.x > ctx->aux_grid_cap) grid.x = ctx->aux_grid_cap;
   auto kern = unroll == 1 ? adam_kernel<1> : (unroll == 4 ? adam_kernel<4> : adam_kernel<2>);
   RVAE_CUDA(launch_kernel(ctx, kern, grid, dim3(threads), (size_t)0,
                           stream, p, g, m, v, n, off_b, n_b, lr, beta1, beta2, eps, weight_decay, grad_scale, step,

@@ -50,6 +50,8 @@ torch.cuda.synchronize()
 NAMES = ["F1", "F2", "F3", "F4", "B4d", "B4w", "B3d", "B3w", "B2d", "B2w", "B1w"]
 if os.environ.get("RVAE_DUAL_PAIRS", "64") != "0":   # backward stages 0..2 are fused dgrad + wgrad launches
     NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
+    if os.environ.get("RVAE_SPLIT_STAGE1", "1") != "0":   # stage 1: latent dgrad, then latent kernel || fc3 weight gradient
+        NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d", "B3w", "B2d+B2w", "B1w"]
     if os.environ.get("RVAE_FUSE_FORWARD", "0") != "0":   # fc1 + head and fc3 + fc4 are chained launches
         NAMES = ["F1>F2>F3>F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
 NSTEP = 3
@@ -114,37 +116,51 @@ if WORLD > 1:
     dist.barrier()
     dist.destroy_process_group()
 
-# per-tile role summary of one launch of the last traced step (TRACE_LAUNCH = index within the step, default 0)
-li = int(os.environ.get("TRACE_LAUNCH", "0"))
+# per-tile role summary of launches of the last traced step (TRACE_LAUNCH = comma-separated indices within the step,
+# default 0); TRACE_PAIRS = comma-separated CTA indices whose own unit-by-unit timeline is printed as well
 NE, NT = ops.TRACE_EVENTS, ops.TRACE_TILES
-i = (NSTEP - 1) * len(NAMES) + li
-hdr = t[i, :, :HDR].astype(np.float64)
-ev = t[i, :, HDR:].reshape(nsm, NT, NE).astype(np.float64)
-live = hdr[:, 1] > 0
-ghz = float(np.median((hdr[live, 5] - hdr[live, 1]) / np.maximum(hdr[live, 6] - hdr[live, 0], 1)))
-us = lambda c: c / ghz / 1e3
-print(f"---- roles of launch {li} ({NAMES[li]}), {int(live.sum())} CTAs, clock {ghz:.2f} GHz; times in us since the CTA passed its PDL wait")
-# TRACE_SPLIT=n: summarise CTAs [0, n) and [n, ..) separately (fused launches: the two problems' CTA pairs)
 split = int(os.environ.get("TRACE_SPLIT", "0"))
-groups = [("", live)]
-if split > 0:
-    lo = live.copy(); lo[split:] = False
-    hi = live.copy(); hi[:split] = False
-    groups = [(f"ctas < {split}", lo), (f"ctas >= {split}", hi)]
-for gname, gl in groups:
-  if gname:
-    print(f" -- {gname}: exit {us(np.median(hdr[gl, 5] - hdr[gl, 3])):6.1f} us after the PDL wait (max {us(np.max(hdr[gl, 5] - hdr[gl, 3])):6.1f})")
-  for it in range(NT):
-    e = ev[gl, it, :]
-    ran = e[:, 6] > 0
-    if not ran.any():
-        break
-    e = e[ran]; base = hdr[gl, 3][ran]
-    mm = e[:, 3] > 0
-    med = lambda a: float(np.median(a)) if len(a) else float("nan")
-    mx = lambda a: float(np.max(a)) if len(a) else float("nan")
-    print(f"   tile {it:2d} ({int(ran.sum()):3d} CTAs): prod start {us(med(e[:,0]-base)):6.1f} | mma acc-wait {us(med(e[mm,3]-e[mm,2])):5.2f} "
-          f"data-wait med {us(med(e[mm,4]-e[mm,3])):5.2f} max {us(mx(e[mm,4]-e[mm,3])):5.2f} issue {us(med(e[mm,5]-e[mm,4])):5.2f} commit at {us(med(e[mm,5]-base[mm])):6.1f} (max {us(mx(e[mm,5]-base[mm])):6.1f}) | "
-          f"epi {us(med(e[:,6]-base)):6.1f}->{us(med(e[:,7]-base)):6.1f}"
-          + ("  ev10..15 after acc-ready: " + " ".join(f"{us(med(e[e[:,k]>0,k]-e[e[:,k]>0,6])):5.1f}" for k in range(10, 16))
-             if os.environ.get("TRACE_EPI_DETAIL") else ""))
+pairs = [int(v) for v in os.environ.get("TRACE_PAIRS", "").split(",") if v]
+for li in [int(v) for v in os.environ.get("TRACE_LAUNCH", "0").split(",")]:
+    i = (NSTEP - 1) * len(NAMES) + li
+    hdr = t[i, :, :HDR].astype(np.float64)
+    ev = t[i, :, HDR:].reshape(nsm, NT, NE).astype(np.float64)
+    live = hdr[:, 1] > 0
+    ghz = float(np.median((hdr[live, 5] - hdr[live, 1]) / np.maximum(hdr[live, 6] - hdr[live, 0], 1)))
+    us = lambda c: c / ghz / 1e3
+    print(f"---- roles of launch {li} ({NAMES[li]}), {int(live.sum())} CTAs, clock {ghz:.2f} GHz; times in us since the CTA passed its PDL wait; "
+          f"CTA lifetime after the PDL wait: median {us(np.median(hdr[live, 5] - hdr[live, 3])):.1f} max {us(np.max(hdr[live, 5] - hdr[live, 3])):.1f}")
+    groups = [("", live)]
+    if split > 0:
+        lo = live.copy(); lo[split:] = False
+        hi = live.copy(); hi[:split] = False
+        groups = [(f"ctas < {split}", lo), (f"ctas >= {split}", hi)]
+    for gname, gl in groups:
+        if gname:
+            print(f" -- {gname}: exit {us(np.median(hdr[gl, 5] - hdr[gl, 3])):6.1f} us after the PDL wait (max {us(np.max(hdr[gl, 5] - hdr[gl, 3])):6.1f})")
+        for it in range(NT):
+            e = ev[gl, it, :]
+            ran = e[:, 6] > 0
+            if not ran.any():
+                break
+            e = e[ran]; base = hdr[gl, 3][ran]
+            mm = e[:, 3] > 0
+            med = lambda a: float(np.median(a)) if len(a) else float("nan")
+            mx = lambda a: float(np.max(a)) if len(a) else float("nan")
+            print(f"   tile {it:2d} ({int(ran.sum()):3d} CTAs): prod start {us(med(e[:,0]-base)):6.1f} | mma acc-wait {us(med(e[mm,3]-e[mm,2])):5.2f} "
+                  f"data-wait med {us(med(e[mm,4]-e[mm,3])):5.2f} max {us(mx(e[mm,4]-e[mm,3])):5.2f} issue {us(med(e[mm,5]-e[mm,4])):5.2f} commit at {us(med(e[mm,5]-base[mm])):6.1f} (max {us(mx(e[mm,5]-base[mm])):6.1f}) | "
+                  f"epi {us(med(e[:,6]-base)):6.1f}->{us(med(e[:,7]-base)):6.1f}"
+                  + ("  ev10..15 after acc-ready: " + " ".join(f"{us(med(e[e[:,k]>0,k]-e[e[:,k]>0,6])):5.1f}" for k in range(10, 16))
+                     if os.environ.get("TRACE_EPI_DETAIL") else ""))
+    for c in pairs:
+        if c >= nsm or hdr[c, 1] <= 0:
+            continue
+        b0 = hdr[c, 3]
+        print(f"   CTA {c}: exits {us(hdr[c, 5] - b0):.1f} us after its PDL wait")
+        for it in range(NT):
+            e = ev[c, it, :]
+            if e[6] <= 0:
+                break
+            f = lambda k: us(e[k] - b0) if e[k] > 0 else float('nan')
+            print(f"      unit {it:2d}: prod {f(0):6.1f}..{f(1):6.1f} | mma wait-acc {f(2):6.1f} got {f(3):6.1f} data {f(4):6.1f} commit {f(5):6.1f} | "
+                  f"epi team0 {f(6):6.1f}..{f(7):6.1f} team1 {f(8):6.1f}..{f(9):6.1f}")
