@@ -439,6 +439,43 @@ int gemm_prepare_chain(const Ctx* ctx, const PreparedGemm* const* g, int count, 
     sched[(size_t)best * kSchedMax + cnt[best]++] = u.id;
     load[best] += u.cost;
   }
+  if (dep_flags == nullptr) {
+    // Order WITHIN a pair (independent problems only). A unit's epilogue overlaps the next unit's MMAs, so a pair is
+    // fastest when long-MMA units (split-K weight gradients: light epilogue) sit BETWEEN short-MMA, epilogue-heavy
+    // units (dgrad tiles) instead of in front of them, where nothing overlaps their main loop: the heavy units are
+    // spread evenly through the light ones, never first (measured on the role traces, profiles/README.md).
+    static const int order_mode = getenv("RVAE_CHAIN_ORDER") ? atoi(getenv("RVAE_CHAIN_ORDER")) : 1;
+    auto prob_of = [&](int id) { int q = 0; while (q + 1 < count && id >= base[q + 1]) ++q; return q; };
+    for (int pidx = 0; pidx < pairs && order_mode == 1; ++pidx) {
+      int* row = &sched[(size_t)pidx * kSchedMax];
+      std::vector<int> heavy, light;
+      double min_mma = 1e30;
+      for (int k = 0; k < cnt[pidx]; ++k) {
+        const PreparedGemm& gq = *g[prob_of(row[k])];
+        min_mma = std::min(min_mma, (double)gq.params.kb_per_split * gq.params.num_passes);
+      }
+      for (int k = 0; k < cnt[pidx]; ++k) {
+        const PreparedGemm& gq = *g[prob_of(row[k])];
+        const double mma = (double)gq.params.kb_per_split * gq.params.num_passes;
+        (mma > 1.5 * min_mma ? heavy : light).push_back(row[k]);
+      }
+      if (heavy.empty() || light.size() < 2) continue;
+      std::vector<int> merged;
+      const size_t nh = heavy.size(), nl = light.size();
+      size_t li = 0;
+      for (size_t h = 0; h < nh; ++h) {
+        // light units before heavy unit h: an even share, at least one (two before the first when there are enough)
+        size_t upto = (h + 1) * nl / (nh + 1);
+        if (h == 0 && upto < 2 && nl >= 3) upto = 2;
+        if (upto < li + (h == 0 ? 1 : 0)) upto = li + (h == 0 ? 1 : 0);
+        if (upto > nl) upto = nl;
+        while (li < upto) merged.push_back(light[li++]);
+        merged.push_back(heavy[h]);
+      }
+      while (li < nl) merged.push_back(light[li++]);
+      for (size_t k = 0; k < merged.size(); ++k) row[k] = merged[k];
+    }
+  }
   RVAE_CUDA(cudaMemcpy(sched_dev, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice));
   PreparedChain& d = *out;
   memset(&d, 0, sizeof(d));
