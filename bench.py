@@ -248,7 +248,8 @@ def run_ours(args):
 
     # synthetic corpus resident in HBM (every rank holds it; rank r draws its own frame indices)
     corpus = synth_corpus(args.files, args.seconds)
-    audio = torch.from_numpy(corpus).to(dev)
+    from rawaudiovae_kelsey_b200.dataset import resident_audio
+    audio = resident_audio(corpus, dev)     # the product's loader path: 16-bit PCM content stays int16 in HBM (lossless)
     n_frames = (len(corpus) + HOP - 1) // HOP - S // HOP + 1
 
     # Steady state before anything is timed. A CUDA-graph step function captures one graph per input signature after
@@ -259,7 +260,12 @@ def run_ours(args):
     NEED = 4
     pre_steps = max(args.warmup, 2 * step_fn.graph_warmup + 2 + NEED) if args.graph else args.warmup
     est_ms = 0.35 if args.precision == "bf16" else 1.0
-    n_blocks = args.blocks if args.blocks > 0 else int(min(200, max(7, math.ceil(300.0 / (args.steps * est_ms)))))
+    # headline statistic: the median of >= 7 blocks of exactly --steps steps covering >= 200 steps (SURVEY.md 8d:
+    # "CUDA-event timed over >= 200 steps after >= 20 warm-up"). A run this short stays at boost clocks; what a job that
+    # runs for hours sees - the board's power cap pulls the SM clock down after ~100 ms of load - is measured afterwards
+    # by a separate long pass and reported as `sustained` (never mixed into `value`).
+    n_blocks = args.blocks if args.blocks > 0 else int(max(7, math.ceil(200.0 / args.steps)))
+    sus_blocks = 0 if (args.blocks > 0 or args.no_sustained) else int(min(200, math.ceil(400.0 / (args.steps * est_ms))))
 
     # batch i = a fresh random 8192-frame gather; a pool of index sets is cycled (the pool's footprint is far larger
     # than L2). Step i also hands the step function batch i + 1, which it gathers (and draws the noise for) on its
@@ -284,12 +290,12 @@ def run_ours(args):
             raise RuntimeError(f"graph replay not steady after {pre_steps} pre-steps: {step_fn.stats}")
         return i
 
-    def timed_blocks(step_once, i, end_of_block=None):
+    def timed_blocks(step_once, i, end_of_block=None, blocks=None):
         """n_blocks blocks of EXACTLY --steps steps, each bracketed by barrier + synchronize; block times are the
         max over ranks. Returns (block ms list, next step index, last loss, stats delta)."""
         s0 = dict(step_fn.stats)
         times, loss = [], None
-        for _ in range(n_blocks):
+        for _ in range(blocks or n_blocks):
             barrier()
             e0.record()
             for _ in range(args.steps):
@@ -384,6 +390,23 @@ def run_ours(args):
     if args.graph:
         assert e2e_delta["captures"] == 0 and e2e_delta["eager"] == 0, f"capture / eager step in the e2e region: {e2e_delta}"
 
+    # ---- sustained: the `value` leg again, for ~0.4 s of continuous load (power-capped clocks); second half's median
+    sustained = None
+    if sus_blocks > 0:
+        if args.prefetch:   # the e2e leg left its own batch prefetched: one untimed step re-enters the value leg's stream
+            device_step(i); i += 1
+        sclk = NvmlSampler(dev)
+        if rank == 0:
+            sclk.start()
+        sus_ms, i, _, sus_delta = timed_blocks(device_step, i, blocks=sus_blocks)
+        sc = sclk.stop() if rank == 0 else None
+        tail = sus_ms[len(sus_ms) // 2:]
+        sm = float(np.median(tail))
+        sustained = {"value": BATCH * world * args.steps / (sm * 1e-3), "unit": "frames/s", "ms_per_step": sm / args.steps,
+                     "blocks": sus_blocks, "statistic": "median of the second half of the blocks", "clocks": sc,
+                     "block_ms": [round(v, 4) for v in sus_ms],
+                     "captures_in_timed_region": sus_delta["captures"], "eager_steps_in_timed_region": sus_delta["eager"]}
+
     # ---- roofline of the dominant kernel family (tcgen05 GEMMs), timed live with CUDA events on the launch stream
     roofline, breakdown = None, None
     if rank == 0:
@@ -410,7 +433,7 @@ def run_ours(args):
             ncu_json = ROOT / "profiles" / name
             if ncu_json.exists() and args.precision == "bf16":
                 try:
-                    traffic = json.loads(ncu_json.read_text())["dram_bytes_per_step"]
+                    traffic = float(json.loads(ncu_json.read_text())["dram_bytes_per_step"])
                     traffic_src = f"profiles/{name} (ncu --set full, sum over the 11 GEMM launches of a step)"
                     break
                 except Exception:
@@ -452,7 +475,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "hop": HOP,
                        "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph), "prefetch_next_batch": bool(args.prefetch),
                        "l2": "per-step working set ~330 MB (activations + weights + moments) exceeds the 126 MB L2; "
-                             "a different random 8192-frame gather from a %.0f MB corpus every step" % (corpus.nbytes / 1e6),
+                             "a different random 8192-frame gather from a %.0f MB corpus (%s in HBM) every step"
+                             % (audio.numel() * audio.element_size() / 1e6, "16-bit PCM, lossless" if audio.dtype == torch.int16 else "float32"),
                        "corpus": f"{args.files} files x {args.seconds:.0f} s, 0.5*sin+0.05*noise, rng 1234"},
             "timing": {"blocks": n_blocks, "steps_per_block": args.steps, "statistic": "median block, max over ranks",
                        "pre_steps_untimed": pre_steps, "block_ms": [round(v, 4) for v in block_ms],
@@ -468,11 +492,16 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roofline,
-            "roofline_whole_step": {"bound": "tensor", "achieved": whole_tflops, "peak": peaks["bf16_sustained"],
-                                    "unit": "TFLOP/s", "frac": whole_tflops / peaks["bf16_sustained"],
-                                    "frac_of_burst": whole_tflops / peaks["bf16_burst"],
-                                    "peak_kind": f"bf16_tflops_sustained ({peaks['source']}): whole step incl. framing, "
-                                                 "loss, Adam" + (", all-reduce" if world > 1 else "")},
+            # whole step (framing, loss, Adam, all-reduce included) per GPU: the short `value` run against the burst
+            # peak, the long `sustained` run against the sustained peak - like with like
+            "roofline_whole_step": {"bound": "tensor", "achieved": whole_tflops, "peak": peaks["bf16_burst"],
+                                    "unit": "TFLOP/s", "frac": whole_tflops / peaks["bf16_burst"],
+                                    "peak_kind": f"bf16_tflops burst ({peaks['source']}): `value` is a 200-step run",
+                                    "sustained_achieved": (sustained["value"] * FLOP_PER_FRAME / world / 1e12) if sustained else None,
+                                    "sustained_peak": peaks["bf16_sustained"],
+                                    "sustained_frac": (sustained["value"] * FLOP_PER_FRAME / world / 1e12 / peaks["bf16_sustained"])
+                                    if sustained else None},
+            "sustained": sustained,
             "gemm_breakdown": breakdown,
             "cpu_baseline": cpu_baseline,
         }
@@ -639,6 +668,7 @@ def main():
     ap.add_argument("--files", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the long power-capped pass (key `sustained`)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the side legs (fp32 mode, kelsey_iterable.ini streaming, widened-VAE inference)")
     ap.add_argument("--blocks", type=int, default=0,

@@ -965,7 +965,10 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
     cudaStream_t s_l = p->s1_order == 0 ? p->hp2 : st;
     auto run_wgrad = [&]() -> int {
       PreparedGemm w = gs->g[G_B3W];
-      if (w.grid > p->s1_wgrad_ctas) w.grid = p->s1_wgrad_ctas;   // persistent: the pairs stride over the units
+      // persistent: the pairs stride over the units. Under data parallelism the all-reduce kernels live on the spare
+      // SMs too: 64 CTAs there (measured at N = 2: 96 costs 3 %), 96 in a single process
+      const int cap = (p->dp_enabled && p->ctx->dp_world > 1 && p->s1_wgrad_ctas > 64) ? 64 : p->s1_wgrad_ctas;
+      if (w.grid > cap) w.grid = cap;
       return gemm_run(&p->ctx->c, w, s_w);
     };
     auto run_latent = [&]() -> int {

@@ -8,6 +8,7 @@ the framing kernel (rvae_frame_gather) turns into fc1's bf16 operand directly.
 """
 from __future__ import annotations
 
+import os
 import pathlib
 import random
 import threading
@@ -174,6 +175,24 @@ def shard_bounds(batch: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def resident_audio(audio_np, device) -> torch.Tensor:
+    """The corpus as it lives in HBM. int16 input stays int16. A float array whose every sample is k / 32768 with k an
+    int16 - what decoding a 16-bit PCM wav yields (librosa / torchaudio / soundfile agree) - is
+    stored as that int16: half the footprint and half the bytes the framing kernel reads, and LOSSLESS, because the
+    kernel's int16 * (1 / 32768) reproduces the float exactly (checked here, sample by sample, before it is relied on).
+    Anything else (float wavs, resampled audio) stays float32. RVAE_PCM16_RESIDENT=0 turns the detection off."""
+    a = np.ascontiguousarray(audio_np)
+    if a.dtype == np.int16:
+        return torch.from_numpy(a).to(device)
+    a = a.astype(np.float32, copy=False)
+    if os.environ.get("RVAE_PCM16_RESIDENT", "1") not in ("0", ""):
+        q = a * np.float32(32768.0)
+        k = np.rint(q)
+        if a.size and np.array_equal(q, k) and float(k.min()) >= -32768.0 and float(k.max()) <= 32767.0:
+            return torch.from_numpy(k.astype(np.int16)).to(device)
+    return torch.from_numpy(a).to(device)
+
+
 class GpuFrameLoader:
     """Map-style batches on the GPU: the (padded) audio array lives in HBM once; every epoch draws the sampler
     permutation on the host exactly as DataLoader(shuffle=True) does, ships the indices (8 B/frame), and yields
@@ -184,11 +203,7 @@ class GpuFrameLoader:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("GpuFrameLoader needs a CUDA device (no CPU fallback)")
-        a = np.ascontiguousarray(audio_np)
-        if a.dtype == np.int16:
-            self.audio = torch.from_numpy(a).to(self.device)
-        else:
-            self.audio = torch.from_numpy(a.astype(np.float32, copy=False)).to(self.device)
+        self.audio = resident_audio(audio_np, self.device)
         self.n_frames, self.hop, self.segment_length = int(n_frames), int(hop), int(segment_length)
         self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
         self.rank, self.world = rank, world

@@ -378,3 +378,24 @@ def test_pcm16_passthrough_view_equals_the_decoded_file(tmp_path):
     x, _ = audio_io.load_wav_channels(tmp_path / "s.wav")
     assert sr == 48000 and d.shape == (4000, 2) and np.array_equal(np.asarray(d[:, 0]).astype(np.float32) / 32768.0, x[0])
     assert audio_io.open_pcm16(tmp_path / "f.wav")[0] is None
+
+
+def test_resident_audio_keeps_16_bit_pcm_content_as_int16_only_when_lossless(monkeypatch):
+    """dataset.resident_audio: a float corpus decoded from 16-bit PCM (k / 32768) is held as int16 - the framing kernel's
+    int16 * (1 / 32768) gives back every float exactly - anything else stays float32; RVAE_PCM16_RESIDENT=0 disables."""
+    from rawaudiovae_kelsey_b200 import dataset as D
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32768, 10000, dtype=np.int64).astype(np.int16)
+    pcm[:2] = (-32768, 32767)
+    as_float = pcm.astype(np.float32) / 32768.0
+    t = D.resident_audio(as_float, "cpu")
+    assert t.dtype == torch.int16 and np.array_equal(t.numpy(), pcm)
+    assert np.array_equal(t.numpy().astype(np.float32) * np.float32(1.0 / 32768.0), as_float)     # what the kernel computes
+    assert D.resident_audio(pcm, "cpu").dtype == torch.int16
+    noisy = as_float.copy()
+    noisy[1234] += 1e-6                                   # one sample off the 16-bit grid: not lossless any more
+    assert D.resident_audio(noisy, "cpu").dtype == torch.float32
+    assert D.resident_audio(np.array([1.0, 0.0], dtype=np.float32), "cpu").dtype == torch.float32   # +1.0 = 32768 / 32768
+    assert D.resident_audio(rng.standard_normal(100), "cpu").dtype == torch.float32
+    monkeypatch.setenv("RVAE_PCM16_RESIDENT", "0")
+    assert D.resident_audio(as_float, "cpu").dtype == torch.float32

@@ -57,6 +57,7 @@ def main(rep, out, step=False):
         "chain_tflops": sum(GFLOP) / tot_us * 1e3,
         "chain_weighted_tensor_pipe_active_pct_elapsed": sum(g["tensor_active_pct_elapsed"] * g["us"] for g in gemms) / tot_us,
         "dram_MB_per_step": sum(g["dram_read_MB"] + g["dram_write_MB"] for g in gemms),
+        "dram_bytes_per_step": 1e6 * sum(g["dram_read_MB"] + g["dram_write_MB"] for g in gemms),
     }
     json.dump(summary, open(out, "w"), indent=1)
     for g in gemms:
