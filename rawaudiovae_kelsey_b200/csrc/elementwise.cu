@@ -53,7 +53,7 @@ __device__ __forceinline__ float block_sum_to_warp0(float v, float* smem) {
 // tail, rawvae/dataset.py:102-104,141-143). idx = frame_idx[f] (shuffled map-style batches) or first_frame + f
 // (streaming / sequential). One thread converts 8 consecutive samples.
 // ------------------------------------------------------------------------------------------------
-template <bool I16>
+template <bool I16, int U>
 __global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_samples,
                                     const int64_t* __restrict__ frame_idx, int64_t first_frame, int64_t n_frames,
                                     int hop, int S, __nv_bfloat16* __restrict__ out_hi,
@@ -64,8 +64,7 @@ __global__ void frame_gather_kernel(const void* __restrict__ audio, int64_t n_sa
   const int vec_per_frame = S >> 3;
   const int64_t total = n_frames * vec_per_frame;
   // U groups of 8 samples per thread and trip: the U frame indices are fetched first, then all 2 U 16-byte loads are
-  // issued before the first convert / store, so each thread keeps U x 32 bytes of dependent-address loads in flight
-  constexpr int U = 4;
+  // issued before the first convert / store (U = 1 by default: occupancy beats per-thread unrolling here)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
     int64_t fr[U], s0[U];
@@ -152,14 +151,27 @@ int launch_frame_gather(Ctx* ctx, const void* audio, int audio_is_i16, int64_t n
   RVAE_REQUIRE(S > 0 && S % 8 == 0 && hop > 0, RVAE_ERR_UNSUPPORTED, "frame_gather: S=%d must be a multiple of 8", S);
   if (n_frames <= 0) return RVAE_OK;
   const int threads = 256;
-  const int grid = grid_for(ctx, (n_frames * (S / 8) + 3) / 4, threads, 8);
+  // RVAE_GATHER_UNROLL (1 / 2 / 4 groups of 8 samples per thread and trip), RVAE_GATHER_WAVES: tuning knobs
+  // measured (profiles/README.md, round 2): one group per thread and trip with 16 blocks per SM is the fastest alone
+  // (16.4 us vs 24.6 us for 4 groups) and no slower inside a step, where the kernel runs on the background stream
+  static const int unroll = getenv("RVAE_GATHER_UNROLL") ? atoi(getenv("RVAE_GATHER_UNROLL")) : 1;
+  static const int waves = getenv("RVAE_GATHER_WAVES") ? atoi(getenv("RVAE_GATHER_WAVES")) : 16;
+  const int u = unroll == 1 ? 1 : (unroll == 2 ? 2 : 4);
+  const int grid = grid_for(ctx, (n_frames * (S / 8) + u - 1) / u, threads, waves > 0 ? waves : 8);
   const AuxTrace tr = next_aux(ctx, 1);
-  if (audio_is_i16)
-    RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<true>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop, S,
-                                                            out_hi, out_lo, out_f32, tr));
-  else
-    RVAE_CUDA(launch_kernel(ctx, frame_gather_kernel<false>, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx, first_frame, n_frames, hop,
-                                                             S, out_hi, out_lo, out_f32, tr));
+  auto go = [&](auto kern) {
+    return launch_kernel(ctx, kern, dim3(grid), dim3(threads), (size_t)0, stream, audio, n_samples, frame_idx,
+                         first_frame, n_frames, hop, S, out_hi, out_lo, out_f32, tr);
+  };
+  if (audio_is_i16) {
+    if (u == 1) RVAE_CUDA(go(frame_gather_kernel<true, 1>));
+    else if (u == 2) RVAE_CUDA(go(frame_gather_kernel<true, 2>));
+    else RVAE_CUDA(go(frame_gather_kernel<true, 4>));
+  } else {
+    if (u == 1) RVAE_CUDA(go(frame_gather_kernel<false, 1>));
+    else if (u == 2) RVAE_CUDA(go(frame_gather_kernel<false, 2>));
+    else RVAE_CUDA(go(frame_gather_kernel<false, 4>));
+  }
   RVAE_LAUNCH_CHECK(ctx);
   return RVAE_OK;
 }

@@ -23,6 +23,7 @@ NP = 5772800
 g = lambda *s: torch.randn(*s, device=dev)
 
 audio = g(30 * 44100 * 32).clamp_(-1, 1)
+audio16 = torch.round(audio * 32767).to(torch.int16)
 nfr_total = (audio.numel() - S) // hop + 1
 idx = torch.randint(0, nfr_total, (B,), device=dev, dtype=torch.int64)
 p, gr, m, v = g(NP), g(NP), g(NP), g(NP).abs_()
@@ -40,6 +41,8 @@ CASES = [
     # name, callable, algorithmic bytes
     ("frame_gather (fp32 wav -> bf16 frames, random 8192 of the corpus)",
      lambda: ops.frame_gather(audio, B, hop, S, frame_idx=idx, out_f32=False, out_bf16=True), B * S * (4 + 2)),
+    ("frame_gather pcm16 (int16 wav -> bf16 frames, random 8192 of the corpus)",
+     lambda: ops.frame_gather(audio16, B, hop, S, frame_idx=idx, out_f32=False, out_bf16=True), B * S * (2 + 2)),
     ("randn (eps [8192,256] fp32)", lambda: ops.randn((B, L), 1, 0), B * L * 4),
     ("adam (5 772 800 params + bf16 shadow, gradient cleared)",
      lambda: ops.adam_step(p, gr, m, v, step, 1e-4, shadow_hi=shadow, increment_step=False), NP * 30),
