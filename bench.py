@@ -464,6 +464,13 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extras:
         extras = extra_legs(dev, audio, n_frames, peaks)
 
+    exchange = None
+    if world > 1:
+        from rawaudiovae_kelsey_b200 import _lib as rlib
+        mc = bool(rlib.load().rvae_dp_uses_multicast(ops.ctx(dev)))
+        exchange = ("own all-reduce kernel, in-switch reduction over an NVLS multicast mapping (multimem.ld_reduce / multimem.st)"
+                    if mc else ("NCCL all-reduce" if os.environ.get("RVAE_DP_BACKEND", "auto") == "nccl"
+                                else "own all-reduce kernel over NVLink peer memory (peer loads + posted peer writes)"))
     if rank == 0:
         ms_per_step = ms / args.steps
         whole_tflops = value * FLOP_PER_FRAME / world / 1e12
@@ -473,7 +480,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "hop": HOP,
-                       "precision": args.precision, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph), "prefetch_next_batch": bool(args.prefetch),
+                       "precision": args.precision, "parallelism": f"dp{world}", "exchange": exchange, "cuda_graph": bool(args.graph), "prefetch_next_batch": bool(args.prefetch),
                        "l2": "per-step working set ~330 MB (activations + weights + moments) exceeds the 126 MB L2; "
                              "a different random 8192-frame gather from a %.0f MB corpus (%s in HBM) every step"
                              % (audio.numel() * audio.element_size() / 1e6, "16-bit PCM, lossless" if audio.dtype == torch.int16 else "float32"),

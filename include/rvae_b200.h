@@ -78,6 +78,17 @@ int rvae_dp_sym_alloc(rvae_ctx* ctx, size_t data_bytes, void** data_ptr, void* i
  * otherwise. What rvae_plan_train_step issues per gradient bucket. */
 int rvae_dp_allreduce(rvae_ctx* ctx, float* ptr, int64_t count, int bucket, void* stream);
 int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world);
+/* The same set-up from a symmetric allocation the CALLER made and mapped (e.g. torch.distributed._symmetric_memory):
+ * peer_bases[p] = this process' mapping of rank p's buffer ([rank] = the local one), each rvae_dp_sym_flag_bytes() of
+ * zeroed flag area followed by data_bytes of gradient buffer; multicast_base = the NVLS multicast mapping of the same
+ * allocation (NULL = none). With a multicast mapping the all-reduce kernel reduces each slice INSIDE THE NVSWITCH
+ * (multimem.ld_reduce) and multicasts the sum to all ranks (multimem.st): 1 / W of the bucket crosses a rank's links
+ * once per direction instead of (W - 1) / W peer reads + (W - 1) / W posted writes. The caller keeps the allocation
+ * alive and unmaps it; RVAE_NVLS=0 ignores the multicast mapping. */
+size_t rvae_dp_sym_flag_bytes(void);
+int rvae_dp_sym_adopt(rvae_ctx* ctx, const void* const* peer_bases, void* multicast_base, size_t data_bytes, int rank,
+                      int world);
+int rvae_dp_uses_multicast(const rvae_ctx* ctx);
 /* Health of the peer-memory all-reduce. Its barriers wait for a slower peer for RVAE_P2P_TIMEOUT_S seconds (default
  * 600) and never trap; the first wait that gives up records bit 31 | peer << 8 | flag set << 4 | phase here, and every
  * later wait falls through at once, so the process stays alive and the host can report the failure. 0 = healthy.

@@ -46,6 +46,9 @@ SIGNATURES = {
     "rvae_dp_world": (c_int, [P]),
     "rvae_dp_sym_alloc": (c_int, [P, c_size_t, C.POINTER(P), P]),
     "rvae_dp_sym_open": (c_int, [P, P, c_int, c_int]),
+    "rvae_dp_sym_flag_bytes": (c_size_t, []),
+    "rvae_dp_sym_adopt": (c_int, [P, C.POINTER(P), P, c_size_t, c_int, c_int]),
+    "rvae_dp_uses_multicast": (c_int, [P]),
     "rvae_dp_allreduce": (c_int, [P, P, c_int64, c_int, P]),
     "rvae_frame_gather": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int64, c_int, c_int, P, P, P, P]),
     "rvae_overlap_add": (c_int, [P, P, c_int64, c_int, c_int, P, c_int64, c_int64, P]),

@@ -38,6 +38,7 @@ struct rvae_ctx {
   int dp_rank, dp_world;
   // peer-memory all-reduce: this rank's symmetric allocation ([flags | gradient data]) and the peers' mappings
   uint8_t* sym_base;
+  bool sym_owned;      // rvae_dp_sym_alloc made the allocation (else adopted from the caller: rvae_dp_sym_adopt)
   size_t sym_data_bytes;
   void* peer_base[kP2PMaxWorld];
   P2PArgs p2p;
@@ -80,7 +81,7 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
   ctx->c.aux_grid_cap = 0;
   memset(&ctx->nccl, 0, sizeof(ctx->nccl));
   ctx->comm = nullptr; ctx->dp_rank = 0; ctx->dp_world = 1;
-  ctx->sym_base = nullptr; ctx->sym_data_bytes = 0; ctx->p2p_ready = false; ctx->p2p_ctas = 20; ctx->p2p_ctas_last = 48;
+  ctx->sym_base = nullptr; ctx->sym_owned = true; ctx->sym_data_bytes = 0; ctx->p2p_ready = false; ctx->p2p_ctas = 20; ctx->p2p_ctas_last = 48;
   memset(ctx->peer_base, 0, sizeof(ctx->peer_base));
   memset(&ctx->p2p, 0, sizeof(ctx->p2p));
   if (const char* e = getenv("RVAE_P2P_CTAS")) {
@@ -109,9 +110,11 @@ int rvae_ctx_create(int device, rvae_ctx** out) {
 void rvae_ctx_destroy(rvae_ctx* ctx) {
   if (!ctx) return;
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
-  for (int p = 0; p < kP2PMaxWorld; ++p)
-    if (ctx->peer_base[p] && p != ctx->dp_rank) cudaIpcCloseMemHandle(ctx->peer_base[p]);
-  if (ctx->sym_base) cudaFree(ctx->sym_base);
+  if (ctx->sym_owned) {
+    for (int p = 0; p < kP2PMaxWorld; ++p)
+      if (ctx->peer_base[p] && p != ctx->dp_rank) cudaIpcCloseMemHandle(ctx->peer_base[p]);
+    if (ctx->sym_base) cudaFree(ctx->sym_base);
+  }
   delete ctx;
 }
 
@@ -196,6 +199,35 @@ int rvae_dp_sym_alloc(rvae_ctx* ctx, size_t data_bytes, void** data_ptr, void* i
   return RVAE_OK;
 }
 
+// shared tail of rvae_dp_sym_open / rvae_dp_sym_adopt: ctx->peer_base[0..world) are mapped
+static int finish_p2p_setup(rvae_ctx* ctx, int rank, int world);
+
+size_t rvae_dp_sym_flag_bytes(void) { return kP2PFlagBytes; }
+
+int rvae_dp_sym_adopt(rvae_ctx* ctx, const void* const* peer_bases, void* multicast_base, size_t data_bytes, int rank,
+                      int world) {
+  RVAE_REQUIRE(ctx && peer_bases && data_bytes > 0, RVAE_ERR_INVALID, "dp_sym_adopt: bad argument");
+  RVAE_REQUIRE(ctx->sym_base == nullptr, RVAE_ERR_STATE, "dp_sym_adopt: a symmetric buffer is already set up");
+  RVAE_REQUIRE(world >= 2 && world <= kP2PMaxWorld && rank >= 0 && rank < world, RVAE_ERR_INVALID,
+               "dp_sym_adopt: rank %d of %d (at most %d ranks)", rank, world, kP2PMaxWorld);
+  for (int p = 0; p < world; ++p)
+    RVAE_REQUIRE(peer_bases[p] != nullptr && (reinterpret_cast<uintptr_t>(peer_bases[p]) & 255) == 0, RVAE_ERR_INVALID,
+                 "dp_sym_adopt: peer %d base %p (need 256-byte alignment)", p, peer_bases[p]);
+  RVAE_REQUIRE((reinterpret_cast<uintptr_t>(multicast_base) & 255) == 0, RVAE_ERR_INVALID, "dp_sym_adopt: multicast base");
+  RVAE_CUDA(cudaSetDevice(ctx->c.device));
+  for (int p = 0; p < world; ++p) ctx->peer_base[p] = const_cast<void*>(peer_bases[p]);
+  ctx->sym_base = reinterpret_cast<uint8_t*>(ctx->peer_base[rank]);
+  ctx->sym_data_bytes = data_bytes;
+  ctx->sym_owned = false;   // the caller owns the allocation and the peer mappings
+  RVAE_CHECK(finish_p2p_setup(ctx, rank, world));
+  ctx->p2p.mc_data = multicast_base ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(multicast_base) + kP2PFlagBytes)
+                                    : nullptr;
+  if (const char* e = getenv("RVAE_NVLS")) if (atoi(e) == 0) ctx->p2p.mc_data = nullptr;
+  return RVAE_OK;
+}
+
+int rvae_dp_uses_multicast(const rvae_ctx* ctx) { return ctx && ctx->p2p_ready && ctx->p2p.mc_data != nullptr; }
+
 int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world) {
   RVAE_REQUIRE(ctx && handles && ctx->sym_base, RVAE_ERR_STATE, "dp_sym_open: call rvae_dp_sym_alloc first");
   RVAE_REQUIRE(world >= 2 && world <= kP2PMaxWorld && rank >= 0 && rank < world, RVAE_ERR_INVALID,
@@ -209,9 +241,17 @@ int rvae_dp_sym_open(rvae_ctx* ctx, const void* handles, int rank, int world) {
       RVAE_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
     }
     ctx->peer_base[p] = base;
+  }
+  return finish_p2p_setup(ctx, rank, world);
+}
+
+static int finish_p2p_setup(rvae_ctx* ctx, int rank, int world) {
+  for (int p = 0; p < world; ++p) {
+    void* base = ctx->peer_base[p];
     ctx->p2p.flags[p] = reinterpret_cast<uint32_t*>(base);
     ctx->p2p.data[p] = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + kP2PFlagBytes);
   }
+  ctx->p2p.mc_data = nullptr;
   // local: epochs and tickets behind the flag table
   static_assert(kP2PMaxBuckets * kP2PMaxCtas * kP2PMaxWorld * kP2PFlagStride * 4 + 2 * kP2PMaxBuckets * 4 + 4 <= kP2PFlagBytes,
                 "flag area");

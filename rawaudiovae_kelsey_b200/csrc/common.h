@@ -192,6 +192,9 @@ constexpr int kP2PFlagStride = 32;            // one 128-byte line per flag: no 
 constexpr size_t kP2PFlagBytes = 1024 * 1024;  // flags [bucket][cta][src rank] + epochs + tickets, at the start of the allocation
 struct P2PArgs {
   float* data[kP2PMaxWorld];       // gradient buffer of rank p (peer-mapped; [rank] is local)
+  float* mc_data;                  // NVLS multicast mapping of the same buffer (all ranks at once), nullptr = none:
+                                   // multimem.ld_reduce sums a location over all ranks inside the switch, multimem.st
+                                   // writes it to all ranks (rvae_dp_sym_adopt)
   uint32_t* flags[kP2PMaxWorld];   // flag area of rank p
   uint32_t* epoch;                 // local: [kP2PMaxBuckets]
   unsigned int* ticket;            // local: [kP2PMaxBuckets]

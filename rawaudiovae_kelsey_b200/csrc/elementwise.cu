@@ -1025,6 +1025,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// NVLS (NVSwitch multicast): one load returns the SUM of the location over every rank's buffer, reduced in the switch;
+// one store writes every rank's buffer
+__device__ __forceinline__ float4 ld_reduce_mc(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mc(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -1107,6 +1119,25 @@ __global__ void __launch_bounds__(512, 1) allreduce_p2p_kernel(P2PArgs a, P2PSeg
     const int64_t s0 = (int64_t)me * per_rank;
     const int64_t s1 = min(s0 + per_rank, n4);
     const int64_t b0 = min(s0 + (int64_t)c * per_cta, s1), b1 = min(b0 + per_cta, s1);
+    if (a.mc_data != nullptr) {
+      // NVLS: the switch reduces my slice over all ranks (1 / W of the bucket crosses my links, once, instead of
+      // (W - 1) / W peer reads) and multicasts the result back into every rank's buffer
+      constexpr int UM = MAXW * U < 16 ? MAXW * U : 16;
+      float4* mc = reinterpret_cast<float4*>(a.mc_data);
+      for (int64_t base = b0 + threadIdx.x; base < b1; base += T * UM) {
+        float4 v[UM];
+#pragma unroll
+        for (int u = 0; u < UM; ++u) {
+          const int64_t i = base + u * T;
+          if (i < b1) v[u] = ld_reduce_mc(mc + at(i));
+        }
+#pragma unroll
+        for (int u = 0; u < UM; ++u) {
+          const int64_t i = base + u * T;
+          if (i < b1) st_mc(mc + at(i), v[u]);
+        }
+      }
+    } else
     for (int64_t base = b0 + threadIdx.x; base < b1; base += T * U) {
       float4 v[MAXW][U];
 #pragma unroll

@@ -83,6 +83,62 @@ class _DevBuffer:
         self.__cuda_array_interface__ = {"shape": (n_float32,), "typestr": "<f4", "data": (ptr, False), "version": 3}
 
 
+_SYMM_KEEP = []   # (buffer tensor, rendezvous handle): the symmetric allocations stay alive with the process
+
+
+def _adopt_torch_symmetric(lib, flat, group, rank, world):
+    """Gradient buffer [flag area | total fp32] in torch symmetric memory, mapped by every rank, with its NVLS multicast
+    mapping handed to the library (rvae_dp_sym_adopt). Returns the gradient tensor, or None when ANY rank could not
+    set it up (then nobody uses it)."""
+    from . import _lib, ops
+    import ctypes as C
+    ok, buf, hdl, err = True, None, None, ""
+    flag_bytes = int(lib.rvae_dp_sym_flag_bytes())
+    n_data = (flat.total + 63) // 64 * 64
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        g = group if group is not None else dist.group.WORLD
+        with torch.cuda.device(flat.device):
+            buf = symm_mem.empty(flag_bytes // 4 + n_data, dtype=torch.float32, device=flat.device)
+            buf.zero_()
+            torch.cuda.synchronize(flat.device)
+            hdl = symm_mem.rendezvous(buf, g)
+        off = buf.data_ptr() - int(hdl.buffer_ptrs[rank])
+        ok = off >= 0 and len(hdl.buffer_ptrs) == world and (buf.data_ptr() % 256) == 0
+    except Exception as e:   # no symmetric memory on this build / box: fall back, on every rank
+        ok, err = False, repr(e)[:200]
+    box = [None] * world
+    dist.all_gather_object(box, ok, group=group)
+    if not all(box):
+        if not ok and rank == 0:
+            print(f"[rank {rank}] torch symmetric memory unavailable ({err}); using the CUDA-IPC gradient buffer", flush=True)
+        return None
+    peers = (C.c_void_p * world)(*[int(hdl.buffer_ptrs[p]) + off for p in range(world)])
+    mc = int(hdl.multicast_ptr) + off if int(hdl.multicast_ptr) else 0
+    try:
+        with torch.cuda.device(flat.device):
+            _lib.check(lib.rvae_dp_sym_adopt(ops.ctx(flat.device), peers, C.c_void_p(mc or None), n_data * 4, rank, world))
+    except _lib.RvaeError as e:
+        ok = False
+        print(f"[rank {rank}] rvae_dp_sym_adopt failed ({e})", flush=True)
+    box = [None] * world
+    dist.all_gather_object(box, ok, group=group)
+    if not all(box):
+        raise RuntimeError("data parallel set-up: rvae_dp_sym_adopt failed on some ranks (see above)")
+    _SYMM_KEEP.append((buf, hdl))
+    dist.barrier(group=group)      # every rank's flag area is zeroed and mapped before anyone signals
+    return buf[flag_bytes // 4: flag_bytes // 4 + flat.total]
+
+
+def _move_grads(model, flat, grads):
+    if flat.grads.data_ptr() != grads.data_ptr():
+        grads.copy_(flat.grads)
+        flat.grads = grads
+        model._plans = {}              # plans bind raw pointers: rebuild them on the new gradient buffer
+        for _, p in model._named():
+            p.grad = None
+
+
 def adopt_symmetric_grads(model, group=None) -> bool:
     """Move the model's flat gradient buffer into a symmetric allocation that every rank of the group maps over
     CUDA IPC, so the gradient all-reduce can be done by librvae_b200's own NVLink peer-memory kernel instead of NCCL.
@@ -91,7 +147,7 @@ def adopt_symmetric_grads(model, group=None) -> bool:
     import ctypes as C
     flat = model._ensure_flat()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    if os.environ.get("RVAE_DP_BACKEND", "p2p") == "nccl" or world > 8:
+    if os.environ.get("RVAE_DP_BACKEND", "auto") == "nccl" or world > 8:
         return False
     key = flat.device.index
     if key in _SYM_READY:
@@ -99,9 +155,21 @@ def adopt_symmetric_grads(model, group=None) -> bool:
             return False               # one symmetric gradient buffer per device: other models use NCCL
         grads = _SYM_READY[key][0]
     else:
+        lib = _lib.load()
+        # First choice: a symmetric allocation from torch.distributed's symmetric memory (plumbing: it creates, exchanges
+        # and maps the handles) WITH an NVLS multicast mapping, so the all-reduce kernel reduces in the NVSwitch.
+        # Default ("auto"): from 3 ranks up. Measured on one box (profiles/README.md): N = 8 +5.4 %, N = 4 +2.6 %, N = 2
+        # -3.5 % (with two ranks a rank's own slice travels to the switch and back for nothing), so two ranks keep the
+        # library's own CUDA-IPC allocation and peer loads. RVAE_DP_BACKEND=nvls / p2p / nccl force one.
+        backend = os.environ.get("RVAE_DP_BACKEND", "auto")
+        if backend == "nvls" or (backend == "auto" and world >= 3):
+            grads = _adopt_torch_symmetric(lib, flat, group, rank, world)
+            if grads is not None:
+                _SYM_READY[key] = (grads, flat.total)
+                _move_grads(model, flat, grads)
+                return True
         # Every step below is agreed on by ALL ranks before anyone relies on it: if a single rank cannot allocate,
         # export or map the buffers (no CUDA IPC in this container, no peer access), the whole group stays on NCCL.
-        lib = _lib.load()
         ptr, handle = C.c_void_p(), (C.c_char * 64)()
         ok = True
         with torch.cuda.device(flat.device):

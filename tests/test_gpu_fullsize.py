@@ -283,16 +283,20 @@ def _need_gpus(n):
         pytest.skip(f"needs {n} GPUs (gpurun --gpus {n}); logs of the multi-GPU runs are under profiles/")
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_data_parallel_step_equals_single_process_step_on_gpus(world):
+@pytest.mark.parametrize("world,backend", [(2, "p2p"), (2, "nvls"), (4, "auto"), (8, "auto"), (8, "p2p")])
+def test_data_parallel_step_equals_single_process_step_on_gpus(world, backend):
     """SURVEY.md section 4 'distributed' row on hardware: W ranks, each with its shard of a global batch, through
-    DataParallelTrainStep (the NVLink peer-memory all-reduce kernel, per-bucket Adam) == the single-process
+    DataParallelTrainStep (the library's own all-reduce kernel, per-bucket Adam) == the single-process
     FusedTrainStep on the concatenated batch - losses, weights, Adam moments, 3 steps, unequal shards - and the
-    replicas stay bit-identical. Also with in-library noise: the ranks' Philox draws are the single-process draw."""
+    replicas stay bit-identical. Also with in-library noise: the ranks' Philox draws are the single-process draw.
+    Both exchange flavours: peer loads + posted peer writes over CUDA-IPC mappings ("p2p"), and the in-switch reduction
+    over an NVLS multicast mapping (multimem.ld_reduce / multimem.st, "nvls"; "auto" picks it from 3 ranks up)."""
     _need_gpus(world)
-    res = _torchrun(world, ROOT / "tools" / "dp_check.py")
+    res = _torchrun(world, ROOT / "tools" / "dp_check.py", env={"RVAE_DP_BACKEND": backend})
     assert res.returncode == 0 and "DP CHECK PASSED" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
     assert "philox shards match the single-process draw: True" in res.stdout, res.stdout[-3000:]
+    want_mc = backend == "nvls" or (backend == "auto" and world >= 3)
+    assert f"multicast exchange: {want_mc}" in res.stdout, res.stdout[-3000:]
 
 
 def test_stream_trainer_under_torchrun_survives_a_slow_checkpoint(tmp_path):

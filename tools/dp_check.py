@@ -81,6 +81,8 @@ same = bool(torch.equal(ref, m_dp._flat.params))
 flag = torch.tensor([int(ok and same)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
+    from rawaudiovae_kelsey_b200 import _lib, ops
+    print("multicast exchange:", bool(_lib.load().rvae_dp_uses_multicast(ops.ctx(dev))))
     print("replicas identical:", same, "| DP CHECK", "PASSED" if int(flag) else "FAILED")
 dist.barrier()
 dist.destroy_process_group()
