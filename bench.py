@@ -429,8 +429,10 @@ def run_ours(args):
         flops = sum(v[1] * v[2] for v in tm.values()) / nroof
         passes = 3 if args.precision == "fp32" else 1
         achieved = flops / (gemm_ms * 1e-3) / 1e12
-        # the attribution pass times each GEMM launch ALONE (events serialise the stream, ~10 ms in total): that is
-        # a burst measurement, so the denominator is the measured burst peak
+        # the attribution pass runs the step's OWN launches (the fused dgrad + weight-gradient launches included, their
+        # flops booked together) one at a time: events around each launch serialise the stream (no overlap of a kernel's
+        # prologue with its predecessor's tail, no background stream), ~6 ms in total: a burst measurement, so the
+        # denominator is the measured burst peak
         peak = peaks["bf16_burst"]
         traffic, traffic_src = None, None
         for name in ("r2_gemms_ncu.json", "r1_gemms_ncu.json"):   # dram__bytes_read + write of the 11 GEMMs, one ncu capture
@@ -444,12 +446,16 @@ def run_ours(args):
                     traffic = None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src,
-                    "kernel": "rvae::gemm_kernel<*> (11 GEMMs/step; the training step fuses 6 of them into 3 launches)",
+                    "kernel": "rvae::gemm_kernel<*> / gemm_chain_kernel_2cta<*>: the 11 GEMMs of a step in the 9 launches the step "
+                              "uses (stages 0 and 2 of backward: dgrad + weight gradient fused into one launch)",
+                    "launches_per_step": sum(v[1] for v in tm.values()) / nroof,
                     "peak_kind": f"bf16_tflops burst ({peaks['source']}): each launch timed alone",
                     "algorithmic_flops_per_step": flops, "gemm_ms_per_step": gemm_ms,
                     "tensor_passes": passes}
-        breakdown = {k: {"us": 1e3 * v[0] / max(v[1], 1), "tflops": (v[2] / (v[0] / max(v[1], 1) * 1e-3) / 1e12)
-                         if v[0] > 0 else None} for k, v in tm.items() if v[1] > 0}
+        fused_with = {"B4d": "B4w", "B2d": "B2w", "B3d": "B3w"}   # a fused launch is booked on the dgrad's slot
+        label = lambda k: f"{k}+{fused_with[k]}" if k in fused_with and tm.get(fused_with[k], (0, 0, 0))[1] == 0 else k
+        breakdown = {label(k): {"us": 1e3 * v[0] / max(v[1], 1), "tflops": (v[2] / (v[0] / max(v[1], 1) * 1e-3) / 1e12)
+                                if v[0] > 0 else None} for k, v in tm.items() if v[1] > 0}
         breakdown["other_kernels_us_per_step"] = aux
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores

@@ -987,6 +987,27 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   if (stage == 1 && ext == nullptr && latent_fused(p)) return backward_stage_latent_fused(p, st);
   if (stage == 1 && !p->dz_zeroed)
     RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
+  if (stage == 1 && p->split_stage1 && p->timing && p->batch > kBlockM) {
+    // per-kernel timing of the split stage: the same three kernels, one after the other on `st`
+    GemmSet* gs;
+    RVAE_CHECK(get_set(p, &gs));
+    RVAE_CHECK(run(p, G_B3D, st));
+    RVAE_CHECK(prepare(p, *gs, G_B3W));
+    {
+      TimedScope ts(p, G_B3W, st);
+      PreparedGemm w = gs->g[G_B3W];
+      p->t_flops[G_B3W] = 2.0 * w.params.M * w.params.N * w.params.K;
+      if (w.grid > p->s1_wgrad_ctas) w.grid = p->s1_wgrad_ctas;
+      RVAE_CHECK(gemm_run(&p->ctx->c, w, st));
+    }
+    TimedScope ts(p, T_LATENT, st);
+    RVAE_CHECK(launch_latent_bwd(&p->ctx->c, p->dz, p->eps, ext ? ext->lv : p->lv, p->mu, ext ? ext->g_mu : nullptr,
+                                 ext ? ext->g_lv : nullptr, p->kl_c0, p->batch, L, p->dml.hi, p->dml.lo, grads + ly.b2, 1,
+                                 p->fin_pending ? &p->fin : nullptr, st));
+    p->fin_pending = false;
+    p->dz_zeroed = true;
+    return RVAE_OK;
+  }
   if (stage == 1 && p->split_stage1 && p->two_streams && !p->timing && p->batch > kBlockM) {
     // latent dgrad, then the latent backward kernel (HBM-bound, feeds stage 2: the critical chain) on `st` while the fc3
     // weight gradient runs beside it on a second stream, held to a part of the machine
@@ -1026,7 +1047,7 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   }
   // dgrad and weight gradient of the stage as ONE persistent launch over a mixed, load-balanced tile list
   bool fused = false;
-  if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && !p->timing && sched_usable(p)) {
+  if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && sched_usable(p)) {
     // under data parallelism the fused launches leave the same spare SMs as the single GEMMs do: NCCL's kernels
     // run there
     int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
@@ -1051,6 +1072,14 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
       if (rc == RVAE_OK) p->sched_batch = p->batch;
     }
     if (gs->dual_state[stage] == 1) {
+      // per-kernel timing: the fused launch IS the kernel of this stage - its time and the flops of both problems are
+      // booked on the dgrad's slot (the weight gradient's slot stays empty)
+      TimedScope ts(p, kDgrad[stage], st);
+      if (p->timing) {
+        const GemmParams& a = gs->g[kDgrad[stage]].params;
+        const GemmParams& b = gs->g[kWgrad[stage]].params;
+        p->t_flops[kDgrad[stage]] = 2.0 * a.M * a.N * a.K + 2.0 * b.M * b.N * b.K;
+      }
       RVAE_CHECK(gemm_run_chain(&p->ctx->c, gs->dual[stage], st));
       fused = true;
     }

@@ -878,3 +878,34 @@ def test_frames_read_in_place_equal_gathered_frames(dev, monkeypatch, precision,
         res[span_on] = (torch.stack(out).cpu(), model._flat.params.clone())
     assert torch.allclose(res[True][0], res[False][0], rtol=1e-4, atol=0)
     assert rel(res[True][1], res[False][1]) < 1e-3
+
+
+def test_per_kernel_timing_mode_runs_the_same_step(dev):
+    """bench.py's roofline attribution (rvae_plan_enable_timing): the step's own launches - the fused dgrad + weight
+    gradient launches of backward stages 0 and 2 included, booked on the dgrad's slot with the flops of both problems -
+    run one at a time between CUDA events. The step computes the same thing as the untimed step."""
+    from rawvae.model import VAE, FusedTrainStep
+    from rawaudiovae_kelsey_b200.optim import Adam
+    S, H, L, B = 1024, 2048, 256, 8192      # default.ini at the bench's batch: the shapes whose stages fuse
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.rand(B, S, generator=gen) * 2 - 1).to(dev)
+    eps = torch.randn(B, L, generator=gen).to(dev)
+    res = {}
+    for timed in (False, True):
+        torch.manual_seed(0)
+        model = VAE(S, H, L).to(dev)
+        step = FusedTrainStep(model, Adam(model.parameters(), lr=1e-3), 1e-3)
+        plan = model._plan_for(B)
+        plan.enable_timing(timed)
+        losses = [step(x, eps=eps).clone() for _ in range(3)]
+        torch.cuda.synchronize()
+        if timed:
+            tm = plan.read_timing()
+            plan.enable_timing(False)
+            assert tm["B4d"][1] == 3 and tm["B2d"][1] == 3 and tm["B3d"][1] == 3 and tm["B3w"][1] == 3 and tm["B1w"][1] == 3
+            assert tm["B4w"][1] == 0 and tm["B2w"][1] == 0, "stages 0 and 2 run as ONE fused launch each"
+            assert tm["B4d"][2] == 2.0 * B * H * S * 2 and tm["B2d"][2] == 2.0 * B * H * 2 * L * 2    # both problems' flops
+            assert all(tm[k][0] > 0 for k in ("F1", "F2", "F3", "F4_out", "B4d", "B3d", "B3w", "B2d", "B1w", "adam", "latent_bwd"))
+        res[timed] = (torch.stack(losses).cpu(), model._flat.params.clone())
+    assert torch.allclose(res[True][0], res[False][0], rtol=1e-4, atol=0)
+    assert rel(res[True][1], res[False][1]) < 2e-3      # reduction-order noise (split-K reduce-adds) through 3 Adam steps
