@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RVAE_ABI_VERSION 4
+#define RVAE_ABI_VERSION 5
 
 typedef struct rvae_ctx rvae_ctx;   /* per-device context (SM count, launch counter) */
 typedef struct rvae_plan rvae_plan; /* a bound training / inference step for fixed shapes and buffers */
@@ -164,9 +164,12 @@ int rvae_step_inc(rvae_ctx* ctx, float* step, void* stream);
 /* Fused Adam over a flat fp32 buffer (torch.optim.Adam semantics; train.py:163,193; train_iterable.py:180,210):
  *   g' = g*grad_scale (+ weight_decay*p); m += (1-b1)(g'-m); v = b2 v + (1-b2) g'^2;
  *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps),  t = *step.
+ * lr, beta1, beta2, eps, weight_decay are DOUBLES - what torch.optim.Adam holds - and every scalar of the update is
+ * derived from them as torch derives it: 1 - beta and the bias corrections 1 - beta^t in double, then rounded to
+ * fp32 (a float beta would make (1 - b2) 1.3e-5 off). The arithmetic on the tensors is fp32.
  * Optionally re-emits the bf16 shadow planes of p (what the GEMMs read). */
-int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, float grad_scale, const float* step, void* shadow_hi,
+int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, float grad_scale, const float* step, void* shadow_hi,
                    void* shadow_lo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -337,17 +340,17 @@ int rvae_plan_note_prefetched(rvae_plan* plan, int count, int span_hop /* 0 = ga
 /* Adam over the flat buffers (+ shadow refresh). grad_scale rescales the gradients (1 for SUM all-reduced,
  * globally normalised gradients). zero_grads != 0: the kernel also clears bufs.grads after consuming it - the
  * optimizer.zero_grad() of the next iteration (train.py:184) - which lets the next backward skip its memsets. */
-int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
+int rvae_plan_adam(rvae_plan* plan, double lr, double beta1, double beta2, double eps, double weight_decay,
                    float grad_scale, int zero_grads, void* stream);
 /* Adam restricted to the gradient buckets in bucket_mask (bit s = bucket s of rvae_plan_bucket): lets a caller update
  * a bucket as soon as its gradient (and, under data parallelism, its all-reduce) is complete. The caller orders the
  * launch after the backward stage that completes the bucket: that stage's dgrad GEMM reads the bucket's bf16 shadow. */
-int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, float lr, float beta1, float beta2, float eps,
-                           float weight_decay, float grad_scale, int zero_grads, void* stream);
+int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, double lr, double beta1, double beta2, double eps,
+                           double weight_decay, float grad_scale, int zero_grads, void* stream);
 /* forward + loss + backward + Adam in one call (single-GPU training step). Adam runs per bucket on an internal
  * stream underneath the later backward stages; everything is joined back into `stream` before the call returns. */
-int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream);
+int rvae_plan_train_step(rvae_plan* plan, float kl_beta, double lr, double beta1, double beta2, double eps,
+                         double weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream);
 
 /* Device pointers into the workspace for the current batch (valid after forward): fp32 [batch, ...]. */
 const float* rvae_plan_mu(const rvae_plan* plan);

@@ -13,9 +13,10 @@ from . import _build
 
 _LIB = None
 _LOCK = threading.Lock()
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_int64, c_uint64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+c_double = C.c_double
 
 
 class RvaeError(RuntimeError):
@@ -64,8 +65,8 @@ SIGNATURES = {
     "rvae_tanh_bwd": (c_int, [P, P, P, c_int64, P, P, P]),
     "rvae_colsum": (c_int, [P, P, P, c_int64, c_int, c_int, P, c_int, P]),
     "rvae_step_inc": (c_int, [P, P, P]),
-    "rvae_adam_step": (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, P, P, P,
-                               P]),
+    "rvae_adam_step": (c_int, [P, P, P, P, P, c_int64, c_double, c_double, c_double, c_double, c_double, c_float, P, P,
+                               P, P]),
     "rvae_linear_act_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     "rvae_encode_head_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "rvae_out_tanh_mse_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, c_int, P, P, P, c_float, P, P, P]),
@@ -98,9 +99,9 @@ SIGNATURES = {
     "rvae_plan_load_span": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, P]),
     "rvae_plan_prefetch_span": (c_int, [P, P, c_int, c_int64, P, c_int64, c_int, c_int, c_uint64, c_uint64, c_int]),
     "rvae_plan_join_background": (c_int, [P, P]),
-    "rvae_plan_adam_buckets": (c_int, [P, C.c_uint, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
-    "rvae_plan_adam": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P]),
-    "rvae_plan_train_step": (c_int, [P, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P, c_int, P]),
+    "rvae_plan_adam_buckets": (c_int, [P, C.c_uint, c_double, c_double, c_double, c_double, c_double, c_float, c_int, P]),
+    "rvae_plan_adam": (c_int, [P, c_double, c_double, c_double, c_double, c_double, c_float, c_int, P]),
+    "rvae_plan_train_step": (c_int, [P, c_float, c_double, c_double, c_double, c_double, c_double, c_int, P, c_int, P]),
     "rvae_plan_mu": (P, [P]),
     "rvae_plan_logvar": (P, [P]),
     "rvae_plan_xhat": (P, [P]),

@@ -365,8 +365,8 @@ int rvae_step_inc(rvae_ctx* ctx, float* step, void* stream) {
   CTX_OR_FAIL(ctx);
   return launch_step_inc(&ctx->c, step, S_(stream));
 }
-int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, float grad_scale, const float* step, void* shadow_hi,
+int rvae_adam_step(rvae_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, float grad_scale, const float* step, void* shadow_hi,
                    void* shadow_lo, void* stream) {
   CTX_OR_FAIL(ctx);
   return launch_adam(&ctx->c, p, const_cast<float*>(g), m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
@@ -875,7 +875,7 @@ int ensure_side_stream(rvae_plan* p) {
 
 // Adam over the gradient buckets selected by `mask` (bit s = bucket s of rvae_plan_bucket): the selected buckets are
 // merged into contiguous segments of the flat buffer and updated with one launch per pair of segments.
-int adam_buckets(rvae_plan* p, unsigned mask, float lr, float beta1, float beta2, float eps, float weight_decay,
+int adam_buckets(rvae_plan* p, unsigned mask, double lr, double beta1, double beta2, double eps, double weight_decay,
                  float grad_scale, int zero_grads, int step_bias, bool advance_step, cudaStream_t st) {
   const rvae_layout& ly = p->lay;
   const rvae_plan_buffers& b = p->bufs;
@@ -1575,13 +1575,13 @@ int rvae_plan_note_prefetched(rvae_plan* plan, int count, int span_hop) {
   return RVAE_OK;
 }
 
-int rvae_plan_adam(rvae_plan* plan, float lr, float beta1, float beta2, float eps, float weight_decay,
+int rvae_plan_adam(rvae_plan* plan, double lr, double beta1, double beta2, double eps, double weight_decay,
                    float grad_scale, int zero_grads, void* stream) {
   return rvae_plan_adam_buckets(plan, 0x1f, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grads, stream);
 }
 
-int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, float lr, float beta1, float beta2, float eps,
-                           float weight_decay, float grad_scale, int zero_grads, void* stream) {
+int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, double lr, double beta1, double beta2, double eps,
+                           double weight_decay, float grad_scale, int zero_grads, void* stream) {
   RVAE_CHECK(check_ready(plan, false));
   const rvae_plan_buffers& b = plan->bufs;
   RVAE_REQUIRE(b.grads && b.exp_avg && b.exp_avg_sq && b.step, RVAE_ERR_STATE,
@@ -1594,8 +1594,8 @@ int rvae_plan_adam_buckets(rvae_plan* plan, unsigned bucket_mask, float lr, floa
                       S_(stream));
 }
 
-int rvae_plan_train_step(rvae_plan* plan, float kl_beta, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream) {
+int rvae_plan_train_step(rvae_plan* plan, float kl_beta, double lr, double beta1, double beta2, double eps,
+                         double weight_decay, int zero_grads, float* loss_out, int ring_size, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
   const rvae_plan_buffers& b = plan->bufs;
   RVAE_REQUIRE(b.grads && b.exp_avg && b.exp_avg_sq && b.step, RVAE_ERR_STATE,

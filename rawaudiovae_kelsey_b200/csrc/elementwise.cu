@@ -722,22 +722,28 @@ int launch_lerp_reparam(Ctx* ctx, const float* mu_a, const float* lv_a, const fl
 // multiples of 4 then): the per-bucket launches of a training step (W3|W4, W2, W1 + bias block).
 template <int U>
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, int64_t off_b, int64_t n_b, float lr, float beta1,
-                            float beta2, float eps, float weight_decay, float grad_scale, float* step,
+                            float* __restrict__ v, int64_t n, int64_t off_b, int64_t n_b, double lr, double beta1_d,
+                            double beta2_d, double eps_d, double weight_decay_d, float grad_scale, float* step,
                             int step_bias, unsigned int* ticket, __nv_bfloat16* __restrict__ sh_hi,
                             __nv_bfloat16* __restrict__ sh_lo, int zero_grads, AuxTrace tr) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   aux_begin(tr, 4);
+  // The hyper-parameters arrive as doubles - what torch.optim.Adam holds (python floats) - and every scalar the
+  // update uses is derived from them exactly as torch derives it: 1 - beta in DOUBLE, then rounded to fp32 (the weight
+  // of lerp_ / the value of addcmul_; (1.f - 0.999f) would be off by 1.3e-5 relative), beta2 and eps rounded to fp32.
+  const float omb1 = static_cast<float>(1.0 - beta1_d), beta2 = static_cast<float>(beta2_d);
+  const float omb2 = static_cast<float>(1.0 - beta2_d), eps = static_cast<float>(eps_d);
+  const float weight_decay = static_cast<float>(weight_decay_d);
   // bias corrections in double, as torch computes them on the host (python floats); one thread per block does the
   // fp64 pow()s and broadcasts the two scalars
   __shared__ float s_consts[2];
   if (threadIdx.x == 0) {
     // t = *step + step_bias: step_bias = 1 when the step counter is advanced only at the end of the step (ticket)
     const double t = static_cast<double>(*reinterpret_cast<volatile float*>(step)) + step_bias;
-    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
-    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
-    s_consts[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+    const double bc1 = 1.0 - pow(beta1_d, t);
+    const double bc2 = 1.0 - pow(beta2_d, t);
+    s_consts[0] = static_cast<float>(lr / bc1);
     s_consts[1] = static_cast<float>(sqrt(bc2));
   }
   __syncthreads();
@@ -778,8 +784,8 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
       for (int j = 0; j < 4; ++j) {
         float gr = ga[j] * grad_scale;
         if (weight_decay != 0.f) gr = fmaf(weight_decay, pa[j], gr);
-        ma[j] = ma[j] + (1.f - beta1) * (gr - ma[j]);
-        va[j] = beta2 * va[j] + (1.f - beta2) * gr * gr;
+        ma[j] = ma[j] + omb1 * (gr - ma[j]);
+        va[j] = beta2 * va[j] + omb2 * gr * gr;
         const float denom = sqrtf(va[j]) / sqrt_bc2 + eps;
         pa[j] = pa[j] - step_size * (ma[j] / denom);
       }
@@ -803,8 +809,8 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     for (int64_t j = (nvec << 2) + threadIdx.x; j < n; j += blockDim.x) {
       float gr = g[j] * grad_scale;
       if (weight_decay != 0.f) gr = fmaf(weight_decay, p[j], gr);
-      const float mj = m[j] + (1.f - beta1) * (gr - m[j]);
-      const float vj = beta2 * v[j] + (1.f - beta2) * gr * gr;
+      const float mj = m[j] + omb1 * (gr - m[j]);
+      const float vj = beta2 * v[j] + omb2 * gr * gr;
       const float pj = p[j] - step_size * (mj / (sqrtf(vj) / sqrt_bc2 + eps));
       m[j] = mj; v[j] = vj; p[j] = pj;
       if (zero_grads) g[j] = 0.f;
@@ -831,15 +837,15 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
-int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                float eps, float weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
+int launch_adam(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                double eps, double weight_decay, float grad_scale, const float* step, __nv_bfloat16* shadow_hi,
                 __nv_bfloat16* shadow_lo, int zero_grads, cudaStream_t stream) {
   return launch_adam2(ctx, p, g, m, v, n, 0, 0, lr, beta1, beta2, eps, weight_decay, grad_scale,
                       const_cast<float*>(step), 0, nullptr, shadow_hi, shadow_lo, zero_grads, stream);
 }
 
-int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, int64_t off_b, int64_t n_b, float lr,
-                 float beta1, float beta2, float eps, float weight_decay, float grad_scale, float* step, int step_bias,
+int launch_adam2(Ctx* ctx, float* p, float* g, float* m, float* v, int64_t n, int64_t off_b, int64_t n_b, double lr,
+                 double beta1, double beta2, double eps, double weight_decay, float grad_scale, float* step, int step_bias,
                  unsigned int* ticket, __nv_bfloat16* shadow_hi, __nv_bfloat16* shadow_lo, int zero_grads,
                  cudaStream_t stream) {
   RVAE_REQUIRE(p && g && m && v && step, RVAE_ERR_INVALID, "adam: null buffer");

@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rvae_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.rvae_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.rvae_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_param_layout_matches_reference_parameter_count():
