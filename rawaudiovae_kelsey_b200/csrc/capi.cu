@@ -521,6 +521,8 @@ struct GemmSet {
   int dual_state[3];      // 0 = not tried, 1 = ready, -1 = unsupported for these shapes (separate launches)
   PreparedChain dual_lat; // stage 1 with the fused latent epilogue (G_B3D_LAT + G_B3W)
   int dual_lat_state;
+  PreparedChain tri;      // stage 2 with stage 1's weight gradient riding along: B2d + B2w + B3w in one launch
+  int tri_state;
   PreparedChain fwd;      // forward: fc1 -> encoder head -> fc3 -> fc4/loss chained by tile-level dependencies
   int fwd_state;
 };
@@ -546,7 +548,7 @@ struct rvae_plan {
   // side input and the fc1 weight gradient's B operand read frame i at row pitch hop through overlapping-row tensor
   // maps. 0 = the planes hold dense [count, S] rows (gather / tensor input).
   int x_pitch, x_pitch_alt;
-  int* sched_dev;          // schedules of the fused launches: [2 input sets][5 launches][128 pairs][kSchedMax]
+  int* sched_dev;          // schedules of the fused launches: [2 input sets][6 launches][128 pairs][kSchedMax]
   int sched_batch;         // the batch size those schedules were built for (0 = none yet): the buffer holds ONE set of
                            // schedules, so other batch sizes of this plan (a ragged last batch) run separate launches
   unsigned int* dep_flags; // row-block counters of the chained forward launch: [3 layer transitions][256]
@@ -595,6 +597,14 @@ struct rvae_plan {
   cudaEvent_t ev_s1_fork, ev_s1_join;
   bool split_stage1;
   int s1_wgrad_ctas, s1_order;
+  // The fc3 weight gradient (B3w) needs only da3 and z, so it does not have to run in stage 1: when all four stages of a
+  // backward pass are issued together (rvae_plan_train_step, rvae_plan_backward(-1), the autograd backward), stage 1 is
+  // just latent dgrad -> latent kernel on the whole machine, and B3w's MMA-heavy units ride in stage 2's fused launch,
+  // whose dgrad tiles are epilogue-bound and leave the tensor pipe idle (B2d + B2w + B3w). Gradient bucket 1 (fc3) is
+  // then complete after stage 2 instead of stage 1.
+  bool merge_b3w;        // env RVAE_MERGE_B3W in RVAE_EXPERIMENTS builds; default off: measured, not a win (profiles/README.md)
+  bool allow_defer;      // set by the callers that issue all stages of a pass
+  bool b3w_deferred;     // stage 1 of the current pass left B3w to stage 2
   int adam_bg_blocks;    // grid cap of the single-process background Adam launch (0 = none)
   // data parallelism: gradient all-reduces run on their own stream, bucket by bucket as backward completes them
   cudaStream_t comm_stream;
@@ -645,7 +655,7 @@ size_t carve(rvae_plan* p, uint8_t* base) {
   p->eps = reinterpret_cast<float*>(take(B * L * 4));
   p->eps_alt = reinterpret_cast<float*>(take(B * L * 4));
   p->ticket = reinterpret_cast<unsigned int*>(take(256));
-  p->sched_dev = reinterpret_cast<int*>(take(sizeof(int) * 2 * 5 * 128 * kSchedMax));
+  p->sched_dev = reinterpret_cast<int*>(take(sizeof(int) * 2 * 6 * 128 * kSchedMax));
   p->dep_flags = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 3 * 256));
   p->dz = reinterpret_cast<float*>(take(B * L * 4));
   p->xhat = reinterpret_cast<float*>(take(B * S * 4));
@@ -952,7 +962,7 @@ int backward_stage_latent_fused(rvae_plan* p, cudaStream_t st) {
     if (gs->dual_lat_state == 0) {
       RVAE_CHECK(prepare(p, *gs, G_B3D_LAT));
       RVAE_CHECK(prepare(p, *gs, G_B3W));
-      int* sched = p->sched_dev + ((size_t)p->cur * 5 + 4) * 128 * kSchedMax;
+      int* sched = p->sched_dev + ((size_t)p->cur * 6 + 4) * 128 * kSchedMax;
       const PreparedGemm* both[2] = {&gs->g[G_B3D_LAT], &gs->g[G_B3W]};
       const int rc = gemm_prepare_chain(&p->ctx->c, both, 2, pairs, sched, &gs->dual_lat);
       gs->dual_lat_state = rc == RVAE_OK ? 1 : -1;
@@ -987,6 +997,60 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   if (stage == 1 && ext == nullptr && latent_fused(p)) return backward_stage_latent_fused(p, st);
   if (stage == 1 && !p->dz_zeroed)
     RVAE_CUDA(cudaMemsetAsync(p->dz, 0, sizeof(float) * (size_t)p->max_batch * L, st));
+  auto stage_pairs = [&](int st_idx) {
+    // under data parallelism the fused launches leave the same spare SMs as the single GEMMs do: the exchange kernels
+    // run there
+    int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
+    const char* names[3] = {"RVAE_DUAL_PAIRS_S0", "RVAE_DUAL_PAIRS_S1", "RVAE_DUAL_PAIRS_S2"};
+    if (const char* e = getenv(names[st_idx])) {   // experiments
+      const int v = atoi(e);
+      if (v >= 1 && 2 * v <= p->ctx->c.num_sms_total) pairs = v;
+    }
+    return pairs;
+  };
+  if (stage == 1 && p->allow_defer && p->merge_b3w && p->dual_pairs > 0 && sched_usable(p) && p->batch > kBlockM) {
+    // leave B3w to stage 2 - if the three-problem launch exists for these shapes
+    GemmSet* gs;
+    RVAE_CHECK(get_set(p, &gs));
+    if (gs->tri_state == 0) {
+      RVAE_CHECK(prepare(p, *gs, G_B2D));
+      RVAE_CHECK(prepare(p, *gs, G_B2W));
+      RVAE_CHECK(prepare(p, *gs, G_B3W));
+      int* sched = p->sched_dev + ((size_t)p->cur * 6 + 5) * 128 * kSchedMax;
+      const PreparedGemm* three[3] = {&gs->g[G_B2D], &gs->g[G_B2W], &gs->g[G_B3W]};
+      const int rc = gemm_prepare_chain(&p->ctx->c, three, 3, stage_pairs(2), sched, &gs->tri);
+      gs->tri_state = rc == RVAE_OK ? 1 : -1;
+      if (rc != RVAE_OK && rc != RVAE_ERR_UNSUPPORTED) return rc;
+      if (rc == RVAE_OK) p->sched_batch = p->batch;
+    }
+    if (gs->tri_state == 1) {
+      RVAE_CHECK(run(p, G_B3D, st));
+      {
+        TimedScope ts(p, T_LATENT, st);
+        RVAE_CHECK(launch_latent_bwd(&p->ctx->c, p->dz, p->eps, ext ? ext->lv : p->lv, p->mu, ext ? ext->g_mu : nullptr,
+                                     ext ? ext->g_lv : nullptr, p->kl_c0, p->batch, L, p->dml.hi, p->dml.lo, grads + ly.b2,
+                                     1, p->fin_pending ? &p->fin : nullptr, st));
+      }
+      p->fin_pending = false;
+      p->dz_zeroed = true;
+      p->b3w_deferred = true;
+      return RVAE_OK;
+    }
+  }
+  if (stage == 2 && p->b3w_deferred) {
+    GemmSet* gs;
+    RVAE_CHECK(get_set(p, &gs));
+    RVAE_REQUIRE(gs->tri_state == 1, RVAE_ERR_STATE, "plan_backward: stage 1 deferred the fc3 weight gradient but the "
+                 "three-problem launch is not prepared (batch or input set changed between the stages)");
+    p->b3w_deferred = false;
+    TimedScope ts(p, G_B2D, st);   // per-kernel timing: one kernel, the flops of all three problems
+    if (p->timing) {
+      double f = 0.0;
+      for (int id : {G_B2D, G_B2W, G_B3W}) { const GemmParams& q = gs->g[id].params; f += 2.0 * q.M * q.N * q.K; }
+      p->t_flops[G_B2D] = f;
+    }
+    return gemm_run_chain(&p->ctx->c, gs->tri, st);
+  }
   if (stage == 1 && p->split_stage1 && p->timing && p->batch > kBlockM) {
     // per-kernel timing of the split stage: the same three kernels, one after the other on `st`
     GemmSet* gs;
@@ -1048,23 +1112,14 @@ int backward_stage(rvae_plan* p, int stage, const LatentExt* ext, cudaStream_t s
   // dgrad and weight gradient of the stage as ONE persistent launch over a mixed, load-balanced tile list
   bool fused = false;
   if (kDgrad[stage] >= 0 && p->dual_pairs > 0 && sched_usable(p)) {
-    // under data parallelism the fused launches leave the same spare SMs as the single GEMMs do: NCCL's kernels
-    // run there
-    int pairs = (p->dp_enabled && p->ctx->dp_world > 1 && p->dual_pairs > 64) ? 64 : p->dual_pairs;
-    if (stage == 1 && pairs > 64) pairs = 64;   // the small stage gains nothing from 10 more pairs; the background stream does
-    {  // experiments: RVAE_DUAL_PAIRS_S<stage> overrides the pair count of one stage
-      const char* names[3] = {"RVAE_DUAL_PAIRS_S0", "RVAE_DUAL_PAIRS_S1", "RVAE_DUAL_PAIRS_S2"};
-      if (const char* e = getenv(names[stage])) {
-        const int v = atoi(e);
-        if (v >= 1 && 2 * v <= p->ctx->c.num_sms_total) pairs = v;
-      }
-    }
+    int pairs = stage_pairs(stage);
+    if (stage == 1 && pairs > 64 && !getenv("RVAE_DUAL_PAIRS_S1")) pairs = 64;   // the small stage gains nothing from 10 more pairs
     GemmSet* gs;
     RVAE_CHECK(get_set(p, &gs));
     if (gs->dual_state[stage] == 0) {
       RVAE_CHECK(prepare(p, *gs, kDgrad[stage]));
       RVAE_CHECK(prepare(p, *gs, kWgrad[stage]));
-      int* sched = p->sched_dev + ((size_t)p->cur * 5 + stage) * 128 * kSchedMax;
+      int* sched = p->sched_dev + ((size_t)p->cur * 6 + stage) * 128 * kSchedMax;
       const PreparedGemm* both[2] = {&gs->g[kDgrad[stage]], &gs->g[kWgrad[stage]]};
       const int rc = gemm_prepare_chain(&p->ctx->c, both, 2, pairs, sched, &gs->dual[stage]);
       gs->dual_state[stage] = rc == RVAE_OK ? 1 : -1;
@@ -1131,6 +1186,10 @@ int rvae_plan_create(rvae_ctx* ctx, int S, int H, int L, int max_batch, int prec
   p->split_stage1 = true;
   p->s1_wgrad_ctas = 96;   // measured (profiles/README.md): 96 CTAs, weight gradient first
   p->s1_order = 0;
+  p->merge_b3w = false; p->allow_defer = false; p->b3w_deferred = false;
+#if RVAE_EXPERIMENTS
+  if (const char* e = getenv("RVAE_MERGE_B3W")) p->merge_b3w = atoi(e) != 0;
+#endif
   p->adam_bg_blocks = 0;
   if (const char* e = getenv("RVAE_ADAM_BG_BLOCKS")) p->adam_bg_blocks = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("RVAE_S1_ORDER")) p->s1_order = atoi(e) != 0;
@@ -1403,7 +1462,7 @@ int rvae_plan_forward(rvae_plan* plan, float kl_beta, int fused_loss, int want_x
         RVAE_CHECK(prepare(p, *gs, kLayers[k]));
         layers[k] = &gs->g[kLayers[k]];
       }
-      int* sched = p->sched_dev + ((size_t)p->cur * 5 + 3) * 128 * kSchedMax;
+      int* sched = p->sched_dev + ((size_t)p->cur * 6 + 3) * 128 * kSchedMax;
       int fpairs = p->dual_pairs;
       if (const char* e = getenv("RVAE_DUAL_PAIRS_F")) {
         const int v = atoi(e);
@@ -1468,8 +1527,11 @@ int rvae_plan_backward(rvae_plan* plan, int stage, void* stream) {
   RVAE_CHECK(check_ready(plan, true));
   RVAE_REQUIRE(plan->bufs.grads, RVAE_ERR_STATE, "plan_backward: no grads buffer bound");
   if (stage == -1) {
-    for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(plan, s, nullptr, S_(stream)));
-    return RVAE_OK;
+    plan->allow_defer = true;   // all four stages follow each other
+    int rc = RVAE_OK;
+    for (int s = 0; s < 4 && rc == RVAE_OK; ++s) rc = backward_stage(plan, s, nullptr, S_(stream));
+    plan->allow_defer = false;
+    return rc;
   }
   return backward_stage(plan, stage, nullptr, S_(stream));
 }
@@ -1488,8 +1550,11 @@ int rvae_plan_backward_external(rvae_plan* plan, const float* g_xhat, const floa
   { TimedScope ts(p, T_COLSUM, st);
     RVAE_CHECK(launch_colsum(&p->ctx->c, p->da4.hi, p->da4.lo, p->batch, p->S, p->S, p->bufs.grads + p->lay.b4, 1, st)); }
   const LatentExt ext = {g_mu, g_logvar, logvar};
-  for (int s = 0; s < 4; ++s) RVAE_CHECK(backward_stage(p, s, &ext, st));
-  return RVAE_OK;
+  p->allow_defer = true;   // all four stages follow each other
+  int rc = RVAE_OK;
+  for (int s = 0; s < 4 && rc == RVAE_OK; ++s) rc = backward_stage(p, s, &ext, st);
+  p->allow_defer = false;
+  return rc;
 }
 
 int rvae_plan_finish_loss(rvae_plan* plan, float kl_beta, float* loss_out, int ring_size, void* stream) {
@@ -1696,19 +1761,30 @@ int rvae_plan_train_step(rvae_plan* plan, float kl_beta, double lr, double beta1
     plan->fin_pending = false;
     return RVAE_OK;
   };
+  // all stages of this pass are issued here: stage 1 may leave the fc3 weight gradient to stage 2's fused launch
+  struct DeferGuard {
+    rvae_plan* p;
+    explicit DeferGuard(rvae_plan* p_) : p(p_) { p->allow_defer = true; }
+    ~DeferGuard() { p->allow_defer = false; p->b3w_deferred = false; }
+  } defer_guard(plan);
+  bool w3_with_stage2 = false;
   for (int s = 0; s < 3; ++s) {
     RVAE_CHECK(rvae_plan_backward(plan, s, st));
+    if (s == 1) w3_with_stage2 = plan->b3w_deferred;
     if (dp) {
-      // four exchanges per step: W4 after stage 0, W3 after stage 1, W2 + all biases after stage 2 (kept small: it
-      // must be out of the way when stage 3 ends), W1 after stage 3
+      // exchanges per step: W4 after stage 0, W3 after stage 1 (or, when stage 1 left its weight gradient to stage 2,
+      // together with the next one), W2 + all biases after stage 2 (kept small: it must be out of the way when stage
+      // 3 ends), W1 after stage 3
       static const unsigned kExchange[3] = {0x1u, 0x2u, 0x14u};
+      if (s == 1 && w3_with_stage2) continue;   // bucket 1 is not complete yet
+      const unsigned extra = (s == 2 && w3_with_stage2) ? 0x2u : 0u;
       RVAE_CUDA(cudaEventRecord(plan->ev_comm_fork, st));
       RVAE_CUDA(cudaStreamWaitEvent(cs, plan->ev_comm_fork, 0));
-      RVAE_CHECK(allreduce_buckets(kExchange[s], s, cx->p2p_ctas, cs));
+      RVAE_CHECK(allreduce_buckets(kExchange[s] | extra, s, cx->p2p_ctas, cs));
       RVAE_CUDA(cudaEventRecord(plan->ev_comm_done[s], cs));
       RVAE_CUDA(cudaStreamWaitEvent(bg, plan->ev_comm_done[s], 0));
       if (s == 0) RVAE_CHECK(finalize_on_bg());
-      RVAE_CHECK(adam_buckets(plan, kBucketMask[s], lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
+      RVAE_CHECK(adam_buckets(plan, kBucketMask[s] | extra, lr, beta1, beta2, eps, weight_decay, 1.0f, zero_grads, 1, false, bg));
       continue;
     }
     // single process: only W4 (the first bucket to complete, with the most GEMM time left to hide under) is updated

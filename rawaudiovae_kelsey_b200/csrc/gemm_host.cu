@@ -341,7 +341,11 @@ static const ChainVariant kChainVariants[] = {
     {2, {RVAE_KID(KDrelu), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDrelu, KWgrad, NoKind, NoKind>},
     // split-K latent dgrad | weight gradient         (backward stage 1)
     {2, {RVAE_KID(KDz), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDz, KWgrad, NoKind, NoKind>},
+
 #if RVAE_EXPERIMENTS
+    // dgrad + ReLU mask | weight gradient | the previous stage's weight gradient   (stage 2 with B3w riding along:
+    // measured equal at N = 1 and 1.2 % slower at N = 2 than the split stage 1, profiles/README.md)
+    {3, {RVAE_KID(KDrelu), RVAE_KID(KWgrad), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDrelu, KWgrad, KWgrad, NoKind>},
     // latent dgrad with fused reparameterisation / KL backward | weight gradient   (backward stage 1, bf16 mode)
     {2, {RVAE_KID(KDlat), RVAE_KID(KWgrad)}, gemm_chain_kernel_2cta<256, KDlat, KWgrad, NoKind, NoKind>},
     // layers chained by tile-level dependencies: fc1 -> head, fc3 -> fc4 + loss, and the whole forward pass

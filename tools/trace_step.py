@@ -50,7 +50,9 @@ torch.cuda.synchronize()
 NAMES = ["F1", "F2", "F3", "F4", "B4d", "B4w", "B3d", "B3w", "B2d", "B2w", "B1w"]
 if os.environ.get("RVAE_DUAL_PAIRS", "64") != "0":   # backward stages 0..2 are fused dgrad + wgrad launches
     NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
-    if os.environ.get("RVAE_SPLIT_STAGE1", "1") != "0":   # stage 1: latent dgrad, then latent kernel || fc3 weight gradient
+    if os.environ.get("RVAE_MERGE_B3W", "0") != "0":      # experiments: stage 1 = latent dgrad + latent kernel; B3w rides in stage 2's launch
+        NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d", "B2d+B2w+B3w", "B1w"]
+    elif os.environ.get("RVAE_SPLIT_STAGE1", "1") != "0":   # stage 1: latent dgrad, then latent kernel || fc3 weight gradient
         NAMES = ["F1", "F2", "F3", "F4", "B4d+B4w", "B3d", "B3w", "B2d+B2w", "B1w"]
     if os.environ.get("RVAE_FUSE_FORWARD", "0") != "0":   # fc1 + head and fc3 + fc4 are chained launches
         NAMES = ["F1>F2>F3>F4", "B4d+B4w", "B3d+B3w", "B2d+B2w", "B1w"]
